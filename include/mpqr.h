@@ -1,0 +1,158 @@
+/*
+ * mpqr.h — C-ABI of libmpqr.so: B200-native (sm_100a) mixed-precision blocked Householder QR.
+ *
+ * Drop-in boundary for the block-QR path of jaidonlybbert/MixedPrecisionBlockQR.  The
+ * reference has no FFI layer; its operator API is four C++ free functions with
+ * C-compatible signatures (reference Cuda/qr.cuh:129-137):
+ *     void dev_mixed_precision_block_qr(float* A, float* Q, int m, int n, int r);
+ *     void dev_block_qr_wy            (float* A, float* Q, int m, int n, int r);
+ *     void dev_block_qr               (float* A, float* Q, int m, int n, int r);
+ *     void h_block_qr                 (float* A, float* Q, int m, int n, int r);
+ * Every entry point below names the reference interface it replaces.  Plain pointers and
+ * sizes only; no C++ / torch types.  All matrices are ROW-MAJOR FP32.
+ *
+ * Packed factor layout (reference Cuda/qr.cu:283-285, :1062):
+ *   buffer of (m+1) rows x n cols; on return rows<=cols hold R, and the UNIT Householder
+ *   vector w_k (H_k = I - 2 w_k w_k^T) of column k sits at rows k+1..m of column k (one
+ *   row BELOW the diagonal).  sign rule w ~ u + sign(u0)||u|| e1 with sign(0)=+1; an
+ *   all-zero column is skipped.
+ *
+ * Error behaviour: the reference is `void` and exit(1)s on CUDA errors
+ * (Cuda/helper_cuda.h:583-595).  Here every call returns 0 on success or a negative
+ * MPQR_E* code and never exits; mpqr_last_error() gives the message.  There is NO CPU
+ * fallback: without a CUDA device the calls fail with MPQR_ECUDA.
+ */
+#ifndef MPQR_H_
+#define MPQR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPQR_OK 0
+#define MPQR_EINVAL (-1)  /* bad argument */
+#define MPQR_ECUDA (-2)   /* CUDA runtime / driver error (see mpqr_last_error) */
+#define MPQR_ENOMEM (-3)  /* device allocation failed */
+#define MPQR_ENCCL (-4)   /* NCCL error */
+#define MPQR_ESTATE (-5)  /* call sequence error (e.g. form_q before factor) */
+
+/* flags */
+#define MPQR_FP32 0x0u       /* FP32 SIMT trailing update  (replaces dev_block_qr_wy, Cuda/qr.cu:958) */
+#define MPQR_FP16 0x1u       /* FP16 operands / FP32 accumulate on tcgen05 (replaces
+                                dev_mixed_precision_block_qr, Cuda/qr.cu:1049) */
+#define MPQR_BF16 0x2u       /* BF16 operands / FP32 accumulate on tcgen05 */
+#define MPQR_PRECISION_MASK 0x3u
+#define MPQR_KEEP_WY 0x10u   /* retain W (=Y T) for every outer block so that Q can be formed /
+                                WY factors read back after the factorisation */
+
+typedef struct mpqr_handle mpqr_handle;
+
+const char* mpqr_last_error(void);
+const char* mpqr_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-pointer drop-ins (same ownership contract as the reference drivers: caller owns
+ * A ((m+1)*n floats, rows 0..m-1 = input, row m = 0) and Q (m*m floats); callee moves
+ * data to the current device, factors, moves results back, leaves nothing resident).
+ *   mpqr_block_qr_host(..., MPQR_FP16) == dev_mixed_precision_block_qr  (Cuda/qr.cu:1049-1226)
+ *   mpqr_block_qr_host(..., MPQR_FP32) == dev_block_qr_wy / dev_block_qr (Cuda/qr.cu:958, :877)
+ * Q may be NULL (skip explicit Q).  On entry Q's contents are ignored (the reference
+ * requires identity, Cuda/qr.cu:1868-1872; identity in => same result).
+ * r is the reference's panel width; internally min(r,128) columns are factored per panel
+ * (the packed result does not depend on the grouping beyond rounding).
+ * ------------------------------------------------------------------------------------- */
+int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned flags);
+
+/* ---------------------------------------------------------------------------------------
+ * Device-resident API (what bench.py times as `value`): plan once, factor many times.
+ * ------------------------------------------------------------------------------------- */
+/* Allocates all workspaces for an m x n problem on the current device.
+ * r  : panel width (1..128 effective).  nb : outer block width for two-level blocking
+ * (multiple of the effective r; 0 = automatic).  flags as above. */
+int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags);
+int mpqr_destroy(mpqr_handle* h);
+
+/* Factor in place.  dA: device pointer to the packed (m+1) x lda FP32 buffer (lda >= n,
+ * row m must be present; its content on entry is ignored).  stream: cudaStream_t (NULL =
+ * legacy default stream).  Asynchronous with respect to the host.
+ * Replaces the body of dev_mixed_precision_block_qr's panel loop, Cuda/qr.cu:1074-1219. */
+int mpqr_factor_device(mpqr_handle* h, float* dA, long lda, void* stream);
+
+/* Explicit Q = H_1 ... H_min(m,n) (m x m, ldq >= m) by blocked backward accumulation
+ * (reference: Q[:, l:] <- Q[:, l:] (I - W Y^T), Cuda/qr.cu:1109-1207; h_q_backward_accumulation
+ * Cuda/qr.cu:296-335).  Needs MPQR_KEEP_WY at create time and a preceding factor call. */
+int mpqr_form_q_device(mpqr_handle* h, float* dQ, long ldq, void* stream);
+
+/* Compact-WY / WY factors of the last factorisation (north_star: "returning Q, or the WY
+ * factors, and R").  Panel p covers columns [p*r_eff, min((p+1)*r_eff, kmax)).
+ * T: r_eff x r_eff upper triangular FP32 with Q_p = I - Y_p T_p Y_p^T, copied to dT (device,
+ * ld >= r_eff).  Replaces what dev_wy_transform (Cuda/qr.cu:535-600) computes and frees. */
+int mpqr_get_panel_T(mpqr_handle* h, int panel, float* dT, int ldt, void* stream);
+int mpqr_num_panels(const mpqr_handle* h);
+int mpqr_effective_r(const mpqr_handle* h);
+int mpqr_effective_nb(const mpqr_handle* h);
+/* Number of kernels launched by the last factor / form_q call (for bench.py's gpu_launches). */
+long mpqr_last_launch_count(const mpqr_handle* h);
+
+/* ---------------------------------------------------------------------------------------
+ * Single kernels exposed for parity tests against the oracle (tests/ call these through
+ * ctypes).  All pointers are device pointers.
+ * ------------------------------------------------------------------------------------- */
+/* Panel factorisation of columns [lam, lam+pw) rows [lam, m) of the packed buffer; also
+ * emits Y, W = Y T (D x pw row-major FP32, ld = pw, D = m-lam) and T (pw x pw).
+ * Replaces h_householder_qr (Cuda/qr.cu:198-293) + dev_wy_transform's W/Y (Cuda/qr.cu:535-600).
+ * Any of dY, dW, dT may be NULL. */
+int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
+                             float* dY, float* dW, float* dT, void* stream);
+
+/* Tensor-core GEMM primitives of the trailing update (tcgen05, FP16/BF16 operands, FP32
+ * accumulate); they replace shared_mem_mmult_in_place_transpose_a + dev_cpy_strided_array
+ * (Cuda/mmult.cu:236-288, Cuda/mmult.cuh:104-151) and dev_tensorcore_mmult_tiled
+ * (Cuda/mmult.cuh:252-300).  `bf16` selects the operand type.  Operands are 16-bit,
+ * row-major, leading dimensions multiples of 8 elements, base pointers 16-byte aligned.
+ *   tn : S[M x N] (fp32, lds) = X^T Z,  X is [K x M] (ldx), Z is [K x N] (ldz)
+ *   nn : C[M x N] (fp32, ldc) -= X S,   X is [M x K] (ldx), S is [K x N] (lds16);
+ *        if dC16 != NULL the updated C is also written rounded to 16 bit (ldc16). */
+int mpqr_gemm_tn_device(const void* dX, long ldx, const void* dZ, long ldz, float* dS, long lds,
+                        int M, int N, int K, int bf16, void* stream);
+int mpqr_gemm_nn_device(const void* dX, long ldx, const void* dS16, long lds16, float* dC, long ldc,
+                        void* dC16, long ldc16, int M, int N, int K, int bf16, void* stream);
+
+/* Deterministic synthetic input: element (i,j) of an m x n matrix = uniform[0,1) from a
+ * stateless hash of (seed, i*n+j) (distribution of h_generate_random_matrix,
+ * Cuda/mmult.cuh:39-60).  Writes rows [row0,row0+rows) x cols [col0,col0+cols) into dA
+ * (row-major, lda), i.e. any shard can be generated in place on any GPU. */
+int mpqr_fill_uniform_device(float* dA, long lda, long n_total, long row0, long rows, long col0,
+                             long cols, uint64_t seed, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU): 1-D column-block-cyclic over `nranks` GPUs of one
+ * NVSwitch box; each panel block is factored by its owner and its Y/W broadcast with NCCL.
+ * The NCCL communicator is owned by the library; bootstrap the unique id through any
+ * out-of-band channel (bench.py uses torch.distributed).
+ * ------------------------------------------------------------------------------------- */
+#define MPQR_NCCL_UID_BYTES 128
+int mpqr_mg_get_unique_id(void* uid_out /* MPQR_NCCL_UID_BYTES */);
+int mpqr_mg_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags, int rank,
+                   int nranks, const void* uid);
+/* Number of columns this rank owns and the global column of local column j. */
+int mpqr_mg_local_cols(const mpqr_handle* h);
+int mpqr_mg_global_col(const mpqr_handle* h, int local_col);
+/* dA_local: (m+1) x lda_local packed buffer holding this rank's columns (block-cyclic). */
+int mpqr_mg_factor_device(mpqr_handle* h, float* dA_local, long lda_local, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Tall-skinny QR (replaces python/ca_qr.py:25-43 ts_qr): A is m x n (m >> n), row-major FP32
+ * on the device.  Row blocks are factored independently, the n x n R factors are reduced by
+ * a tree; R (n x n, ldr) is returned and, if dQ != NULL, the thin Q (m x n, ldq).
+ * ------------------------------------------------------------------------------------- */
+int mpqr_tsqr_device(const float* dA, long lda, long m, int n, float* dQ, long ldq, float* dR,
+                     long ldr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPQR_H_ */

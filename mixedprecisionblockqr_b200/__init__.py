@@ -1,0 +1,154 @@
+"""mixedprecisionblockqr_b200 — B200-native mixed-precision blocked Householder QR.
+
+Thin Python host mirror over the C-ABI of libmpqr.so (include/mpqr.h).  The functions
+`dev_mixed_precision_block_qr`, `dev_block_qr_wy`, `dev_block_qr` keep the names, argument
+meaning and in-place semantics of the reference drivers (reference Cuda/qr.cuh:129-137,
+Cuda/qr.cu:877/:958/:1049) so parity tests read like the reference's own tests.
+
+There is NO CPU fallback: every compute entry point goes through libmpqr.so and raises
+MpqrError when the library or a CUDA device is missing.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpqr.so")
+
+MPQR_FP32 = 0x0
+MPQR_FP16 = 0x1
+MPQR_BF16 = 0x2
+MPQR_KEEP_WY = 0x10
+NCCL_UID_BYTES = 128
+
+# every symbol include/mpqr.h declares (tests/test_abi.py checks they are all exported)
+ABI_SYMBOLS = (
+    "mpqr_last_error", "mpqr_version", "mpqr_block_qr_host", "mpqr_create", "mpqr_destroy",
+    "mpqr_factor_device", "mpqr_form_q_device", "mpqr_get_panel_T", "mpqr_num_panels",
+    "mpqr_effective_r", "mpqr_effective_nb", "mpqr_last_launch_count", "mpqr_panel_factor_device",
+    "mpqr_gemm_tn_device", "mpqr_gemm_nn_device", "mpqr_fill_uniform_device", "mpqr_mg_get_unique_id",
+    "mpqr_mg_create", "mpqr_mg_local_cols", "mpqr_mg_global_col", "mpqr_mg_factor_device",
+    "mpqr_tsqr_device",
+)
+
+
+class MpqrError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads libmpqr.so; fails loudly (no fallback) if the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MpqrError(f"{LIB_PATH} is missing: run `python -m mixedprecisionblockqr_b200.build` "
+                            "(or __graft_entry__.build()); there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, c_int, c_long, c_uint = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_uint
+        L.mpqr_last_error.restype = ctypes.c_char_p
+        L.mpqr_version.restype = ctypes.c_char_p
+        L.mpqr_block_qr_host.argtypes = [vp, vp, c_int, c_int, c_int, c_uint]
+        L.mpqr_create.argtypes = [ctypes.POINTER(vp), c_int, c_int, c_int, c_int, c_uint]
+        L.mpqr_destroy.argtypes = [vp]
+        L.mpqr_factor_device.argtypes = [vp, vp, c_long, vp]
+        L.mpqr_form_q_device.argtypes = [vp, vp, c_long, vp]
+        L.mpqr_get_panel_T.argtypes = [vp, c_int, vp, c_int, vp]
+        for f in ("mpqr_num_panels", "mpqr_effective_r", "mpqr_effective_nb", "mpqr_mg_local_cols"):
+            getattr(L, f).argtypes = [vp]
+        L.mpqr_last_launch_count.argtypes = [vp]
+        L.mpqr_last_launch_count.restype = c_long
+        L.mpqr_panel_factor_device.argtypes = [vp, c_long, c_int, c_int, c_int, c_int, vp, vp, vp, vp]
+        L.mpqr_gemm_tn_device.argtypes = [vp, c_long, vp, c_long, vp, c_long, c_int, c_int, c_int, c_int, vp]
+        L.mpqr_gemm_nn_device.argtypes = [vp, c_long, vp, c_long, vp, c_long, vp, c_long, c_int, c_int, c_int, c_int, vp]
+        L.mpqr_fill_uniform_device.argtypes = [vp, c_long, c_long, c_long, c_long, c_long, c_long, ctypes.c_uint64, vp]
+        L.mpqr_mg_get_unique_id.argtypes = [vp]
+        L.mpqr_mg_create.argtypes = [ctypes.POINTER(vp), c_int, c_int, c_int, c_int, c_uint, c_int, c_int, vp]
+        L.mpqr_mg_global_col.argtypes = [vp, c_int]
+        L.mpqr_mg_factor_device.argtypes = [vp, vp, c_long, vp]
+        L.mpqr_tsqr_device.argtypes = [vp, c_long, c_long, c_int, vp, c_long, vp, c_long, vp]
+        _lib = L
+    return _lib
+
+
+def check(rc, what="mpqr call"):
+    if rc != 0:
+        raise MpqrError(f"{what} failed (code {rc}): {lib().mpqr_last_error().decode()}")
+
+
+def householder_flops(m, n):
+    """BASELINE.json count 2mn^2 - 2n^3/3 (m >= n); 2m^2 n - 2m^3/3 for m < n."""
+    m, n = float(m), float(n)
+    return 2 * m * n * n - 2 * n ** 3 / 3 if m >= n else 2 * m * m * n - 2 * m ** 3 / 3
+
+
+# ------------------------------------------------------------------ reference-named host drivers
+def _host_driver(A, Q, m, n, r, flags):
+    if not (isinstance(A, np.ndarray) and A.dtype == np.float32 and A.flags.c_contiguous and A.size == (m + 1) * n):
+        raise MpqrError("A must be a C-contiguous float32 array of (m+1)*n elements (reference Cuda/qr.cu:1866)")
+    if Q is not None and not (Q.dtype == np.float32 and Q.flags.c_contiguous and Q.size == m * m):
+        raise MpqrError("Q must be a C-contiguous float32 array of m*m elements")
+    rc = lib().mpqr_block_qr_host(A.ctypes.data, Q.ctypes.data if Q is not None else None, m, n, r, flags)
+    check(rc, "mpqr_block_qr_host")
+
+
+def dev_mixed_precision_block_qr(A, Q, m, n, r, bf16=False):
+    """In-place drop-in for reference dev_mixed_precision_block_qr (Cuda/qr.cu:1049): A is the
+    (m+1) x n packed host buffer, Q the m x m host buffer (or None)."""
+    _host_driver(A, Q, m, n, r, MPQR_BF16 if bf16 else MPQR_FP16)
+
+
+def dev_block_qr_wy(A, Q, m, n, r):
+    """In-place drop-in for reference dev_block_qr_wy (Cuda/qr.cu:958), FP32 trailing update."""
+    _host_driver(A, Q, m, n, r, MPQR_FP32)
+
+
+dev_block_qr = dev_block_qr_wy  # reference Cuda/qr.cu:877 (older variant, same contract)
+
+
+# ------------------------------------------------------------------ device-resident plan
+class BlockQR:
+    """Device-resident plan (mpqr_create / mpqr_factor_device / mpqr_form_q_device).  Pointers
+    are raw device addresses (e.g. torch.Tensor.data_ptr()); stream is a cudaStream_t int."""
+
+    def __init__(self, m, n, r, nb=0, precision="fp16", keep_wy=False):
+        flags = {"fp32": MPQR_FP32, "fp16": MPQR_FP16, "bf16": MPQR_BF16}[precision]
+        if keep_wy:
+            flags |= MPQR_KEEP_WY
+        self._h = ctypes.c_void_p()
+        check(lib().mpqr_create(ctypes.byref(self._h), m, n, r, nb, flags), "mpqr_create")
+        self.m, self.n = m, n
+        self.r = lib().mpqr_effective_r(self._h)
+        self.nb = lib().mpqr_effective_nb(self._h)
+        self.num_panels = lib().mpqr_num_panels(self._h)
+
+    def factor(self, dA_ptr, lda, stream=0):
+        check(lib().mpqr_factor_device(self._h, dA_ptr, lda, stream), "mpqr_factor_device")
+
+    def form_q(self, dQ_ptr, ldq, stream=0):
+        check(lib().mpqr_form_q_device(self._h, dQ_ptr, ldq, stream), "mpqr_form_q_device")
+
+    def panel_T(self, panel, dT_ptr, ldt, stream=0):
+        check(lib().mpqr_get_panel_T(self._h, panel, dT_ptr, ldt, stream), "mpqr_get_panel_T")
+
+    @property
+    def last_launches(self):
+        return int(lib().mpqr_last_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().mpqr_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fill_uniform(dA_ptr, lda, n_total, row0, rows, col0, cols, seed, stream=0):
+    check(lib().mpqr_fill_uniform_device(dA_ptr, lda, n_total, row0, rows, col0, cols, seed, stream), "mpqr_fill_uniform_device")

@@ -1,0 +1,571 @@
+// api.cu — C-ABI (include/mpqr.h) and the blocked Householder QR drivers.
+//
+// Host C++ only issues kernels on one stream; the matrix stays device-resident for the whole
+// factorisation (the reference moves the full (m+1) x n matrix over PCIe twice per panel:
+// Cuda/qr.cu:1082, :1215, and synchronises after every launch).
+//
+// Driver structure (replaces dev_mixed_precision_block_qr / dev_block_qr_wy panel loops,
+// Cuda/qr.cu:1074-1219 / :980-1040; panel bounds tau = min(lam + r, n) as :1076):
+//
+//   FP32 path  : for each panel  [panel kernel] -> S = W^T A22 -> A22 -= Y S        (SIMT)
+//   FP16/BF16  : two-level blocking.  Outer block of nb columns, inner panels of r:
+//       [panel kernel]  -> in-block update with the panel's own (Y_p, W_p)   (K = r)
+//                       -> WY accumulation W_p <- W_p - W_prev (Y_prev^T W_p)  (GVL 5.1.2 WY form,
+//                          the reference's W recurrence Cuda/qr.cu:361-399 done blockwise)
+//       far update  A[c0:, c1:] -= Y_blk (W_blk^T A[c0:, c1:])                 (K = nb)
+//     so the FP32 master of the far trailing matrix is read and written once per nb columns
+//     instead of once per r columns (SURVEY 7 "hard parts": K >= ~512 needed to be
+//     tensor-bound rather than HBM-bound).
+//   The trailing update uses the identity  Q_panel^T A = A - Y (W^T A)  with W = Y T
+//   ("mind the transpose").
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace mpqr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int get_device_info(DeviceInfo* out) {
+    static DeviceInfo cached;
+    static int cached_dev = -1;
+    int dev;
+    MPQR_CUDA(cudaGetDevice(&dev));
+    if (dev != cached_dev) {
+        MPQR_CUDA(cudaDeviceGetAttribute(&cached.num_sms, cudaDevAttrMultiProcessorCount, dev));
+        MPQR_CUDA(cudaDeviceGetAttribute(&cached.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        MPQR_CUDA(cudaDeviceGetAttribute(&cached.coop, cudaDevAttrCooperativeLaunch, dev));
+        int major = 0;
+        MPQR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        if (major != 10) {
+            set_error("libmpqr is built for sm_100a only; device has compute capability major %d", major);
+            return MPQR_ECUDA;
+        }
+        cached_dev = dev;
+    }
+    *out = cached;
+    return MPQR_OK;
+}
+
+// ------------------------------------------------------------------------ utility kernels
+namespace {
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void fill_uniform_kernel(float* A, long lda, long n_total, long row0, long rows, long col0,
+                                    long cols, uint64_t seed_mixed) {
+    long total = rows * cols;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long i = idx / cols, j = idx - i * cols;
+        uint64_t h = mix64(seed_mixed + (uint64_t)((row0 + i) * n_total + (col0 + j)));
+        A[i * lda + j] = (float)(h >> 40) * (1.0f / 16777216.0f);
+    }
+}
+
+__device__ __forceinline__ void cvt16(float v, __half* d) { *d = __float2half_rn(v); }
+__device__ __forceinline__ void cvt16(float v, __nv_bfloat16* d) { *d = __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void convert_kernel(const float* __restrict__ src, long lds, T* __restrict__ dst, long ldd, long rows, long cols) {
+    long total = rows * cols;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long i = idx / cols, j = idx - i * cols;
+        cvt16(src[i * lds + j], dst + i * ldd + j);
+    }
+}
+
+__global__ void identity_kernel(float* Q, long ldq, int m) {
+    long total = (long)m * m;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long i = idx / m, j = idx - i * m;
+        Q[i * ldq + j] = (i == j) ? 1.f : 0.f;
+    }
+}
+
+__global__ void zero16_kernel(uint16_t* dst, long ldd, long rows, long cols) {
+    long total = rows * cols;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long i = idx / cols, j = idx - i * cols;
+        dst[i * ldd + j] = 0;
+    }
+}
+
+int grid_for(long total) {
+    long g = (total + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+int fill_uniform(float* A, long lda, long n_total, long row0, long rows, long col0, long cols, uint64_t seed,
+                 cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return MPQR_OK;
+    // host-side twin of mix64 for the seed (oracle/mpqr_oracle.c:orc_uniform01)
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    fill_uniform_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(A, lda, n_total, row0, rows, col0, cols, z);
+    MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+
+int convert_f32_to_16(const float* src, long lds, void* dst, long ldd, long rows, long cols, int bf16,
+                      cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return MPQR_OK;
+    if (bf16) convert_kernel<__nv_bfloat16><<<grid_for(rows * cols), 256, 0, stream>>>(src, lds, (__nv_bfloat16*)dst, ldd, rows, cols);
+    else convert_kernel<__half><<<grid_for(rows * cols), 256, 0, stream>>>(src, lds, (__half*)dst, ldd, rows, cols);
+    MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+
+int set_identity(float* Q, long ldq, int m, cudaStream_t stream) {
+    identity_kernel<<<grid_for((long)m * m), 256, 0, stream>>>(Q, ldq, m);
+    MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+
+int fill_zero_16(void* dst, long ldd, long rows, long cols, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return MPQR_OK;
+    zero16_kernel<<<grid_for(rows * cols), 256, 0, stream>>>((uint16_t*)dst, ldd, rows, cols);
+    MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+
+}  // namespace mpqr
+
+using namespace mpqr;
+
+// ------------------------------------------------------------------------------ the handle
+struct mpqr_handle {
+    int m = 0, n = 0, r = 0, nb = 0, kmax = 0;
+    unsigned flags = 0;
+    int prec = 0;  // 0 fp32, 1 fp16, 2 bf16
+    bool keep_wy = false;
+    int npanels = 0;
+    bool factored = false;
+    long launches = 0;
+
+    // common
+    float* sync_ws = nullptr;
+    float* scratch = nullptr;
+    long scratch_rows = 0;
+    float* T = nullptr;    // npanels * r * r
+    float* S32 = nullptr;  // sk x lds32
+    long lds32 = 0;
+    int sk = 0;
+
+    // FP32 path: compact Y/W.  keep_wy: m x ld32 full arrays, else m x r panel buffers
+    float* Y32 = nullptr;
+    float* W32 = nullptr;
+    long ld32 = 0;
+
+    // 16-bit path
+    void* Ah = nullptr;  // m x ldh shadow of A (operands); factored columns hold Y
+    long ldh = 0;
+    void* W16 = nullptr;  // keep_wy: m x ldw16 (all blocks) else m x nb (current block)
+    long ldw16 = 0;
+    float* Wblk32 = nullptr;  // m x ldwb FP32 W of the current outer block
+    long ldwb = 0;
+    void* S16 = nullptr;      // sk x lds16
+    long lds16 = 0;
+    void* Qh = nullptr;  // m x ldqh shadow of Q (form_q)
+    long ldqh = 0;
+
+    // multi-GPU (mg.cu)
+    void* mg = nullptr;
+
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+int dev_alloc(mpqr_handle* h, void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return MPQR_ENOMEM;
+    }
+    h->allocs.push_back(*p);
+    return MPQR_OK;
+}
+
+inline char* at16(void* base, long ld, long row, long col) { return (char*)base + ((size_t)row * ld + col) * 2; }
+
+int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
+    const int m = h->m, n = h->n, r = h->r;
+    for (int lam = 0, p = 0; lam < h->kmax; lam += r, ++p) {
+        const int pw = (lam + r < h->kmax) ? r : h->kmax - lam;
+        const int tau = lam + pw, D = m - lam, nt = n - tau;
+        float *Y, *W;
+        long ld;
+        if (h->keep_wy) {
+            Y = h->Y32 + (size_t)lam * h->ld32 + lam;
+            W = h->W32 + (size_t)lam * h->ld32 + lam;
+            ld = h->ld32;
+        } else {
+            Y = h->Y32;
+            W = h->W32;
+            ld = r;
+        }
+        PanelArgs a{};
+        a.A = A; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.pw = pw; a.blk_row0 = lam;
+        a.Y32 = Y; a.W32 = W; a.ld32 = ld;
+        a.T = h->T + (size_t)p * r * r; a.ldt = r;
+        a.sync_ws = h->sync_ws; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
+        MPQR_TRY(launch_panel(a, st, &h->launches));
+        if (nt > 0) {
+            float* A22 = A + (size_t)lam * lda + tau;
+            MPQR_TRY(sgemm_tn(W, ld, A22, lda, h->S32, h->lds32, pw, nt, D, st, &h->launches));
+            MPQR_TRY(sgemm_nn_sub(Y, ld, h->S32, h->lds32, A22, lda, D, nt, pw, st, &h->launches));
+        }
+    }
+    return MPQR_OK;
+}
+
+int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
+    const int m = h->m, n = h->n, r = h->r, nb = h->nb;
+    const int bf = h->prec == 2;
+    if ((lda & 3) || ((uintptr_t)A & 15)) {
+        set_error("factor: the tensor-core path needs lda %% 4 == 0 and a 16-byte aligned dA (lda=%ld)", lda);
+        return MPQR_EINVAL;
+    }
+    // operand shadow of the whole matrix
+    MPQR_TRY(convert_f32_to_16(A, lda, h->Ah, h->ldh, m, n, bf, st));
+    h->launches += 1;
+    for (int c0 = 0; c0 < h->kmax; c0 += nb) {
+        const int c1 = (c0 + nb < h->kmax) ? c0 + nb : h->kmax;
+        const int Dblk = m - c0;
+        // W of this block: FP32 master (Wblk32, Dblk x nb) + 16-bit operand copy
+        void* Wb16;
+        long ldw;
+        if (h->keep_wy) {
+            Wb16 = at16(h->W16, h->ldw16, c0, c0);
+            ldw = h->ldw16;
+        } else {
+            Wb16 = h->W16;
+            ldw = h->ldw16;
+        }
+        for (int lam = c0; lam < c1; lam += r) {
+            const int p = lam / r;
+            const int pw = (lam + r < c1) ? r : c1 - lam;
+            const int tau = lam + pw, D = m - lam, jc = lam - c0;
+            PanelArgs a{};
+            a.A = A; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.pw = pw; a.blk_row0 = c0;
+            a.W32 = h->Wblk32 + jc; a.ld32 = h->ldwb;  // Y32 not needed
+            a.Y16 = at16(h->Ah, h->ldh, c0, lam); a.ldy16 = h->ldh;
+            a.W16 = (char*)Wb16 + (size_t)jc * 2; a.ldw16 = ldw;
+            a.bf16 = bf;
+            a.T = h->T + (size_t)p * r * r; a.ldt = r;
+            a.sync_ws = h->sync_ws; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
+            MPQR_TRY(launch_panel(a, st, &h->launches));
+            const int nin = c1 - tau;  // in-block trailing columns
+            if (nin > 0) {
+                // S = W_p^T A[lam:, tau:c1]   (operands: 16-bit W_p rows lam.., shadow of A)
+                const void* Wp = (char*)Wb16 + ((size_t)jc * ldw + jc) * 2;
+                MPQR_TRY(tc_gemm_tn(Wp, ldw, at16(h->Ah, h->ldh, lam, tau), h->ldh, h->S32, h->lds32, pw, nin, D, bf, st, &h->launches));
+                MPQR_TRY(convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, pw, nin, bf, st));
+                h->launches += 1;
+                // A[lam:, tau:c1] -= Y_p S   (+ shadow)
+                MPQR_TRY(tc_gemm_nn(at16(h->Ah, h->ldh, lam, lam), h->ldh, h->S16, h->lds16, A + (size_t)lam * lda + tau, lda,
+                                    at16(h->Ah, h->ldh, lam, tau), h->ldh, D, nin, pw, bf, st, &h->launches));
+            }
+            if (jc > 0) {
+                // WY accumulation: X = Y_prev^T W_p ; W_p -= W_prev X   (rows c0..m)
+                const void* Wp = (char*)Wb16 + (size_t)jc * 2;
+                MPQR_TRY(tc_gemm_tn(at16(h->Ah, h->ldh, c0, c0), h->ldh, Wp, ldw, h->S32, h->lds32, jc, pw, Dblk, bf, st, &h->launches));
+                MPQR_TRY(convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, jc, pw, bf, st));
+                h->launches += 1;
+                MPQR_TRY(tc_gemm_nn(Wb16, ldw, h->S16, h->lds16, h->Wblk32 + jc, h->ldwb, (void*)Wp, ldw, Dblk, pw, jc, bf, st, &h->launches));
+            }
+        }
+        const int nfar = n - c1, kb = c1 - c0;
+        if (nfar > 0) {
+            MPQR_TRY(tc_gemm_tn(Wb16, ldw, at16(h->Ah, h->ldh, c0, c1), h->ldh, h->S32, h->lds32, kb, nfar, Dblk, bf, st, &h->launches));
+            MPQR_TRY(convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, kb, nfar, bf, st));
+            h->launches += 1;
+            MPQR_TRY(tc_gemm_nn(at16(h->Ah, h->ldh, c0, c0), h->ldh, h->S16, h->lds16, A + (size_t)c0 * lda + c1, lda,
+                                at16(h->Ah, h->ldh, c0, c1), h->ldh, Dblk, nfar, kb, bf, st, &h->launches));
+        }
+    }
+    return MPQR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mpqr_last_error(void) { return g_err; }
+const char* mpqr_version(void) { return "mpqr-b200 0.1 (sm_100a)"; }
+
+int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) {
+    if (!out || m < 1 || n < 1 || r < 1) {
+        set_error("mpqr_create: bad arguments m=%d n=%d r=%d", m, n, r);
+        return MPQR_EINVAL;
+    }
+    unsigned prec = flags & MPQR_PRECISION_MASK;
+    if (prec == 3) {
+        set_error("mpqr_create: choose one of MPQR_FP16 / MPQR_BF16");
+        return MPQR_EINVAL;
+    }
+    DeviceInfo di;
+    MPQR_TRY(get_device_info(&di));
+    mpqr_handle* h = new mpqr_handle();
+    h->m = m; h->n = n; h->flags = flags; h->prec = (int)prec;
+    h->keep_wy = (flags & MPQR_KEEP_WY) != 0;
+    h->kmax = m < n ? m : n;
+    h->r = r > kPanelMaxWidth ? kPanelMaxWidth : r;
+    if (h->r > h->kmax) h->r = h->kmax;
+    if (prec == 0) {
+        h->nb = h->r;
+    } else {
+        int want = nb > 0 ? nb : 1024;
+        if (want < h->r) want = h->r;
+        want = (want / h->r) * h->r;
+        // keep at least ~2 outer blocks' worth of work; tiny problems use one level
+        if (want > h->kmax) want = ceil_div(h->kmax, h->r) * h->r;
+        h->nb = want;
+    }
+    h->npanels = ceil_div(h->kmax, h->r);
+    int rc = MPQR_OK;
+    do {
+        if ((rc = dev_alloc(h, (void**)&h->sync_ws, panel_sync_ws_bytes()))) break;
+        // panel scratch only needed when a panel slice cannot live in shared memory
+        long rows_fit = (long)di.num_sms * 288;
+        if (m > rows_fit) {
+            h->scratch_rows = m;
+            if ((rc = dev_alloc(h, (void**)&h->scratch, panel_scratch_bytes(m)))) break;
+        }
+        if ((rc = dev_alloc(h, (void**)&h->T, (size_t)h->npanels * h->r * h->r * sizeof(float)))) break;
+        const int wide = m > n ? m : n;
+        h->sk = h->nb;
+        h->lds32 = round_up(wide, 8);
+        if ((rc = dev_alloc(h, (void**)&h->S32, (size_t)h->sk * h->lds32 * sizeof(float)))) break;
+        if (prec == 0) {
+            if (h->keep_wy) {
+                h->ld32 = round_up(h->kmax, 4);
+                if ((rc = dev_alloc(h, (void**)&h->Y32, (size_t)m * h->ld32 * sizeof(float)))) break;
+                if ((rc = dev_alloc(h, (void**)&h->W32, (size_t)m * h->ld32 * sizeof(float)))) break;
+            } else {
+                h->ld32 = h->r;
+                if ((rc = dev_alloc(h, (void**)&h->Y32, (size_t)m * h->r * sizeof(float)))) break;
+                if ((rc = dev_alloc(h, (void**)&h->W32, (size_t)m * h->r * sizeof(float)))) break;
+            }
+        } else {
+            h->ldh = round_up(n, 8);
+            if ((rc = dev_alloc(h, &h->Ah, (size_t)m * h->ldh * 2))) break;
+            h->ldw16 = h->keep_wy ? round_up(h->kmax, 8) : round_up(h->nb, 8);
+            if ((rc = dev_alloc(h, &h->W16, (size_t)m * h->ldw16 * 2))) break;
+            h->ldwb = round_up(h->nb, 4);
+            if ((rc = dev_alloc(h, (void**)&h->Wblk32, (size_t)m * h->ldwb * sizeof(float)))) break;
+            h->lds16 = h->lds32;
+            if ((rc = dev_alloc(h, &h->S16, (size_t)h->sk * h->lds16 * 2))) break;
+        }
+    } while (0);
+    if (rc != MPQR_OK) {
+        mpqr_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return MPQR_OK;
+}
+
+int mpqr_destroy(mpqr_handle* h) {
+    if (!h) return MPQR_OK;
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+    return MPQR_OK;
+}
+
+int mpqr_factor_device(mpqr_handle* h, float* dA, long lda, void* stream) {
+    if (!h || !dA || lda < h->n) {
+        set_error("mpqr_factor_device: bad arguments");
+        return MPQR_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    h->launches = 0;
+    int rc = h->prec == 0 ? factor_fp32(h, dA, lda, st) : factor_16(h, dA, lda, st);
+    h->factored = (rc == MPQR_OK);
+    return rc;
+}
+
+int mpqr_form_q_device(mpqr_handle* h, float* dQ, long ldq, void* stream) {
+    if (!h || !dQ || ldq < h->m) {
+        set_error("mpqr_form_q_device: bad arguments");
+        return MPQR_EINVAL;
+    }
+    if (!h->factored || !h->keep_wy) {
+        set_error("mpqr_form_q_device: needs MPQR_KEEP_WY and a completed mpqr_factor_device");
+        return MPQR_ESTATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m = h->m;
+    h->launches = 0;
+    MPQR_TRY(set_identity(dQ, ldq, m, st));
+    h->launches += 1;
+    if (h->prec == 0) {
+        // Q <- Q_p Q = Q - W_p (Y_p^T Q), panels last to first; only Q[lam:, lam:] changes.
+        for (int p = h->npanels - 1; p >= 0; --p) {
+            const int lam = p * h->r;
+            const int pw = (lam + h->r < h->kmax) ? h->r : h->kmax - lam;
+            const int D = m - lam;
+            float* Y = h->Y32 + (size_t)lam * h->ld32 + lam;
+            float* W = h->W32 + (size_t)lam * h->ld32 + lam;
+            float* Qs = dQ + (size_t)lam * ldq + lam;
+            MPQR_TRY(sgemm_tn(Y, h->ld32, Qs, ldq, h->S32, h->lds32, pw, D, D, st, &h->launches));
+            MPQR_TRY(sgemm_nn_sub(W, h->ld32, h->S32, h->lds32, Qs, ldq, D, D, pw, st, &h->launches));
+        }
+        return MPQR_OK;
+    }
+    const int bf = h->prec == 2;
+    if ((ldq & 3) || ((uintptr_t)dQ & 15)) {
+        set_error("form_q: the tensor-core path needs ldq %% 4 == 0 and a 16-byte aligned dQ");
+        return MPQR_EINVAL;
+    }
+    if (!h->Qh) {
+        h->ldqh = round_up(m, 8);
+        MPQR_TRY(dev_alloc(h, &h->Qh, (size_t)m * h->ldqh * 2));
+    }
+    MPQR_TRY(convert_f32_to_16(dQ, ldq, h->Qh, h->ldqh, m, m, bf, st));
+    h->launches += 1;
+    const int nblk = ceil_div(h->kmax, h->nb);
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int c0 = b * h->nb;
+        const int c1 = (c0 + h->nb < h->kmax) ? c0 + h->nb : h->kmax;
+        const int D = m - c0, kb = c1 - c0;
+        const void* Yb = at16(h->Ah, h->ldh, c0, c0);
+        const void* Wb = at16(h->W16, h->ldw16, c0, c0);
+        MPQR_TRY(tc_gemm_tn(Yb, h->ldh, at16(h->Qh, h->ldqh, c0, c0), h->ldqh, h->S32, h->lds32, kb, D, D, bf, st, &h->launches));
+        MPQR_TRY(convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, kb, D, bf, st));
+        h->launches += 1;
+        MPQR_TRY(tc_gemm_nn(Wb, h->ldw16, h->S16, h->lds16, dQ + (size_t)c0 * ldq + c0, ldq, at16(h->Qh, h->ldqh, c0, c0),
+                            h->ldqh, D, D, kb, bf, st, &h->launches));
+    }
+    return MPQR_OK;
+}
+
+int mpqr_get_panel_T(mpqr_handle* h, int panel, float* dT, int ldt, void* stream) {
+    if (!h || !dT || panel < 0 || panel >= h->npanels || ldt < h->r) {
+        set_error("mpqr_get_panel_T: bad arguments");
+        return MPQR_EINVAL;
+    }
+    if (!h->factored) {
+        set_error("mpqr_get_panel_T: factor first");
+        return MPQR_ESTATE;
+    }
+    MPQR_CUDA(cudaMemcpy2DAsync(dT, (size_t)ldt * sizeof(float), h->T + (size_t)panel * h->r * h->r,
+                                (size_t)h->r * sizeof(float), (size_t)h->r * sizeof(float), h->r,
+                                cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return MPQR_OK;
+}
+
+int mpqr_num_panels(const mpqr_handle* h) { return h ? h->npanels : MPQR_EINVAL; }
+int mpqr_effective_r(const mpqr_handle* h) { return h ? h->r : MPQR_EINVAL; }
+int mpqr_effective_nb(const mpqr_handle* h) { return h ? h->nb : MPQR_EINVAL; }
+long mpqr_last_launch_count(const mpqr_handle* h) { return h ? h->launches : MPQR_EINVAL; }
+
+int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned flags) {
+    if (!A_packed || m < 1 || n < 1 || r < 1) {
+        set_error("mpqr_block_qr_host: bad arguments m=%d n=%d r=%d", m, n, r);
+        return MPQR_EINVAL;
+    }
+    mpqr_handle* h = nullptr;
+    unsigned f = (flags & MPQR_PRECISION_MASK) | (Q ? MPQR_KEEP_WY : 0u);
+    MPQR_TRY(mpqr_create(&h, m, n, r, 0, f));
+    const long lda = round_up(n, 8), ldq = round_up(m, 8);
+    float *dA = nullptr, *dQ = nullptr;
+    int rc = MPQR_OK;
+    do {
+        if ((rc = dev_alloc(h, (void**)&dA, (size_t)(m + 1) * lda * sizeof(float)))) break;
+        if (Q && (rc = dev_alloc(h, (void**)&dQ, (size_t)m * ldq * sizeof(float)))) break;
+        cudaError_t e = cudaMemcpy2D(dA, lda * sizeof(float), A_packed, (size_t)n * sizeof(float), (size_t)n * sizeof(float),
+                                     m + 1, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; break; }
+        if ((rc = mpqr_factor_device(h, dA, lda, nullptr))) break;
+        if (Q && (rc = mpqr_form_q_device(h, dQ, ldq, nullptr))) break;
+        e = cudaMemcpy2D(A_packed, (size_t)n * sizeof(float), dA, lda * sizeof(float), (size_t)n * sizeof(float), m + 1,
+                         cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && Q)
+            e = cudaMemcpy2D(Q, (size_t)m * sizeof(float), dQ, ldq * sizeof(float), (size_t)m * sizeof(float), m,
+                             cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("D2H copy / kernel execution failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; break; }
+    } while (0);
+    mpqr_destroy(h);
+    return rc;
+}
+
+int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw, float* dY, float* dW, float* dT,
+                             void* stream) {
+    if (!dA || lda < n) {
+        set_error("mpqr_panel_factor_device: bad arguments");
+        return MPQR_EINVAL;
+    }
+    DeviceInfo di;
+    MPQR_TRY(get_device_info(&di));
+    float *ws = nullptr, *scratch = nullptr;
+    MPQR_CUDA(cudaMalloc(&ws, panel_sync_ws_bytes()));
+    long scratch_rows = 0;
+    if (m - lam > (long)di.num_sms * 288) {
+        scratch_rows = m;
+        if (cudaMalloc(&scratch, panel_scratch_bytes(m)) != cudaSuccess) {
+            cudaFree(ws);
+            set_error("panel scratch allocation failed");
+            return MPQR_ENOMEM;
+        }
+    }
+    PanelArgs a{};
+    a.A = dA; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.pw = pw; a.blk_row0 = lam;
+    a.Y32 = dY; a.W32 = dW; a.ld32 = pw;
+    if (dW && !dY) { set_error("mpqr_panel_factor_device: dW needs dY"); cudaFree(ws); cudaFree(scratch); return MPQR_EINVAL; }
+    a.T = dT; a.ldt = pw;
+    a.sync_ws = ws; a.scratch = scratch; a.scratch_rows = scratch_rows;
+    int rc = launch_panel(a, (cudaStream_t)stream, nullptr);
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(ws);
+    cudaFree(scratch);
+    if (rc == MPQR_OK && e != cudaSuccess) {
+        set_error("panel kernel failed: %s", cudaGetErrorString(e));
+        rc = MPQR_ECUDA;
+    }
+    return rc;
+}
+
+int mpqr_gemm_tn_device(const void* dX, long ldx, const void* dZ, long ldz, float* dS, long lds, int M, int N, int K,
+                        int bf16, void* stream) {
+    if (!dX || !dZ || !dS || K < 1) { set_error("mpqr_gemm_tn_device: bad arguments"); return MPQR_EINVAL; }
+    return tc_gemm_tn(dX, ldx, dZ, ldz, dS, lds, M, N, K, bf16, (cudaStream_t)stream, nullptr);
+}
+
+int mpqr_gemm_nn_device(const void* dX, long ldx, const void* dS16, long lds16, float* dC, long ldc, void* dC16,
+                        long ldc16, int M, int N, int K, int bf16, void* stream) {
+    if (!dX || !dS16 || !dC) { set_error("mpqr_gemm_nn_device: bad arguments"); return MPQR_EINVAL; }
+    return tc_gemm_nn(dX, ldx, dS16, lds16, dC, ldc, dC16, ldc16, M, N, K, bf16, (cudaStream_t)stream, nullptr);
+}
+
+int mpqr_fill_uniform_device(float* dA, long lda, long n_total, long row0, long rows, long col0, long cols,
+                             uint64_t seed, void* stream) {
+    if (!dA) { set_error("mpqr_fill_uniform_device: null pointer"); return MPQR_EINVAL; }
+    return fill_uniform(dA, lda, n_total, row0, rows, col0, cols, seed, (cudaStream_t)stream);
+}
+
+}  // extern "C"

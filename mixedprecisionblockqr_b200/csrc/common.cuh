@@ -1,0 +1,104 @@
+// common.cuh — shared declarations of libmpqr (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mpqr.h"
+
+namespace mpqr {
+
+void set_error(const char* fmt, ...);
+
+#define MPQR_CUDA(expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            ::mpqr::set_error("CUDA error at %s:%d code=%d(%s) \"%s\"", __FILE__, __LINE__,   \
+                              (int)e__, cudaGetErrorName(e__), #expr);                        \
+            return MPQR_ECUDA;                                                                \
+        }                                                                                     \
+    } while (0)
+
+#define MPQR_TRY(expr)               \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != MPQR_OK) return rc__; \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long ceil_divl(long a, long b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+struct DeviceInfo {
+    int num_sms;
+    int max_smem_optin;
+    int coop;
+};
+int get_device_info(DeviceInfo* out);
+
+// ------------------------------------------------------------------ panel factorisation
+constexpr int kPanelMaxWidth = 128;
+
+// Sync workspace of one panel launch (floats): dots[pwp][pwp] | pivot rows[pwp][pwp] |
+// gram[pwp][pwp] | counter.  Must be zero on entry; the launcher memsets it.
+size_t panel_sync_ws_bytes();
+// Scratch for the non-shared-memory-resident variant: rows x 128 floats.
+size_t panel_scratch_bytes(int max_rows);
+
+struct PanelArgs {
+    float* A;      // packed master, (m+1) x lda
+    long lda;
+    int m, n;
+    int lam;       // first column (== first row) of the panel
+    int pw;        // panel width (<= 128), lam + pw <= n
+    int blk_row0;  // first row of the enclosing outer block (<= lam): Y/W outputs are zero-filled
+                   // for rows [blk_row0, lam)
+    // Compact outputs at UNSHIFTED positions; each pointer addresses element
+    // (row = blk_row0, col = first panel column) of its array.  Any may be null.
+    float* Y32;
+    float* W32;
+    long ld32;
+    void* Y16;     // __half or __nv_bfloat16
+    void* W16;
+    long ldy16, ldw16;
+    int bf16;
+    float* T;      // pw x pw (ldt), upper triangular, Q_p = I - Y T Y^T
+    int ldt;
+    float* sync_ws;
+    float* scratch;     // may be null if the panel fits in shared memory
+    long scratch_rows;  // capacity of scratch in rows
+};
+int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches);
+
+// ------------------------------------------------------------------ FP32 SIMT GEMMs
+// S[M x N] = X^T Z ; X [K x M] (ldx), Z [K x N] (ldz).  S is overwritten.
+int sgemm_tn(const float* X, long ldx, const float* Z, long ldz, float* S, long lds, int M, int N,
+             int K, cudaStream_t stream, long* launches);
+// C[M x N] -= X S ; X [M x K] (ldx), S [K x N] (lds).
+int sgemm_nn_sub(const float* X, long ldx, const float* S, long lds, float* C, long ldc, int M,
+                 int N, int K, cudaStream_t stream, long* launches);
+
+// ------------------------------------------------------------------ tcgen05 GEMMs
+struct TcGemm;  // opaque per-handle state (TMA descriptor cache etc.)
+// S[M x N] (fp32) = X^T Z with 16-bit X [K x M], Z [K x N]; split-K with TMA reduce-add when
+// the tile count cannot fill the GPU (S is zeroed internally in that case).
+int tc_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long lds, int M, int N,
+               int K, int bf16, cudaStream_t stream, long* launches);
+// C[M x N] (fp32) -= X S16, X [M x K] 16-bit (K-major), S16 [K x N] 16-bit; optionally mirrors
+// the updated C into C16 (16-bit shadow).
+int tc_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16,
+               long ldc16, int M, int N, int K, int bf16, cudaStream_t stream, long* launches);
+
+// ------------------------------------------------------------------ small utility kernels
+int fill_uniform(float* A, long lda, long n_total, long row0, long rows, long col0, long cols,
+                 uint64_t seed, cudaStream_t stream);
+int convert_f32_to_16(const float* src, long lds, void* dst, long ldd, long rows, long cols, int bf16,
+                      cudaStream_t stream);
+int set_identity(float* Q, long ldq, int m, cudaStream_t stream);
+int fill_zero_16(void* dst, long ldd, long rows, long cols, cudaStream_t stream);
+
+}  // namespace mpqr

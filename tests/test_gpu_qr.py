@@ -1,0 +1,91 @@
+"""Whole-factorisation parity through the C-ABI host drivers (the reference-named entry points)
+against the oracle, on the reference's own shape list (Cuda/qr.cu:1762-1783) and its pass
+criteria (err <= m * 2^-bits, bits = 23 FP32 / 11 mixed; Cuda/qr.cu:120-129, :1836, :1889)."""
+import numpy as np
+import pytest
+
+import mixedprecisionblockqr_b200 as pkg
+import oracle
+from conftest import REF_SHAPES
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(fn, A, r, **kw):
+    m, n = A.shape
+    P = oracle.pack(A)
+    Q = np.full((m, m), np.nan, np.float32)
+    fn(P, Q, m, n, r, **kw)
+    return P, Q
+
+
+@pytest.mark.parametrize("m,n,r", REF_SHAPES)
+def test_fp32_driver_vs_oracle(m, n, r):
+    A = oracle.uniform_matrix(m, n, 1000 * m + n + r)
+    P, Q = _run(pkg.dev_block_qr_wy, A, r)
+    Pref, Qref = oracle.block_qr(A, r)
+    R = oracle.strip_R(P)
+    be = oracle.backward_error(A, R, Q)
+    assert be <= m * 2.0 ** -23                      # reference criterion
+    assert be <= 3e-6                                # FP32-vs-FP32: tighter
+    assert oracle.q_error_max(Q) <= m * 2.0 ** -23
+    assert oracle.orthogonality_fro(Q) <= 2e-5
+    scale = np.abs(Pref).max()
+    assert np.abs(P - Pref).max() <= 5e-5 * scale    # packed factor incl. Householder vectors
+    assert np.abs(Q - Qref).max() <= 5e-5
+
+
+@pytest.mark.parametrize("m,n,r", REF_SHAPES)
+@pytest.mark.parametrize("bf16", [False, True])
+def test_mixed_driver_vs_oracle(m, n, r, bf16):
+    A = oracle.uniform_matrix(m, n, 1000 * m + n + r)
+    P, Q = _run(pkg.dev_mixed_precision_block_qr, A, r, bf16=bf16)
+    Pref, Qref = oracle.block_qr(A, r)
+    R, Rref = oracle.strip_R(P), oracle.strip_R(Pref)
+    eps = 2.0 ** -8 if bf16 else 2.0 ** -11
+    be = oracle.backward_error(A, R, Q)
+    assert be <= m * 2.0 ** -11                      # reference criterion (mixed)
+    assert be <= 12 * eps                            # what FP16 operands should actually give
+    assert oracle.orthogonality_fro(Q) <= 40 * eps * np.sqrt(m)
+    # elementwise |R| agreement at FP16-GEMM error level
+    assert np.abs(np.abs(R) - np.abs(Rref)).max() <= 40 * eps * np.abs(Rref).max()
+
+
+@pytest.mark.parametrize("m,n,r,prec", [(1024, 1024, 32, "fp32"), (1024, 1024, 32, "fp16"), (2048, 2048, 32, "fp16"),
+                                         (1536, 1000, 64, "fp16"), (2048, 2048, 128, "bf16"), (512, 2048, 64, "fp16"),
+                                         (512, 2048, 64, "fp32")])
+def test_larger_shapes_backward_error(m, n, r, prec):
+    A = oracle.uniform_matrix(m, n, 77 + m + n)
+    P = oracle.pack(A)
+    fn = pkg.dev_block_qr_wy if prec == "fp32" else pkg.dev_mixed_precision_block_qr
+    kw = {"bf16": True} if prec == "bf16" else {}
+    fn(P, None, m, n, r, **kw)
+    be = oracle.backward_error_packed(A, P)
+    lim = {"fp32": 5e-6, "fp16": 12 * 2.0 ** -11, "bf16": 12 * 2.0 ** -8}[prec]
+    assert be <= lim, be
+    Pref, _ = oracle.block_qr(A, r, want_q=False)
+    Rref = oracle.strip_R(Pref)
+    dr = np.abs(np.abs(oracle.strip_R(P)) - np.abs(Rref)).max() / np.abs(Rref).max()
+    assert dr <= (2e-5 if prec == "fp32" else 60 * lim / 12), dr
+
+
+def test_python_fixtures_match_lapack():
+    # python/test_data.py:4-57 fixtures; the reference checks allclose vs np.linalg.qr (test_all.py:36-37).
+    # |R| must agree (the reference reflects the last column of a square matrix, LAPACK does not).
+    fixtures = [
+        np.array([[1, 2, 3], [4, 5, 6], [7, 8, 7], [4, 2, 3], [4, 2, 2]], np.float32),
+        np.array([[0, 3, 1], [0, 4, -2], [2, 1, 1]], np.float32),
+        np.array([[12, -51, 4], [6, 167, -68], [-4, 24, -41]], np.float32),
+        np.array([[10, 20, 30, 40, 50, 60], [32, 32, 44, 55, 66, 35], [23, 66, 74, 64, 45, 65],
+                  [67, 28, 46, 26, 46, 42], [95, 95, 52, 88, 65, 11], [75, 53, 96, 47, 32, 32]], np.float32),
+        np.array([[1, 2, 3], [1, 2, 3], [1, 2, 3]], np.float32),
+        np.array([[1, 0, 0], [0, 2, 0], [0, 0, 3]], np.float32),
+        np.array([[1, 2, 3], [0, 0, 0], [0, 0, 0]], np.float32),
+    ]
+    for A in fixtures:
+        m, n = A.shape
+        P, Q = _run(pkg.dev_block_qr_wy, A, 2)
+        R = oracle.strip_R(P)
+        _, Rl = np.linalg.qr(A.astype(np.float64), mode="complete")
+        assert np.allclose(np.abs(R), np.abs(Rl), atol=2e-4 * max(1, np.abs(A).max()))
+        assert np.allclose(Q.astype(np.float64) @ R, A, atol=2e-4 * max(1, np.abs(A).max()))
