@@ -165,6 +165,7 @@ struct mpqr_handle {
 
     // common
     float* sync_ws = nullptr;
+    unsigned sync_ctr = 0;  // host mirror of the panel barrier counter
     float* scratch = nullptr;
     long scratch_rows = 0;
     float* T = nullptr;    // npanels * r * r
@@ -232,7 +233,7 @@ int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         a.A = A; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.pw = pw; a.blk_row0 = lam;
         a.Y32 = Y; a.W32 = W; a.ld32 = ld;
         a.T = h->T + (size_t)p * r * r; a.ldt = r;
-        a.sync_ws = h->sync_ws; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
+        a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
         MPQR_TRY(launch_panel(a, st, &h->launches));
         if (nt > 0) {
             float* A22 = A + (size_t)lam * lda + tau;
@@ -277,35 +278,35 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
             a.W16 = (char*)Wb16 + (size_t)jc * 2; a.ldw16 = ldw;
             a.bf16 = bf;
             a.T = h->T + (size_t)p * r * r; a.ldt = r;
-            a.sync_ws = h->sync_ws; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
+            a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
             MPQR_TRY(launch_panel(a, st, &h->launches));
             const int nin = c1 - tau;  // in-block trailing columns
             if (nin > 0) {
                 // S = W_p^T A[lam:, tau:c1]   (operands: 16-bit W_p rows lam.., shadow of A)
                 const void* Wp = (char*)Wb16 + ((size_t)jc * ldw + jc) * 2;
-                MPQR_TRY(tc_gemm_tn(Wp, ldw, at16(h->Ah, h->ldh, lam, tau), h->ldh, h->S32, h->lds32, pw, nin, D, bf, st, &h->launches));
+                MPQR_TRY(tc_gemm_tn(Wp, ldw, at16(h->Ah, h->ldh, lam, tau), h->ldh, h->S32, h->lds32, pw, nin, D, bf, 1, st, &h->launches));
                 MPQR_TRY(convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, pw, nin, bf, st));
                 h->launches += 1;
                 // A[lam:, tau:c1] -= Y_p S   (+ shadow)
                 MPQR_TRY(tc_gemm_nn(at16(h->Ah, h->ldh, lam, lam), h->ldh, h->S16, h->lds16, A + (size_t)lam * lda + tau, lda,
-                                    at16(h->Ah, h->ldh, lam, tau), h->ldh, D, nin, pw, bf, st, &h->launches));
+                                    at16(h->Ah, h->ldh, lam, tau), h->ldh, D, nin, pw, bf, c1 == n, st, &h->launches));
             }
             if (jc > 0) {
                 // WY accumulation: X = Y_prev^T W_p ; W_p -= W_prev X   (rows c0..m)
                 const void* Wp = (char*)Wb16 + (size_t)jc * 2;
-                MPQR_TRY(tc_gemm_tn(at16(h->Ah, h->ldh, c0, c0), h->ldh, Wp, ldw, h->S32, h->lds32, jc, pw, Dblk, bf, st, &h->launches));
+                MPQR_TRY(tc_gemm_tn(at16(h->Ah, h->ldh, c0, c0), h->ldh, Wp, ldw, h->S32, h->lds32, jc, pw, Dblk, bf, 1, st, &h->launches));
                 MPQR_TRY(convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, jc, pw, bf, st));
                 h->launches += 1;
-                MPQR_TRY(tc_gemm_nn(Wb16, ldw, h->S16, h->lds16, h->Wblk32 + jc, h->ldwb, (void*)Wp, ldw, Dblk, pw, jc, bf, st, &h->launches));
+                MPQR_TRY(tc_gemm_nn(Wb16, ldw, h->S16, h->lds16, h->Wblk32 + jc, h->ldwb, (void*)Wp, ldw, Dblk, pw, jc, bf, 1, st, &h->launches));
             }
         }
         const int nfar = n - c1, kb = c1 - c0;
         if (nfar > 0) {
-            MPQR_TRY(tc_gemm_tn(Wb16, ldw, at16(h->Ah, h->ldh, c0, c1), h->ldh, h->S32, h->lds32, kb, nfar, Dblk, bf, st, &h->launches));
+            MPQR_TRY(tc_gemm_tn(Wb16, ldw, at16(h->Ah, h->ldh, c0, c1), h->ldh, h->S32, h->lds32, kb, nfar, Dblk, bf, 1, st, &h->launches));
             MPQR_TRY(convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, kb, nfar, bf, st));
             h->launches += 1;
             MPQR_TRY(tc_gemm_nn(at16(h->Ah, h->ldh, c0, c0), h->ldh, h->S16, h->lds16, A + (size_t)c0 * lda + c1, lda,
-                                at16(h->Ah, h->ldh, c0, c1), h->ldh, Dblk, nfar, kb, bf, st, &h->launches));
+                                at16(h->Ah, h->ldh, c0, c1), h->ldh, Dblk, nfar, kb, bf, 1, st, &h->launches));
         }
     }
     return MPQR_OK;
@@ -350,6 +351,7 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
     int rc = MPQR_OK;
     do {
         if ((rc = dev_alloc(h, (void**)&h->sync_ws, panel_sync_ws_bytes()))) break;
+        if (cudaMemset(h->sync_ws, 0, panel_sync_ws_bytes()) != cudaSuccess) { set_error("memset failed"); rc = MPQR_ECUDA; break; }
         // panel scratch only needed when a panel slice cannot live in shared memory
         long rows_fit = (long)di.num_sms * 288;
         if (m > rows_fit) {
@@ -455,11 +457,11 @@ int mpqr_form_q_device(mpqr_handle* h, float* dQ, long ldq, void* stream) {
         const int D = m - c0, kb = c1 - c0;
         const void* Yb = at16(h->Ah, h->ldh, c0, c0);
         const void* Wb = at16(h->W16, h->ldw16, c0, c0);
-        MPQR_TRY(tc_gemm_tn(Yb, h->ldh, at16(h->Qh, h->ldqh, c0, c0), h->ldqh, h->S32, h->lds32, kb, D, D, bf, st, &h->launches));
+        MPQR_TRY(tc_gemm_tn(Yb, h->ldh, at16(h->Qh, h->ldqh, c0, c0), h->ldqh, h->S32, h->lds32, kb, D, D, bf, 1, st, &h->launches));
         MPQR_TRY(convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, kb, D, bf, st));
         h->launches += 1;
         MPQR_TRY(tc_gemm_nn(Wb, h->ldw16, h->S16, h->lds16, dQ + (size_t)c0 * ldq + c0, ldq, at16(h->Qh, h->ldqh, c0, c0),
-                            h->ldqh, D, D, kb, bf, st, &h->launches));
+                            h->ldqh, D, D, kb, bf, 1, st, &h->launches));
     }
     return MPQR_OK;
 }
@@ -524,6 +526,8 @@ int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
     MPQR_TRY(get_device_info(&di));
     float *ws = nullptr, *scratch = nullptr;
     MPQR_CUDA(cudaMalloc(&ws, panel_sync_ws_bytes()));
+    MPQR_CUDA(cudaMemset(ws, 0, panel_sync_ws_bytes()));
+    unsigned host_ctr = 0;
     long scratch_rows = 0;
     if (m - lam > (long)di.num_sms * 288) {
         scratch_rows = m;
@@ -538,7 +542,7 @@ int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
     a.Y32 = dY; a.W32 = dW; a.ld32 = pw;
     if (dW && !dY) { set_error("mpqr_panel_factor_device: dW needs dY"); cudaFree(ws); cudaFree(scratch); return MPQR_EINVAL; }
     a.T = dT; a.ldt = pw;
-    a.sync_ws = ws; a.scratch = scratch; a.scratch_rows = scratch_rows;
+    a.sync_ws = ws; a.host_ctr = &host_ctr; a.scratch = scratch; a.scratch_rows = scratch_rows;
     int rc = launch_panel(a, (cudaStream_t)stream, nullptr);
     cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(ws);
@@ -550,16 +554,42 @@ int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
     return rc;
 }
 
+// Tuning/profiling hook (tools/panel_probe.py; not part of the public header): runs the panel
+// kernel `reps` times on copies of the same panel with phase profiling enabled.
+int mpqr_debug_panel_probe(float* dA, long lda, int m, int n, int lam, int pw, int rows_hint, int want_wy,
+                           long long* dDbg, void* stream) {
+    DeviceInfo di;
+    MPQR_TRY(get_device_info(&di));
+    float *ws = nullptr, *Y = nullptr, *W = nullptr, *T = nullptr;
+    MPQR_CUDA(cudaMalloc(&ws, panel_sync_ws_bytes()));
+    MPQR_CUDA(cudaMemset(ws, 0, panel_sync_ws_bytes()));
+    if (want_wy) {
+        MPQR_CUDA(cudaMalloc(&Y, (size_t)(m - lam) * pw * 4));
+        MPQR_CUDA(cudaMalloc(&W, (size_t)(m - lam) * pw * 4));
+        MPQR_CUDA(cudaMalloc(&T, (size_t)pw * pw * 4));
+    }
+    unsigned host_ctr = 0;
+    PanelArgs a{};
+    a.A = dA; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.pw = pw; a.blk_row0 = lam;
+    a.Y32 = Y; a.W32 = W; a.ld32 = pw; a.T = T; a.ldt = pw;
+    a.sync_ws = ws; a.host_ctr = &host_ctr; a.dbg = dDbg; a.rows_hint = rows_hint;
+    int rc = launch_panel(a, (cudaStream_t)stream, nullptr);
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(ws); cudaFree(Y); cudaFree(W); cudaFree(T);
+    if (rc == MPQR_OK && e != cudaSuccess) { set_error("panel probe failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; }
+    return rc;
+}
+
 int mpqr_gemm_tn_device(const void* dX, long ldx, const void* dZ, long ldz, float* dS, long lds, int M, int N, int K,
                         int bf16, void* stream) {
     if (!dX || !dZ || !dS || K < 1) { set_error("mpqr_gemm_tn_device: bad arguments"); return MPQR_EINVAL; }
-    return tc_gemm_tn(dX, ldx, dZ, ldz, dS, lds, M, N, K, bf16, (cudaStream_t)stream, nullptr);
+    return tc_gemm_tn(dX, ldx, dZ, ldz, dS, lds, M, N, K, bf16, 0, (cudaStream_t)stream, nullptr);
 }
 
 int mpqr_gemm_nn_device(const void* dX, long ldx, const void* dS16, long lds16, float* dC, long ldc, void* dC16,
                         long ldc16, int M, int N, int K, int bf16, void* stream) {
     if (!dX || !dS16 || !dC) { set_error("mpqr_gemm_nn_device: bad arguments"); return MPQR_EINVAL; }
-    return tc_gemm_nn(dX, ldx, dS16, lds16, dC, ldc, dC16, ldc16, M, N, K, bf16, (cudaStream_t)stream, nullptr);
+    return tc_gemm_nn(dX, ldx, dS16, lds16, dC, ldc, dC16, ldc16, M, N, K, bf16, 0, (cudaStream_t)stream, nullptr);
 }
 
 int mpqr_fill_uniform_device(float* dA, long lda, long n_total, long row0, long rows, long col0, long cols,

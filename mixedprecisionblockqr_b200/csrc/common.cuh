@@ -43,8 +43,8 @@ int get_device_info(DeviceInfo* out);
 // ------------------------------------------------------------------ panel factorisation
 constexpr int kPanelMaxWidth = 128;
 
-// Sync workspace of one panel launch (floats): dots[pwp][pwp] | pivot rows[pwp][pwp] |
-// gram[pwp][pwp] | counter.  Must be zero on entry; the launcher memsets it.
+// Sync workspace of the panel kernel: per-CTA slots (double buffered) | Gram accumulator |
+// barrier counter.  Zeroed ONCE when allocated; the counter only grows (host_ctr mirrors it).
 size_t panel_sync_ws_bytes();
 // Scratch for the non-shared-memory-resident variant: rows x 128 floats.
 size_t panel_scratch_bytes(int max_rows);
@@ -69,8 +69,12 @@ struct PanelArgs {
     float* T;      // pw x pw (ldt), upper triangular, Q_p = I - Y T Y^T
     int ldt;
     float* sync_ws;
+    unsigned* host_ctr; // host-side mirror of the barrier counter in sync_ws (running total)
+    unsigned ctr_base;  // filled in by launch_panel
     float* scratch;     // may be null if the panel fits in shared memory
     long scratch_rows;  // capacity of scratch in rows
+    long long* dbg;     // optional device buffer (16 x int64) for phase profiling, else null
+    int rows_hint;      // > 0: override the rows-per-CTA heuristic (tuning)
 };
 int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches);
 
@@ -82,16 +86,21 @@ int sgemm_tn(const float* X, long ldx, const float* Z, long ldz, float* S, long 
 int sgemm_nn_sub(const float* X, long ldx, const float* S, long lds, float* C, long ldc, int M,
                  int N, int K, cudaStream_t stream, long* launches);
 
+// 16-bit-operand CUDA-core fallbacks (sub-blocks that are not 16-byte aligned, see gemm_tc.cu)
+int simt16_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long lds, int M, int N, int K,
+                   int bf16, cudaStream_t stream);
+int simt16_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16, long ldc16,
+                   int M, int N, int K, int bf16, cudaStream_t stream);
+
 // ------------------------------------------------------------------ tcgen05 GEMMs
-struct TcGemm;  // opaque per-handle state (TMA descriptor cache etc.)
 // S[M x N] (fp32) = X^T Z with 16-bit X [K x M], Z [K x N]; split-K with TMA reduce-add when
 // the tile count cannot fill the GPU (S is zeroed internally in that case).
 int tc_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long lds, int M, int N,
-               int K, int bf16, cudaStream_t stream, long* launches);
+               int K, int bf16, int pad_ok, cudaStream_t stream, long* launches);
 // C[M x N] (fp32) -= X S16, X [M x K] 16-bit (K-major), S16 [K x N] 16-bit; optionally mirrors
 // the updated C into C16 (16-bit shadow).
 int tc_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16,
-               long ldc16, int M, int N, int K, int bf16, cudaStream_t stream, long* launches);
+               long ldc16, int M, int N, int K, int bf16, int pad_ok, cudaStream_t stream, long* launches);
 
 // ------------------------------------------------------------------ small utility kernels
 int fill_uniform(float* A, long lda, long n_total, long row0, long rows, long col0, long cols,

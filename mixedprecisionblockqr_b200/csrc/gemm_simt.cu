@@ -17,10 +17,19 @@ constexpr int GT = (BM / TM) * (BN / TN);  // 256 threads
 // TRANS_A = true : X stored [K x M] (row k contiguous in i)  -> S = X^T Z
 // TRANS_A = false: X stored [M x K]                            -> C -= X S
 // MODE 0: store, 1: subtract from C, 2: atomicAdd (split-K over blockIdx.z)
-template <bool TRANS_A, int MODE>
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st16(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void st16(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void st16(float*, float) {}
+
+// TI: operand element type (float for the FP32 driver; __half / __nv_bfloat16 when this kernel
+// serves as the general-shape fallback of the tensor-core path).  H: optional 16-bit shadow.
+template <bool TRANS_A, int MODE, typename TI>
 __global__ void __launch_bounds__(GT)
-sgemm_kernel(const float* __restrict__ X, long ldx, const float* __restrict__ Z, long ldz,
-             float* __restrict__ C, long ldc, int M, int N, int K, int kchunk) {
+sgemm_kernel(const TI* __restrict__ X, long ldx, const TI* __restrict__ Z, long ldz,
+             float* __restrict__ C, long ldc, TI* __restrict__ H, long ldh, int M, int N, int K, int kchunk) {
     __shared__ float Xs[BK][BM + 4];
     __shared__ float Zs[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -39,19 +48,19 @@ sgemm_kernel(const float* __restrict__ X, long ldx, const float* __restrict__ Z,
         for (int idx = tid; idx < BK * BN; idx += GT) {
             int kk = idx / BN, j = idx % BN;
             int gk = k0 + kk, gj = j0 + j;
-            Zs[kk][j] = (gk < kend && gj < N) ? Z[(size_t)gk * ldz + gj] : 0.f;
+            Zs[kk][j] = (gk < kend && gj < N) ? ldf(Z + (size_t)gk * ldz + gj) : 0.f;
         }
         if (TRANS_A) {
             for (int idx = tid; idx < BK * BM; idx += GT) {
                 int kk = idx / BM, i = idx % BM;
                 int gk = k0 + kk, gi = i0 + i;
-                Xs[kk][i] = (gk < kend && gi < M) ? X[(size_t)gk * ldx + gi] : 0.f;
+                Xs[kk][i] = (gk < kend && gi < M) ? ldf(X + (size_t)gk * ldx + gi) : 0.f;
             }
         } else {
             for (int idx = tid; idx < BK * BM; idx += GT) {
                 int i = idx / BK, kk = idx % BK;
                 int gk = k0 + kk, gi = i0 + i;
-                Xs[kk][i] = (gk < kend && gi < M) ? X[(size_t)gi * ldx + gk] : 0.f;
+                Xs[kk][i] = (gk < kend && gi < M) ? ldf(X + (size_t)gi * ldx + gk) : 0.f;
             }
         }
         __syncthreads();
@@ -79,17 +88,18 @@ sgemm_kernel(const float* __restrict__ X, long ldx, const float* __restrict__ Z,
             if (gj >= N) continue;
             float* p = C + (size_t)gi * ldc + gj;
             if (MODE == 0) *p = acc[u][v];
-            else if (MODE == 1) *p = *p - acc[u][v];
-            else atomicAdd(p, acc[u][v]);
+            else if (MODE == 1) {
+                float nv = *p - acc[u][v];
+                *p = nv;
+                if (sizeof(TI) == 2 && H) st16(H + (size_t)gi * ldh + gj, nv);
+            } else atomicAdd(p, acc[u][v]);
         }
     }
 }
 
-}  // namespace
-
-int sgemm_tn(const float* X, long ldx, const float* Z, long ldz, float* S, long lds, int M, int N,
-             int K, cudaStream_t stream, long* launches) {
-    if (M <= 0 || N <= 0) return MPQR_OK;
+template <typename TI>
+int tn_any(const TI* X, long ldx, const TI* Z, long ldz, float* S, long lds, int M, int N, int K,
+           cudaStream_t stream) {
     DeviceInfo di;
     MPQR_TRY(get_device_info(&di));
     int tiles = ceil_div(M, BM) * ceil_div(N, BN);
@@ -104,11 +114,29 @@ int sgemm_tn(const float* X, long ldx, const float* Z, long ldz, float* S, long 
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
     if (splits > 1) {
         MPQR_CUDA(cudaMemset2DAsync(S, lds * sizeof(float), 0, (size_t)N * sizeof(float), M, stream));
-        sgemm_kernel<true, 2><<<grid, GT, 0, stream>>>(X, ldx, Z, ldz, S, lds, M, N, K, kchunk);
+        sgemm_kernel<true, 2, TI><<<grid, GT, 0, stream>>>(X, ldx, Z, ldz, S, lds, nullptr, 0, M, N, K, kchunk);
     } else {
-        sgemm_kernel<true, 0><<<grid, GT, 0, stream>>>(X, ldx, Z, ldz, S, lds, M, N, K, kchunk);
+        sgemm_kernel<true, 0, TI><<<grid, GT, 0, stream>>>(X, ldx, Z, ldz, S, lds, nullptr, 0, M, N, K, kchunk);
     }
     MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+
+template <typename TI>
+int nn_any(const TI* X, long ldx, const TI* S, long lds, float* C, long ldc, TI* H, long ldh, int M, int N, int K,
+           cudaStream_t stream) {
+    dim3 grid(ceil_div(N, BN), ceil_div(M, BM), 1);
+    sgemm_kernel<false, 1, TI><<<grid, GT, 0, stream>>>(X, ldx, S, lds, C, ldc, H, ldh, M, N, K, K);
+    MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+
+}  // namespace
+
+int sgemm_tn(const float* X, long ldx, const float* Z, long ldz, float* S, long lds, int M, int N,
+             int K, cudaStream_t stream, long* launches) {
+    if (M <= 0 || N <= 0) return MPQR_OK;
+    MPQR_TRY(tn_any<float>(X, ldx, Z, ldz, S, lds, M, N, K, stream));
     if (launches) *launches += 1;
     return MPQR_OK;
 }
@@ -116,11 +144,23 @@ int sgemm_tn(const float* X, long ldx, const float* Z, long ldz, float* S, long 
 int sgemm_nn_sub(const float* X, long ldx, const float* S, long lds, float* C, long ldc, int M,
                  int N, int K, cudaStream_t stream, long* launches) {
     if (M <= 0 || N <= 0 || K <= 0) return MPQR_OK;
-    dim3 grid(ceil_div(N, BN), ceil_div(M, BM), 1);
-    sgemm_kernel<false, 1><<<grid, GT, 0, stream>>>(X, ldx, S, lds, C, ldc, M, N, K, K);
-    MPQR_CUDA(cudaGetLastError());
+    MPQR_TRY(nn_any<float>(X, ldx, S, lds, C, ldc, nullptr, 0, M, N, K, stream));
     if (launches) *launches += 1;
     return MPQR_OK;
+}
+
+// General-shape fallbacks of the tensor-core GEMMs (16-bit operands, FP32 accumulate on CUDA
+// cores): used only when a sub-block does not start on a 16-byte boundary, which TMA requires.
+int simt16_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long lds, int M, int N, int K,
+                   int bf16, cudaStream_t stream) {
+    if (bf16) return tn_any<__nv_bfloat16>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)Z, ldz, S, lds, M, N, K, stream);
+    return tn_any<__half>((const __half*)X, ldx, (const __half*)Z, ldz, S, lds, M, N, K, stream);
+}
+
+int simt16_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16, long ldc16,
+                   int M, int N, int K, int bf16, cudaStream_t stream) {
+    if (bf16) return nn_any<__nv_bfloat16>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)S16, lds16, C, ldc, (__nv_bfloat16*)C16, ldc16, M, N, K, stream);
+    return nn_any<__half>((const __half*)X, ldx, (const __half*)S16, lds16, C, ldc, (__half*)C16, ldc16, M, N, K, stream);
 }
 
 }  // namespace mpqr

@@ -470,10 +470,11 @@ int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, 
     return MPQR_OK;
 }
 
-// Split an (array base, leading dim) + block pointer into 16-byte aligned base + element coords.
-// We keep it simple: the block pointer itself must be expressible as base + y*ld + x with the
-// caller-provided base; callers pass the block pointer and we derive an aligned base by
-// rounding the address down to 16 bytes and putting the remainder into the x coordinate.
+// TMA needs 16-byte aligned box origins.  x0 = misalignment of a block pointer in elements;
+// blocks with x0 != 0 are routed to the CUDA-core fallback (gemm_simt.cu).  TMA stores also
+// write whole 16-byte granules (measured on B200: a store clipped at column N still zeroes the
+// rest of the granule), so an output block whose last column is not granule-aligned may only go
+// through TMA when the caller says the spill is harmless (pad_ok: row padding / dead columns).
 struct Blk {
     const void* base;
     int x0;
@@ -489,12 +490,18 @@ int pick_bn(int N) { return N > 128 ? 256 : 128; }
 }  // namespace
 
 int tc_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long lds, int M, int N, int K,
-               int bf16, cudaStream_t stream, long* launches) {
+               int bf16, int pad_ok, cudaStream_t stream, long* launches) {
     if (M <= 0 || N <= 0) return MPQR_OK;
     DeviceInfo di;
     MPQR_TRY(get_device_info(&di));
     const int BN = pick_bn(N);
     Blk bx = align_blk(X, 2), bz = align_blk(Z, 2), bs = align_blk(S, 4);
+    if (bx.x0 || bz.x0 || bs.x0 || (ldx & 7) || (ldz & 7) || (lds & 3) || (!pad_ok && (N & 3))) {
+        // TMA box origins must be 16-byte aligned: general-shape CUDA-core fallback
+        int rc = simt16_gemm_tn(X, ldx, Z, ldz, S, lds, M, N, K, bf16, stream);
+        if (rc == MPQR_OK && launches) *launches += 1;
+        return rc;
+    }
     CUtensorMap tA, tB, tC;
     MPQR_TRY(make_map(&tA, bx.base, 2, bf16, bx.x0 + M, K, ldx, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B));
     MPQR_TRY(make_map(&tB, bz.base, 2, bf16, bz.x0 + N, K, ldz, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B));
@@ -524,12 +531,18 @@ int tc_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long 
 }
 
 int tc_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16, long ldc16,
-               int M, int N, int K, int bf16, cudaStream_t stream, long* launches) {
+               int M, int N, int K, int bf16, int pad_ok, cudaStream_t stream, long* launches) {
     if (M <= 0 || N <= 0 || K <= 0) return MPQR_OK;
     DeviceInfo di;
     MPQR_TRY(get_device_info(&di));
     const int BN = pick_bn(N);
     Blk bx = align_blk(X, 2), bs = align_blk(S16, 2), bc = align_blk(C, 4);
+    if (bx.x0 || bs.x0 || bc.x0 || (C16 && align_blk(C16, 2).x0) || (ldx & 7) || (lds16 & 7) || (ldc & 3) ||
+        (C16 && (ldc16 & 7)) || (!pad_ok && (N & (C16 ? 7 : 3)))) {
+        int rc = simt16_gemm_nn(X, ldx, S16, lds16, C, ldc, C16, ldc16, M, N, K, bf16, stream);
+        if (rc == MPQR_OK && launches) *launches += 1;
+        return rc;
+    }
     CUtensorMap tA, tB, tC, tH;
     MPQR_TRY(make_map(&tA, bx.base, 2, bf16, bx.x0 + K, M, ldx, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B));
     MPQR_TRY(make_map(&tB, bs.base, 2, bf16, bs.x0 + N, K, lds16, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B));

@@ -26,7 +26,11 @@ namespace {
 constexpr int NT = 512;
 constexpr int NW = NT / 32;
 constexpr int WS_LD = kPanelMaxWidth;                       // row stride of the global sync arrays
-constexpr int WS_ARRAY = kPanelMaxWidth * kPanelMaxWidth;   // floats per sync array
+constexpr int WS_ARRAY = kPanelMaxWidth * kPanelMaxWidth;   // floats of the Gram accumulator
+constexpr int MAXG = 160;                                   // max CTAs of one panel launch (>= #SMs)
+constexpr int SLOT_FLOATS = 2 * WS_LD;                      // per-CTA slot: partial dots | pivot row
+// sync workspace (floats): slots[2][MAXG][SLOT_FLOATS] | gram[WS_ARRAY] | counter
+constexpr size_t WS_SLOTS = (size_t)2 * MAXG * SLOT_FLOATS;
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
@@ -34,18 +38,30 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     return v;
 }
 
-// All CTAs of the (cooperatively launched, co-resident) grid arrive; monotonically increasing
-// counter, so no reset between barriers.
+// All CTAs of the (cooperatively launched, co-resident) grid arrive.  The counter only ever
+// increases (across barriers AND across launches: the host passes the base), so it is never
+// reset; comparisons are wrap-safe.  Release: bar.sync orders the CTA's slot stores before
+// thread 0's fence + red; acquire: ld.acquire by thread 0, then bar.sync, then .cg loads.
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        while (ld_acquire_gpu(ctr) < target) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        while ((int)(ld_acquire_gpu(ctr) - target) < 0) {
         }
     }
     __syncthreads();
 }
+
+// Optional phase profiling (PanelArgs.dbg != null): CTA 0 / thread 0 accumulates clock64 deltas.
+// dbg[0]=pass dbg[1]=local reduce+publish dbg[2]=grid barrier dbg[3]=gather dbg[4]=scalars
+// dbg[5]=load dbg[6]=store+tail dbg[7]=steps dbg[8]=G dbg[9]=rows_per_cta
+#define PROF_MARK(slot)                                               \
+    if (prof) {                                                       \
+        long long t__ = clock64();                                    \
+        a.dbg[slot] += t__ - tprev;                                   \
+        tprev = t__;                                                  \
+    }
 
 template <int CPL>
 struct RowVec;
@@ -119,19 +135,25 @@ panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int G) {
     const int r1 = (r0 + rows_per_cta < D) ? r0 + rows_per_cta : D;
     const int nrows = r1 > r0 ? r1 - r0 : 0;
     float* slice = use_smem ? slice_sm : a.scratch + (size_t)r0 * PWP;
-    float* dots_g = a.sync_ws;
-    float* prow_g = dots_g + WS_ARRAY;
-    float* gram_g = prow_g + WS_ARRAY;
+    float* slots = a.sync_ws;
+    float* gram_g = slots + WS_SLOTS;
     unsigned* ctr = reinterpret_cast<unsigned*>(gram_g + WS_ARRAY);
+    constexpr int NG = NT / PWP;  // gather groups
     const long lda = a.lda;
     float* Ablk = a.A + (size_t)lam * lda + lam;  // element (lam, lam)
 
+    const bool prof = (a.dbg != nullptr) && blockIdx.x == 0 && tid == 0;
+    long long tprev = prof ? clock64() : 0;
     // ---- load the slice (coalesced along the panel row), zero-pad columns >= pw
     for (int idx = tid; idx < nrows * PWP; idx += NT) {
         int li = idx / PWP, c = idx - li * PWP;
         slice[idx] = (c < pw) ? Ablk[(size_t)(r0 + li) * lda + c] : 0.f;
     }
+    // the Gram accumulator is used (atomically) only after >= 1 grid barrier: zero it here
+    if (G > 1)
+        for (int idx = blockIdx.x * NT + tid; idx < WS_ARRAY; idx += G * NT) gram_g[idx] = 0.f;
     __syncthreads();
+    PROF_MARK(5);
 
     unsigned bar_id = 0;
     float tau[CPL];
@@ -181,26 +203,55 @@ panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int G) {
 #pragma unroll
         for (int q = 0; q < CPL; ++q) red[warp * PWP + lane * CPL + q] = acc[q];
         __syncthreads();
+        PROF_MARK(0);
         if (tid < PWP) {
             float s = 0.f;
 #pragma unroll
             for (int w = 0; w < NW; ++w) s += red[w * PWP + tid];
             if (G > 1) {
-                if (tid >= step && tid < pw) atomicAdd(&dots_g[step * WS_LD + tid], s);
-                if (step >= r0 && step < r1) prow_g[step * WS_LD + tid] = slice[(size_t)(step - r0) * PWP + tid];
+                // publish this CTA's partial dots (and the pivot row if it owns it) in its slot;
+                // slots are double-buffered by step parity and fully rewritten, never reset
+                float* myslot = slots + ((size_t)(step & 1) * MAXG + blockIdx.x) * SLOT_FLOATS;
+                __stcg(&myslot[tid], s);
+                if (step >= r0 && step < r1) __stcg(&myslot[WS_LD + tid], slice[(size_t)(step - r0) * PWP + tid]);
             } else {
                 gsum[tid] = s;
                 prow[tid] = slice[(size_t)step * PWP + tid];
             }
         }
+        PROF_MARK(1);
         if (G > 1) {
-            grid_barrier(ctr, (unsigned)G * (++bar_id));
+            grid_barrier(ctr, a.ctr_base + (unsigned)G * (++bar_id));
+            PROF_MARK(2);
+            // deterministic gather: group grp sums CTAs grp, grp+NG, ... for column j.
+            // Loads are issued in batches of 8 before the first use (each is an L2 round trip).
+            const int j = tid % PWP, grp = tid / PWP;
+            const float* sl = slots + (size_t)(step & 1) * MAXG * SLOT_FLOATS;
+            float s = 0.f;
+            if (j >= step) {
+                for (int c0 = grp; c0 < G; c0 += NG * 8) {
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        int c = c0 + u * NG;
+                        v[u] = (c < G) ? __ldcg(&sl[(size_t)c * SLOT_FLOATS + j]) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) s += v[u];
+                }
+            }
+            red[grp * PWP + j] = s;
+            if (tid < PWP) prow[tid] = __ldcg(&sl[(size_t)(step / rows_per_cta) * SLOT_FLOATS + WS_LD + tid]);
+            __syncthreads();
             if (tid < PWP) {
-                gsum[tid] = __ldcg(&dots_g[step * WS_LD + tid]);
-                prow[tid] = __ldcg(&prow_g[step * WS_LD + tid]);
+                float t = 0.f;
+#pragma unroll
+                for (int gq = 0; gq < NG; ++gq) t += red[gq * PWP + tid];
+                gsum[tid] = t;
             }
         }
         __syncthreads();
+        PROF_MARK(3);
 
         // reflector scalars (every thread, redundantly)
         const float gk = gsum[step], ak = prow[step];
@@ -217,6 +268,7 @@ panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int G) {
         }
         if (skip) smu = 0.f;
         if (tid == 0) diag[step] = skip ? ak : -smu;
+        PROF_MARK(4);
         // (gsum/prow are rewritten only after the next pass's __syncthreads)
     }
     __syncthreads();
@@ -236,6 +288,8 @@ panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int G) {
     }
     __syncthreads();
 
+    PROF_MARK(6);
+    if (prof) { a.dbg[7] += kr; a.dbg[8] = G; a.dbg[9] = rows_per_cta; }
     const bool want16y = a.Y16 != nullptr, want16w = a.W16 != nullptr;
     const bool need_t = a.T || a.W32 || want16w;
     if (!(a.Y32 || want16y || need_t)) return;
@@ -308,7 +362,7 @@ panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int G) {
         }
     }
     if (G > 1) {
-        grid_barrier(ctr, (unsigned)G * (++bar_id));
+        grid_barrier(ctr, a.ctr_base + (unsigned)G * (++bar_id));
         for (int idx = tid; idx < PWP * PWP; idx += NT) {
             int t = idx / PWP, c = idx - t * PWP;
             if (t < c && c < kr) gt[t * GLD + c] = __ldcg(&gram_g[t * WS_LD + c]);
@@ -337,6 +391,7 @@ panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int G) {
             a.T[(size_t)t * a.ldt + c] = (t <= c && c < kr) ? gt[t * GLD + c] : 0.f;
         }
     }
+    PROF_MARK(10);
     if (!(a.W32 || want16w)) return;
 
     // ---- W = Y T on the slice rows; lane <-> columns lane + 32 q (conflict-free T reads)
@@ -390,9 +445,15 @@ int launch_t(const PanelArgs& a, cudaStream_t stream, const DeviceInfo& di) {
         rows_per_cta = D;
         G = 1;
     } else {
+        // measured (tools/panel_probe.py, profiles/r1_panel_probe.txt): the local pass costs
+        // ~16 cycles/row/step while the gather grows only ~8 cycles per extra CTA -> use many CTAs
         rows_per_cta = ceil_div(D, di.num_sms);
+        if (a.rows_hint > 0) rows_per_cta = a.rows_hint;
         if (rows_per_cta < 64) rows_per_cta = 64;
         rows_per_cta = round_up(rows_per_cta, NW);
+        const int cap = max_rows_smem - (max_rows_smem % NW);
+        if (rows_per_cta > cap) rows_per_cta = cap;
+        if (ceil_div(D, rows_per_cta) > di.num_sms) rows_per_cta = round_up(ceil_div(D, di.num_sms), NW);
         if (rows_per_cta > max_rows_smem) {
             // does not fit: keep the slice in a global scratch buffer (L2-resident for moderate D)
             use_smem = 0;
@@ -415,8 +476,23 @@ int launch_t(const PanelArgs& a, cudaStream_t stream, const DeviceInfo& di) {
                                        di.max_smem_optin));
         attr_set = true;
     }
-    if (G > 1) MPQR_CUDA(cudaMemsetAsync(a.sync_ws, 0, panel_sync_ws_bytes(), stream));
+    if (G > MAXG) {
+        set_error("panel: %d CTAs exceed the sync workspace (MAXG=%d)", G, MAXG);
+        return MPQR_EINVAL;
+    }
     PanelArgs args = a;
+    if (G > 1) {
+        // grid barriers executed by this launch: one per reflector + one for the Gram reduction
+        const int kr = a.pw < D ? a.pw : D;
+        const bool need_t = a.T || a.W32 || a.W16;
+        unsigned nbar = (unsigned)kr + (need_t ? 1u : 0u);
+        if (!a.host_ctr) {
+            set_error("panel: host_ctr missing");
+            return MPQR_EINVAL;
+        }
+        args.ctr_base = *a.host_ctr;
+        *a.host_ctr += (unsigned)G * nbar;
+    }
     if (G > 1) {
         void* kargs[] = {(void*)&args, (void*)&rows_per_cta, (void*)&use_smem, (void*)&G};
         MPQR_CUDA(cudaLaunchCooperativeKernel((void*)panel_kernel<CPL>, dim3(G), dim3(NT), kargs, smem, stream));
@@ -429,7 +505,7 @@ int launch_t(const PanelArgs& a, cudaStream_t stream, const DeviceInfo& di) {
 
 }  // namespace
 
-size_t panel_sync_ws_bytes() { return (size_t)3 * WS_ARRAY * sizeof(float) + 256; }
+size_t panel_sync_ws_bytes() { return (WS_SLOTS + WS_ARRAY) * sizeof(float) + 256; }
 size_t panel_scratch_bytes(int max_rows) { return (size_t)max_rows * kPanelMaxWidth * sizeof(float); }
 
 int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
