@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — block-QR TFLOP/s (Householder count 2mn^2 - 2n^3/3) on synthetic matrices.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU block QR
+
+A "step" is one complete factorisation of the workload matrix (BASELINE.json configs[3]:
+32768 x 32768, r = 128; it fits one B200, so it is the N = 1 workload too).  At N > 1 the
+matrix is distributed 1-D column-block-cyclic and the SAME matrix is factored (strong scaling).
+Inputs are generated on the device from a stateless hash (oracle-identical), a pristine copy
+stays resident in HBM and is restored inside the timed region before each factorisation
+(the algorithm is in place).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (m, n, r)   — BASELINE.json configs
+    "c4": (32768, 32768, 128),
+    "c3": (4096, 16384, 64),
+    "c2": (2048, 2048, 32),
+    "c16k": (16384, 16384, 128),
+    "c8k": (8192, 8192, 128),
+}
+REF_SAMPLE = (640, 640, 32)  # bounded sample of the same workload family for the CPU reference arm
+
+
+def householder_flops(m, n):
+    m, n = float(m), float(n)
+    return 2 * m * n * n - 2 * n ** 3 / 3 if m >= n else 2 * m * m * n - 2 * m ** 3 / 3
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tc_burst": d["bf16_tflops"], "tc_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tc_burst": 1590.0, "tc_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, smax = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference_sample(steps, warmup):
+    """Times the reference's own CPU implementation of the path (h_block_qr, Cuda/qr.cu:1275)
+    from oracle/_ref when it was compiled, else the oracle port; single thread (the reference
+    has no threading)."""
+    import numpy as np
+    import oracle
+    m, n, r = REF_SAMPLE
+    A = oracle.uniform_matrix(m, n, 640640)
+    kind = "reference" if oracle.ref_available() else "port"
+    fn = (lambda: oracle.ref_block_qr(A, r)) if kind == "reference" else (lambda: oracle.block_qr(A, r, dense=True))
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        P, Q = fn()
+    dt = (time.perf_counter() - t0) / steps
+    be = oracle.backward_error(A, oracle.strip_R(P), Q)
+    tf = householder_flops(m, n) / dt / 1e12
+    return {"value": tf, "unit": "TFLOP/s", "cores": 1, "kind": kind,
+            "sample": f"{m}x{n} r={r} uniform[0,1) FP32, h_block_qr (Cuda/qr.cu:1275) incl. explicit Q, {dt:.2f} s/step",
+            "backward_error": be, "seconds_per_step": dt}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = run_reference_sample(args.steps, args.warmup)
+    m, n, r = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": "block-QR TFLOP/s (2mn^2-2n^3/3)", "value": cb["value"], "unit": "TFLOP/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"{m}x{n} r={r} block QR", "timed_sample": cb["sample"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "backward_error": cb["backward_error"]}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- native arm
+def sampled_backward_error(torch, A0, P, r, k=16):
+    """||(A - QR) X||_F / (||A||_F sqrt(k)), Gaussian X, FP64, straight from the packed factor."""
+    m, n = A0.shape
+    g = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.randn(n, k, device="cuda", dtype=torch.float64, generator=g)
+    AX = torch.zeros(m, k, device="cuda", dtype=torch.float64)
+    Z = torch.zeros(m, k, device="cuda", dtype=torch.float64)
+    anorm2 = 0.0
+    step = 4096
+    for i in range(0, m, step):   # chunked to bound FP64 temporaries
+        blk = A0[i:i + step].double()
+        AX[i:i + step] = blk @ X
+        anorm2 += float((blk * blk).sum())
+        Z[i:i + step] = torch.triu(P[i:i + step].double(), diagonal=i) @ X
+    kmax = min(m, n)
+    for lam in range(((kmax - 1) // r) * r, -1, -r):
+        pw = min(r, kmax - lam)
+        Y = torch.tril(P[lam + 1:m + 1, lam:lam + pw].double())
+        Tinv = torch.triu(Y.T @ Y, 1) + 0.5 * torch.eye(pw, device="cuda", dtype=torch.float64)
+        Z[lam:] -= Y @ torch.linalg.solve_triangular(Tinv, Y.T @ Z[lam:], upper=True)
+    return float(torch.linalg.norm(AX - Z)) / (anorm2 ** 0.5 * k ** 0.5)
+
+
+def main_native(args):
+    import torch
+    import mixedprecisionblockqr_b200 as pkg
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+    m, n, r = WORKLOADS[args.workload]
+    F = householder_flops(m, n)
+    st = torch.cuda.current_stream().cuda_stream
+    peaks = load_peaks()
+
+    if world == 1:
+        plan = pkg.BlockQR(m, n, r, nb=args.nb, precision=args.precision)
+        nloc, lda = n, (n + 7) // 8 * 8
+        A0 = torch.zeros(m, lda, device="cuda")
+        pkg.fill_uniform(A0.data_ptr(), lda, n, 0, m, 0, n, args.seed, st)
+    else:
+        uid = [pkg.mg_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        plan = pkg.MultiGpuBlockQR(m, n, r, args.nb, rank, world, uid[0], precision=args.precision)
+        nloc = plan.local_cols
+        lda = (max(nloc, 8) + 7) // 8 * 8
+        A0 = torch.zeros(m, lda, device="cuda")
+        # every local block is generated in place from the global (row, col) hash: no transfers
+        for lb in range((nloc + plan.nb - 1) // plan.nb):
+            g0 = (lb * world + rank) * plan.nb
+            w = min(plan.nb, n - g0)
+            pkg.fill_uniform(A0.data_ptr() + 4 * lb * plan.nb, lda, n, 0, m, g0, w, args.seed, st)
+    A = torch.zeros(m + 1, lda, device="cuda")
+
+    def step():
+        A[:m].copy_(A0)                        # restore the input (HBM -> HBM), inside the timed region
+        plan.factor(A.data_ptr(), lda, st)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    plan.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = plan.profile()
+    plan.set_profiling(False)
+    launches = plan.last_launches * args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.float64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_per_step = ms / args.steps
+    value = F / (ms_per_step * 1e-3) / 1e12
+
+    # ---- accuracy of the last timed factorisation (outside the timed region)
+    be = None
+    if world == 1 and not args.no_check:
+        be = sampled_backward_error(torch, A0[:, :n], A[:, :n], plan.r)
+
+    # ---- end to end through the host-pointer C-ABI (pinned host buffers, H2D + D2H inside)
+    e2e = None
+    esteps = max(1, min(args.steps, args.e2e_steps))
+    if world == 1:
+        host = torch.empty((m + 1, n), dtype=torch.float32, pin_memory=True)
+        host[:m].copy_(A0[:, :n])
+        host[m].zero_()
+        src = host.clone().pin_memory()
+        flags = {"fp16": pkg.MPQR_FP16, "bf16": pkg.MPQR_BF16, "fp32": pkg.MPQR_FP32}[args.precision]
+        torch.cuda.synchronize()
+        for w in range(1 + esteps):   # one warm-up
+            host.copy_(src)
+            if w == 1:
+                t0 = time.perf_counter()
+            pkg.check(pkg.lib().mpqr_block_qr_host(host.data_ptr(), None, m, n, r, flags), "mpqr_block_qr_host")
+        dt = (time.perf_counter() - t0) / esteps
+        # note: host.copy_(src) (host memcpy restoring the input) is inside dt as well
+        nbytes = (m + 1) * n * 4
+        e2e = {"value": F / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "ms_per_step": dt * 1e3, "path": "mpqr_block_qr_host(A_host_pinned, Q=NULL): alloc + H2D + factor + D2H"}
+        del host, src
+    else:
+        hostA = torch.empty((m + 1, lda), dtype=torch.float32, pin_memory=True)
+        hostA[:m].copy_(A0)
+        hostA[m].zero_()
+        hostSrc = hostA.clone().pin_memory()
+        barrier()
+        for w in range(1 + esteps):
+            if w == 1:
+                barrier()
+                t0 = time.perf_counter()
+            hostA.copy_(hostSrc)                      # restore the host input (host memcpy)
+            A.copy_(hostA, non_blocking=True)         # H2D of this rank's shard
+            plan.factor(A.data_ptr(), lda, st)
+            hostA.copy_(A, non_blocking=True)         # D2H of the packed factor shard
+            torch.cuda.synchronize()
+        barrier()
+        dt = (time.perf_counter() - t0) / esteps
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        nbytes = (m + 1) * lda * 4
+        e2e = {"value": F / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
+               "ms_per_step": dt * 1e3, "path": "per rank: pinned host shard -> H2D -> mpqr_mg_factor_device -> D2H"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline per kernel class (CUDA events recorded inside the library on the launch stream)
+    by_kernel, total_kernel_ms = {}, sum(v["ms"] for v in prof.values()) or 1.0
+    traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
+    for name, v in prof.items():
+        if v["launches"] == 0:
+            continue
+        avg_ms = v["ms"] / v["launches"]
+        if name in ("gemm_tn", "gemm_nn"):
+            ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            by_kernel[name] = {"bound": "tensor", "achieved": ach, "peak": peaks["tc_sustained"], "unit": "TFLOP/s",
+                               "frac": ach / peaks["tc_sustained"], "traffic": traffic.get(name),
+                               "hbm_gbs_algorithmic": v["bytes"] / (v["ms"] * 1e-3) / 1e9}
+        else:
+            ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            by_kernel[name] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                               "frac": ach / peaks["hbm_gbs"], "traffic": traffic.get(name)}
+        by_kernel[name].update({"share_of_kernel_time": v["ms"] / total_kernel_ms, "avg_launch_ms": avg_ms,
+                                "launches_per_step": v["launches"] / args.steps})
+    dominant = max(by_kernel, key=lambda k: by_kernel[k]["share_of_kernel_time"])
+    roofline = dict(by_kernel[dominant])
+    roofline["kernel"] = dominant
+    roofline["peak_source"] = peaks["source"] + (", sustained bf16 cuBLAS" if roofline["bound"] == "tensor" else ", copy bandwidth")
+    # whole-QR roofline: every class at its own bound (SURVEY 8d T_roof)
+    t_roof = sum(max(v["flops"] / (peaks["tc_sustained"] * 1e12) if k in ("gemm_tn", "gemm_nn") else 0.0,
+                     v["bytes"] / (peaks["hbm_gbs"] * 1e9)) for k, v in prof.items()) / args.steps
+    whole = {"t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / ms_per_step,
+             "frac_of_tensor_peak": value / peaks["tc_sustained"]}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = run_reference_sample(1, 0)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {
+        "metric": "block-QR TFLOP/s (2mn^2-2n^3/3)", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"{m}x{n} r={r} mixed-precision block QR ({args.workload})", "effective_r": plan.r, "outer_block_nb": plan.nb,
+                   "parallelism": "single GPU" if world == 1 else f"1-D column-block-cyclic x{world}, NCCL broadcast of Y|W",
+                   "seed": args.seed, "l2": "inputs (>= 4 GB at c4) are larger than L2; input restored HBM->HBM inside the timed region",
+                   "flop_model": "2mn^2-2n^3/3 (m>=n) / 2m^2n-2m^3/3 (m<n)"},
+        "backward_error_sampled": be, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "roofline": roofline, "roofline_by_kernel": by_kernel, "whole_qr_roofline": whole, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--nb", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=32768128)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3   # timing rule: at least 3 warm-up steps
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_native(a)

@@ -97,6 +97,17 @@ int mpqr_effective_nb(const mpqr_handle* h);
 /* Number of kernels launched by the last factor / form_q call (for bench.py's gpu_launches). */
 long mpqr_last_launch_count(const mpqr_handle* h);
 
+/* Per-kernel-class timing with CUDA events recorded on the launch stream (bench.py's roofline
+ * object).  Classes: 0 = panel factorisation (+fused WY), 1 = GEMM TN (S = W^T A), 2 = GEMM NN
+ * (A -= Y S, incl. shadow), 3 = casts / small utility kernels.  Enable before a factor call;
+ * mpqr_get_profile synchronises on the recorded events and returns totals accumulated since the
+ * last mpqr_set_profiling(h, 1): device milliseconds, launches, algorithmic flops and
+ * algorithmic HBM bytes (panel: 8*D*pw; NN: 10*M*N; TN: 2*K*(M+N)+4*M*N). */
+#define MPQR_NUM_KERNEL_CLASSES 4
+int mpqr_set_profiling(mpqr_handle* h, int on);
+int mpqr_get_profile(mpqr_handle* h, int kernel_class, double* ms_total, long* launches, double* flops,
+                     double* bytes);
+
 /* ---------------------------------------------------------------------------------------
  * Single kernels exposed for parity tests against the oracle (tests/ call these through
  * ctypes).  All pointers are device pointers.
@@ -135,6 +146,10 @@ int mpqr_fill_uniform_device(float* dA, long lda, long n_total, long row0, long 
  * out-of-band channel (bench.py uses torch.distributed).
  * ------------------------------------------------------------------------------------- */
 #define MPQR_NCCL_UID_BYTES 128
+/* Pure host layout helpers (no device needed): columns of an n-column matrix owned by `rank`
+ * for block width nb, and the global column of a local column (-1 if out of range). */
+int mpqr_mg_layout_local_cols(int n, int nb, int rank, int nranks);
+int mpqr_mg_layout_global_col(int n, int nb, int rank, int nranks, int local_col);
 int mpqr_mg_get_unique_id(void* uid_out /* MPQR_NCCL_UID_BYTES */);
 int mpqr_mg_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags, int rank,
                    int nranks, const void* uid);

@@ -26,8 +26,10 @@ NCCL_UID_BYTES = 128
 ABI_SYMBOLS = (
     "mpqr_last_error", "mpqr_version", "mpqr_block_qr_host", "mpqr_create", "mpqr_destroy",
     "mpqr_factor_device", "mpqr_form_q_device", "mpqr_get_panel_T", "mpqr_num_panels",
-    "mpqr_effective_r", "mpqr_effective_nb", "mpqr_last_launch_count", "mpqr_panel_factor_device",
-    "mpqr_gemm_tn_device", "mpqr_gemm_nn_device", "mpqr_fill_uniform_device", "mpqr_mg_get_unique_id",
+    "mpqr_effective_r", "mpqr_effective_nb", "mpqr_last_launch_count", "mpqr_set_profiling", "mpqr_get_profile",
+    "mpqr_panel_factor_device",
+    "mpqr_gemm_tn_device", "mpqr_gemm_nn_device", "mpqr_fill_uniform_device", "mpqr_mg_layout_local_cols",
+    "mpqr_mg_layout_global_col", "mpqr_mg_get_unique_id",
     "mpqr_mg_create", "mpqr_mg_local_cols", "mpqr_mg_global_col", "mpqr_mg_factor_device",
     "mpqr_tsqr_device",
 )
@@ -61,10 +63,15 @@ def lib():
             getattr(L, f).argtypes = [vp]
         L.mpqr_last_launch_count.argtypes = [vp]
         L.mpqr_last_launch_count.restype = c_long
+        L.mpqr_set_profiling.argtypes = [vp, c_int]
+        L.mpqr_get_profile.argtypes = [vp, c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_long),
+                                       ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.mpqr_panel_factor_device.argtypes = [vp, c_long, c_int, c_int, c_int, c_int, vp, vp, vp, vp]
         L.mpqr_gemm_tn_device.argtypes = [vp, c_long, vp, c_long, vp, c_long, c_int, c_int, c_int, c_int, vp]
         L.mpqr_gemm_nn_device.argtypes = [vp, c_long, vp, c_long, vp, c_long, vp, c_long, c_int, c_int, c_int, c_int, vp]
         L.mpqr_fill_uniform_device.argtypes = [vp, c_long, c_long, c_long, c_long, c_long, c_long, ctypes.c_uint64, vp]
+        L.mpqr_mg_layout_local_cols.argtypes = [c_int] * 4
+        L.mpqr_mg_layout_global_col.argtypes = [c_int] * 5
         L.mpqr_mg_get_unique_id.argtypes = [vp]
         L.mpqr_mg_create.argtypes = [ctypes.POINTER(vp), c_int, c_int, c_int, c_int, c_uint, c_int, c_int, vp]
         L.mpqr_mg_global_col.argtypes = [vp, c_int]
@@ -134,6 +141,20 @@ class BlockQR:
     def panel_T(self, panel, dT_ptr, ldt, stream=0):
         check(lib().mpqr_get_panel_T(self._h, panel, dT_ptr, ldt, stream), "mpqr_get_panel_T")
 
+    KERNEL_CLASSES = ("panel", "gemm_tn", "gemm_nn", "cast")
+
+    def set_profiling(self, on):
+        check(lib().mpqr_set_profiling(self._h, int(on)), "mpqr_set_profiling")
+
+    def profile(self):
+        """{class: dict(ms, launches, flops, bytes)} accumulated since set_profiling(True)."""
+        out = {}
+        for c, name in enumerate(self.KERNEL_CLASSES):
+            ms, fl, by, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_long()
+            check(lib().mpqr_get_profile(self._h, c, ctypes.byref(ms), ctypes.byref(cnt), ctypes.byref(fl), ctypes.byref(by)))
+            out[name] = {"ms": ms.value, "launches": cnt.value, "flops": fl.value, "bytes": by.value}
+        return out
+
     @property
     def last_launches(self):
         return int(lib().mpqr_last_launch_count(self._h))
@@ -152,3 +173,61 @@ class BlockQR:
 
 def fill_uniform(dA_ptr, lda, n_total, row0, rows, col0, cols, seed, stream=0):
     check(lib().mpqr_fill_uniform_device(dA_ptr, lda, n_total, row0, rows, col0, cols, seed, stream), "mpqr_fill_uniform_device")
+
+
+def tsqr(dA_ptr, lda, m, n, dQ_ptr, ldq, dR_ptr, ldr, stream=0):
+    """Device TSQR (replaces python/ca_qr.py:25-43 ts_qr): R (n x n) and optionally thin Q (m x n)."""
+    check(lib().mpqr_tsqr_device(dA_ptr, lda, m, n, dQ_ptr, ldq, dR_ptr, ldr, stream), "mpqr_tsqr_device")
+
+
+# ------------------------------------------------------------------ multi-GPU (one process per GPU)
+def mg_layout_local_cols(n, nb, rank, nranks):
+    return lib().mpqr_mg_layout_local_cols(n, nb, rank, nranks)
+
+
+def mg_layout_global_cols(n, nb, rank, nranks):
+    """Global column index of every local column of `rank` (numpy int array) — pure host logic."""
+    nloc = mg_layout_local_cols(n, nb, rank, nranks)
+    return np.array([lib().mpqr_mg_layout_global_col(n, nb, rank, nranks, j) for j in range(nloc)], dtype=np.int64)
+
+
+def mg_unique_id():
+    buf = ctypes.create_string_buffer(NCCL_UID_BYTES)
+    check(lib().mpqr_mg_get_unique_id(buf), "mpqr_mg_get_unique_id")
+    return buf.raw
+
+
+class MultiGpuBlockQR:
+    """1-D column-block-cyclic plan (mpqr_mg_create / mpqr_mg_factor_device).  `uid` is the 128-byte
+    NCCL unique id produced by rank 0's mg_unique_id() and shared out of band."""
+
+    def __init__(self, m, n, r, nb, rank, nranks, uid, precision="fp16"):
+        flags = {"fp16": MPQR_FP16, "bf16": MPQR_BF16}[precision]
+        self._h = ctypes.c_void_p()
+        check(lib().mpqr_mg_create(ctypes.byref(self._h), m, n, r, nb, flags, rank, nranks, uid), "mpqr_mg_create")
+        self.m, self.n, self.rank, self.nranks = m, n, rank, nranks
+        self.r = lib().mpqr_effective_r(self._h)
+        self.nb = lib().mpqr_effective_nb(self._h)
+        self.local_cols = lib().mpqr_mg_local_cols(self._h)
+
+    def factor(self, dA_local_ptr, lda_local, stream=0):
+        check(lib().mpqr_mg_factor_device(self._h, dA_local_ptr, lda_local, stream), "mpqr_mg_factor_device")
+
+    set_profiling = BlockQR.set_profiling
+    profile = BlockQR.profile
+    KERNEL_CLASSES = BlockQR.KERNEL_CLASSES
+
+    @property
+    def last_launches(self):
+        return int(lib().mpqr_last_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().mpqr_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

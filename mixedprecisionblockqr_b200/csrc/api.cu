@@ -21,9 +21,7 @@
 #include <stdarg.h>
 #include <string.h>
 
-#include <vector>
-
-#include "common.cuh"
+#include "internal.h"
 
 namespace mpqr {
 
@@ -153,65 +151,9 @@ int fill_zero_16(void* dst, long ldd, long rows, long cols, cudaStream_t stream)
 
 using namespace mpqr;
 
-// ------------------------------------------------------------------------------ the handle
-struct mpqr_handle {
-    int m = 0, n = 0, r = 0, nb = 0, kmax = 0;
-    unsigned flags = 0;
-    int prec = 0;  // 0 fp32, 1 fp16, 2 bf16
-    bool keep_wy = false;
-    int npanels = 0;
-    bool factored = false;
-    long launches = 0;
-
-    // common
-    float* sync_ws = nullptr;
-    unsigned sync_ctr = 0;  // host mirror of the panel barrier counter
-    float* scratch = nullptr;
-    long scratch_rows = 0;
-    float* T = nullptr;    // npanels * r * r
-    float* S32 = nullptr;  // sk x lds32
-    long lds32 = 0;
-    int sk = 0;
-
-    // FP32 path: compact Y/W.  keep_wy: m x ld32 full arrays, else m x r panel buffers
-    float* Y32 = nullptr;
-    float* W32 = nullptr;
-    long ld32 = 0;
-
-    // 16-bit path
-    void* Ah = nullptr;  // m x ldh shadow of A (operands); factored columns hold Y
-    long ldh = 0;
-    void* W16 = nullptr;  // keep_wy: m x ldw16 (all blocks) else m x nb (current block)
-    long ldw16 = 0;
-    float* Wblk32 = nullptr;  // m x ldwb FP32 W of the current outer block
-    long ldwb = 0;
-    void* S16 = nullptr;      // sk x lds16
-    long lds16 = 0;
-    void* Qh = nullptr;  // m x ldqh shadow of Q (form_q)
-    long ldqh = 0;
-
-    // multi-GPU (mg.cu)
-    void* mg = nullptr;
-
-    std::vector<void*> allocs;
-};
+using namespace mpqr;
 
 namespace {
-
-int dev_alloc(mpqr_handle* h, void** p, size_t bytes) {
-    *p = nullptr;
-    if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMalloc(p, bytes);
-    if (e != cudaSuccess) {
-        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-        cudaGetLastError();
-        return MPQR_ENOMEM;
-    }
-    h->allocs.push_back(*p);
-    return MPQR_OK;
-}
-
-inline char* at16(void* base, long ld, long row, long col) { return (char*)base + ((size_t)row * ld + col) * 2; }
 
 int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     const int m = h->m, n = h->n, r = h->r;
@@ -230,89 +172,121 @@ int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
             ld = r;
         }
         PanelArgs a{};
-        a.A = A; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.pw = pw; a.blk_row0 = lam;
+        a.A = A; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.acol = lam; a.pw = pw; a.blk_row0 = lam;
         a.Y32 = Y; a.W32 = W; a.ld32 = ld;
         a.T = h->T + (size_t)p * r * r; a.ldt = r;
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
-        MPQR_TRY(launch_panel(a, st, &h->launches));
+        PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         if (nt > 0) {
             float* A22 = A + (size_t)lam * lda + tau;
-            MPQR_TRY(sgemm_tn(W, ld, A22, lda, h->S32, h->lds32, pw, nt, D, st, &h->launches));
-            MPQR_TRY(sgemm_nn_sub(Y, ld, h->S32, h->lds32, A22, lda, D, nt, pw, st, &h->launches));
+            PROF(1, 2.0 * pw * nt * D, 4.0 * D * (pw + nt), sgemm_tn(W, ld, A22, lda, h->S32, h->lds32, pw, nt, D, st, &h->launches));
+            PROF(2, 2.0 * D * nt * pw, 8.0 * D * nt, sgemm_nn_sub(Y, ld, h->S32, h->lds32, A22, lda, D, nt, pw, st, &h->launches));
         }
     }
     return MPQR_OK;
 }
 
 int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
-    const int m = h->m, n = h->n, r = h->r, nb = h->nb;
+    const int m = h->m, n = h->n, nb = h->nb;
     const int bf = h->prec == 2;
     if ((lda & 3) || ((uintptr_t)A & 15)) {
         set_error("factor: the tensor-core path needs lda %% 4 == 0 and a 16-byte aligned dA (lda=%ld)", lda);
         return MPQR_EINVAL;
     }
     // operand shadow of the whole matrix
-    MPQR_TRY(convert_f32_to_16(A, lda, h->Ah, h->ldh, m, n, bf, st));
+    PROF(3, 0, 6.0 * m * n, convert_f32_to_16(A, lda, h->Ah, h->ldh, m, n, bf, st));
     h->launches += 1;
     for (int c0 = 0; c0 < h->kmax; c0 += nb) {
         const int c1 = (c0 + nb < h->kmax) ? c0 + nb : h->kmax;
-        const int Dblk = m - c0;
-        // W of this block: FP32 master (Wblk32, Dblk x nb) + 16-bit operand copy
-        void* Wb16;
-        long ldw;
-        if (h->keep_wy) {
-            Wb16 = at16(h->W16, h->ldw16, c0, c0);
-            ldw = h->ldw16;
-        } else {
-            Wb16 = h->W16;
-            ldw = h->ldw16;
-        }
-        for (int lam = c0; lam < c1; lam += r) {
-            const int p = lam / r;
-            const int pw = (lam + r < c1) ? r : c1 - lam;
-            const int tau = lam + pw, D = m - lam, jc = lam - c0;
-            PanelArgs a{};
-            a.A = A; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.pw = pw; a.blk_row0 = c0;
-            a.W32 = h->Wblk32 + jc; a.ld32 = h->ldwb;  // Y32 not needed
-            a.Y16 = at16(h->Ah, h->ldh, c0, lam); a.ldy16 = h->ldh;
-            a.W16 = (char*)Wb16 + (size_t)jc * 2; a.ldw16 = ldw;
-            a.bf16 = bf;
-            a.T = h->T + (size_t)p * r * r; a.ldt = r;
-            a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
-            MPQR_TRY(launch_panel(a, st, &h->launches));
-            const int nin = c1 - tau;  // in-block trailing columns
-            if (nin > 0) {
-                // S = W_p^T A[lam:, tau:c1]   (operands: 16-bit W_p rows lam.., shadow of A)
-                const void* Wp = (char*)Wb16 + ((size_t)jc * ldw + jc) * 2;
-                MPQR_TRY(tc_gemm_tn(Wp, ldw, at16(h->Ah, h->ldh, lam, tau), h->ldh, h->S32, h->lds32, pw, nin, D, bf, 1, st, &h->launches));
-                MPQR_TRY(convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, pw, nin, bf, st));
-                h->launches += 1;
-                // A[lam:, tau:c1] -= Y_p S   (+ shadow)
-                MPQR_TRY(tc_gemm_nn(at16(h->Ah, h->ldh, lam, lam), h->ldh, h->S16, h->lds16, A + (size_t)lam * lda + tau, lda,
-                                    at16(h->Ah, h->ldh, lam, tau), h->ldh, D, nin, pw, bf, c1 == n, st, &h->launches));
-            }
-            if (jc > 0) {
-                // WY accumulation: X = Y_prev^T W_p ; W_p -= W_prev X   (rows c0..m)
-                const void* Wp = (char*)Wb16 + (size_t)jc * 2;
-                MPQR_TRY(tc_gemm_tn(at16(h->Ah, h->ldh, c0, c0), h->ldh, Wp, ldw, h->S32, h->lds32, jc, pw, Dblk, bf, 1, st, &h->launches));
-                MPQR_TRY(convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, jc, pw, bf, st));
-                h->launches += 1;
-                MPQR_TRY(tc_gemm_nn(Wb16, ldw, h->S16, h->lds16, h->Wblk32 + jc, h->ldwb, (void*)Wp, ldw, Dblk, pw, jc, bf, 1, st, &h->launches));
-            }
-        }
-        const int nfar = n - c1, kb = c1 - c0;
-        if (nfar > 0) {
-            MPQR_TRY(tc_gemm_tn(Wb16, ldw, at16(h->Ah, h->ldh, c0, c1), h->ldh, h->S32, h->lds32, kb, nfar, Dblk, bf, 1, st, &h->launches));
-            MPQR_TRY(convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, kb, nfar, bf, st));
-            h->launches += 1;
-            MPQR_TRY(tc_gemm_nn(at16(h->Ah, h->ldh, c0, c0), h->ldh, h->S16, h->lds16, A + (size_t)c0 * lda + c1, lda,
-                                at16(h->Ah, h->ldh, c0, c1), h->ldh, Dblk, nfar, kb, bf, 1, st, &h->launches));
-        }
+        BlockCtx c{};
+        c.A = A; c.lda = lda; c.acol0 = c0; c.Ah = h->Ah; c.ldh = h->ldh;
+        c.Y16 = at16(h->Ah, h->ldh, c0, c0); c.ldy = h->ldh;  // Y lives in the shadow's dead columns
+        c.W16 = h->keep_wy ? (void*)at16(h->W16, h->ldw16, c0, c0) : h->W16;
+        c.ldw = h->ldw16;
+        MPQR_TRY(block_phase(h, c, c0, c1, c1 == n, st));
+        MPQR_TRY(far_update(h, c, c0, c1, c1, n - c1, st));
     }
     return MPQR_OK;
 }
 
 }  // namespace
+
+namespace mpqr {
+
+int dev_alloc(mpqr_handle* h, void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return MPQR_ENOMEM;
+    }
+    h->allocs.push_back(*p);
+    return MPQR_OK;
+}
+
+int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_matrix_end, cudaStream_t st) {
+    const int m = h->m, n = h->n, r = h->r;
+    const int bf = h->prec == 2;
+    const int Dblk = m - c0;
+    for (int lam = c0; lam < c1; lam += r) {
+        const int p = lam / r;
+        const int pw = (lam + r < c1) ? r : c1 - lam;
+        const int tau = lam + pw, D = m - lam, jc = lam - c0;
+        PanelArgs a{};
+        a.A = c.A; a.lda = c.lda; a.m = m; a.n = n; a.lam = lam; a.acol = c.acol0 + jc; a.pw = pw; a.blk_row0 = c0;
+        a.W32 = h->Wblk32 + jc; a.ld32 = h->ldwb;  // FP32 master of W (Y32 not needed)
+        a.Y16 = (char*)c.Y16 + (size_t)jc * 2; a.ldy16 = c.ldy;
+        a.W16 = (char*)c.W16 + (size_t)jc * 2; a.ldw16 = c.ldw;
+        a.bf16 = bf;
+        a.T = h->T + (size_t)p * r * r; a.ldt = r;
+        a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
+        PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
+        const int nin = c1 - tau;  // in-block trailing columns
+        const int acol_tau = c.acol0 + jc + pw;
+        if (nin > 0) {
+            // S = W_p^T A[lam:, tau:c1]   (operands: 16-bit W_p rows lam.., shadow of A)
+            const void* Wp = (char*)c.W16 + ((size_t)jc * c.ldw + jc) * 2;
+            const void* Yp = (char*)c.Y16 + ((size_t)jc * c.ldy + jc) * 2;
+            PROF(1, 2.0 * pw * nin * D, tn_bytes(pw, nin, D),
+                 tc_gemm_tn(Wp, c.ldw, at16(c.Ah, c.ldh, lam, acol_tau), c.ldh, h->S32, h->lds32, pw, nin, D, bf, 1, st, &h->launches));
+            PROF(3, 0, 6.0 * pw * nin, convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, pw, nin, bf, st));
+            h->launches += 1;
+            // A[lam:, tau:c1] -= Y_p S   (+ shadow)
+            PROF(2, 2.0 * D * nin * pw, nn_bytes(D, nin, pw),
+                 tc_gemm_nn(Yp, c.ldy, h->S16, h->lds16, c.A + (size_t)lam * c.lda + acol_tau, c.lda,
+                            at16(c.Ah, c.ldh, lam, acol_tau), c.ldh, D, nin, pw, bf, end_is_matrix_end, st, &h->launches));
+        }
+        if (jc > 0) {
+            // WY accumulation: X = Y_prev^T W_p ; W_p -= W_prev X   (rows c0..m)
+            const void* Wp = (char*)c.W16 + (size_t)jc * 2;
+            PROF(1, 2.0 * jc * pw * Dblk, tn_bytes(jc, pw, Dblk),
+                 tc_gemm_tn(c.Y16, c.ldy, Wp, c.ldw, h->S32, h->lds32, jc, pw, Dblk, bf, 1, st, &h->launches));
+            PROF(3, 0, 6.0 * jc * pw, convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, jc, pw, bf, st));
+            h->launches += 1;
+            PROF(2, 2.0 * Dblk * pw * jc, nn_bytes(Dblk, pw, jc),
+                 tc_gemm_nn(c.W16, c.ldw, h->S16, h->lds16, h->Wblk32 + jc, h->ldwb, (void*)Wp, c.ldw, Dblk, pw, jc, bf, 1, st, &h->launches));
+        }
+    }
+    return MPQR_OK;
+}
+
+int far_update(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int afar, int nfar, cudaStream_t st) {
+    if (nfar <= 0) return MPQR_OK;
+    const int bf = h->prec == 2;
+    const int Dblk = h->m - c0, kb = c1 - c0;
+    PROF(1, 2.0 * kb * nfar * Dblk, tn_bytes(kb, nfar, Dblk),
+         tc_gemm_tn(c.W16, c.ldw, at16(c.Ah, c.ldh, c0, afar), c.ldh, h->S32, h->lds32, kb, nfar, Dblk, bf, 1, st, &h->launches));
+    PROF(3, 0, 6.0 * kb * nfar, convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, kb, nfar, bf, st));
+    h->launches += 1;
+    PROF(2, 2.0 * Dblk * nfar * kb, nn_bytes(Dblk, nfar, kb),
+         tc_gemm_nn(c.Y16, c.ldy, h->S16, h->lds16, c.A + (size_t)c0 * c.lda + afar, c.lda, at16(c.Ah, c.ldh, c0, afar), c.ldh,
+                    Dblk, nfar, kb, bf, 1, st, &h->launches));
+    return MPQR_OK;
+}
+
+}  // namespace mpqr
 
 extern "C" {
 
@@ -394,7 +368,10 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
 
 int mpqr_destroy(mpqr_handle* h) {
     if (!h) return MPQR_OK;
+    mg_destroy(h->mg);
     for (void* p : h->allocs) cudaFree(p);
+    for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto e : h->prof_pool) cudaEventDestroy(e);
     delete h;
     return MPQR_OK;
 }
@@ -486,6 +463,34 @@ int mpqr_effective_r(const mpqr_handle* h) { return h ? h->r : MPQR_EINVAL; }
 int mpqr_effective_nb(const mpqr_handle* h) { return h ? h->nb : MPQR_EINVAL; }
 long mpqr_last_launch_count(const mpqr_handle* h) { return h ? h->launches : MPQR_EINVAL; }
 
+int mpqr_set_profiling(mpqr_handle* h, int on) {
+    if (!h) return MPQR_EINVAL;
+    for (auto& r : h->prof_recs) { h->prof_pool.push_back(r.e0); h->prof_pool.push_back(r.e1); }
+    h->prof_recs.clear();
+    for (int c = 0; c < MPQR_NUM_KERNEL_CLASSES; ++c) h->prof_flops[c] = h->prof_bytes[c] = 0;
+    h->prof = on != 0;
+    return MPQR_OK;
+}
+
+int mpqr_get_profile(mpqr_handle* h, int cls, double* ms_total, long* launches, double* flops, double* bytes) {
+    if (!h || cls < 0 || cls >= MPQR_NUM_KERNEL_CLASSES) return MPQR_EINVAL;
+    double ms = 0;
+    long cnt = 0;
+    for (auto& r : h->prof_recs) {
+        if (r.cls != cls) continue;
+        MPQR_CUDA(cudaEventSynchronize(r.e1));
+        float t = 0;
+        MPQR_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms += t;
+        ++cnt;
+    }
+    if (ms_total) *ms_total = ms;
+    if (launches) *launches = cnt;
+    if (flops) *flops = h->prof_flops[cls];
+    if (bytes) *bytes = h->prof_bytes[cls];
+    return MPQR_OK;
+}
+
 int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned flags) {
     if (!A_packed || m < 1 || n < 1 || r < 1) {
         set_error("mpqr_block_qr_host: bad arguments m=%d n=%d r=%d", m, n, r);
@@ -538,7 +543,7 @@ int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
         }
     }
     PanelArgs a{};
-    a.A = dA; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.pw = pw; a.blk_row0 = lam;
+    a.A = dA; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.acol = lam; a.pw = pw; a.blk_row0 = lam;
     a.Y32 = dY; a.W32 = dW; a.ld32 = pw;
     if (dW && !dY) { set_error("mpqr_panel_factor_device: dW needs dY"); cudaFree(ws); cudaFree(scratch); return MPQR_EINVAL; }
     a.T = dT; a.ldt = pw;
@@ -570,7 +575,7 @@ int mpqr_debug_panel_probe(float* dA, long lda, int m, int n, int lam, int pw, i
     }
     unsigned host_ctr = 0;
     PanelArgs a{};
-    a.A = dA; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.pw = pw; a.blk_row0 = lam;
+    a.A = dA; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.acol = lam; a.pw = pw; a.blk_row0 = lam;
     a.Y32 = Y; a.W32 = W; a.ld32 = pw; a.T = T; a.ldt = pw;
     a.sync_ws = ws; a.host_ctr = &host_ctr; a.dbg = dDbg; a.rows_hint = rows_hint;
     int rc = launch_panel(a, (cudaStream_t)stream, nullptr);

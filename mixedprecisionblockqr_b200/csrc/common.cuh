@@ -53,7 +53,8 @@ struct PanelArgs {
     float* A;      // packed master, (m+1) x lda
     long lda;
     int m, n;
-    int lam;       // first column (== first row) of the panel
+    int lam;       // first ROW of the panel = global index of its first column
+    int acol;      // column of A holding the panel's first column (== lam on a single GPU)
     int pw;        // panel width (<= 128), lam + pw <= n
     int blk_row0;  // first row of the enclosing outer block (<= lam): Y/W outputs are zero-filled
                    // for rows [blk_row0, lam)

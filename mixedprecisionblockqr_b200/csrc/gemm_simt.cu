@@ -149,6 +149,16 @@ int sgemm_nn_sub(const float* X, long ldx, const float* S, long lds, float* C, l
     return MPQR_OK;
 }
 
+// C = X S (store), used by the TSQR thin-Q product
+int sgemm_nn_store(const float* X, long ldx, const float* S, long lds, float* C, long ldc, int M, int N, int K,
+                   cudaStream_t stream) {
+    if (M <= 0 || N <= 0) return MPQR_OK;
+    dim3 grid(ceil_div(N, BN), ceil_div(M, BM), 1);
+    sgemm_kernel<false, 0, float><<<grid, GT, 0, stream>>>(X, ldx, S, lds, C, ldc, nullptr, 0, M, N, K, K);
+    MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+
 // General-shape fallbacks of the tensor-core GEMMs (16-bit operands, FP32 accumulate on CUDA
 // cores): used only when a sub-block does not start on a 16-byte boundary, which TMA requires.
 int simt16_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long lds, int M, int N, int K,

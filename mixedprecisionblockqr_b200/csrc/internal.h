@@ -1,0 +1,118 @@
+// internal.h — handle layout and helpers shared by api.cu and mg.cu (not installed).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------ the handle
+struct mpqr_handle {
+    int m = 0, n = 0, r = 0, nb = 0, kmax = 0;
+    unsigned flags = 0;
+    int prec = 0;  // 0 fp32, 1 fp16, 2 bf16
+    bool keep_wy = false;
+    int npanels = 0;
+    bool factored = false;
+    long launches = 0;
+
+    // common
+    float* sync_ws = nullptr;
+    unsigned sync_ctr = 0;  // host mirror of the panel barrier counter
+    float* scratch = nullptr;
+    long scratch_rows = 0;
+    float* T = nullptr;    // npanels * r * r
+    float* S32 = nullptr;  // sk x lds32
+    long lds32 = 0;
+    int sk = 0;
+
+    // FP32 path: compact Y/W.  keep_wy: m x ld32 full arrays, else m x r panel buffers
+    float* Y32 = nullptr;
+    float* W32 = nullptr;
+    long ld32 = 0;
+
+    // 16-bit path
+    void* Ah = nullptr;  // m x ldh shadow of A (operands); factored columns hold Y
+    long ldh = 0;
+    void* W16 = nullptr;  // keep_wy: m x ldw16 (all blocks) else m x nb (current block)
+    long ldw16 = 0;
+    float* Wblk32 = nullptr;  // m x ldwb FP32 W of the current outer block
+    long ldwb = 0;
+    void* S16 = nullptr;      // sk x lds16
+    long lds16 = 0;
+    void* Qh = nullptr;  // m x ldqh shadow of Q (form_q)
+    long ldqh = 0;
+
+    // multi-GPU (mg.cu)
+    void* mg = nullptr;
+
+    // per-class event profiling
+    bool prof = false;
+    struct ProfRec { int cls; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_flops[MPQR_NUM_KERNEL_CLASSES] = {0, 0, 0, 0};
+    double prof_bytes[MPQR_NUM_KERNEL_CLASSES] = {0, 0, 0, 0};
+
+    std::vector<void*> allocs;
+};
+
+
+namespace mpqr {
+
+int dev_alloc(mpqr_handle* h, void** p, size_t bytes);
+void mg_destroy(void* state);
+
+// RAII event pair around one launch (only when profiling is on)
+struct ProfScope {
+    mpqr_handle* h;
+    cudaStream_t st;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(mpqr_handle* h_, int cls, cudaStream_t st_, double flops, double bytes) : h(h_), st(st_) {
+        if (!h->prof) return;
+        cudaEvent_t e0;
+        auto get = [&](cudaEvent_t* e) {
+            if (!h->prof_pool.empty()) { *e = h->prof_pool.back(); h->prof_pool.pop_back(); }
+            else cudaEventCreate(e);
+        };
+        get(&e0);
+        get(&e1);
+        cudaEventRecord(e0, st);
+        h->prof_recs.push_back({cls, e0, e1});
+        h->prof_flops[cls] += flops;
+        h->prof_bytes[cls] += bytes;
+    }
+    ~ProfScope() {
+        if (e1) cudaEventRecord(e1, st);
+    }
+};
+#define PROF(cls, flops, bytes, call)                         \
+    do {                                                      \
+        ProfScope ps__(h, cls, st, flops, bytes);             \
+        MPQR_TRY(call);                                       \
+    } while (0)
+
+inline double tn_bytes(double M, double N, double K) { return 2.0 * K * (M + N) + 4.0 * M * N; }
+inline double nn_bytes(double M, double N, double K) { return 10.0 * M * N + 2.0 * K * (M + N); }
+
+
+inline char* at16(void* base, long ld, long row, long col) { return (char*)base + ((size_t)row * ld + col) * 2; }
+
+// One outer block [c0, c1) of the two-level driver.  Row indices are global; column indices
+// refer to the arrays given here (single GPU: global columns; multi GPU: local columns).
+struct BlockCtx {
+    float* A;      // packed FP32 master
+    long lda;
+    int acol0;     // column of A (and of the shadow) holding global column c0
+    void* Ah;      // 16-bit shadow of A
+    long ldh;
+    void* Y16;     // Y of the block: element (row c0, block column 0)
+    long ldy;
+    void* W16;     // W of the block: element (row c0, block column 0)
+    long ldw;
+};
+// panels + in-block updates + WY accumulation of block [c0, c1); `ncols_in` = columns of A
+// (starting at acol0) that belong to the block's own panel region (= c1 - c0)
+int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int n_end_is_matrix_end, cudaStream_t st);
+// A[c0:, afar : afar+nfar) -= Y (W^T A[c0:, afar : afar+nfar))
+int far_update(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int afar, int nfar, cudaStream_t st);
+
+}  // namespace mpqr

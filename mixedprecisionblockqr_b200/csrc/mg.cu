@@ -1,0 +1,233 @@
+// mg.cu — multi-GPU driver: 1-D column-block-cyclic over the GPUs of one NVSwitch box, one
+// process per GPU (the reference is single-GPU, Cuda/qr.cu has no device selection).
+//
+//   * global outer block b (columns [b*nb, (b+1)*nb)) lives on rank b % P; every rank stores
+//     all m(+1) rows of its own blocks, concatenated in block order (row-major, lda_local);
+//   * block b is factored by its owner exactly like on one GPU (block_phase: panel kernel +
+//     in-block tcgen05 updates + WY accumulation), producing the block's Y and W as contiguous
+//     16-bit staging buffers;
+//   * owner broadcasts Y|W (2 * D * nb * 2 bytes) with ncclBroadcast over NVLink; every rank
+//     applies the far update to its own later columns (far_update: the same tcgen05 GEMM pair).
+//
+// NCCL is dlopen()ed so that libmpqr.so loads on machines without it (CPU symbol tests); the
+// communicator is owned by the handle.  The unique id is exchanged out of band (bench.py and
+// the tests use torch.distributed).
+#include <dlfcn.h>
+#include <string.h>
+
+#include "internal.h"
+
+using namespace mpqr;
+
+namespace {
+
+// minimal NCCL ABI (nccl.h 2.x): opaque comm, 128-byte unique id, result code 0 = success
+typedef struct ncclComm* ncclComm_t;
+struct NcclUid { char internal[MPQR_NCCL_UID_BYTES]; };
+typedef int (*fn_GetUniqueId)(NcclUid*);
+typedef int (*fn_CommInitRank)(ncclComm_t*, int, NcclUid, int);
+typedef int (*fn_CommDestroy)(ncclComm_t);
+typedef int (*fn_Broadcast)(const void*, void*, size_t, int /*dtype*/, int /*root*/, ncclComm_t, cudaStream_t);
+typedef const char* (*fn_GetErrorString)(int);
+constexpr int kNcclChar = 0;
+
+struct NcclApi {
+    void* lib = nullptr;
+    fn_GetUniqueId GetUniqueId = nullptr;
+    fn_CommInitRank CommInitRank = nullptr;
+    fn_CommDestroy CommDestroy = nullptr;
+    fn_Broadcast Broadcast = nullptr;
+    fn_GetErrorString GetErrorString = nullptr;
+};
+
+int load_nccl(NcclApi** out) {
+    static NcclApi api;
+    if (!api.lib) {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) {
+            set_error("cannot dlopen libnccl.so.2: %s", dlerror());
+            return MPQR_ENCCL;
+        }
+        api.GetUniqueId = (fn_GetUniqueId)dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (fn_CommInitRank)dlsym(api.lib, "ncclCommInitRank");
+        api.CommDestroy = (fn_CommDestroy)dlsym(api.lib, "ncclCommDestroy");
+        api.Broadcast = (fn_Broadcast)dlsym(api.lib, "ncclBroadcast");
+        api.GetErrorString = (fn_GetErrorString)dlsym(api.lib, "ncclGetErrorString");
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Broadcast) {
+            set_error("libnccl lacks a required symbol");
+            api.lib = nullptr;
+            return MPQR_ENCCL;
+        }
+    }
+    *out = &api;
+    return MPQR_OK;
+}
+
+struct MgState {
+    NcclApi* api = nullptr;
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    int nloc = 0;        // local columns
+    void* YW16 = nullptr;  // staging: Y block then W block, each m x ldw 16-bit
+    long ldw = 0;
+    void* Ah = nullptr;  // local shadow, m x ldh
+    long ldh = 0;
+};
+
+#define MPQR_NCCL(api, expr)                                                                     \
+    do {                                                                                         \
+        int r__ = (expr);                                                                        \
+        if (r__ != 0) {                                                                          \
+            set_error("NCCL error %d (%s) at %s:%d", r__,                                        \
+                      (api)->GetErrorString ? (api)->GetErrorString(r__) : "?", __FILE__, __LINE__); \
+            return MPQR_ENCCL;                                                                   \
+        }                                                                                        \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+// ---- pure host layout helpers (no CUDA needed; tests/test_mg_layout.py uses them on CPU)
+// number of columns of an n-column matrix owned by `rank` with block width nb
+int mpqr_mg_layout_local_cols(int n, int nb, int rank, int nranks) {
+    if (n < 0 || nb < 1 || nranks < 1 || rank < 0 || rank >= nranks) return MPQR_EINVAL;
+    int nblk = (n + nb - 1) / nb, cols = 0;
+    for (int b = rank; b < nblk; b += nranks) cols += (b * nb + nb <= n) ? nb : n - b * nb;
+    return cols;
+}
+// global column of local column j on `rank` (or -1)
+int mpqr_mg_layout_global_col(int n, int nb, int rank, int nranks, int local_col) {
+    if (nb < 1 || nranks < 1 || local_col < 0) return -1;
+    int lb = local_col / nb, off = local_col % nb;
+    int g = (lb * nranks + rank) * nb + off;
+    return g < n ? g : -1;
+}
+
+int mpqr_mg_get_unique_id(void* uid_out) {
+    NcclApi* api;
+    MPQR_TRY(load_nccl(&api));
+    NcclUid id;
+    MPQR_NCCL(api, api->GetUniqueId(&id));
+    memcpy(uid_out, &id, sizeof(id));
+    return MPQR_OK;
+}
+
+int mpqr_mg_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags, int rank, int nranks,
+                   const void* uid) {
+    if (!out || !uid || nranks < 1 || rank < 0 || rank >= nranks) {
+        set_error("mpqr_mg_create: bad arguments");
+        return MPQR_EINVAL;
+    }
+    if ((flags & MPQR_PRECISION_MASK) == 0) flags |= MPQR_FP16;  // the multi-GPU path is tensor-core only
+    if (flags & MPQR_KEEP_WY) {
+        set_error("mpqr_mg_create: MPQR_KEEP_WY / explicit Q is not available on the multi-GPU path yet");
+        return MPQR_EINVAL;
+    }
+    mpqr_handle* h = nullptr;
+    // The base handle provides T, sync workspace, S32/S16, Wblk32; its own shadow/W16 buffers are
+    // sized for the full matrix, so create it for a 1-column-block-wide dummy and add ours below.
+    int nb_eff = nb > 0 ? nb : 1024;
+    MPQR_TRY(mpqr_create(&h, m, n, r, nb_eff, flags));
+    MgState* g = new MgState();
+    h->mg = g;
+    g->rank = rank;
+    g->nranks = nranks;
+    g->nloc = mpqr_mg_layout_local_cols(n, h->nb, rank, nranks);
+    int rc = MPQR_OK;
+    do {
+        if ((rc = load_nccl(&g->api))) break;
+        NcclUid id;
+        memcpy(&id, uid, sizeof(id));
+        int nr = g->api->CommInitRank(&g->comm, nranks, id, rank);
+        if (nr != 0) {
+            set_error("ncclCommInitRank failed: %d", nr);
+            rc = MPQR_ENCCL;
+            break;
+        }
+        g->ldw = round_up(h->nb, 8);
+        if ((rc = dev_alloc(h, &g->YW16, (size_t)2 * m * g->ldw * 2))) break;
+        g->ldh = round_up(g->nloc > 0 ? g->nloc : 8, 8);
+        if ((rc = dev_alloc(h, &g->Ah, (size_t)m * g->ldh * 2))) break;
+    } while (0);
+    if (rc != MPQR_OK) {
+        mpqr_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return MPQR_OK;
+}
+
+int mpqr_mg_local_cols(const mpqr_handle* h) {
+    if (!h || !h->mg) return MPQR_EINVAL;
+    return ((MgState*)h->mg)->nloc;
+}
+
+int mpqr_mg_global_col(const mpqr_handle* h, int local_col) {
+    if (!h || !h->mg) return MPQR_EINVAL;
+    MgState* g = (MgState*)h->mg;
+    return mpqr_mg_layout_global_col(h->n, h->nb, g->rank, g->nranks, local_col);
+}
+
+int mpqr_mg_factor_device(mpqr_handle* h, float* dA, long lda, void* stream) {
+    if (!h || !h->mg || !dA) {
+        set_error("mpqr_mg_factor_device: bad arguments");
+        return MPQR_EINVAL;
+    }
+    MgState* g = (MgState*)h->mg;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m = h->m, n = h->n, nb = h->nb, P = g->nranks;
+    const int bf = h->prec == 2;
+    if (lda < g->nloc || (lda & 3) || ((uintptr_t)dA & 15)) {
+        set_error("mpqr_mg_factor_device: needs lda_local >= local cols, lda %% 4 == 0, 16-byte aligned dA");
+        return MPQR_EINVAL;
+    }
+    h->launches = 0;
+    if (g->nloc > 0) {
+        PROF(3, 0, 6.0 * m * g->nloc, convert_f32_to_16(dA, lda, g->Ah, g->ldh, m, g->nloc, bf, st));
+        h->launches += 1;
+    }
+    void* Y16 = g->YW16;
+    void* W16 = (char*)g->YW16 + (size_t)m * g->ldw * 2;
+    for (int c0 = 0, b = 0; c0 < h->kmax; c0 += nb, ++b) {
+        const int c1 = (c0 + nb < h->kmax) ? c0 + nb : h->kmax;
+        const int owner = b % P, Dblk = m - c0;
+        BlockCtx c{};
+        c.A = dA; c.lda = lda; c.Ah = g->Ah; c.ldh = g->ldh;
+        c.Y16 = Y16; c.ldy = g->ldw; c.W16 = W16; c.ldw = g->ldw;
+        if (owner == g->rank) {
+            c.acol0 = (b / P) * nb;
+            // the block's own trailing columns end where the next local block (a later global block)
+            // begins, so a spill past the last in-block column would hit live data unless it is the
+            // physical end of the local matrix
+            const int end_ok = (c.acol0 + (c1 - c0) == g->nloc);
+            MPQR_TRY(block_phase(h, c, c0, c1, end_ok, st));
+        }
+        // Y and W of block b to everyone (rows c0..m of each staging half are contiguous)
+        const size_t bytes = (size_t)Dblk * g->ldw * 2;
+        MPQR_NCCL(g->api, g->api->Broadcast(Y16, Y16, bytes, kNcclChar, owner, g->comm, st));
+        MPQR_NCCL(g->api, g->api->Broadcast(W16, W16, bytes, kNcclChar, owner, g->comm, st));
+        // local columns that belong to global blocks > b
+        const int li0 = (b >= g->rank) ? (b - g->rank) / P + 1 : 0;
+        const int afar = li0 * nb;
+        if (afar < g->nloc) MPQR_TRY(far_update(h, c, c0, c1, afar, g->nloc - afar, st));
+    }
+    h->factored = true;
+    (void)n;
+    return MPQR_OK;
+}
+
+}  // extern "C"
+
+namespace mpqr {
+void mg_destroy(void* state) {
+    MgState* g = (MgState*)state;
+    if (!g) return;
+    if (g->comm && g->api) g->api->CommDestroy(g->comm);
+    delete g;
+}
+}  // namespace mpqr

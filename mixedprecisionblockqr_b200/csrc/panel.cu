@@ -140,7 +140,7 @@ panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int G) {
     unsigned* ctr = reinterpret_cast<unsigned*>(gram_g + WS_ARRAY);
     constexpr int NG = NT / PWP;  // gather groups
     const long lda = a.lda;
-    float* Ablk = a.A + (size_t)lam * lda + lam;  // element (lam, lam)
+    float* Ablk = a.A + (size_t)lam * lda + a.acol;  // element (row lam, panel column 0)
 
     const bool prof = (a.dbg != nullptr) && blockIdx.x == 0 && tid == 0;
     long long tprev = prof ? clock64() : 0;
@@ -509,7 +509,7 @@ size_t panel_sync_ws_bytes() { return (WS_SLOTS + WS_ARRAY) * sizeof(float) + 25
 size_t panel_scratch_bytes(int max_rows) { return (size_t)max_rows * kPanelMaxWidth * sizeof(float); }
 
 int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
-    if (a.pw < 1 || a.pw > kPanelMaxWidth || a.lam < 0 || a.lam + a.pw > a.n || a.lam >= a.m ||
+    if (a.pw < 1 || a.pw > kPanelMaxWidth || a.lam < 0 || a.acol < 0 || a.lam >= a.m ||
         a.blk_row0 > a.lam) {
         set_error("panel: bad arguments lam=%d pw=%d m=%d n=%d", a.lam, a.pw, a.m, a.n);
         return MPQR_EINVAL;

@@ -1,0 +1,54 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/mpqr.h declares, and
+fails loudly (no CPU fallback) when asked to compute without a device."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mixedprecisionblockqr_b200 as pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_all_exported():
+    hdr = open(os.path.join(ROOT, "include", "mpqr.h")).read()
+    declared = set(re.findall(r"\b(mpqr_[A-Za-z0-9_]+)\s*\(", hdr)) - {"mpqr_handle"}
+    assert declared == set(pkg.ABI_SYMBOLS), declared ^ set(pkg.ABI_SYMBOLS)
+    L = pkg.lib()
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert b"sm_100a" in L.mpqr_version()
+
+
+def test_no_cpu_fallback():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    A = np.zeros((5, 4), np.float32)
+    with pytest.raises(pkg.MpqrError):
+        pkg.dev_mixed_precision_block_qr(A, None, 4, 4, 2)
+    with pytest.raises(pkg.MpqrError):
+        pkg.BlockQR(64, 64, 16)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mixedprecisionblockqr_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "oracle/" not in src.replace("oracle/mpqr_oracle.c:orc_uniform01", ""), f
+
+
+def test_argument_validation_messages():
+    L = pkg.lib()
+    assert L.mpqr_block_qr_host(None, None, 4, 4, 2, 0) == -1
+    assert b"bad arguments" in L.mpqr_last_error()
+
+
+def test_flop_formula():
+    assert pkg.householder_flops(32768, 32768) == pytest.approx(4.691e13, rel=1e-3)
+    assert pkg.householder_flops(4096, 16384) > 0

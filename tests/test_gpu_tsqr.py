@@ -1,0 +1,55 @@
+"""Device TSQR vs the oracle restatement of ts_qr (python/ca_qr.py:25-43) and LAPACK."""
+import numpy as np
+import pytest
+import torch
+
+import mixedprecisionblockqr_b200 as pkg
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _tsqr(A, want_q=True):
+    m, n = A.shape
+    dA = torch.from_numpy(A).cuda()
+    dQ = torch.zeros(m, n, device="cuda") if want_q else None
+    dR = torch.zeros(n, n, device="cuda")
+    pkg.tsqr(dA.data_ptr(), n, m, n, dQ.data_ptr() if want_q else None, n, dR.data_ptr(), n,
+             torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return (dQ.cpu().numpy() if want_q else None), dR.cpu().numpy()
+
+
+def test_tsqr_reference_case():
+    # python/ca_qr.py:86-92: seed 0, 24 x 3, compared with np.linalg.qr
+    np.random.seed(0)
+    A = np.random.random((4 * 6, 3)).astype(np.float32)
+    Q, R = _tsqr(A)
+    Qo, Ro = oracle.tsqr(A, 4)
+    _, Rl = np.linalg.qr(A.astype(np.float64))
+    assert np.allclose(np.abs(R), np.abs(Rl), atol=2e-6)
+    assert np.allclose(np.abs(R), np.abs(Ro), atol=2e-6)
+    assert np.allclose(Q @ R, A, atol=2e-6)
+    assert np.allclose(Q.T @ Q, np.eye(3), atol=2e-6)
+
+
+@pytest.mark.parametrize("m,n", [(4096, 64), (70000, 32), (100000, 256), (65536 + 300, 128)])
+def test_tsqr_shapes(m, n):
+    A = oracle.uniform_matrix(m, n, m + n)
+    Q, R = _tsqr(A)
+    _, Rl = np.linalg.qr(A.astype(np.float64))
+    assert np.allclose(np.triu(R), R)
+    assert np.abs(np.abs(R) - np.abs(Rl)).max() <= 2e-5 * np.abs(Rl).max()
+    Ad = A.astype(np.float64)
+    assert np.linalg.norm(Ad - Q.astype(np.float64) @ R) / np.linalg.norm(Ad) <= 5e-6
+    assert np.linalg.norm(Q.astype(np.float64).T @ Q - np.eye(n)) <= 5e-5
+    if m // 4 >= n:
+        _, Ro = oracle.tsqr(A, 4)
+        assert np.abs(np.abs(R) - np.abs(Ro)).max() <= 2e-5 * np.abs(Ro).max()
+
+
+def test_tsqr_r_only():
+    A = oracle.uniform_matrix(50000, 48, 5)
+    _, R = _tsqr(A, want_q=False)
+    _, Rl = np.linalg.qr(A.astype(np.float64))
+    assert np.abs(np.abs(R) - np.abs(Rl)).max() <= 2e-5 * np.abs(Rl).max()
