@@ -561,7 +561,7 @@ int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
 
 // Tuning/profiling hook (tools/panel_probe.py; not part of the public header): runs the panel
 // kernel `reps` times on copies of the same panel with phase profiling enabled.
-int mpqr_debug_panel_probe(float* dA, long lda, int m, int n, int lam, int pw, int rows_hint, int want_wy,
+int mpqr_debug_panel_probe(float* dA, long lda, int m, int n, int lam, int pw, int rows_hint, int force_cs, int want_wy,
                            long long* dDbg, void* stream) {
     DeviceInfo di;
     MPQR_TRY(get_device_info(&di));
@@ -574,14 +574,23 @@ int mpqr_debug_panel_probe(float* dA, long lda, int m, int n, int lam, int pw, i
         MPQR_CUDA(cudaMalloc(&T, (size_t)pw * pw * 4));
     }
     unsigned host_ctr = 0;
+    float* scratch = nullptr;
+    cudaMalloc(&scratch, panel_scratch_bytes(m));
     PanelArgs a{};
+    a.scratch = scratch; a.scratch_rows = m;
     a.A = dA; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.acol = lam; a.pw = pw; a.blk_row0 = lam;
     a.Y32 = Y; a.W32 = W; a.ld32 = pw; a.T = T; a.ldt = pw;
-    a.sync_ws = ws; a.host_ctr = &host_ctr; a.dbg = dDbg; a.rows_hint = rows_hint;
+    a.sync_ws = ws; a.host_ctr = &host_ctr; a.dbg = dDbg; a.rows_hint = rows_hint; a.force_cs = force_cs;
+    int caps[3] = {0, 0, 0};
+    a.dbg_caps = caps;
     int rc = launch_panel(a, (cudaStream_t)stream, nullptr);
     cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
-    cudaFree(ws); cudaFree(Y); cudaFree(W); cudaFree(T);
+    cudaFree(ws); cudaFree(Y); cudaFree(W); cudaFree(T); cudaFree(scratch);
     if (rc == MPQR_OK && e != cudaSuccess) { set_error("panel probe failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; }
+    if (rc == MPQR_OK && dDbg) {
+        long long c[3] = {caps[0], caps[1], caps[2]};
+        cudaMemcpy(dDbg + 13, c, sizeof(c), cudaMemcpyHostToDevice);
+    }
     return rc;
 }
 

@@ -76,6 +76,8 @@ struct PanelArgs {
     long scratch_rows;  // capacity of scratch in rows
     long long* dbg;     // optional device buffer (16 x int64) for phase profiling, else null
     int rows_hint;      // > 0: override the rows-per-CTA heuristic (tuning)
+    int force_cs;       // > 0: cap the cluster size (tuning / tests)
+    int* dbg_caps;      // optional HOST array[3]: max cluster size, co-resident clusters of 16 / 8
 };
 int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches);
 

@@ -5,12 +5,17 @@
 // the 3r+2 launches of dev_wy_transform (Cuda/qr.cu:535-600, K1-K4 of SURVEY 2.4) by ONE
 // persistent kernel per panel:
 //
-//   * the D x pw panel is distributed by rows over G CTAs and stays resident in shared
-//     memory (<= ~150 KB/CTA) for all pw reflector steps: HBM sees one coalesced read and
-//     one coalesced write of the panel (algorithmic bytes 8*D*pw);
-//   * per column ONE grid-wide reduction: the dots g_j = u^T a_j (j >= k) give both the
-//     column norm (g_k) and v^T a_j = g_j + s*mu*a_kj, so the rank-1 update of step k and
-//     the dots of step k+1 are fused into a single pass over the slice;
+//   * the D x pw panel is distributed by rows over NC clusters x CS CTAs and stays resident in
+//     shared memory for all pw reflector steps: HBM sees one coalesced read and one coalesced
+//     write of the panel (algorithmic bytes 8*D*pw);
+//   * per column ONE reduction: the dots g_j = u^T a_j (j >= k) give both the column norm (g_k)
+//     and v^T a_j = g_j + s*mu*a_kj, so the rank-1 update of step k and the dots of step k+1
+//     are fused into a single pass over the slice (4 rows in flight per warp for ILP);
+//   * the reduction is hierarchical: inside a thread-block cluster the partial vectors are
+//     all-gathered through distributed shared memory and one hardware cluster barrier; only
+//     the cluster leaders exchange through L2 (per-leader slots + monotonic counter) and
+//     broadcast the result back through DSMEM.  Panels that fit one cluster (all of C2/C3)
+//     never touch L2 inside the column loop;
 //   * tail (still in shared memory): Gram matrix Y^T Y -> T by the larft recurrence
 //     (T[0:c,c] = -2 T[0:c,0:c] G[0:c,c], T[c,c] = 2) -> W = Y T, emitted as FP32 and as
 //     the FP16/BF16 operands of the tensor-core trailing update.
@@ -25,41 +30,46 @@ namespace {
 
 constexpr int NT = 512;
 constexpr int NW = NT / 32;
-constexpr int WS_LD = kPanelMaxWidth;                       // row stride of the global sync arrays
+constexpr int RI = 4;                                       // rows in flight per warp
+constexpr int CSMAX = 16;                                   // max cluster size
+constexpr int WS_LD = kPanelMaxWidth;
 constexpr int WS_ARRAY = kPanelMaxWidth * kPanelMaxWidth;   // floats of the Gram accumulator
-constexpr int MAXG = 160;                                   // max CTAs of one panel launch (>= #SMs)
-constexpr int SLOT_FLOATS = 2 * WS_LD;                      // per-CTA slot: partial dots | pivot row
-// sync workspace (floats): slots[2][MAXG][SLOT_FLOATS] | gram[WS_ARRAY] | counter
-constexpr size_t WS_SLOTS = (size_t)2 * MAXG * SLOT_FLOATS;
+constexpr int MAXNC = 160;                                  // max clusters of one launch (CS = 1: every CTA)
+constexpr int SLOT_FLOATS = 2 * WS_LD;                      // per-cluster slot: partial dots | pivot row
+// sync workspace (floats): slots[2][MAXNC][SLOT_FLOATS] | gram[WS_ARRAY] | counter
+constexpr size_t WS_SLOTS = (size_t)2 * MAXNC * SLOT_FLOATS;
 
+// ------------------------------------------------------------------ cluster / DSMEM PTX
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, unsigned rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster(uint32_t remote_addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote_addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
-// All CTAs of the (cooperatively launched, co-resident) grid arrive.  The counter only ever
-// increases (across barriers AND across launches: the host passes the base), so it is never
-// reset; comparisons are wrap-safe.  Release: bar.sync orders the CTA's slot stores before
-// thread 0's fence + red; acquire: ld.acquire by thread 0, then bar.sync, then .cg loads.
-__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-        while ((int)(ld_acquire_gpu(ctr) - target) < 0) {
-        }
-    }
-    __syncthreads();
-}
-
 // Optional phase profiling (PanelArgs.dbg != null): CTA 0 / thread 0 accumulates clock64 deltas.
-// dbg[0]=pass dbg[1]=local reduce+publish dbg[2]=grid barrier dbg[3]=gather dbg[4]=scalars
-// dbg[5]=load dbg[6]=store+tail dbg[7]=steps dbg[8]=G dbg[9]=rows_per_cta
+// dbg[0]=pass dbg[1]=local reduce+publish dbg[2]=cluster barrier(s)+leader exchange dbg[3]=gather
+// dbg[4]=scalars dbg[5]=load dbg[6]=store dbg[7]=steps dbg[8]=G dbg[9]=rows_per_cta dbg[10]=gram+T
+// dbg[11]=CS dbg[12]=NC
 #define PROF_MARK(slot)                                               \
     if (prof) {                                                       \
         long long t__ = clock64();                                    \
-        a.dbg[slot] += t__ - tprev;                                   \
+        pacc[slot] += t__ - tprev;                                    \
         tprev = t__;                                                  \
     }
 
@@ -104,30 +114,39 @@ __device__ __forceinline__ void store16(void* base, long idx, float v, int bf16)
     else reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
 }
 
-// Shared-memory layout (floats): red[NW*PWP] | gsum[PWP] | prow[PWP] | diag[PWP] | gcol[2*PWP]
-//                                | gt[PWP*(PWP+1)] | pad to 4 | slice[rows*PWP]
+// Shared-memory layout (floats):
+//   red[NW*PWP] | psum[PWP] | gsum[PWP] | prow[PWP] | diag[PWP] | gcol[2*PWP] | gt[PWP*(PWP+1)]
+//   | xslot[2][CSMAX][PWP] | xprow[2][PWP] | fin[2][2*PWP] | pad to 4 | slice[rows*PWP]
 template <int CPL>
 __host__ __device__ constexpr int fixed_floats() {
     constexpr int PWP = 32 * CPL;
-    int f = NW * PWP + 5 * PWP + PWP * (PWP + 1);
+    int f = NW * PWP + 6 * PWP + PWP * (PWP + 1) + 2 * CSMAX * PWP + 2 * PWP + 4 * PWP;
     return (f + 3) & ~3;
 }
 
 template <int CPL>
 __global__ void __launch_bounds__(NT, 1)
-panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int G) {
+panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int CS, int NC) {
     constexpr int PWP = 32 * CPL;
     constexpr int GLD = PWP + 1;
+    constexpr int NG = NT / PWP;                       // gather groups
     extern __shared__ __align__(16) float smem[];
     float* red = smem;
-    float* gsum = red + NW * PWP;
+    float* psum = red + NW * PWP;
+    float* gsum = psum + PWP;
     float* prow = gsum + PWP;
     float* diag = prow + PWP;
-    float* gcol = diag + PWP;  // 2 * PWP (double buffered)
+    float* gcol = diag + PWP;                // 2 * PWP (double buffered)
     float* gt = gcol + 2 * PWP;
+    float* xslot = gt + PWP * GLD;           // [2][CSMAX][PWP]  written by cluster peers
+    float* xprow = xslot + 2 * CSMAX * PWP;  // [2][PWP]         pivot row, written by its owner
+    float* fin = xprow + 2 * PWP;            // [2][2*PWP]       final dots | pivot row from the leader
     float* slice_sm = smem + fixed_floats<CPL>();
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = CS * NC;
+    const unsigned crank = (CS > 1) ? cluster_ctarank() : 0u;
+    const int cid = blockIdx.x / CS;  // cluster index
     const int lam = a.lam, pw = a.pw;
     const int D = a.m - lam;
     const int kr = pw < D ? pw : D;  // reflectors in this panel
@@ -138,24 +157,30 @@ panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int G) {
     float* slots = a.sync_ws;
     float* gram_g = slots + WS_SLOTS;
     unsigned* ctr = reinterpret_cast<unsigned*>(gram_g + WS_ARRAY);
-    constexpr int NG = NT / PWP;  // gather groups
     const long lda = a.lda;
     float* Ablk = a.A + (size_t)lam * lda + a.acol;  // element (row lam, panel column 0)
+    unsigned bar_id = 0;
 
     const bool prof = (a.dbg != nullptr) && blockIdx.x == 0 && tid == 0;
+    long long pacc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // registers: no memory traffic while timing
     long long tprev = prof ? clock64() : 0;
     // ---- load the slice (coalesced along the panel row), zero-pad columns >= pw
     for (int idx = tid; idx < nrows * PWP; idx += NT) {
         int li = idx / PWP, c = idx - li * PWP;
         slice[idx] = (c < pw) ? Ablk[(size_t)(r0 + li) * lda + c] : 0.f;
     }
-    // the Gram accumulator is used (atomically) only after >= 1 grid barrier: zero it here
+    // the Gram accumulator is used (atomically) only after >= 1 grid-wide sync: zero it here
     if (G > 1)
         for (int idx = blockIdx.x * NT + tid; idx < WS_ARRAY; idx += G * NT) gram_g[idx] = 0.f;
-    __syncthreads();
+    // peers must not write into our xslot before we are running: cluster-wide start barrier
+    if (CS > 1) {
+        cluster_arrive();
+        cluster_wait();
+    } else {
+        __syncthreads();
+    }
     PROF_MARK(5);
 
-    unsigned bar_id = 0;
     float tau[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) tau[q] = 0.f;
@@ -167,35 +192,61 @@ panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int G) {
         const bool do_upd = step > 0, do_dot = step < kr;
         const int lk = do_upd ? kprev / CPL : 0, ck = do_upd ? kprev % CPL : 0;
         const int ln = step / CPL, cn = step % CPL;
+        const int par = step & 1;
         float acc[CPL];
 #pragma unroll
         for (int q = 0; q < CPL; ++q) acc[q] = 0.f;
 
         int li0 = kprev - r0;  // first slice row touched by this step
         if (li0 < 0) li0 = 0;
-        // keep the warp <-> row mapping fixed: start at the first row >= li0 owned by this warp
-        int first = li0 + ((warp - li0) % NW + NW) % NW;
-        for (int li = first; li < nrows; li += NW) {
-            const int i = r0 + li;
-            float x[CPL];
-            float* p = slice + (size_t)li * PWP + lane * CPL;
-            RowVec<CPL>::load(p, x);
-            if (do_upd) {
-                float xk = __shfl_sync(0xffffffffu, pick<CPL>(x, ck), lk);
-                float vi = (i == kprev) ? xk + smu : xk;
+        // fixed warp <-> row mapping (row li belongs to warp li % NW); RI rows in flight
+        const int first = li0 + ((warp - li0) & (NW - 1));
+        // columns < kprev (< step when there is no update) are final: their lanes stay out of
+        // shared memory, which is the bandwidth that bounds this loop
+        const bool lane_on = (lane * CPL + CPL - 1) >= (do_upd ? kprev : step);
+        for (int lb = first; lb < nrows; lb += NW * RI) {
+            float x[RI][CPL];
+            bool ok[RI];
 #pragma unroll
-                for (int q = 0; q < CPL; ++q) x[q] = fmaf(-vi, tau[q], x[q]);
-                if (lane == lk) {
-                    float wv = vi * vinv;
+            for (int u = 0; u < RI; ++u) {
+                const int li = lb + u * NW;
+                ok[u] = li < nrows;
+                if (ok[u] && lane_on) {
+                    RowVec<CPL>::load(slice + (size_t)li * PWP + lane * CPL, x[u]);
+                } else {
 #pragma unroll
-                    for (int q = 0; q < CPL; ++q) x[q] = (q == ck) ? wv : x[q];
+                    for (int q = 0; q < CPL; ++q) x[u][q] = 0.f;
                 }
-                RowVec<CPL>::store(p, x);
             }
-            if (do_dot && i >= step) {
-                float xn = __shfl_sync(0xffffffffu, pick<CPL>(x, cn), ln);
+            if (do_upd) {
+                float xk[RI];
 #pragma unroll
-                for (int q = 0; q < CPL; ++q) acc[q] = fmaf(xn, x[q], acc[q]);
+                for (int u = 0; u < RI; ++u) xk[u] = __shfl_sync(0xffffffffu, pick<CPL>(x[u], ck), lk);
+#pragma unroll
+                for (int u = 0; u < RI; ++u) {
+                    const int i = r0 + lb + u * NW;
+                    const float vi = (i == kprev) ? xk[u] + smu : xk[u];
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) x[u][q] = fmaf(-vi, tau[q], x[u][q]);
+                    if (lane == lk) {
+                        const float wv = vi * vinv;
+#pragma unroll
+                        for (int q = 0; q < CPL; ++q) x[u][q] = (q == ck) ? wv : x[u][q];
+                    }
+                    if (ok[u] && lane_on) RowVec<CPL>::store(slice + (size_t)(lb + u * NW) * PWP + lane * CPL, x[u]);
+                }
+            }
+            if (do_dot) {
+                float xn[RI];
+#pragma unroll
+                for (int u = 0; u < RI; ++u) xn[u] = __shfl_sync(0xffffffffu, pick<CPL>(x[u], cn), ln);
+#pragma unroll
+                for (int u = 0; u < RI; ++u) {
+                    const int i = r0 + lb + u * NW;
+                    const float xv = (ok[u] && i >= step) ? xn[u] : 0.f;
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) acc[q] = fmaf(xv, x[u][q], acc[q]);
+                }
             }
         }
         if (!do_dot) break;
@@ -209,58 +260,138 @@ panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int G) {
 #pragma unroll
             for (int w = 0; w < NW; ++w) s += red[w * PWP + tid];
             if (G > 1) {
-                // publish this CTA's partial dots (and the pivot row if it owns it) in its slot;
-                // slots are double-buffered by step parity and fully rewritten, never reset
-                float* myslot = slots + ((size_t)(step & 1) * MAXG + blockIdx.x) * SLOT_FLOATS;
-                __stcg(&myslot[tid], s);
-                if (step >= r0 && step < r1) __stcg(&myslot[WS_LD + tid], slice[(size_t)(step - r0) * PWP + tid]);
+                psum[tid] = s;
             } else {
                 gsum[tid] = s;
                 prow[tid] = slice[(size_t)step * PWP + tid];
             }
         }
-        PROF_MARK(1);
         if (G > 1) {
-            grid_barrier(ctr, a.ctr_base + (unsigned)G * (++bar_id));
-            PROF_MARK(2);
-            // deterministic gather: group grp sums CTAs grp, grp+NG, ... for column j.
-            // Loads are issued in batches of 8 before the first use (each is an L2 round trip).
-            const int j = tid % PWP, grp = tid / PWP;
-            const float* sl = slots + (size_t)(step & 1) * MAXG * SLOT_FLOATS;
-            float s = 0.f;
-            if (j >= step) {
-                for (int c0 = grp; c0 < G; c0 += NG * 8) {
-                    float v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        int c = c0 + u * NG;
-                        v[u] = (c < G) ? __ldcg(&sl[(size_t)c * SLOT_FLOATS + j]) : 0.f;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) s += v[u];
-                }
-            }
-            red[grp * PWP + j] = s;
-            if (tid < PWP) prow[tid] = __ldcg(&sl[(size_t)(step / rows_per_cta) * SLOT_FLOATS + WS_LD + tid]);
             __syncthreads();
-            if (tid < PWP) {
-                float t = 0.f;
-#pragma unroll
-                for (int gq = 0; gq < NG; ++gq) t += red[gq * PWP + tid];
-                gsum[tid] = t;
+            // ---- level 1: all-gather the partial vectors inside the cluster through DSMEM
+            if (CS > 1) {
+                for (int idx = tid; idx < CS * PWP; idx += NT) {
+                    const int peer = idx / PWP, j = idx - peer * PWP;
+                    if (j >= step)
+                        st_cluster(map_to_cta(smem_addr(&xslot[(par * CSMAX + (int)crank) * PWP + j]), (unsigned)peer), psum[j]);
+                }
+                if (step >= r0 && step < r1) {  // this CTA owns the pivot row
+                    for (int idx = tid; idx < CS * PWP; idx += NT) {
+                        const int peer = idx / PWP, j = idx - peer * PWP;
+                        st_cluster(map_to_cta(smem_addr(&xprow[par * PWP + j]), (unsigned)peer),
+                                   slice[(size_t)(step - r0) * PWP + j]);
+                    }
+                }
+                PROF_MARK(1);
+                cluster_arrive();
+                cluster_wait();
+                if (tid < PWP) {
+                    float t = 0.f;
+                    if (tid >= step)
+                        for (int c = 0; c < CS; ++c) t += xslot[(par * CSMAX + c) * PWP + tid];
+                    psum[tid] = t;  // cluster sum (identical in every CTA of the cluster)
+                }
+                __syncthreads();
+            } else {
+                PROF_MARK(1);
             }
+            if (NC == 1) {
+                if (tid < PWP) {
+                    gsum[tid] = psum[tid];
+                    prow[tid] = xprow[par * PWP + tid];
+                }
+                PROF_MARK(2);
+            } else {
+                // ---- level 2: cluster leaders exchange through L2, then broadcast through DSMEM
+                const int oc = (step / rows_per_cta) / CS;  // cluster that owns the pivot row
+                ++bar_id;
+                if (crank == 0) {
+                    float* myslot = slots + ((size_t)par * MAXNC + cid) * SLOT_FLOATS;
+                    if (tid < PWP) {
+                        __stcg(&myslot[tid], psum[tid]);
+                        if (cid == oc) {
+                            const float pv = (CS > 1) ? xprow[par * PWP + tid] : slice[(size_t)(step - r0) * PWP + tid];
+                            __stcg(&myslot[WS_LD + tid], pv);
+                        }
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+                        const unsigned target = a.ctr_base + (unsigned)NC * bar_id;
+                        while ((int)(ld_acquire_gpu(ctr) - target) < 0) {
+                        }
+                    }
+                    __syncthreads();
+                    const float* sl = slots + (size_t)par * MAXNC * SLOT_FLOATS;
+                    const int j = tid % PWP, grp = tid / PWP;
+                    float s = 0.f;
+                    if (j >= step) {
+                        for (int c0 = grp; c0 < NC; c0 += NG * 8) {  // 8 L2 loads in flight
+                            float v[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int c = c0 + u * NG;
+                                v[u] = (c < NC) ? __ldcg(&sl[(size_t)c * SLOT_FLOATS + j]) : 0.f;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) s += v[u];
+                        }
+                    }
+                    red[grp * PWP + j] = s;
+                    float pv = 0.f;
+                    if (tid < PWP) pv = __ldcg(&sl[(size_t)oc * SLOT_FLOATS + WS_LD + tid]);
+                    __syncthreads();
+                    if (tid < PWP) {
+                        float t = 0.f;
+#pragma unroll
+                        for (int gq = 0; gq < NG; ++gq) t += red[gq * PWP + tid];
+                        if (CS > 1) {
+                            fin[par * 2 * PWP + tid] = t;
+                            fin[par * 2 * PWP + PWP + tid] = pv;
+                        } else {
+                            gsum[tid] = t;
+                            prow[tid] = pv;
+                        }
+                    }
+                    if (CS > 1) {
+                        __syncthreads();
+                        for (int idx = tid; idx < (CS - 1) * 2 * PWP; idx += NT) {
+                            const int peer = 1 + idx / (2 * PWP), j2 = idx % (2 * PWP);
+                            st_cluster(map_to_cta(smem_addr(&fin[par * 2 * PWP + j2]), (unsigned)peer), fin[par * 2 * PWP + j2]);
+                        }
+                    }
+                }
+                if (CS > 1) {
+                    cluster_arrive();
+                    cluster_wait();
+                    if (tid < PWP) {
+                        gsum[tid] = fin[par * 2 * PWP + tid];
+                        prow[tid] = fin[par * 2 * PWP + PWP + tid];
+                    }
+                }
+                PROF_MARK(2);
+            }
+        } else {
+            PROF_MARK(1);
         }
         __syncthreads();
         PROF_MARK(3);
 
-        // reflector scalars (every thread, redundantly)
+        // reflector scalars (every thread, redundantly): MUFU.RSQ + one Newton step each, i.e.
+        // full FP32 accuracy at a fraction of the latency of IEEE sqrt/div
         const float gk = gsum[step], ak = prow[step];
         const bool skip = !(gk > 0.f);
-        const float mu = sqrtf(gk);
+        const float rs = rsqrtf(skip ? 1.f : gk);
+        float mu = gk * rs;
+        mu = fmaf(0.5f * rs, fmaf(-mu, mu, gk), mu);  // sqrt(gk)
+        if (skip) mu = 0.f;
         smu = (ak >= 0.f) ? mu : -mu;
         const float vn2 = 2.f * mu * (mu + fabsf(ak));
-        const float inv2 = skip ? 0.f : 2.f / vn2;
-        vinv = skip ? 0.f : 1.f / sqrtf(vn2);
+        float rv = rsqrtf(skip ? 1.f : vn2);
+        rv = rv * fmaf(-0.5f * vn2, rv * rv, 1.5f);   // 1/sqrt(vn2)
+        vinv = skip ? 0.f : rv;
+        const float inv2 = skip ? 0.f : 2.f * rv * rv;  // 2/vn2
 #pragma unroll
         for (int q = 0; q < CPL; ++q) {
             int col = lane * CPL + q;
@@ -287,151 +418,227 @@ panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int G) {
         }
     }
     __syncthreads();
-
     PROF_MARK(6);
-    if (prof) { a.dbg[7] += kr; a.dbg[8] = G; a.dbg[9] = rows_per_cta; }
+    if (prof) {
+        pacc[7] += kr; a.dbg[8] = G; a.dbg[9] = rows_per_cta; a.dbg[11] = CS; a.dbg[12] = NC;
+    }
+
     const bool want16y = a.Y16 != nullptr, want16w = a.W16 != nullptr;
     const bool need_t = a.T || a.W32 || want16w;
-    if (!(a.Y32 || want16y || need_t)) return;
-
-    // ---- slice := Y (zero strictly above the diagonal and for columns without reflector)
-    for (int idx = tid; idx < nrows * PWP; idx += NT) {
-        int li = idx / PWP, c = idx - li * PWP;
-        int i = r0 + li;
-        if (i < c || c >= kr) slice[idx] = 0.f;
-    }
-    __syncthreads();
     const int rofs = lam - a.blk_row0;  // output row of panel row 0
-    for (int idx = tid; idx < nrows * PWP; idx += NT) {
-        int li = idx / PWP, c = idx - li * PWP;
-        if (c >= pw) continue;
-        long orow = rofs + r0 + li;
-        float v = slice[idx];
-        if (a.Y32) a.Y32[orow * a.ld32 + c] = v;
-        if (want16y) store16(a.Y16, orow * a.ldy16 + c, v, a.bf16);
+    if (a.Y32 || want16y || need_t) {
+        // ---- slice := Y (zero strictly above the diagonal and for columns without reflector)
+        for (int idx = tid; idx < nrows * PWP; idx += NT) {
+            int li = idx / PWP, c = idx - li * PWP;
+            int i = r0 + li;
+            if (i < c || c >= kr) slice[idx] = 0.f;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nrows * PWP; idx += NT) {
+            int li = idx / PWP, c = idx - li * PWP;
+            if (c >= pw) continue;
+            long orow = rofs + r0 + li;
+            float v = slice[idx];
+            if (a.Y32) a.Y32[orow * a.ld32 + c] = v;
+            if (want16y) store16(a.Y16, orow * a.ldy16 + c, v, a.bf16);
+        }
+        // rows [blk_row0, lam) of the outputs are structurally zero
+        for (long idx = (long)blockIdx.x * NT + tid; idx < (long)rofs * pw; idx += (long)G * NT) {
+            long rr = idx / pw;
+            int c = (int)(idx - rr * pw);
+            if (a.Y32) a.Y32[rr * a.ld32 + c] = 0.f;
+            if (a.W32) a.W32[rr * a.ld32 + c] = 0.f;
+            if (want16y) store16(a.Y16, rr * a.ldy16 + c, 0.f, a.bf16);
+            if (want16w) store16(a.W16, rr * a.ldw16 + c, 0.f, a.bf16);
+        }
     }
-    // rows [blk_row0, lam) of the outputs are structurally zero
-    for (long idx = (long)blockIdx.x * NT + tid; idx < (long)rofs * pw; idx += (long)G * NT) {
-        long rr = idx / pw;
-        int c = (int)(idx - rr * pw);
-        if (a.Y32) a.Y32[rr * a.ld32 + c] = 0.f;
-        if (a.W32) a.W32[rr * a.ld32 + c] = 0.f;
-        if (want16y) store16(a.Y16, rr * a.ldy16 + c, 0.f, a.bf16);
-        if (want16w) store16(a.W16, rr * a.ldw16 + c, 0.f, a.bf16);
-    }
-    if (!need_t) return;
-
-    // ---- Gram matrix G[t][c] = sum_i y_it y_ic (strict upper part is what T needs)
-    for (int idx = tid; idx < PWP * GLD; idx += NT) gt[idx] = 0.f;
-    __syncthreads();
-    {
-        constexpr int NTC = PWP / 4, NTR = PWP / 8;
-        if (tid < NTR * NTC) {
-            const int tr = tid / NTC, tc = tid - tr * NTC;
-            if (8 * tr < 4 * tc + 3) {  // tile contains at least one (t < c)
-                float g[8][4];
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) g[u][v] = 0.f;
-                int lstart = 4 * tc - r0;  // y_ic = 0 for i < c  => rows below 4*tc contribute nothing
-                if (lstart < 0) lstart = 0;
-                for (int li = lstart; li < nrows; ++li) {
-                    const float* row = slice + (size_t)li * PWP;
-                    float4 t0 = *reinterpret_cast<const float4*>(row + 8 * tr);
-                    float4 t1 = *reinterpret_cast<const float4*>(row + 8 * tr + 4);
-                    float4 cc = *reinterpret_cast<const float4*>(row + 4 * tc);
-                    float yt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-                    float yc[4] = {cc.x, cc.y, cc.z, cc.w};
+    if (need_t) {
+        // ---- Gram matrix G[t][c] = sum_i y_it y_ic (strict upper part is what T needs)
+        for (int idx = tid; idx < PWP * GLD; idx += NT) gt[idx] = 0.f;
+        __syncthreads();
+        {
+            constexpr int NTC = PWP / 4, NTR = PWP / 8;
+            if (tid < NTR * NTC) {
+                const int tr = tid / NTC, tc = tid - tr * NTC;
+                if (8 * tr < 4 * tc + 3) {  // tile contains at least one (t < c)
+                    float g[8][4];
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) g[u][v] = fmaf(yt[u], yc[v], g[u][v]);
+                        for (int v = 0; v < 4; ++v) g[u][v] = 0.f;
+                    int lstart = 4 * tc - r0;  // y_ic = 0 for i < c
+                    if (lstart < 0) lstart = 0;
+                    for (int li = lstart; li < nrows; ++li) {
+                        const float* row = slice + (size_t)li * PWP;
+                        float4 t0 = *reinterpret_cast<const float4*>(row + 8 * tr);
+                        float4 t1 = *reinterpret_cast<const float4*>(row + 8 * tr + 4);
+                        float4 cc = *reinterpret_cast<const float4*>(row + 4 * tc);
+                        float yt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                        float yc[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) g[u][v] = fmaf(yt[u], yc[v], g[u][v]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            int t = 8 * tr + u, c = 4 * tc + v;
+                            if (t < c && c < kr) {
+                                if (G > 1) atomicAdd(&gram_g[t * WS_LD + c], g[u][v]);
+                                else gt[t * GLD + c] = g[u][v];
+                            }
+                        }
+                }
+            }
+        }
+        if (G > 1) {
+            // grid-wide sync: cluster barrier, leaders through L2, cluster barrier
+            if (CS > 1) {
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");  // order this CTA's global atomics
+                cluster_arrive();
+                cluster_wait();
+            } else {
+                __syncthreads();
+            }
+            if (NC > 1) {
+                ++bar_id;
+                if (crank == 0 && tid == 0) {
+                    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+                    const unsigned target = a.ctr_base + (unsigned)NC * bar_id;
+                    while ((int)(ld_acquire_gpu(ctr) - target) < 0) {
+                    }
+                }
+                if (CS > 1) {
+                    cluster_arrive();
+                    cluster_wait();
+                } else {
+                    __syncthreads();
+                }
+            }
+            for (int idx = tid; idx < PWP * PWP; idx += NT) {
+                int t = idx / PWP, c = idx - t * PWP;
+                if (t < c && c < kr) gt[t * GLD + c] = __ldcg(&gram_g[t * WS_LD + c]);
+            }
+        }
+        __syncthreads();
+
+        // ---- T in place: column c of gt goes from G[0:c,c] to T[0:c,c]
+        for (int c = 0; c < kr; ++c) {
+            float* gc = gcol + (c & 1) * PWP;
+            if (tid < c) gc[tid] = gt[tid * GLD + c];
+            __syncthreads();
+            const int t = tid >> 2, part = tid & 3;
+            float s = 0.f;
+            if (t < c)
+                for (int u = t + part; u < c; u += 4) s = fmaf(gt[t * GLD + u], gc[u], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (part == 0 && t < c) gt[t * GLD + c] = -2.f * s;
+            if (tid == c) gt[c * GLD + c] = 2.f;
+        }
+        __syncthreads();
+        if (a.T && blockIdx.x == 0) {
+            for (int idx = tid; idx < pw * pw; idx += NT) {
+                int t = idx / pw, c = idx - t * pw;
+                a.T[(size_t)t * a.ldt + c] = (t <= c && c < kr) ? gt[t * GLD + c] : 0.f;
+            }
+        }
+        PROF_MARK(10);
+        if (a.W32 || want16w) {
+            // ---- W = Y T on the slice rows; lane <-> columns lane + 32 q (conflict-free T reads)
+            for (int base = warp * 8; base < nrows; base += NW * 8) {
+                float w[8][CPL];
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr)
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) w[rr][q] = 0.f;
+                int tmax = r0 + base + 8;  // y_it = 0 for t > i
+                if (tmax > kr) tmax = kr;
+                for (int t = 0; t < tmax; ++t) {
+                    float tt[CPL];
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        int col = lane + 32 * q;
+                        tt[q] = (col >= t) ? gt[t * GLD + col] : 0.f;
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        int li = base + rr;
+                        float y = (li < nrows) ? slice[(size_t)li * PWP + t] : 0.f;
+#pragma unroll
+                        for (int q = 0; q < CPL; ++q) w[rr][q] = fmaf(y, tt[q], w[rr][q]);
+                    }
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
+                for (int rr = 0; rr < 8; ++rr) {
+                    int li = base + rr;
+                    if (li >= nrows) continue;
+                    long orow = rofs + r0 + li;
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        int t = 8 * tr + u, c = 4 * tc + v;
-                        if (t < c && c < kr) {
-                            if (G > 1) atomicAdd(&gram_g[t * WS_LD + c], g[u][v]);
-                            else gt[t * GLD + c] = g[u][v];
-                        }
+                    for (int q = 0; q < CPL; ++q) {
+                        int col = lane + 32 * q;
+                        if (col >= pw) continue;
+                        if (a.W32) a.W32[orow * a.ld32 + col] = w[rr][q];
+                        if (want16w) store16(a.W16, orow * a.ldw16 + col, w[rr][q], a.bf16);
                     }
+                }
             }
         }
     }
-    if (G > 1) {
-        grid_barrier(ctr, a.ctr_base + (unsigned)G * (++bar_id));
-        for (int idx = tid; idx < PWP * PWP; idx += NT) {
-            int t = idx / PWP, c = idx - t * PWP;
-            if (t < c && c < kr) gt[t * GLD + c] = __ldcg(&gram_g[t * WS_LD + c]);
-        }
+    if (prof) {
+        for (int i = 0; i < 11; ++i) a.dbg[i] += pacc[i];
     }
-    __syncthreads();
+    // a CTA's shared memory must stay alive until no peer can write into it any more
+    if (CS > 1) {
+        cluster_arrive();
+        cluster_wait();
+    }
+}
 
-    // ---- T in place: column c of gt goes from G[0:c,c] to T[0:c,c]
-    for (int c = 0; c < kr; ++c) {
-        float* gc = gcol + (c & 1) * PWP;
-        if (tid < c) gc[tid] = gt[tid * GLD + c];
-        __syncthreads();
-        const int t = tid >> 2, part = tid & 3;
-        float s = 0.f;
-        if (t < c)
-            for (int u = t + part; u < c; u += 4) s = fmaf(gt[t * GLD + u], gc[u], s);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (part == 0 && t < c) gt[t * GLD + c] = -2.f * s;
-        if (tid == c) gt[c * GLD + c] = 2.f;
-    }
-    __syncthreads();
-    if (a.T && blockIdx.x == 0) {
-        for (int idx = tid; idx < pw * pw; idx += NT) {
-            int t = idx / pw, c = idx - t * pw;
-            a.T[(size_t)t * a.ldt + c] = (t <= c && c < kr) ? gt[t * GLD + c] : 0.f;
-        }
-    }
-    PROF_MARK(10);
-    if (!(a.W32 || want16w)) return;
+struct ClusterCaps {
+    int max_cs;    // largest usable cluster size (16, 8 or 1)
+    int max_nc16;  // co-resident clusters of 16 at full dynamic smem
+    int max_nc8;   // co-resident clusters of 8
+};
 
-    // ---- W = Y T on the slice rows; lane <-> columns lane + 32 q (conflict-free T reads)
-    for (int base = warp * 8; base < nrows; base += NW * 8) {
-        float w[8][CPL];
-#pragma unroll
-        for (int rr = 0; rr < 8; ++rr)
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) w[rr][q] = 0.f;
-        int tmax = r0 + base + 8;  // y_it = 0 for t > i
-        if (tmax > kr) tmax = kr;
-        for (int t = 0; t < tmax; ++t) {
-            float tt[CPL];
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) {
-                int col = lane + 32 * q;
-                tt[q] = (col >= t) ? gt[t * GLD + col] : 0.f;
+template <int CPL>
+int query_caps(const DeviceInfo& di, ClusterCaps* out) {
+    static ClusterCaps caps = {0, 0, 0};
+    static bool done = false;
+    if (!done) {
+        MPQR_CUDA(cudaFuncSetAttribute(panel_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+        cudaError_t e = cudaFuncSetAttribute(panel_kernel<CPL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        const bool np_ok = (e == cudaSuccess);
+        if (!np_ok) cudaGetLastError();
+        auto occ = [&](int cs) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(cs * 4);
+            cfg.blockDim = dim3(NT);
+            cfg.dynamicSmemBytes = di.max_smem_optin;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, panel_kernel<CPL>, &cfg) != cudaSuccess) {
+                cudaGetLastError();
+                n = 0;
             }
-#pragma unroll
-            for (int rr = 0; rr < 8; ++rr) {
-                int li = base + rr;
-                float y = (li < nrows) ? slice[(size_t)li * PWP + t] : 0.f;
-#pragma unroll
-                for (int q = 0; q < CPL; ++q) w[rr][q] = fmaf(y, tt[q], w[rr][q]);
-            }
-        }
-#pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-            int li = base + rr;
-            if (li >= nrows) continue;
-            long orow = rofs + r0 + li;
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) {
-                int col = lane + 32 * q;
-                if (col >= pw) continue;
-                if (a.W32) a.W32[orow * a.ld32 + col] = w[rr][q];
-                if (want16w) store16(a.W16, orow * a.ldw16 + col, w[rr][q], a.bf16);
-            }
-        }
+            return n;
+        };
+        caps.max_nc16 = np_ok ? occ(16) : 0;
+        caps.max_nc8 = occ(8);
+        caps.max_cs = caps.max_nc16 > 0 ? 16 : (caps.max_nc8 > 0 ? 8 : 1);
+        done = true;
     }
+    *out = caps;
+    return MPQR_OK;
 }
 
 template <int CPL>
@@ -440,49 +647,53 @@ int launch_t(const PanelArgs& a, cudaStream_t stream, const DeviceInfo& di) {
     const int D = a.m - a.lam;
     const size_t fixed = (size_t)fixed_floats<CPL>() * sizeof(float);
     const int max_rows_smem = (int)(((size_t)di.max_smem_optin - fixed - 256) / (PWP * sizeof(float)));
-    int rows_per_cta, G, use_smem = 1;
-    if (D <= 512 && D <= max_rows_smem) {
+    const int cap = max_rows_smem - (max_rows_smem % NW);
+    ClusterCaps caps;
+    MPQR_TRY(query_caps<CPL>(di, &caps));
+    if (a.force_cs > 0 && a.force_cs < caps.max_cs) caps.max_cs = a.force_cs;
+    if (a.dbg_caps) { a.dbg_caps[0] = caps.max_cs; a.dbg_caps[1] = caps.max_nc16; a.dbg_caps[2] = caps.max_nc8; }
+    int rows_per_cta, CS = 1, NC = 1, use_smem = 1;
+    if (D <= cap && (D <= 256 || caps.max_cs == 1)) {
         rows_per_cta = D;
-        G = 1;
     } else {
-        // measured (tools/panel_probe.py, profiles/r1_panel_probe.txt): the local pass costs
-        // ~16 cycles/row/step while the gather grows only ~8 cycles per extra CTA -> use many CTAs
-        rows_per_cta = ceil_div(D, di.num_sms);
-        if (a.rows_hint > 0) rows_per_cta = a.rows_hint;
-        if (rows_per_cta < 64) rows_per_cta = 64;
-        rows_per_cta = round_up(rows_per_cta, NW);
-        const int cap = max_rows_smem - (max_rows_smem % NW);
-        if (rows_per_cta > cap) rows_per_cta = cap;
-        if (ceil_div(D, rows_per_cta) > di.num_sms) rows_per_cta = round_up(ceil_div(D, di.num_sms), NW);
-        if (rows_per_cta > max_rows_smem) {
-            // does not fit: keep the slice in a global scratch buffer (L2-resident for moderate D)
-            use_smem = 0;
-            rows_per_cta = round_up(ceil_div(D, di.num_sms), NW);
-            if (!a.scratch || a.scratch_rows < D) {
-                set_error("panel: scratch buffer missing/too small for D=%d", D);
-                return MPQR_EINVAL;
+        // ~96 rows per CTA (the pass costs ~10 cycles/row/step with 4 rows in flight, a cluster
+        // barrier ~400), but never more than one cluster unless capacity forces it: a single
+        // cluster never touches L2 inside the column loop
+        const int need = ceil_div(D, cap);  // CTAs needed for capacity
+        int want = ceil_div(D, a.rows_hint > 0 ? a.rows_hint : 96);
+        if (want < need) want = need;
+        if (need <= caps.max_cs && !(a.force_cs == 1)) {
+            // fits one cluster: DSMEM all-gather + one hardware cluster barrier per column
+            // (measured ~1.0k cycles vs 4-8k for any exchange through L2, profiles/r1_panel_probe.txt)
+            CS = 1;
+            while (CS < want && CS < caps.max_cs) CS *= 2;
+            while (CS < need) CS *= 2;
+        } else {
+            // too tall for one cluster: flat exchange through L2 over as many CTAs as possible
+            // (the pass is issue-bound, ~10 cycles per row per step, so rows per CTA must be small)
+            CS = 1;
+            NC = ceil_div(D, a.rows_hint > 0 ? a.rows_hint : 64);
+            if (NC > di.num_sms) NC = di.num_sms;
+            if (NC > MAXNC) NC = MAXNC;
+            if (NC < need) {
+                use_smem = 0;
+                if (!a.scratch || a.scratch_rows < D) {
+                    set_error("panel: scratch buffer missing/too small for D=%d", D);
+                    return MPQR_EINVAL;
+                }
             }
         }
-        G = ceil_div(D, rows_per_cta);
+        rows_per_cta = round_up(ceil_div(D, CS * NC), NW);
+        if (use_smem && rows_per_cta > cap) {
+            set_error("panel: internal sizing error D=%d CS=%d NC=%d rows=%d cap=%d", D, CS, NC, rows_per_cta, cap);
+            return MPQR_EINVAL;
+        }
     }
-    if (G > 1 && !di.coop) {
-        set_error("panel: device lacks cooperative launch");
-        return MPQR_ECUDA;
-    }
+    const int G = CS * NC;
     size_t smem = fixed + (use_smem ? (size_t)rows_per_cta * PWP * sizeof(float) : 0);
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        MPQR_CUDA(cudaFuncSetAttribute(panel_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       di.max_smem_optin));
-        attr_set = true;
-    }
-    if (G > MAXG) {
-        set_error("panel: %d CTAs exceed the sync workspace (MAXG=%d)", G, MAXG);
-        return MPQR_EINVAL;
-    }
     PanelArgs args = a;
-    if (G > 1) {
-        // grid barriers executed by this launch: one per reflector + one for the Gram reduction
+    if (NC > 1) {
+        // L2 barriers executed by the leaders: one per reflector + one for the Gram reduction
         const int kr = a.pw < D ? a.pw : D;
         const bool need_t = a.T || a.W32 || a.W16;
         unsigned nbar = (unsigned)kr + (need_t ? 1u : 0u);
@@ -491,15 +702,31 @@ int launch_t(const PanelArgs& a, cudaStream_t stream, const DeviceInfo& di) {
             return MPQR_EINVAL;
         }
         args.ctr_base = *a.host_ctr;
-        *a.host_ctr += (unsigned)G * nbar;
+        *a.host_ctr += (unsigned)NC * nbar;
     }
-    if (G > 1) {
-        void* kargs[] = {(void*)&args, (void*)&rows_per_cta, (void*)&use_smem, (void*)&G};
-        MPQR_CUDA(cudaLaunchCooperativeKernel((void*)panel_kernel<CPL>, dim3(G), dim3(NT), kargs, smem, stream));
-    } else {
-        panel_kernel<CPL><<<1, NT, smem, stream>>>(args, rows_per_cta, use_smem, G);
-        MPQR_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (CS > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = CS;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        ++na;
     }
+    if (NC > 1) {
+        // all clusters must be co-resident (leaders spin on an L2 counter)
+        at[na].id = cudaLaunchAttributeCooperative;
+        at[na].val.cooperative = 1;
+        ++na;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = na;
+    MPQR_CUDA(cudaLaunchKernelEx(&cfg, panel_kernel<CPL>, args, rows_per_cta, use_smem, CS, NC));
     return MPQR_OK;
 }
 
