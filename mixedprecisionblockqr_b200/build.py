@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libmpqr.so")
 SHIM = os.path.join(_HERE, "libmpqr_refshim.so")
-SOURCES = ["api.cu", "panel.cu", "gemm_simt.cu", "gemm_tc.cu", "mg.cu", "tsqr.cu"]
+SOURCES = ["api.cu", "panel.cu", "panel_legacy.cu", "gemm_simt.cu", "gemm_tc.cu", "mg.cu", "tsqr.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

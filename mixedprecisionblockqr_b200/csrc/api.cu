@@ -176,6 +176,7 @@ int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         a.Y32 = Y; a.W32 = W; a.ld32 = ld;
         a.T = h->T + (size_t)p * r * r; a.ldt = r;
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
+        a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows;
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         if (nt > 0) {
             float* A22 = A + (size_t)lam * lda + tau;
@@ -242,6 +243,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         a.bf16 = bf;
         a.T = h->T + (size_t)p * r * r; a.ldt = r;
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
+        a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows;
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         const int nin = c1 - tau;  // in-block trailing columns
         const int acol_tau = c.acol0 + jc + pw;
@@ -333,6 +335,8 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
             if ((rc = dev_alloc(h, (void**)&h->scratch, panel_scratch_bytes(m)))) break;
         }
         if ((rc = dev_alloc(h, (void**)&h->T, (size_t)h->npanels * h->r * h->r * sizeof(float)))) break;
+        h->panel_ws_rows = m;
+        if ((rc = dev_alloc(h, (void**)&h->panel_ws, panel_ws_bytes(m)))) break;
         const int wide = m > n ? m : n;
         h->sk = h->nb;
         h->lds32 = round_up(wide, 8);
@@ -529,15 +533,20 @@ int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
     }
     DeviceInfo di;
     MPQR_TRY(get_device_info(&di));
-    float *ws = nullptr, *scratch = nullptr;
+    float *ws = nullptr, *scratch = nullptr, *pws = nullptr;
     MPQR_CUDA(cudaMalloc(&ws, panel_sync_ws_bytes()));
     MPQR_CUDA(cudaMemset(ws, 0, panel_sync_ws_bytes()));
+    if (cudaMalloc(&pws, panel_ws_bytes(m - lam)) != cudaSuccess) {
+        cudaFree(ws);
+        set_error("panel workspace allocation failed");
+        return MPQR_ENOMEM;
+    }
     unsigned host_ctr = 0;
     long scratch_rows = 0;
     if (m - lam > (long)di.num_sms * 288) {
         scratch_rows = m;
         if (cudaMalloc(&scratch, panel_scratch_bytes(m)) != cudaSuccess) {
-            cudaFree(ws);
+            cudaFree(ws); cudaFree(pws);
             set_error("panel scratch allocation failed");
             return MPQR_ENOMEM;
         }
@@ -545,13 +554,15 @@ int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
     PanelArgs a{};
     a.A = dA; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.acol = lam; a.pw = pw; a.blk_row0 = lam;
     a.Y32 = dY; a.W32 = dW; a.ld32 = pw;
-    if (dW && !dY) { set_error("mpqr_panel_factor_device: dW needs dY"); cudaFree(ws); cudaFree(scratch); return MPQR_EINVAL; }
+    if (dW && !dY) { set_error("mpqr_panel_factor_device: dW needs dY"); cudaFree(ws); cudaFree(scratch); cudaFree(pws); return MPQR_EINVAL; }
     a.T = dT; a.ldt = pw;
     a.sync_ws = ws; a.host_ctr = &host_ctr; a.scratch = scratch; a.scratch_rows = scratch_rows;
+    a.ws = pws; a.ws_rows = m - lam;
     int rc = launch_panel(a, (cudaStream_t)stream, nullptr);
     cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(ws);
     cudaFree(scratch);
+    cudaFree(pws);
     if (rc == MPQR_OK && e != cudaSuccess) {
         set_error("panel kernel failed: %s", cudaGetErrorString(e));
         rc = MPQR_ECUDA;
@@ -560,32 +571,28 @@ int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
 }
 
 // Tuning/profiling hook (tools/panel_probe.py; not part of the public header): runs the panel
-// kernel `reps` times on copies of the same panel with phase profiling enabled.
-int mpqr_debug_panel_probe(float* dA, long lda, int m, int n, int lam, int pw, int rows_hint, int force_cs, int want_wy,
-                           long long* dDbg, void* stream) {
+// path once with phase profiling enabled.  dDbg: 16 x int64 on the device.
+int mpqr_debug_panel_probe(float* dA, long lda, int m, int n, int lam, int pw, int force_b, int force_cs, int force_rpt,
+                           int want_wy, long long* dDbg, void* stream) {
     DeviceInfo di;
     MPQR_TRY(get_device_info(&di));
-    float *ws = nullptr, *Y = nullptr, *W = nullptr, *T = nullptr;
-    MPQR_CUDA(cudaMalloc(&ws, panel_sync_ws_bytes()));
-    MPQR_CUDA(cudaMemset(ws, 0, panel_sync_ws_bytes()));
+    float *Y = nullptr, *W = nullptr, *T = nullptr, *pws = nullptr;
     if (want_wy) {
         MPQR_CUDA(cudaMalloc(&Y, (size_t)(m - lam) * pw * 4));
         MPQR_CUDA(cudaMalloc(&W, (size_t)(m - lam) * pw * 4));
         MPQR_CUDA(cudaMalloc(&T, (size_t)pw * pw * 4));
     }
-    unsigned host_ctr = 0;
-    float* scratch = nullptr;
-    cudaMalloc(&scratch, panel_scratch_bytes(m));
+    MPQR_CUDA(cudaMalloc(&pws, panel_ws_bytes(m - lam)));
     PanelArgs a{};
-    a.scratch = scratch; a.scratch_rows = m;
     a.A = dA; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.acol = lam; a.pw = pw; a.blk_row0 = lam;
     a.Y32 = Y; a.W32 = W; a.ld32 = pw; a.T = T; a.ldt = pw;
-    a.sync_ws = ws; a.host_ctr = &host_ctr; a.dbg = dDbg; a.rows_hint = rows_hint; a.force_cs = force_cs;
+    a.ws = pws; a.ws_rows = m - lam;
+    a.dbg = dDbg; a.force_b = force_b; a.force_cs = force_cs; a.force_rpt = force_rpt;
     int caps[3] = {0, 0, 0};
     a.dbg_caps = caps;
     int rc = launch_panel(a, (cudaStream_t)stream, nullptr);
     cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
-    cudaFree(ws); cudaFree(Y); cudaFree(W); cudaFree(T); cudaFree(scratch);
+    cudaFree(Y); cudaFree(W); cudaFree(T); cudaFree(pws);
     if (rc == MPQR_OK && e != cudaSuccess) { set_error("panel probe failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; }
     if (rc == MPQR_OK && dDbg) {
         long long c[3] = {caps[0], caps[1], caps[2]};

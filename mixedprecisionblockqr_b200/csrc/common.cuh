@@ -77,8 +77,13 @@ struct PanelArgs {
     long long* dbg;     // optional device buffer (16 x int64) for phase profiling, else null
     int rows_hint;      // > 0: override the rows-per-CTA heuristic (tuning)
     int force_cs;       // > 0: cap the cluster size (tuning / tests)
-    int* dbg_caps;      // optional HOST array[3]: max cluster size, co-resident clusters of 16 / 8
+    int* dbg_caps;      // optional HOST array[3]: max cluster size, chosen cluster size, rows per thread
+    float* ws;          // panel workspace (panel_ws_bytes), needed when pw > one register block
+    long ws_rows;       // rows the workspace was sized for
+    int force_b;        // 16 / 32: override the register-block width (tuning / tests)
+    int force_rpt;      // > 0: override the rows per thread (tuning / tests)
 };
+size_t panel_ws_bytes(long max_rows);
 int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches);
 
 // ------------------------------------------------------------------ FP32 SIMT GEMMs
@@ -93,7 +98,7 @@ int sgemm_nn_sub(const float* X, long ldx, const float* S, long lds, float* C, l
 int simt16_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long lds, int M, int N, int K,
                    int bf16, cudaStream_t stream);
 int simt16_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16, long ldc16,
-                   int M, int N, int K, int bf16, cudaStream_t stream);
+                   int M, int N, int K, int bf16, cudaStream_t stream, int store = 0);
 
 // ------------------------------------------------------------------ tcgen05 GEMMs
 // S[M x N] (fp32) = X^T Z with 16-bit X [K x M], Z [K x N]; split-K with TMA reduce-add when
@@ -104,6 +109,10 @@ int tc_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long 
 // the updated C into C16 (16-bit shadow).
 int tc_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16,
                long ldc16, int M, int N, int K, int bf16, int pad_ok, cudaStream_t stream, long* launches);
+
+// C[M x N] (fp32) = X S16 (store), same operands; C16 optional 16-bit copy.
+int tc_gemm_nn_store(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16,
+                     long ldc16, int M, int N, int K, int bf16, cudaStream_t stream, long* launches);
 
 // ------------------------------------------------------------------ small utility kernels
 int fill_uniform(float* A, long lda, long n_total, long row0, long rows, long col0, long cols,

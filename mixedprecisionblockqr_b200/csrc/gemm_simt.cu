@@ -87,7 +87,10 @@ sgemm_kernel(const TI* __restrict__ X, long ldx, const TI* __restrict__ Z, long 
             int gj = j0 + tx * TN + v;
             if (gj >= N) continue;
             float* p = C + (size_t)gi * ldc + gj;
-            if (MODE == 0) *p = acc[u][v];
+            if (MODE == 0) {
+                *p = acc[u][v];
+                if (sizeof(TI) == 2 && H) st16(H + (size_t)gi * ldh + gj, acc[u][v]);
+            }
             else if (MODE == 1) {
                 float nv = *p - acc[u][v];
                 *p = nv;
@@ -124,9 +127,10 @@ int tn_any(const TI* X, long ldx, const TI* Z, long ldz, float* S, long lds, int
 
 template <typename TI>
 int nn_any(const TI* X, long ldx, const TI* S, long lds, float* C, long ldc, TI* H, long ldh, int M, int N, int K,
-           cudaStream_t stream) {
+           cudaStream_t stream, int store = 0) {
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), 1);
-    sgemm_kernel<false, 1, TI><<<grid, GT, 0, stream>>>(X, ldx, S, lds, C, ldc, H, ldh, M, N, K, K);
+    if (store) sgemm_kernel<false, 0, TI><<<grid, GT, 0, stream>>>(X, ldx, S, lds, C, ldc, H, ldh, M, N, K, K);
+    else sgemm_kernel<false, 1, TI><<<grid, GT, 0, stream>>>(X, ldx, S, lds, C, ldc, H, ldh, M, N, K, K);
     MPQR_CUDA(cudaGetLastError());
     return MPQR_OK;
 }
@@ -168,9 +172,9 @@ int simt16_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, l
 }
 
 int simt16_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16, long ldc16,
-                   int M, int N, int K, int bf16, cudaStream_t stream) {
-    if (bf16) return nn_any<__nv_bfloat16>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)S16, lds16, C, ldc, (__nv_bfloat16*)C16, ldc16, M, N, K, stream);
-    return nn_any<__half>((const __half*)X, ldx, (const __half*)S16, lds16, C, ldc, (__half*)C16, ldc16, M, N, K, stream);
+                   int M, int N, int K, int bf16, cudaStream_t stream, int store) {
+    if (bf16) return nn_any<__nv_bfloat16>((const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)S16, lds16, C, ldc, (__nv_bfloat16*)C16, ldc16, M, N, K, stream, store);
+    return nn_any<__half>((const __half*)X, ldx, (const __half*)S16, lds16, C, ldc, (__half*)C16, ldc16, M, N, K, stream, store);
 }
 
 }  // namespace mpqr

@@ -171,7 +171,7 @@ struct GemmParams {
 };
 
 // kAMN : A operand is MN-major (TN GEMM) else K-major (NN GEMM)
-// kEpi : 0 -> S = acc (store / reduce-add when splits > 1) ; 1 -> C -= acc (+ shadow)
+// kEpi : 0 -> S = acc (store / reduce-add when splits > 1) ; 1 -> C -= acc (+ shadow) ; 2 -> C = acc (+ shadow)
 template <int BN, bool kAMN, int kEpi>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -203,7 +203,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         prefetch_tmap(&tmC);
-        if (kEpi == 1 && p.has_shadow) prefetch_tmap(&tmH);
+        if (kEpi >= 1 && p.has_shadow) prefetch_tmap(&tmH);
     }
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < STAGES; ++i) {
@@ -364,7 +364,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     *pc = r4;
                     o[4 * i] = r4.x; o[4 * i + 1] = r4.y; o[4 * i + 2] = r4.z; o[4 * i + 3] = r4.w;
                 }
-                if (kEpi == 1 && p.has_shadow) {
+                if (kEpi >= 1 && p.has_shadow) {
                     uint8_t* hrow = hb + row * 64;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -394,7 +394,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int cx = p.cx0 + nb * BN + j * CCH, cy = p.cy0 + mb * BM;
                     if (kEpi == 0 && p.splits > 1) tma_reduce_add_2d(&tmC, cb, cx, cy);
                     else tma_store_2d(&tmC, cb, cx, cy);
-                    if (kEpi == 1 && p.has_shadow) tma_store_2d(&tmH, hb, p.hx0 + nb * BN + j * CCH, p.hy0 + mb * BM);
+                    if (kEpi >= 1 && p.has_shadow) tma_store_2d(&tmH, hb, p.hx0 + nb * BN + j * CCH, p.hy0 + mb * BM);
                     tma_commit();
                 }
                 ++g;
@@ -530,8 +530,8 @@ int tc_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long 
     return rc;
 }
 
-int tc_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16, long ldc16,
-               int M, int N, int K, int bf16, int pad_ok, cudaStream_t stream, long* launches) {
+static int tc_gemm_nn_impl(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16, long ldc16,
+                           int M, int N, int K, int bf16, int pad_ok, int store, cudaStream_t stream, long* launches) {
     if (M <= 0 || N <= 0 || K <= 0) return MPQR_OK;
     DeviceInfo di;
     MPQR_TRY(get_device_info(&di));
@@ -539,7 +539,7 @@ int tc_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, l
     Blk bx = align_blk(X, 2), bs = align_blk(S16, 2), bc = align_blk(C, 4);
     if (bx.x0 || bs.x0 || bc.x0 || (C16 && align_blk(C16, 2).x0) || (ldx & 7) || (lds16 & 7) || (ldc & 3) ||
         (C16 && (ldc16 & 7)) || (!pad_ok && (N & (C16 ? 7 : 3)))) {
-        int rc = simt16_gemm_nn(X, ldx, S16, lds16, C, ldc, C16, ldc16, M, N, K, bf16, stream);
+        int rc = simt16_gemm_nn(X, ldx, S16, lds16, C, ldc, C16, ldc16, M, N, K, bf16, stream, store);
         if (rc == MPQR_OK && launches) *launches += 1;
         return rc;
     }
@@ -562,10 +562,23 @@ int tc_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, l
     }
     const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
     int grid = tiles < di.num_sms ? tiles : di.num_sms;
-    int rc = (BN == 256) ? launch<256, false, 1>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream)
-                         : launch<128, false, 1>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream);
+    int rc;
+    if (store) rc = (BN == 256) ? launch<256, false, 2>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream)
+                                : launch<128, false, 2>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream);
+    else rc = (BN == 256) ? launch<256, false, 1>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream)
+                          : launch<128, false, 1>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream);
     if (rc == MPQR_OK && launches) *launches += 1;
     return rc;
+}
+
+int tc_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16, long ldc16,
+               int M, int N, int K, int bf16, int pad_ok, cudaStream_t stream, long* launches) {
+    return tc_gemm_nn_impl(X, ldx, S16, lds16, C, ldc, C16, ldc16, M, N, K, bf16, pad_ok, 0, stream, launches);
+}
+
+int tc_gemm_nn_store(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16, long ldc16,
+                     int M, int N, int K, int bf16, cudaStream_t stream, long* launches) {
+    return tc_gemm_nn_impl(X, ldx, S16, lds16, C, ldc, C16, ldc16, M, N, K, bf16, 1, 1, stream, launches);
 }
 
 }  // namespace mpqr

@@ -19,6 +19,8 @@ struct mpqr_handle {
     unsigned sync_ctr = 0;  // host mirror of the panel barrier counter
     float* scratch = nullptr;
     long scratch_rows = 0;
+    float* panel_ws = nullptr;  // panel.cu workspace (in-panel blocks, Gram, T)
+    long panel_ws_rows = 0;
     float* T = nullptr;    // npanels * r * r
     float* S32 = nullptr;  // sk x lds32
     long lds32 = 0;

@@ -1,24 +1,27 @@
-// panel.cu — multi-CTA Householder panel factorisation + fused compact-WY (sm_100a).
+// panel.cu — Householder panel factorisation + compact-WY (sm_100a), three-level scheme.
 //
-// Replaces the reference's HOST panel factorisation h_householder_qr (Cuda/qr.cu:198-293,
-// single CPU thread, forces a full-matrix PCIe round trip per panel, :1080-1082/:1215) and
-// the 3r+2 launches of dev_wy_transform (Cuda/qr.cu:535-600, K1-K4 of SURVEY 2.4) by ONE
-// persistent kernel per panel:
+// Replaces the reference's HOST panel factorisation h_householder_qr (Cuda/qr.cu:198-293, one
+// CPU thread, full-matrix PCIe round trip per panel, :1080-1082/:1215) and the 3r+2 launches of
+// dev_wy_transform (Cuda/qr.cu:535-600, K1-K4 of SURVEY 2.4).
 //
-//   * the D x pw panel is distributed by rows over NC clusters x CS CTAs and stays resident in
-//     shared memory for all pw reflector steps: HBM sees one coalesced read and one coalesced
-//     write of the panel (algorithmic bytes 8*D*pw);
-//   * per column ONE reduction: the dots g_j = u^T a_j (j >= k) give both the column norm (g_k)
-//     and v^T a_j = g_j + s*mu*a_kj, so the rank-1 update of step k and the dots of step k+1
-//     are fused into a single pass over the slice (4 rows in flight per warp for ILP);
-//   * the reduction is hierarchical: inside a thread-block cluster the partial vectors are
-//     all-gathered through distributed shared memory and one hardware cluster barrier; only
-//     the cluster leaders exchange through L2 (per-leader slots + monotonic counter) and
-//     broadcast the result back through DSMEM.  Panels that fit one cluster (all of C2/C3)
-//     never touch L2 inside the column loop;
-//   * tail (still in shared memory): Gram matrix Y^T Y -> T by the larft recurrence
-//     (T[0:c,c] = -2 T[0:c,0:c] G[0:c,c], T[c,c] = 2) -> W = Y T, emitted as FP32 and as
-//     the FP16/BF16 operands of the tensor-core trailing update.
+//   level 0  panel_block_kernel<B,RPT>: B (16 or 32) columns x D rows, REGISTER resident.  The
+//            D x B block is spread by rows over ONE thread-block cluster (<= 16 CTAs x 512
+//            threads x RPT rows); every thread keeps its rows' B values in registers for all B
+//            reflector steps, so HBM sees one read and one write of the block.  Per column ONE
+//            reduction: the dots g_j = u^T a_j give the norm (j = k), the update coefficients
+//            v^T a_j = g_j + s*mu*a_kj (j > k) and the Gram entries y_j^T y_k (j < k) at once;
+//            the rank-1 update of step k-1 and the dots of step k share one pass.  Reduction:
+//            warp transpose-reduce (shuffles) -> shared memory -> all-gather of the CTA sums
+//            through distributed shared memory with st.async + mbarrier complete_tx (no
+//            cluster-wide barrier, no L2 round trip inside the column loop).  Tail: T of the
+//            block by the larft recurrence, W = Y T, packed output, FP32 + FP16/BF16 copies.
+//   level 1  inside an r-wide panel (r <= 128) the blocks are combined right-looking in FP32:
+//            S = W_j^T A_rest (inpanel_s_kernel), A_rest -= Y_j S (inpanel_u_kernel).
+//   level 2  T of the whole panel from the Gram matrix, T = (striu(Y^T Y) + I/2)^-1
+//            (tinv_kernel, recursive doubling in one CTA), then W = Y T.
+//            Mixed-precision driver: Gram and W on tcgen05 from the SAME 16-bit Y the trailing
+//            GEMMs use (so I - Y16 T Y16^T is orthogonal to FP32-accumulate accuracy);
+//            FP32 driver: SIMT GEMMs.
 //
 // Conventions mirrored from the reference: sign = (u0 >= 0) ? +1 : -1
 // (:229-235); zero column => reflector skipped (:242-244); unit vector w (beta = 2) stored
@@ -26,690 +29,655 @@
 #include "common.cuh"
 
 namespace mpqr {
+
+int launch_panel_legacy(const PanelArgs& a, cudaStream_t stream, long* launches);
+int sgemm_nn_store(const float* X, long ldx, const float* S, long lds, float* C, long ldc, int M, int N, int K,
+                   cudaStream_t stream);
+
 namespace {
 
 constexpr int NT = 512;
 constexpr int NW = NT / 32;
-constexpr int RI = 4;                                       // rows in flight per warp
-constexpr int CSMAX = 16;                                   // max cluster size
-constexpr int WS_LD = kPanelMaxWidth;
-constexpr int WS_ARRAY = kPanelMaxWidth * kPanelMaxWidth;   // floats of the Gram accumulator
-constexpr int MAXNC = 160;                                  // max clusters of one launch (CS = 1: every CTA)
-constexpr int SLOT_FLOATS = 2 * WS_LD;                      // per-cluster slot: partial dots | pivot row
-// sync workspace (floats): slots[2][MAXNC][SLOT_FLOATS] | gram[WS_ARRAY] | counter
-constexpr size_t WS_SLOTS = (size_t)2 * MAXNC * SLOT_FLOATS;
+constexpr int CSMAX = 16;
+constexpr int SLD = 128;   // leading dimension of the S replicas
+constexpr int NREP = 8;    // S replicas (spreads the atomics over L2 slices)
+constexpr int RMAX = kPanelMaxWidth;
 
-// ------------------------------------------------------------------ cluster / DSMEM PTX
+// ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ unsigned cluster_ctarank() {
     unsigned r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, unsigned rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster(uint32_t remote_addr, float v) {
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote_addr), "f"(v) : "memory");
+// remote 4-byte store that signals 4 bytes on the destination CTA's mbarrier
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_mbar) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
 }
-
-// Optional phase profiling (PanelArgs.dbg != null): CTA 0 / thread 0 accumulates clock64 deltas.
-// dbg[0]=pass dbg[1]=local reduce+publish dbg[2]=cluster barrier(s)+leader exchange dbg[3]=gather
-// dbg[4]=scalars dbg[5]=load dbg[6]=store dbg[7]=steps dbg[8]=G dbg[9]=rows_per_cta dbg[10]=gram+T
-// dbg[11]=CS dbg[12]=NC
-#define PROF_MARK(slot)                                               \
-    if (prof) {                                                       \
-        long long t__ = clock64();                                    \
-        pacc[slot] += t__ - tprev;                                    \
-        tprev = t__;                                                  \
-    }
-
-template <int CPL>
-struct RowVec;
-template <>
-struct RowVec<1> {
-    static __device__ __forceinline__ void load(const float* p, float (&x)[1]) { x[0] = p[0]; }
-    static __device__ __forceinline__ void store(float* p, const float (&x)[1]) { p[0] = x[0]; }
-};
-template <>
-struct RowVec<2> {
-    static __device__ __forceinline__ void load(const float* p, float (&x)[2]) {
-        float2 v = *reinterpret_cast<const float2*>(p);
-        x[0] = v.x; x[1] = v.y;
-    }
-    static __device__ __forceinline__ void store(float* p, const float (&x)[2]) {
-        *reinterpret_cast<float2*>(p) = make_float2(x[0], x[1]);
-    }
-};
-template <>
-struct RowVec<4> {
-    static __device__ __forceinline__ void load(const float* p, float (&x)[4]) {
-        float4 v = *reinterpret_cast<const float4*>(p);
-        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-    }
-    static __device__ __forceinline__ void store(float* p, const float (&x)[4]) {
-        *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
-    }
-};
-
-template <int CPL>
-__device__ __forceinline__ float pick(const float (&x)[CPL], int c) {
-    float v = x[0];
-#pragma unroll
-    for (int q = 1; q < CPL; ++q) v = (c == q) ? x[q] : v;
-    return v;
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}"
+        ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
 __device__ __forceinline__ void store16(void* base, long idx, float v, int bf16) {
     if (bf16) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
     else reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
 }
-
-// Shared-memory layout (floats):
-//   red[NW*PWP] | psum[PWP] | gsum[PWP] | prow[PWP] | diag[PWP] | gcol[2*PWP] | gt[PWP*(PWP+1)]
-//   | xslot[2][CSMAX][PWP] | xprow[2][PWP] | fin[2][2*PWP] | pad to 4 | slice[rows*PWP]
-template <int CPL>
-__host__ __device__ constexpr int fixed_floats() {
-    constexpr int PWP = 32 * CPL;
-    int f = NW * PWP + 6 * PWP + PWP * (PWP + 1) + 2 * CSMAX * PWP + 2 * PWP + 4 * PWP;
-    return (f + 3) & ~3;
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, int bf16) {
+    if (bf16) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&t);
+    }
+    __half2 t = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int CPL>
-__global__ void __launch_bounds__(NT, 1)
-panel_kernel(PanelArgs a, int rows_per_cta, int use_smem, int CS, int NC) {
-    constexpr int PWP = 32 * CPL;
-    constexpr int GLD = PWP + 1;
-    constexpr int NG = NT / PWP;                       // gather groups
-    extern __shared__ __align__(16) float smem[];
-    float* red = smem;
-    float* psum = red + NW * PWP;
-    float* gsum = psum + PWP;
-    float* prow = gsum + PWP;
-    float* diag = prow + PWP;
-    float* gcol = diag + PWP;                // 2 * PWP (double buffered)
-    float* gt = gcol + 2 * PWP;
-    float* xslot = gt + PWP * GLD;           // [2][CSMAX][PWP]  written by cluster peers
-    float* xprow = xslot + 2 * CSMAX * PWP;  // [2][PWP]         pivot row, written by its owner
-    float* fin = xprow + 2 * PWP;            // [2][2*PWP]       final dots | pivot row from the leader
-    float* slice_sm = smem + fixed_floats<CPL>();
+// One stage of the warp transpose-reduce: N values per lane -> N/2, partner = lane ^ OFF.
+template <int N, int OFF>
+__device__ __forceinline__ void tr_stage(float* acc, int lane) {
+    const bool hi = (lane & OFF) != 0;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const float send = hi ? acc[i] : acc[i + N / 2];
+        const float keep = hi ? acc[i + N / 2] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
+}
+// After the call lane l holds in acc[0] the warp sum of column (B == 32 ? l : l >> 1).
+template <int B>
+__device__ __forceinline__ void warp_transpose_reduce(float* acc, int lane) {
+    if (B == 32) {
+        tr_stage<32, 16>(acc, lane);
+        tr_stage<16, 8>(acc, lane);
+        tr_stage<8, 4>(acc, lane);
+        tr_stage<4, 2>(acc, lane);
+        tr_stage<2, 1>(acc, lane);
+    } else {
+        tr_stage<16, 16>(acc, lane);
+        tr_stage<8, 8>(acc, lane);
+        tr_stage<4, 4>(acc, lane);
+        tr_stage<2, 2>(acc, lane);
+        acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+    }
+}
+
+struct Out32 {
+    float* p;   // element (block row 0, block column 0); null = not wanted
+    long ld;
+    int zrows;  // rows above the block that must be zero-filled (p - zrows*ld is their first row)
+};
+struct Out16 {
+    void* p;
+    long ld;
+    int zrows;
+};
+
+struct BlockArgs {
+    float* A;   // element (block row 0, block column 0) of the packed FP32 master
+    long lda;
+    int D;      // rows of the block (m - first row)
+    int bw;     // columns (<= B)
+    Out32 Y32, W32;
+    Out16 Y16, W16;
+    int bf16;
+    float* T;   // bw x bw (ldt) upper triangular block T, or null
+    int ldt;
+    float* zero_buf;  // optional buffer to clear (S replicas of the following in-panel update)
+    int zero_n;
+    long long* dbg;   // optional phase timers (tools/panel_probe.py)
+};
+
+template <int B>
+__device__ __forceinline__ void load_row(const float* p, float (&x)[B], int bw, bool vec) {
+    if (vec && bw == B) {
+#pragma unroll
+        for (int q = 0; q < B / 4; ++q) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(p) + q);
+            x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < B; ++c) x[c] = (c < bw) ? __ldg(p + c) : 0.f;
+    }
+}
+template <int B>
+__device__ __forceinline__ void store_row32(float* p, const float (&x)[B], int bw, bool vec) {
+    if (vec && bw == B) {
+#pragma unroll
+        for (int q = 0; q < B / 4; ++q)
+            reinterpret_cast<float4*>(p)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < B; ++c)
+            if (c < bw) p[c] = x[c];
+    }
+}
+template <int B>
+__device__ __forceinline__ void store_row16(void* p, const float (&x)[B], int bw, bool vec, int bf16) {
+    if (vec && bw == B) {
+#pragma unroll
+        for (int q = 0; q < B / 8; ++q)
+            reinterpret_cast<uint4*>(p)[q] = make_uint4(pack16(x[8 * q], x[8 * q + 1], bf16), pack16(x[8 * q + 2], x[8 * q + 3], bf16),
+                                                        pack16(x[8 * q + 4], x[8 * q + 5], bf16), pack16(x[8 * q + 6], x[8 * q + 7], bf16));
+    } else {
+#pragma unroll
+        for (int c = 0; c < B; ++c)
+            if (c < bw) store16(p, c, x[c], bf16);
+    }
+}
+
+// dbg slots: 0 pass, 1 local reduce, 2 exchange wait, 3 gather+scalars, 4 load, 5 tail, 6 steps
+#define PROF_MARK(slot)                     \
+    if (prof) {                             \
+        long long t__ = clock64();          \
+        pacc[slot] += t__ - tprev;          \
+        tprev = t__;                        \
+    }
+
+template <int B, int RPT>
+__global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS) {
+    constexpr int LB = (B == 32) ? 0 : 1;  // lane -> column shift after the transpose-reduce
+    __shared__ __align__(16) float red[2][NW][B];
+    __shared__ __align__(16) float prow[2][B];
+    __shared__ __align__(16) float slot[2][CSMAX][B];
+    __shared__ __align__(16) float pslot[2][B];
+    __shared__ __align__(16) float tauS[NW][B];
+    __shared__ float gt[B][B + 1];
+    __shared__ float diag[B];
+    __shared__ __align__(8) uint64_t mbar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = CS * NC;
     const unsigned crank = (CS > 1) ? cluster_ctarank() : 0u;
-    const int cid = blockIdx.x / CS;  // cluster index
-    const int lam = a.lam, pw = a.pw;
-    const int D = a.m - lam;
-    const int kr = pw < D ? pw : D;  // reflectors in this panel
-    const int r0 = blockIdx.x * rows_per_cta;
-    const int r1 = (r0 + rows_per_cta < D) ? r0 + rows_per_cta : D;
-    const int nrows = r1 > r0 ? r1 - r0 : 0;
-    float* slice = use_smem ? slice_sm : a.scratch + (size_t)r0 * PWP;
-    float* slots = a.sync_ws;
-    float* gram_g = slots + WS_SLOTS;
-    unsigned* ctr = reinterpret_cast<unsigned*>(gram_g + WS_ARRAY);
+    const int D = a.D, bw = a.bw;
+    const int kr = bw < D ? bw : D;  // reflectors of this block
+    const int rbase = (int)crank * (NT * RPT) + tid;  // row of u = 0; row(u) = rbase + u*NT
     const long lda = a.lda;
-    float* Ablk = a.A + (size_t)lam * lda + a.acol;  // element (row lam, panel column 0)
-    unsigned bar_id = 0;
+    const bool vecA = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
 
     const bool prof = (a.dbg != nullptr) && blockIdx.x == 0 && tid == 0;
-    long long pacc[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // registers: no memory traffic while timing
+    long long pacc[7] = {0, 0, 0, 0, 0, 0, 0};
     long long tprev = prof ? clock64() : 0;
-    // ---- load the slice (coalesced along the panel row), zero-pad columns >= pw
-    for (int idx = tid; idx < nrows * PWP; idx += NT) {
-        int li = idx / PWP, c = idx - li * PWP;
-        slice[idx] = (c < pw) ? Ablk[(size_t)(r0 + li) * lda + c] : 0.f;
+
+    float x[RPT][B];
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const int i = rbase + u * NT;
+        if (i < D) {
+            load_row<B>(a.A + (size_t)i * lda, x[u], bw, vecA);
+        } else {
+#pragma unroll
+            for (int c = 0; c < B; ++c) x[u][c] = 0.f;
+        }
     }
-    // the Gram accumulator is used (atomically) only after >= 1 grid-wide sync: zero it here
-    if (G > 1)
-        for (int idx = blockIdx.x * NT + tid; idx < WS_ARRAY; idx += G * NT) gram_g[idx] = 0.f;
-    // peers must not write into our xslot before we are running: cluster-wide start barrier
+    for (int idx = tid; idx < B * (B + 1); idx += NT) (&gt[0][0])[idx] = 0.f;
+    if (a.zero_buf) {
+        const int nthr = CS * NT;
+        for (int idx = (int)crank * NT + tid; idx < a.zero_n; idx += nthr) a.zero_buf[idx] = 0.f;
+    }
     if (CS > 1) {
-        cluster_arrive();
-        cluster_wait();
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster_sync_all();  // peers must not signal a barrier that is not initialised yet
     } else {
         __syncthreads();
     }
-    PROF_MARK(5);
+    PROF_MARK(4);
 
-    float tau[CPL];
+    const uint32_t tx_bytes = (uint32_t)(CS + 1) * B * 4;
+    float tau[B];
 #pragma unroll
-    for (int q = 0; q < CPL; ++q) tau[q] = 0.f;
+    for (int j = 0; j < B; ++j) tau[j] = 0.f;
     float smu = 0.f, vinv = 0.f;
+    const int mycol = (lane >> LB) & (B - 1);  // column this lane owns after the reduce
 
-    // step s: apply reflector s-1 (if s > 0) and accumulate the dots of column s (if s < kr)
-    for (int step = 0; step <= kr; ++step) {
-        const int kprev = step - 1;
-        const bool do_upd = step > 0, do_dot = step < kr;
-        const int lk = do_upd ? kprev / CPL : 0, ck = do_upd ? kprev % CPL : 0;
-        const int ln = step / CPL, cn = step % CPL;
-        const int par = step & 1;
-        float acc[CPL];
+    // step s: apply reflector s-1 (s > 0), accumulate the dots of column s (s < kr)
 #pragma unroll
-        for (int q = 0; q < CPL; ++q) acc[q] = 0.f;
-
-        int li0 = kprev - r0;  // first slice row touched by this step
-        if (li0 < 0) li0 = 0;
-        // fixed warp <-> row mapping (row li belongs to warp li % NW); RI rows in flight
-        const int first = li0 + ((warp - li0) & (NW - 1));
-        // columns < kprev (< step when there is no update) are final: their lanes stay out of
-        // shared memory, which is the bandwidth that bounds this loop
-        const bool lane_on = (lane * CPL + CPL - 1) >= (do_upd ? kprev : step);
-        for (int lb = first; lb < nrows; lb += NW * RI) {
-            float x[RI][CPL];
-            bool ok[RI];
+    for (int s = 0; s <= B; ++s) {
+        if (s > kr) break;
+        float acc[B];
 #pragma unroll
-            for (int u = 0; u < RI; ++u) {
-                const int li = lb + u * NW;
-                ok[u] = li < nrows;
-                if (ok[u] && lane_on) {
-                    RowVec<CPL>::load(slice + (size_t)li * PWP + lane * CPL, x[u]);
-                } else {
+        for (int j = 0; j < B; ++j) acc[j] = 0.f;
 #pragma unroll
-                    for (int q = 0; q < CPL; ++q) x[u][q] = 0.f;
-                }
+        for (int u = 0; u < RPT; ++u) {
+            const int i = rbase + u * NT;
+            if (s > 0) {
+                const float xk = (i >= s - 1) ? x[u][s - 1] : 0.f;  // rows above hold R entries
+                const float vi = (i == s - 1) ? xk + smu : xk;
+#pragma unroll
+                for (int j = s; j < B; ++j) x[u][j] = fmaf(-vi, tau[j], x[u][j]);
+                if (i >= s - 1) x[u][s - 1] = vi * vinv;  // w in place (unshifted)
             }
-            if (do_upd) {
-                float xk[RI];
+            if (s < B) {
+                const float xs = (i >= s) ? x[u][s] : 0.f;
 #pragma unroll
-                for (int u = 0; u < RI; ++u) xk[u] = __shfl_sync(0xffffffffu, pick<CPL>(x[u], ck), lk);
-#pragma unroll
-                for (int u = 0; u < RI; ++u) {
-                    const int i = r0 + lb + u * NW;
-                    const float vi = (i == kprev) ? xk[u] + smu : xk[u];
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) x[u][q] = fmaf(-vi, tau[q], x[u][q]);
-                    if (lane == lk) {
-                        const float wv = vi * vinv;
-#pragma unroll
-                        for (int q = 0; q < CPL; ++q) x[u][q] = (q == ck) ? wv : x[u][q];
-                    }
-                    if (ok[u] && lane_on) RowVec<CPL>::store(slice + (size_t)(lb + u * NW) * PWP + lane * CPL, x[u]);
-                }
-            }
-            if (do_dot) {
-                float xn[RI];
-#pragma unroll
-                for (int u = 0; u < RI; ++u) xn[u] = __shfl_sync(0xffffffffu, pick<CPL>(x[u], cn), ln);
-#pragma unroll
-                for (int u = 0; u < RI; ++u) {
-                    const int i = r0 + lb + u * NW;
-                    const float xv = (ok[u] && i >= step) ? xn[u] : 0.f;
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) acc[q] = fmaf(xv, x[u][q], acc[q]);
-                }
+                for (int j = 0; j < B; ++j) acc[j] = fmaf(xs, x[u][j], acc[j]);
             }
         }
-        if (!do_dot) break;
-
+        if (s == kr) break;
+        if (s < B) {  // (always true here; keeps x[..][s] indices in range for the compiler)
+            const int par = s & 1;
+            PROF_MARK(0);
+            warp_transpose_reduce<B>(acc, lane);
+            if (LB == 0 || (lane & 1) == 0) red[par][warp][mycol] = acc[0];
+            if (crank == 0 && tid == s) {
 #pragma unroll
-        for (int q = 0; q < CPL; ++q) red[warp * PWP + lane * CPL + q] = acc[q];
-        __syncthreads();
-        PROF_MARK(0);
-        if (tid < PWP) {
-            float s = 0.f;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) s += red[w * PWP + tid];
-            if (G > 1) {
-                psum[tid] = s;
-            } else {
-                gsum[tid] = s;
-                prow[tid] = slice[(size_t)step * PWP + tid];
+                for (int j = 0; j < B; ++j) prow[par][j] = x[0][j];  // pivot row (row s is u = 0 of thread s)
             }
-        }
-        if (G > 1) {
+            if (CS > 1 && tid == 0) mbar_arrive_expect_tx(&mbar[par], tx_bytes);
             __syncthreads();
-            // ---- level 1: all-gather the partial vectors inside the cluster through DSMEM
+            float csum = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) csum += red[par][w][lane & (B - 1)];
+            float g, p;
             if (CS > 1) {
-                for (int idx = tid; idx < CS * PWP; idx += NT) {
-                    const int peer = idx / PWP, j = idx - peer * PWP;
-                    if (j >= step)
-                        st_cluster(map_to_cta(smem_addr(&xslot[(par * CSMAX + (int)crank) * PWP + j]), (unsigned)peer), psum[j]);
-                }
-                if (step >= r0 && step < r1) {  // this CTA owns the pivot row
-                    for (int idx = tid; idx < CS * PWP; idx += NT) {
-                        const int peer = idx / PWP, j = idx - peer * PWP;
-                        st_cluster(map_to_cta(smem_addr(&xprow[par * PWP + j]), (unsigned)peer),
-                                   slice[(size_t)(step - r0) * PWP + j]);
+                if (warp < CS) {
+                    const uint32_t rbar = map_to_cta(smem_addr(&mbar[par]), (unsigned)warp);
+                    if (B == 32) {
+                        st_async_f32(map_to_cta(smem_addr(&slot[par][crank][lane]), (unsigned)warp), csum, rbar);
+                        if (crank == 0)
+                            st_async_f32(map_to_cta(smem_addr(&pslot[par][lane]), (unsigned)warp), prow[par][lane], rbar);
+                    } else {
+                        if (lane < 16) st_async_f32(map_to_cta(smem_addr(&slot[par][crank][lane]), (unsigned)warp), csum, rbar);
+                        else if (crank == 0)
+                            st_async_f32(map_to_cta(smem_addr(&pslot[par][lane - 16]), (unsigned)warp), prow[par][lane - 16], rbar);
                     }
                 }
                 PROF_MARK(1);
-                cluster_arrive();
-                cluster_wait();
-                if (tid < PWP) {
-                    float t = 0.f;
-                    if (tid >= step)
-                        for (int c = 0; c < CS; ++c) t += xslot[(par * CSMAX + c) * PWP + tid];
-                    psum[tid] = t;  // cluster sum (identical in every CTA of the cluster)
-                }
-                __syncthreads();
+                mbar_wait_cluster(&mbar[par], (uint32_t)((s >> 1) & 1));
+                PROF_MARK(2);
+                g = 0.f;
+                for (int c = 0; c < CS; ++c) g += slot[par][c][lane & (B - 1)];
+                p = pslot[par][lane & (B - 1)];
             } else {
                 PROF_MARK(1);
+                g = csum;
+                p = prow[par][lane & (B - 1)];
             }
-            if (NC == 1) {
-                if (tid < PWP) {
-                    gsum[tid] = psum[tid];
-                    prow[tid] = xprow[par * PWP + tid];
-                }
-                PROF_MARK(2);
-            } else {
-                // ---- level 2: cluster leaders exchange through L2, then broadcast through DSMEM
-                const int oc = (step / rows_per_cta) / CS;  // cluster that owns the pivot row
-                ++bar_id;
-                if (crank == 0) {
-                    float* myslot = slots + ((size_t)par * MAXNC + cid) * SLOT_FLOATS;
-                    if (tid < PWP) {
-                        __stcg(&myslot[tid], psum[tid]);
-                        if (cid == oc) {
-                            const float pv = (CS > 1) ? xprow[par * PWP + tid] : slice[(size_t)(step - r0) * PWP + tid];
-                            __stcg(&myslot[WS_LD + tid], pv);
-                        }
-                    }
-                    __syncthreads();
-                    if (tid == 0) {
-                        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-                        const unsigned target = a.ctr_base + (unsigned)NC * bar_id;
-                        while ((int)(ld_acquire_gpu(ctr) - target) < 0) {
-                        }
-                    }
-                    __syncthreads();
-                    const float* sl = slots + (size_t)par * MAXNC * SLOT_FLOATS;
-                    const int j = tid % PWP, grp = tid / PWP;
-                    float s = 0.f;
-                    if (j >= step) {
-                        for (int c0 = grp; c0 < NC; c0 += NG * 8) {  // 8 L2 loads in flight
-                            float v[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const int c = c0 + u * NG;
-                                v[u] = (c < NC) ? __ldcg(&sl[(size_t)c * SLOT_FLOATS + j]) : 0.f;
-                            }
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) s += v[u];
-                        }
-                    }
-                    red[grp * PWP + j] = s;
-                    float pv = 0.f;
-                    if (tid < PWP) pv = __ldcg(&sl[(size_t)oc * SLOT_FLOATS + WS_LD + tid]);
-                    __syncthreads();
-                    if (tid < PWP) {
-                        float t = 0.f;
-#pragma unroll
-                        for (int gq = 0; gq < NG; ++gq) t += red[gq * PWP + tid];
-                        if (CS > 1) {
-                            fin[par * 2 * PWP + tid] = t;
-                            fin[par * 2 * PWP + PWP + tid] = pv;
-                        } else {
-                            gsum[tid] = t;
-                            prow[tid] = pv;
-                        }
-                    }
-                    if (CS > 1) {
-                        __syncthreads();
-                        for (int idx = tid; idx < (CS - 1) * 2 * PWP; idx += NT) {
-                            const int peer = 1 + idx / (2 * PWP), j2 = idx % (2 * PWP);
-                            st_cluster(map_to_cta(smem_addr(&fin[par * 2 * PWP + j2]), (unsigned)peer), fin[par * 2 * PWP + j2]);
-                        }
-                    }
-                }
-                if (CS > 1) {
-                    cluster_arrive();
-                    cluster_wait();
-                    if (tid < PWP) {
-                        gsum[tid] = fin[par * 2 * PWP + tid];
-                        prow[tid] = fin[par * 2 * PWP + PWP + tid];
-                    }
-                }
-                PROF_MARK(2);
+            // reflector scalars (every lane redundantly): MUFU.RSQ + one Newton step each
+            const float gk = __shfl_sync(0xffffffffu, g, s);
+            const float ak = __shfl_sync(0xffffffffu, p, s);
+            const bool skip = !(gk > 0.f);
+            const float rs = rsqrtf(skip ? 1.f : gk);
+            float mu = gk * rs;
+            mu = fmaf(0.5f * rs, fmaf(-mu, mu, gk), mu);  // sqrt(gk)
+            if (skip) mu = 0.f;
+            smu = (ak >= 0.f) ? mu : -mu;
+            const float vn2 = 2.f * mu * (mu + fabsf(ak));
+            float rv = rsqrtf(skip ? 1.f : vn2);
+            rv = rv * fmaf(-0.5f * vn2, rv * rv, 1.5f);  // 1/sqrt(vn2)
+            vinv = skip ? 0.f : rv;
+            const float inv2 = skip ? 0.f : 2.f * rv * rv;  // 2/vn2
+            const int col = lane & (B - 1);
+            const float t = fmaf(smu, p, g);
+            if (lane < B) tauS[warp][col] = (col > s && col < bw) ? t * inv2 : 0.f;
+            if (warp == 0 && lane < B) {
+                if (col < s) gt[col][s] = t * vinv;           // Gram entry y_col^T y_s
+                if (col == s) diag[s] = skip ? ak : -smu;     // R_ss
             }
-        } else {
-            PROF_MARK(1);
-        }
-        __syncthreads();
-        PROF_MARK(3);
-
-        // reflector scalars (every thread, redundantly): MUFU.RSQ + one Newton step each, i.e.
-        // full FP32 accuracy at a fraction of the latency of IEEE sqrt/div
-        const float gk = gsum[step], ak = prow[step];
-        const bool skip = !(gk > 0.f);
-        const float rs = rsqrtf(skip ? 1.f : gk);
-        float mu = gk * rs;
-        mu = fmaf(0.5f * rs, fmaf(-mu, mu, gk), mu);  // sqrt(gk)
-        if (skip) mu = 0.f;
-        smu = (ak >= 0.f) ? mu : -mu;
-        const float vn2 = 2.f * mu * (mu + fabsf(ak));
-        float rv = rsqrtf(skip ? 1.f : vn2);
-        rv = rv * fmaf(-0.5f * vn2, rv * rv, 1.5f);   // 1/sqrt(vn2)
-        vinv = skip ? 0.f : rv;
-        const float inv2 = skip ? 0.f : 2.f * rv * rv;  // 2/vn2
+            __syncwarp();
 #pragma unroll
-        for (int q = 0; q < CPL; ++q) {
-            int col = lane * CPL + q;
-            tau[q] = (col > step && col < pw) ? (gsum[col] + smu * prow[col]) * inv2 : 0.f;
+            for (int q = 0; q < B / 4; ++q) {
+                if (4 * q + 3 > s) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(&tauS[warp][4 * q]);
+                    tau[4 * q] = t4.x; tau[4 * q + 1] = t4.y; tau[4 * q + 2] = t4.z; tau[4 * q + 3] = t4.w;
+                }
+            }
+            PROF_MARK(3);
         }
-        if (skip) smu = 0.f;
-        if (tid == 0) diag[step] = skip ? ak : -smu;
-        PROF_MARK(4);
-        // (gsum/prow are rewritten only after the next pass's __syncthreads)
     }
     __syncthreads();
 
-    // ---- packed output: R above the diagonal, R_kk on it, w shifted one row down
-    for (int idx = tid; idx < nrows * PWP; idx += NT) {
-        int li = idx / PWP, c = idx - li * PWP;
-        if (c >= pw) continue;
-        int i = r0 + li;
-        float v = slice[idx];
-        if (i < c) {
-            Ablk[(size_t)i * lda + c] = v;
-        } else {
-            Ablk[(size_t)(i + 1) * lda + c] = v;
-            if (i == c) Ablk[(size_t)i * lda + c] = diag[c];
-        }
-    }
-    __syncthreads();
-    PROF_MARK(6);
-    if (prof) {
-        pacc[7] += kr; a.dbg[8] = G; a.dbg[9] = rows_per_cta; a.dbg[11] = CS; a.dbg[12] = NC;
-    }
-
-    const bool want16y = a.Y16 != nullptr, want16w = a.W16 != nullptr;
-    const bool need_t = a.T || a.W32 || want16w;
-    const int rofs = lam - a.blk_row0;  // output row of panel row 0
-    if (a.Y32 || want16y || need_t) {
-        // ---- slice := Y (zero strictly above the diagonal and for columns without reflector)
-        for (int idx = tid; idx < nrows * PWP; idx += NT) {
-            int li = idx / PWP, c = idx - li * PWP;
-            int i = r0 + li;
-            if (i < c || c >= kr) slice[idx] = 0.f;
-        }
-        __syncthreads();
-        for (int idx = tid; idx < nrows * PWP; idx += NT) {
-            int li = idx / PWP, c = idx - li * PWP;
-            if (c >= pw) continue;
-            long orow = rofs + r0 + li;
-            float v = slice[idx];
-            if (a.Y32) a.Y32[orow * a.ld32 + c] = v;
-            if (want16y) store16(a.Y16, orow * a.ldy16 + c, v, a.bf16);
-        }
-        // rows [blk_row0, lam) of the outputs are structurally zero
-        for (long idx = (long)blockIdx.x * NT + tid; idx < (long)rofs * pw; idx += (long)G * NT) {
-            long rr = idx / pw;
-            int c = (int)(idx - rr * pw);
-            if (a.Y32) a.Y32[rr * a.ld32 + c] = 0.f;
-            if (a.W32) a.W32[rr * a.ld32 + c] = 0.f;
-            if (want16y) store16(a.Y16, rr * a.ldy16 + c, 0.f, a.bf16);
-            if (want16w) store16(a.W16, rr * a.ldw16 + c, 0.f, a.bf16);
-        }
-    }
-    if (need_t) {
-        // ---- Gram matrix G[t][c] = sum_i y_it y_ic (strict upper part is what T needs)
-        for (int idx = tid; idx < PWP * GLD; idx += NT) gt[idx] = 0.f;
-        __syncthreads();
-        {
-            constexpr int NTC = PWP / 4, NTR = PWP / 8;
-            if (tid < NTR * NTC) {
-                const int tr = tid / NTC, tc = tid - tr * NTC;
-                if (8 * tr < 4 * tc + 3) {  // tile contains at least one (t < c)
-                    float g[8][4];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) g[u][v] = 0.f;
-                    int lstart = 4 * tc - r0;  // y_ic = 0 for i < c
-                    if (lstart < 0) lstart = 0;
-                    for (int li = lstart; li < nrows; ++li) {
-                        const float* row = slice + (size_t)li * PWP;
-                        float4 t0 = *reinterpret_cast<const float4*>(row + 8 * tr);
-                        float4 t1 = *reinterpret_cast<const float4*>(row + 8 * tr + 4);
-                        float4 cc = *reinterpret_cast<const float4*>(row + 4 * tc);
-                        float yt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-                        float yc[4] = {cc.x, cc.y, cc.z, cc.w};
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-#pragma unroll
-                            for (int v = 0; v < 4; ++v) g[u][v] = fmaf(yt[u], yc[v], g[u][v]);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            int t = 8 * tr + u, c = 4 * tc + v;
-                            if (t < c && c < kr) {
-                                if (G > 1) atomicAdd(&gram_g[t * WS_LD + c], g[u][v]);
-                                else gt[t * GLD + c] = g[u][v];
-                            }
-                        }
-                }
-            }
-        }
-        if (G > 1) {
-            // grid-wide sync: cluster barrier, leaders through L2, cluster barrier
-            if (CS > 1) {
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");  // order this CTA's global atomics
-                cluster_arrive();
-                cluster_wait();
-            } else {
-                __syncthreads();
-            }
-            if (NC > 1) {
-                ++bar_id;
-                if (crank == 0 && tid == 0) {
-                    asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-                    const unsigned target = a.ctr_base + (unsigned)NC * bar_id;
-                    while ((int)(ld_acquire_gpu(ctr) - target) < 0) {
-                    }
-                }
-                if (CS > 1) {
-                    cluster_arrive();
-                    cluster_wait();
-                } else {
-                    __syncthreads();
-                }
-            }
-            for (int idx = tid; idx < PWP * PWP; idx += NT) {
-                int t = idx / PWP, c = idx - t * PWP;
-                if (t < c && c < kr) gt[t * GLD + c] = __ldcg(&gram_g[t * WS_LD + c]);
-            }
-        }
-        __syncthreads();
-
-        // ---- T in place: column c of gt goes from G[0:c,c] to T[0:c,c]
+    // ---- T of the block by the larft recurrence (warp 0), in place in gt
+    if (warp == 0) {
         for (int c = 0; c < kr; ++c) {
-            float* gc = gcol + (c & 1) * PWP;
-            if (tid < c) gc[tid] = gt[tid * GLD + c];
-            __syncthreads();
-            const int t = tid >> 2, part = tid & 3;
-            float s = 0.f;
-            if (t < c)
-                for (int u = t + part; u < c; u += 4) s = fmaf(gt[t * GLD + u], gc[u], s);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (part == 0 && t < c) gt[t * GLD + c] = -2.f * s;
-            if (tid == c) gt[c * GLD + c] = 2.f;
-        }
-        __syncthreads();
-        if (a.T && blockIdx.x == 0) {
-            for (int idx = tid; idx < pw * pw; idx += NT) {
-                int t = idx / pw, c = idx - t * pw;
-                a.T[(size_t)t * a.ldt + c] = (t <= c && c < kr) ? gt[t * GLD + c] : 0.f;
-            }
-        }
-        PROF_MARK(10);
-        if (a.W32 || want16w) {
-            // ---- W = Y T on the slice rows; lane <-> columns lane + 32 q (conflict-free T reads)
-            for (int base = warp * 8; base < nrows; base += NW * 8) {
-                float w[8][CPL];
-#pragma unroll
-                for (int rr = 0; rr < 8; ++rr)
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) w[rr][q] = 0.f;
-                int tmax = r0 + base + 8;  // y_it = 0 for t > i
-                if (tmax > kr) tmax = kr;
-                for (int t = 0; t < tmax; ++t) {
-                    float tt[CPL];
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        int col = lane + 32 * q;
-                        tt[q] = (col >= t) ? gt[t * GLD + col] : 0.f;
-                    }
-#pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {
-                        int li = base + rr;
-                        float y = (li < nrows) ? slice[(size_t)li * PWP + t] : 0.f;
-#pragma unroll
-                        for (int q = 0; q < CPL; ++q) w[rr][q] = fmaf(y, tt[q], w[rr][q]);
-                    }
-                }
-#pragma unroll
-                for (int rr = 0; rr < 8; ++rr) {
-                    int li = base + rr;
-                    if (li >= nrows) continue;
-                    long orow = rofs + r0 + li;
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        int col = lane + 32 * q;
-                        if (col >= pw) continue;
-                        if (a.W32) a.W32[orow * a.ld32 + col] = w[rr][q];
-                        if (want16w) store16(a.W16, orow * a.ldw16 + col, w[rr][q], a.bf16);
-                    }
-                }
-            }
+            float sacc = 0.f;
+            if (lane < c)
+                for (int u2 = lane; u2 < c; ++u2) sacc = fmaf(gt[lane][u2], gt[u2][c], sacc);
+            __syncwarp();
+            if (lane < c) gt[lane][c] = -2.f * sacc;
+            if (lane == c) gt[c][c] = 2.f;
+            __syncwarp();
         }
     }
+    __syncthreads();
+
+    // ---- outputs
+    const bool want_w = a.W32.p || a.W16.p;
+    const bool vecY32 = a.Y32.p && ((a.Y32.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y32.p) & 15) == 0);
+    const bool vecW32 = a.W32.p && ((a.W32.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.W32.p) & 15) == 0);
+    const bool vecY16 = a.Y16.p && ((a.Y16.ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.Y16.p) & 15) == 0);
+    const bool vecW16 = a.W16.p && ((a.W16.ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.W16.p) & 15) == 0);
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const int i = rbase + u * NT;
+        if (i >= D) continue;
+        // packed factor: R above the diagonal, R_kk on it, w shifted one row down
+        if (i >= bw) {
+            store_row32<B>(a.A + (size_t)(i + 1) * lda, x[u], bw, vecA);
+        } else {
+#pragma unroll
+            for (int c = 0; c < B; ++c) {
+                if (c >= bw) continue;
+                if (i < c) {
+                    a.A[(size_t)i * lda + c] = x[u][c];
+                } else {
+                    a.A[(size_t)(i + 1) * lda + c] = x[u][c];
+                    if (i == c) a.A[(size_t)i * lda + c] = diag[c];
+                }
+            }
+        }
+        // Y: zero strictly above the diagonal and for columns without reflector
+        if (i < B) {
+#pragma unroll
+            for (int c = 0; c < B; ++c)
+                if (i < c) x[u][c] = 0.f;
+        }
+        if (a.Y32.p) store_row32<B>(a.Y32.p + (size_t)i * a.Y32.ld, x[u], bw, vecY32);
+        if (a.Y16.p) store_row16<B>((char*)a.Y16.p + (size_t)i * a.Y16.ld * 2, x[u], bw, vecY16, a.bf16);
+        if (want_w) {
+            float w[B];
+#pragma unroll
+            for (int c = 0; c < B; ++c) w[c] = 0.f;
+#pragma unroll
+            for (int t = 0; t < B; ++t) {
+                const float y = x[u][t];
+#pragma unroll
+                for (int c = t; c < B; ++c) w[c] = fmaf(y, gt[t][c], w[c]);
+            }
+            if (a.W32.p) store_row32<B>(a.W32.p + (size_t)i * a.W32.ld, w, bw, vecW32);
+            if (a.W16.p) store_row16<B>((char*)a.W16.p + (size_t)i * a.W16.ld * 2, w, bw, vecW16, a.bf16);
+        }
+    }
+    // rows above the block are structurally zero in the compact outputs
+    {
+        const int gtid = (int)crank * NT + tid, nthr = CS * NT;
+        if (a.Y32.p)
+            for (long idx = gtid; idx < (long)a.Y32.zrows * bw; idx += nthr) {
+                long rr = idx / bw; int c = (int)(idx - rr * bw);
+                a.Y32.p[(rr - a.Y32.zrows) * a.Y32.ld + c] = 0.f;
+            }
+        if (a.W32.p)
+            for (long idx = gtid; idx < (long)a.W32.zrows * bw; idx += nthr) {
+                long rr = idx / bw; int c = (int)(idx - rr * bw);
+                a.W32.p[(rr - a.W32.zrows) * a.W32.ld + c] = 0.f;
+            }
+        if (a.Y16.p)
+            for (long idx = gtid; idx < (long)a.Y16.zrows * bw; idx += nthr) {
+                long rr = idx / bw; int c = (int)(idx - rr * bw);
+                store16(a.Y16.p, (rr - a.Y16.zrows) * a.Y16.ld + c, 0.f, a.bf16);
+            }
+        if (a.W16.p)
+            for (long idx = gtid; idx < (long)a.W16.zrows * bw; idx += nthr) {
+                long rr = idx / bw; int c = (int)(idx - rr * bw);
+                store16(a.W16.p, (rr - a.W16.zrows) * a.W16.ld + c, 0.f, a.bf16);
+            }
+    }
+    if (a.T && crank == 0) {
+        for (int idx = tid; idx < bw * bw; idx += NT) {
+            int t = idx / bw, c = idx - t * bw;
+            a.T[(size_t)t * a.ldt + c] = (t <= c && c < kr) ? gt[t][c] : 0.f;
+        }
+    }
+    PROF_MARK(5);
     if (prof) {
-        for (int i = 0; i < 11; ++i) a.dbg[i] += pacc[i];
+        pacc[6] = kr;
+        for (int i = 0; i < 7; ++i) a.dbg[i] += pacc[i];
+        a.dbg[7] = CS; a.dbg[8] = RPT; a.dbg[9] = B;
     }
-    // a CTA's shared memory must stay alive until no peer can write into it any more
-    if (CS > 1) {
-        cluster_arrive();
-        cluster_wait();
+    // shared memory must stay alive until no peer can signal into it any more
+    if (CS > 1) cluster_sync_all();
+}
+
+// ------------------------------------------------------------------ level 1: in-panel update
+// S[rep][t][c] += sum_rows W[row][t] * A[row][c]   (FP32; B x ncols, rows split over the grid)
+template <int B>
+__global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict__ W, long ldw, const float* __restrict__ A,
+                                                         long lda, int D, int ncols, float* __restrict__ Srep, int rows_per_cta) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, c = tid & 127, rg = tid >> 7;
+    const int r0 = blockIdx.x * rows_per_cta;
+    int nrows = D - r0;
+    if (nrows > rows_per_cta) nrows = rows_per_cta;
+    if (nrows <= 0) return;
+    const int c0 = blockIdx.y * 128;
+    for (int idx = tid; idx < nrows * B; idx += 512) {
+        int rr = idx / B, t = idx - rr * B;
+        sm[idx] = W[(size_t)(r0 + rr) * ldw + t];
+    }
+    __syncthreads();
+    float acc[B];
+#pragma unroll
+    for (int t = 0; t < B; ++t) acc[t] = 0.f;
+    const bool on = (c0 + c) < ncols;
+    const float* Ac = A + (size_t)r0 * lda + c0 + c;
+    for (int rr = rg; rr < nrows; rr += 16) {
+        float av[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r2 = rr + 4 * u;
+            av[u] = (on && r2 < nrows) ? Ac[(size_t)r2 * lda] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r2 = rr + 4 * u;
+            if (r2 < nrows) {
+                const float* wr = sm + r2 * B;
+#pragma unroll
+                for (int q = 0; q < B / 4; ++q) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wr + 4 * q);
+                    acc[4 * q] = fmaf(w4.x, av[u], acc[4 * q]);
+                    acc[4 * q + 1] = fmaf(w4.y, av[u], acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(w4.z, av[u], acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(w4.w, av[u], acc[4 * q + 3]);
+                }
+            }
+        }
+    }
+    __syncthreads();  // W chunk no longer needed: reuse shared memory for the row-group reduction
+    if (rg > 0) {
+#pragma unroll
+        for (int t = 0; t < B; ++t) sm[((rg - 1) * B + t) * 128 + c] = acc[t];
+    }
+    __syncthreads();
+    if (rg == 0 && on) {
+        float* S = Srep + (size_t)(blockIdx.x % NREP) * RMAX * SLD;
+#pragma unroll
+        for (int t = 0; t < B; ++t) {
+            float v = acc[t] + sm[(0 * B + t) * 128 + c] + sm[(1 * B + t) * 128 + c] + sm[(2 * B + t) * 128 + c];
+            atomicAdd(&S[t * SLD + c0 + c], v);
+        }
     }
 }
 
-struct ClusterCaps {
-    int max_cs;    // largest usable cluster size (16, 8 or 1)
-    int max_nc16;  // co-resident clusters of 16 at full dynamic smem
-    int max_nc8;   // co-resident clusters of 8
-};
+// A[row][c] -= sum_t Y[row][t] * S[t][c],  S = sum of the replicas
+template <int B>
+__global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict__ Y, long ldy, float* __restrict__ A, long lda,
+                                                         int D, int ncols, const float* __restrict__ Srep, int rows_per_cta) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, c = tid & 127, rg = tid >> 7;
+    const int r0 = blockIdx.x * rows_per_cta;
+    int nrows = D - r0;
+    if (nrows > rows_per_cta) nrows = rows_per_cta;
+    if (nrows <= 0) return;
+    const int c0 = blockIdx.y * 128;
+    const bool on = (c0 + c) < ncols;
+    float s[B];
+#pragma unroll
+    for (int t = 0; t < B; ++t) {
+        float v = 0.f;
+        if (on) {
+#pragma unroll
+            for (int rep = 0; rep < NREP; ++rep) v += __ldcg(&Srep[(size_t)rep * RMAX * SLD + t * SLD + c0 + c]);
+        }
+        s[t] = v;
+    }
+    for (int idx = tid; idx < nrows * B; idx += 512) {
+        int rr = idx / B, t = idx - rr * B;
+        sm[idx] = Y[(size_t)(r0 + rr) * ldy + t];
+    }
+    __syncthreads();
+    if (!on) return;
+    float* Ac = A + (size_t)r0 * lda + c0 + c;
+    for (int rr = rg; rr < nrows; rr += 16) {
+        float av[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r2 = rr + 4 * u;
+            av[u] = (r2 < nrows) ? Ac[(size_t)r2 * lda] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r2 = rr + 4 * u;
+            if (r2 < nrows) {
+                const float* yr = sm + r2 * B;
+                float d = 0.f;
+#pragma unroll
+                for (int q = 0; q < B / 4; ++q) {
+                    const float4 y4 = *reinterpret_cast<const float4*>(yr + 4 * q);
+                    d = fmaf(y4.x, s[4 * q], d);
+                    d = fmaf(y4.y, s[4 * q + 1], d);
+                    d = fmaf(y4.z, s[4 * q + 2], d);
+                    d = fmaf(y4.w, s[4 * q + 3], d);
+                }
+                Ac[(size_t)r2 * lda] = av[u] - d;
+            }
+        }
+    }
+}
 
-template <int CPL>
-int query_caps(const DeviceInfo& di, ClusterCaps* out) {
-    static ClusterCaps caps = {0, 0, 0};
-    static bool done = false;
-    if (!done) {
-        MPQR_CUDA(cudaFuncSetAttribute(panel_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
-        cudaError_t e = cudaFuncSetAttribute(panel_kernel<CPL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        const bool np_ok = (e == cudaSuccess);
-        if (!np_ok) cudaGetLastError();
-        auto occ = [&](int cs) {
+// ------------------------------------------------------------------ level 2: T = (striu(G) + I/2)^-1
+// One CTA, recursive doubling: the 16 x 16 diagonal blocks are inverted column by column, then
+// T12 = -T11 (G12 T22) merges pairs of blocks (16 -> 32 -> 64 -> 128).  G is read from global
+// (ldg); T goes to T32 (pw x pw, zero below the diagonal) and optionally to a 16-bit copy.
+constexpr int TLD = RMAX + 1;
+__global__ void __launch_bounds__(1024) tinv_kernel(const float* __restrict__ G, long ldg, int pw, float* __restrict__ T32, int ldt,
+                                                     void* __restrict__ T16, long ldt16, int bf16) {
+    extern __shared__ __align__(16) float sm[];
+    float* Ts = sm;               // RMAX x TLD
+    float* Xs = sm + RMAX * TLD;  // 64 x 65 temp
+    const int tid = threadIdx.x;
+    int R = 16;
+    while (R < pw) R *= 2;
+    for (int idx = tid; idx < R * R; idx += 1024) {
+        int t = idx / R, c = idx - t * R;
+        Ts[t * TLD + c] = (t < c && c < pw) ? G[(size_t)t * ldg + c] : 0.f;
+    }
+    __syncthreads();
+    // diagonal blocks: thread (block b, column c) runs the larft recurrence restricted to the block
+    // column: x_c = 2, x_t = -2 * sum_{u=t+1..c} G[t][u] x_u  (back substitution of (striu(G)+I/2) x = e_c)
+    float xv[16];
+    const int b0 = tid & ~15, cc = tid & 15;
+    if (tid < R) {
+#pragma unroll
+        for (int t = 15; t >= 0; --t) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int u2 = t + 1; u2 < 16; ++u2)
+                if (u2 <= cc) sacc = fmaf(Ts[(b0 + t) * TLD + b0 + u2], xv[u2], sacc);
+            xv[t] = (t == cc) ? 2.f : ((t < cc) ? -2.f * sacc : 0.f);
+        }
+    }
+    __syncthreads();  // every column has read G before anyone overwrites it
+    if (tid < R) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+            if (t <= cc) Ts[(b0 + t) * TLD + b0 + cc] = xv[t];
+    }
+    __syncthreads();
+    for (int h = 16; h < R; h *= 2) {
+        // pairs (p): blocks [o, o+h) and [o+h, o+2h)
+        const int npairs = R / (2 * h);
+        // X = G12 * T22   (h x h per pair)
+        for (int idx = tid; idx < npairs * h * h; idx += 1024) {
+            const int pr = idx / (h * h), e = idx - pr * h * h;
+            const int i = e / h, j = e - i * h, o = pr * 2 * h;
+            float sacc = 0.f;
+            for (int u2 = 0; u2 <= j; ++u2) sacc = fmaf(Ts[(o + i) * TLD + o + h + u2], Ts[(o + h + u2) * TLD + o + h + j], sacc);
+            Xs[(pr * h + i) * 65 + j] = sacc;  // pr*h + i < 64 (npairs*h = R/2 <= 64)
+        }
+        __syncthreads();
+        // T12 = -T11 * X
+        for (int idx = tid; idx < npairs * h * h; idx += 1024) {
+            const int pr = idx / (h * h), e = idx - pr * h * h;
+            const int i = e / h, j = e - i * h, o = pr * 2 * h;
+            float sacc = 0.f;
+            for (int u2 = i; u2 < h; ++u2) sacc = fmaf(Ts[(o + i) * TLD + o + u2], Xs[(pr * h + u2) * 65 + j], sacc);
+            Ts[(o + i) * TLD + o + h + j] = -sacc;
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < pw * pw; idx += 1024) {
+        int t = idx / pw, c = idx - t * pw;
+        const float v = (t <= c) ? Ts[t * TLD + c] : 0.f;
+        if (T32) T32[(size_t)t * ldt + c] = v;
+        if (T16) store16(T16, (long)t * ldt16 + c, v, bf16);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+struct ClusterCaps {
+    int max_cs;
+};
+template <int B, int RPT>
+int prepare_kernel(int* max_cs) {
+    static int cached = 0;
+    if (!cached) {
+        cudaError_t e = cudaFuncSetAttribute(panel_block_kernel<B, RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        int mc = 8;
+        if (e == cudaSuccess) {
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(cs * 4);
+            cfg.gridDim = dim3(16);
             cfg.blockDim = dim3(NT);
-            cfg.dynamicSmemBytes = di.max_smem_optin;
+            cfg.dynamicSmemBytes = 0;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = cs;
+            at[0].val.clusterDim.x = 16;
             at[0].val.clusterDim.y = 1;
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, panel_kernel<CPL>, &cfg) != cudaSuccess) {
-                cudaGetLastError();
-                n = 0;
-            }
-            return n;
-        };
-        caps.max_nc16 = np_ok ? occ(16) : 0;
-        caps.max_nc8 = occ(8);
-        caps.max_cs = caps.max_nc16 > 0 ? 16 : (caps.max_nc8 > 0 ? 8 : 1);
-        done = true;
+            if (cudaOccupancyMaxActiveClusters(&n, panel_block_kernel<B, RPT>, &cfg) == cudaSuccess && n > 0) mc = 16;
+            else cudaGetLastError();
+        } else {
+            cudaGetLastError();
+        }
+        cached = mc;
     }
-    *out = caps;
+    *max_cs = cached;
     return MPQR_OK;
 }
 
-template <int CPL>
-int launch_t(const PanelArgs& a, cudaStream_t stream, const DeviceInfo& di) {
-    constexpr int PWP = 32 * CPL;
-    const int D = a.m - a.lam;
-    const size_t fixed = (size_t)fixed_floats<CPL>() * sizeof(float);
-    const int max_rows_smem = (int)(((size_t)di.max_smem_optin - fixed - 256) / (PWP * sizeof(float)));
-    const int cap = max_rows_smem - (max_rows_smem % NW);
-    ClusterCaps caps;
-    MPQR_TRY(query_caps<CPL>(di, &caps));
-    if (a.force_cs > 0 && a.force_cs < caps.max_cs) caps.max_cs = a.force_cs;
-    if (a.dbg_caps) { a.dbg_caps[0] = caps.max_cs; a.dbg_caps[1] = caps.max_nc16; a.dbg_caps[2] = caps.max_nc8; }
-    int rows_per_cta, CS = 1, NC = 1, use_smem = 1;
-    if (D <= cap && (D <= 256 || caps.max_cs == 1)) {
-        rows_per_cta = D;
-    } else {
-        // ~96 rows per CTA (the pass costs ~10 cycles/row/step with 4 rows in flight, a cluster
-        // barrier ~400), but never more than one cluster unless capacity forces it: a single
-        // cluster never touches L2 inside the column loop
-        const int need = ceil_div(D, cap);  // CTAs needed for capacity
-        int want = ceil_div(D, a.rows_hint > 0 ? a.rows_hint : 96);
-        if (want < need) want = need;
-        if (need <= caps.max_cs && !(a.force_cs == 1)) {
-            // fits one cluster: DSMEM all-gather + one hardware cluster barrier per column
-            // (measured ~1.0k cycles vs 4-8k for any exchange through L2, profiles/r1_panel_probe.txt)
-            CS = 1;
-            while (CS < want && CS < caps.max_cs) CS *= 2;
-            while (CS < need) CS *= 2;
-        } else {
-            // too tall for one cluster: flat exchange through L2 over as many CTAs as possible
-            // (the pass is issue-bound, ~10 cycles per row per step, so rows per CTA must be small)
-            CS = 1;
-            NC = ceil_div(D, a.rows_hint > 0 ? a.rows_hint : 64);
-            if (NC > di.num_sms) NC = di.num_sms;
-            if (NC > MAXNC) NC = MAXNC;
-            if (NC < need) {
-                use_smem = 0;
-                if (!a.scratch || a.scratch_rows < D) {
-                    set_error("panel: scratch buffer missing/too small for D=%d", D);
-                    return MPQR_EINVAL;
-                }
-            }
-        }
-        rows_per_cta = round_up(ceil_div(D, CS * NC), NW);
-        if (use_smem && rows_per_cta > cap) {
-            set_error("panel: internal sizing error D=%d CS=%d NC=%d rows=%d cap=%d", D, CS, NC, rows_per_cta, cap);
-            return MPQR_EINVAL;
-        }
-    }
-    const int G = CS * NC;
-    size_t smem = fixed + (use_smem ? (size_t)rows_per_cta * PWP * sizeof(float) : 0);
-    PanelArgs args = a;
-    if (NC > 1) {
-        // L2 barriers executed by the leaders: one per reflector + one for the Gram reduction
-        const int kr = a.pw < D ? a.pw : D;
-        const bool need_t = a.T || a.W32 || a.W16;
-        unsigned nbar = (unsigned)kr + (need_t ? 1u : 0u);
-        if (!a.host_ctr) {
-            set_error("panel: host_ctr missing");
-            return MPQR_EINVAL;
-        }
-        args.ctr_base = *a.host_ctr;
-        *a.host_ctr += (unsigned)NC * nbar;
-    }
+template <int B, int RPT>
+int launch_block_t(const BlockArgs& a, int CS, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(G);
+    cfg.gridDim = dim3(CS);
     cfg.blockDim = dim3(NT);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
-    cudaLaunchAttribute at[2];
+    cudaLaunchAttribute at[1];
     int na = 0;
     if (CS > 1) {
         at[na].id = cudaLaunchAttributeClusterDimension;
@@ -718,37 +686,230 @@ int launch_t(const PanelArgs& a, cudaStream_t stream, const DeviceInfo& di) {
         at[na].val.clusterDim.z = 1;
         ++na;
     }
-    if (NC > 1) {
-        // all clusters must be co-resident (leaders spin on an L2 counter)
-        at[na].id = cudaLaunchAttributeCooperative;
-        at[na].val.cooperative = 1;
-        ++na;
-    }
     cfg.attrs = at;
     cfg.numAttrs = na;
-    MPQR_CUDA(cudaLaunchKernelEx(&cfg, panel_kernel<CPL>, args, rows_per_cta, use_smem, CS, NC));
+    MPQR_CUDA(cudaLaunchKernelEx(&cfg, panel_block_kernel<B, RPT>, a, CS));
+    return MPQR_OK;
+}
+
+int g_max_cs = 0;
+int max_cluster() {
+    if (!g_max_cs) {
+        int a1, a2, a3, a4, a5;
+        prepare_kernel<16, 1>(&a1);
+        prepare_kernel<16, 2>(&a2);
+        prepare_kernel<16, 4>(&a3);
+        prepare_kernel<32, 1>(&a4);
+        prepare_kernel<32, 2>(&a5);
+        int mc = a1;
+        if (a2 < mc) mc = a2;
+        if (a3 < mc) mc = a3;
+        if (a4 < mc) mc = a4;
+        if (a5 < mc) mc = a5;
+        g_max_cs = mc;
+    }
+    return g_max_cs;
+}
+
+// rows a block kernel of width B can hold
+long block_capacity(int B) { return (long)max_cluster() * NT * (B == 32 ? 2 : 4); }
+
+// Picks (RPT, CS) for D rows; returns false if the block does not fit one cluster.
+bool pick_shape(int B, int D, int force_cs, int force_rpt, int* rpt, int* cs) {
+    const int mc = max_cluster();
+    const int max_rpt = (B == 32) ? 2 : 4;
+    if ((long)D > (long)mc * NT * max_rpt) return false;
+    int R = 1, C = 1;
+    if (D <= NT) { R = 1; C = 1; }
+    else if (D <= 2 * NT) { R = 2; C = 1; }
+    else {
+        // prefer one row per thread and more CTAs: the exchange costs the same for any CS > 1
+        R = 1;
+        C = 2;
+        while (C < mc && (long)C * NT * R < D) C *= 2;
+        while ((long)C * NT * R < D) R *= 2;
+    }
+    if (force_rpt > 0 && force_rpt <= max_rpt) {
+        R = force_rpt;
+        C = 1;
+        while ((long)C * NT * R < D && C < mc) C *= 2;
+        if ((long)C * NT * R < D) return false;
+    }
+    if (force_cs > 0 && force_cs <= mc) {
+        C = force_cs;
+        if (force_rpt <= 0) R = 1;
+        while ((long)C * NT * R < D && R < max_rpt) R *= 2;
+        if ((long)C * NT * R < D) return false;
+    }
+    *rpt = R;
+    *cs = C;
+    return true;
+}
+
+int launch_block(int B, const BlockArgs& a, int RPT, int CS, cudaStream_t st) {
+    if (B == 32) {
+        if (RPT == 1) return launch_block_t<32, 1>(a, CS, st);
+        return launch_block_t<32, 2>(a, CS, st);
+    }
+    if (RPT == 1) return launch_block_t<16, 1>(a, CS, st);
+    if (RPT == 2) return launch_block_t<16, 2>(a, CS, st);
+    return launch_block_t<16, 4>(a, CS, st);
+}
+
+// workspace layout (floats): Y32p [rows x RMAX] | Wj [rows x 32] | Srep [NREP x RMAX x SLD] | G [RMAX x RMAX] |
+// T32 [RMAX x RMAX] | T16 [RMAX x RMAX 16-bit]
+struct Ws {
+    float* Y32p;
+    float* Wj;
+    float* Srep;
+    float* G;
+    float* T32;
+    void* T16;
+};
+Ws carve(float* ws, long rows) {
+    Ws w;
+    w.Y32p = ws;
+    w.Wj = w.Y32p + (size_t)rows * RMAX;
+    w.Srep = w.Wj + (size_t)rows * 32;
+    w.G = w.Srep + (size_t)NREP * RMAX * SLD;
+    w.T32 = w.G + (size_t)RMAX * RMAX;
+    w.T16 = (void*)(w.T32 + (size_t)RMAX * RMAX);
+    return w;
+}
+
+template <int B>
+int launch_su(const float* Wj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, int num_sms,
+              cudaStream_t st, long* launches) {
+    static bool attr = false;
+    const int max_rows = 256;
+    int rows = ceil_div(D, num_sms);
+    rows = round_up(rows < 16 ? 16 : rows, 16);
+    if (rows > max_rows) rows = max_rows;
+    const size_t smem_s = (size_t)((rows * B > 3 * B * 128) ? rows * B : 3 * B * 128) * sizeof(float);
+    const size_t smem_u = (size_t)rows * B * sizeof(float);
+    if (!attr) {
+        MPQR_CUDA(cudaFuncSetAttribute(inpanel_s_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 32 * 128 * 4));
+        attr = true;
+    }
+    dim3 grid(ceil_div(D, rows), ceil_div(ncols, 128));
+    inpanel_s_kernel<B><<<grid, 512, smem_s, st>>>(Wj, B, Arest, lda, D, ncols, Srep, rows);
+    MPQR_CUDA(cudaGetLastError());
+    inpanel_u_kernel<B><<<grid, 512, smem_u, st>>>(Yj, ldy, Arest, lda, D, ncols, Srep, rows);
+    MPQR_CUDA(cudaGetLastError());
+    if (launches) *launches += 2;
     return MPQR_OK;
 }
 
 }  // namespace
 
-size_t panel_sync_ws_bytes() { return (WS_SLOTS + WS_ARRAY) * sizeof(float) + 256; }
-size_t panel_scratch_bytes(int max_rows) { return (size_t)max_rows * kPanelMaxWidth * sizeof(float); }
+size_t panel_ws_bytes(long max_rows) {
+    return ((size_t)max_rows * (RMAX + 32) + (size_t)NREP * RMAX * SLD + 2 * (size_t)RMAX * RMAX) * sizeof(float) +
+           (size_t)RMAX * RMAX * 2 + 256;
+}
 
+// PanelArgs output pointers address (row blk_row0, first panel column); zr = lam - blk_row0 rows
+// above the panel are structurally zero.
 int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
-    if (a.pw < 1 || a.pw > kPanelMaxWidth || a.lam < 0 || a.acol < 0 || a.lam >= a.m ||
-        a.blk_row0 > a.lam) {
+    if (a.pw < 1 || a.pw > kPanelMaxWidth || a.lam < 0 || a.acol < 0 || a.lam >= a.m || a.blk_row0 > a.lam) {
         set_error("panel: bad arguments lam=%d pw=%d m=%d n=%d", a.lam, a.pw, a.m, a.n);
         return MPQR_EINVAL;
     }
     DeviceInfo di;
     MPQR_TRY(get_device_info(&di));
-    int rc;
-    if (a.pw <= 32) rc = launch_t<1>(a, stream, di);
-    else if (a.pw <= 64) rc = launch_t<2>(a, stream, di);
-    else rc = launch_t<4>(a, stream, di);
-    if (rc == MPQR_OK && launches) *launches += 1;
-    return rc;
+    const int D = a.m - a.lam, pw = a.pw;
+    // register-block width: 32 columns when two rows per thread are enough, else 16
+    int B = (a.force_b == 16 || a.force_b == 32) ? a.force_b : ((pw > 16 && (long)D <= block_capacity(32)) ? 32 : 16);
+    if ((long)D > block_capacity(B)) {
+        if ((long)D <= block_capacity(16)) B = 16;
+        else return launch_panel_legacy(a, stream, launches);
+    }
+    const int nblk = ceil_div(pw, B);
+    const int zr = a.lam - a.blk_row0;
+    float* Ablk = a.A + (size_t)a.lam * a.lda + a.acol;
+    // outputs at panel row 0 (= global row lam)
+    float* Y32l = a.Y32 ? a.Y32 + (size_t)zr * a.ld32 : nullptr;
+    float* W32l = a.W32 ? a.W32 + (size_t)zr * a.ld32 : nullptr;
+    char* Y16l = a.Y16 ? (char*)a.Y16 + (size_t)zr * a.ldy16 * 2 : nullptr;
+    char* W16l = a.W16 ? (char*)a.W16 + (size_t)zr * a.ldw16 * 2 : nullptr;
+    int rpt = 1, cs = 1;
+
+    if (nblk == 1) {
+        if (!pick_shape(B, D, a.force_cs, a.force_rpt, &rpt, &cs)) { set_error("panel: sizing error D=%d", D); return MPQR_EINVAL; }
+        BlockArgs b{};
+        b.A = Ablk; b.lda = a.lda; b.D = D; b.bw = pw;
+        b.Y32 = {Y32l, a.ld32, zr}; b.W32 = {W32l, a.ld32, zr};
+        b.Y16 = {Y16l, a.ldy16, zr}; b.W16 = {W16l, a.ldw16, zr};
+        b.bf16 = a.bf16; b.T = a.T; b.ldt = a.ldt; b.dbg = a.dbg;
+        MPQR_TRY(launch_block(B, b, rpt, cs, stream));
+        if (a.dbg_caps) { a.dbg_caps[0] = max_cluster(); a.dbg_caps[1] = cs; a.dbg_caps[2] = rpt; }
+        if (launches) *launches += 1;
+        return MPQR_OK;
+    }
+
+    if (!a.ws || a.ws_rows < D) {
+        set_error("panel: workspace missing/too small (pw=%d needs %d blocks, D=%d, ws_rows=%ld)", pw, nblk, D, a.ws ? a.ws_rows : 0L);
+        return MPQR_EINVAL;
+    }
+    const bool mixed = a.Y16 && a.W16;
+    const bool need_t = a.T || a.W32 || a.W16;
+    if (need_t && !mixed && a.W32 && !a.Y32) { set_error("panel: W32 needs Y32 on the FP32 path"); return MPQR_EINVAL; }
+    if (mixed && !a.W32) { set_error("panel: the mixed path needs the FP32 W master"); return MPQR_EINVAL; }
+    Ws w = carve(a.ws, a.ws_rows);
+    // FP32 Y of the whole panel: caller's array if given, else the workspace
+    float* Yp = Y32l ? Y32l : w.Y32p;
+    const long ldyp = Y32l ? a.ld32 : RMAX;
+    for (int jb = 0; jb < nblk; ++jb) {
+        const int j0 = jb * B;
+        const int bw = (j0 + B < pw) ? B : pw - j0;
+        const int Dj = D - j0;
+        if (Dj <= 0) break;
+        if (!pick_shape(B, Dj, a.force_cs, a.force_rpt, &rpt, &cs)) { set_error("panel: sizing error D=%d", Dj); return MPQR_EINVAL; }
+        const int nrest = pw - (j0 + bw);
+        BlockArgs b{};
+        b.A = Ablk + (size_t)j0 * a.lda + j0; b.lda = a.lda; b.D = Dj; b.bw = bw;
+        b.Y32 = {Yp + (size_t)j0 * ldyp + j0, ldyp, j0 + (Y32l ? zr : 0)};
+        if (nrest > 0) b.W32 = {w.Wj, B, 0};
+        if (Y16l) b.Y16 = {Y16l + ((size_t)j0 * a.ldy16 + j0) * 2, a.ldy16, j0 + zr};
+        b.bf16 = a.bf16; b.dbg = a.dbg;
+        if (nrest > 0) { b.zero_buf = w.Srep; b.zero_n = NREP * RMAX * SLD; }
+        MPQR_TRY(launch_block(B, b, rpt, cs, stream));
+        if (launches) *launches += 1;
+        if (nrest > 0) {
+            float* Arest = b.A + bw;
+            if (B == 32) MPQR_TRY(launch_su<32>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, di.num_sms, stream, launches));
+            else MPQR_TRY(launch_su<16>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, di.num_sms, stream, launches));
+        }
+    }
+    if (a.dbg_caps) { a.dbg_caps[0] = max_cluster(); a.dbg_caps[1] = cs; a.dbg_caps[2] = rpt; }
+    if (!need_t) return MPQR_OK;
+
+    static bool tattr = false;
+    const size_t tsmem = ((size_t)RMAX * TLD + 64 * 65) * sizeof(float);
+    if (!tattr) {
+        MPQR_CUDA(cudaFuncSetAttribute(tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        tattr = true;
+    }
+    const int Dz = D + zr;  // W is produced from the enclosing block's first row on (zero rows of Y give zero rows of W)
+    float* Tdst = a.T ? a.T : w.T32;
+    const int ldt = a.T ? a.ldt : RMAX;
+    if (mixed) {
+        // Gram and W on tensor cores, from the 16-bit Y the trailing update uses
+        MPQR_TRY(tc_gemm_tn(Y16l, a.ldy16, Y16l, a.ldy16, w.G, RMAX, pw, pw, D, a.bf16, 1, stream, launches));
+        tinv_kernel<<<1, 1024, tsmem, stream>>>(w.G, RMAX, pw, Tdst, ldt, w.T16, RMAX, a.bf16);
+        MPQR_CUDA(cudaGetLastError());
+        if (launches) *launches += 1;
+        MPQR_TRY(tc_gemm_nn_store(a.Y16, a.ldy16, w.T16, RMAX, a.W32, a.ld32, a.W16, a.ldw16, Dz, pw, pw, a.bf16, stream, launches));
+    } else {
+        MPQR_TRY(sgemm_tn(Yp, ldyp, Yp, ldyp, w.G, RMAX, pw, pw, D, stream, launches));
+        tinv_kernel<<<1, 1024, tsmem, stream>>>(w.G, RMAX, pw, Tdst, ldt, nullptr, 0, 0);
+        MPQR_CUDA(cudaGetLastError());
+        if (launches) *launches += 1;
+        if (a.W32) {
+            MPQR_TRY(sgemm_nn_store(a.Y32, a.ld32, Tdst, ldt, a.W32, a.ld32, Dz, pw, pw, stream));
+            if (launches) *launches += 1;
+        }
+    }
+    return MPQR_OK;
 }
 
 }  // namespace mpqr

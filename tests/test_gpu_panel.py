@@ -41,7 +41,19 @@ def test_panel_vs_oracle(m, n, lam, pw):
 
 
 def test_panel_large_multi_cta():
+    # taller than one cluster can hold in registers: shared-memory fallback kernel
     _check_panel(40000, 128, 0, 128, seed=3, tol=5e-5)
+
+
+@pytest.mark.parametrize("m,n,lam,pw", [
+    (9000, 128, 0, 128),      # 32-wide register blocks, cluster of 16 + 2 rows/thread
+    (20000, 128, 0, 128),     # 16-wide register blocks, 4 rows/thread
+    (32768, 64, 0, 64),       # capacity limit of one cluster
+    (3000, 96, 32, 50),       # ragged block widths (32 + 18)
+    (700, 40, 0, 40),
+])
+def test_panel_register_blocks_tall(m, n, lam, pw):
+    _check_panel(m, n, lam, pw, seed=m + pw, tol=5e-5)
 
 
 def test_panel_zero_column_and_signs():

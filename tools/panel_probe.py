@@ -1,28 +1,28 @@
-"""Phase profile of the panel kernel (clock64 deltas of CTA 0): python tools/panel_probe.py m pw [rows_hint ...]"""
+"""Phase profile of the register-resident panel block kernel (clock64 deltas of CTA 0, thread 0).
+python tools/panel_probe.py m,pw[,B,CS,RPT,wy] ...   (0 = automatic)"""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import mixedprecisionblockqr_b200 as pkg
 
 L = pkg.lib()
-L.mpqr_debug_panel_probe.argtypes = [ctypes.c_void_p, ctypes.c_long] + [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_void_p]
-names = ["pass", "reduce+publish", "exchange", "gather", "scalars", "load", "store", "steps", "G", "rows", "tail(gram+T)", "CS", "NC"]
-clk = torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 0
+L.mpqr_debug_panel_probe.argtypes = [ctypes.c_void_p, ctypes.c_long] + [ctypes.c_int] * 8 + [ctypes.c_void_p, ctypes.c_void_p]
+names = ["pass", "reduce", "exchange", "gather+scalars"]
 for spec in sys.argv[1:]:
-    m, pw, hint, wy, fcs = (list(map(int, spec.split(","))) + [0, 0, 0])[:5]
+    m, pw, fb, fcs, frpt, wy = (list(map(int, spec.split(","))) + [0, 0, 0, 0])[:6]
     n = pw
     A = torch.rand(m + 1, n, device="cuda")
-    for rep in range(2):
+    best = 1e9
+    for rep in range(3):
         dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
         B = A.clone()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        e0.record()
-        pkg.check(L.mpqr_debug_panel_probe(B.data_ptr(), n, m, n, 0, pw, hint, fcs, wy, dbg.data_ptr(), torch.cuda.current_stream().cuda_stream))
-        e1.record()
+        pkg.check(L.mpqr_debug_panel_probe(B.data_ptr(), n, m, n, 0, pw, fb, fcs, frpt, wy, dbg.data_ptr(), torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
     d = dbg.cpu().tolist()
-    steps = max(1, d[7])
-    per = {names[i]: d[i] / steps for i in range(5)}
-    print(f"m={m} pw={pw} G={d[8]} CS={d[11]} NC={d[12]} rows/cta={d[9]} wy={wy}: per-step cycles " + " ".join(f"{k}={v:.0f}" for k, v in per.items())
-          + f" caps(cs,nc16,nc8)={d[13:16]} | total/step={sum(per.values()):.0f} | load={d[5]} store={d[6]} tail={d[10]} | event(ms incl. alloc)={e0.elapsed_time(e1):.3f}", flush=True)
+    steps = max(1, d[6])
+    nblk = max(1, (pw + d[9] - 1) // max(1, d[9]))
+    per = {names[i]: d[i] / (steps * nblk) * 1.0 for i in range(4)}
+    print(f"m={m} pw={pw} B={d[9]} CS={d[7]} RPT={d[8]} (caps max_cs,cs,rpt={d[13:16]}): per-step cycles "
+          + " ".join(f"{k}={v:.0f}" for k, v in per.items())
+          + f" | total/step={sum(per.values()):.0f} | load={d[4] / nblk:.0f} tail={d[5] / nblk:.0f} (sum over {nblk} blocks / nblk; steps/blk={steps})", flush=True)
