@@ -176,7 +176,7 @@ int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         a.Y32 = Y; a.W32 = W; a.ld32 = ld;
         a.T = h->T + (size_t)p * r * r; a.ldt = r;
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
-        a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows;
+        a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         if (nt > 0) {
             float* A22 = A + (size_t)lam * lda + tau;
@@ -243,7 +243,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         a.bf16 = bf;
         a.T = h->T + (size_t)p * r * r; a.ldt = r;
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
-        a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows;
+        a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         const int nin = c1 - tau;  // in-block trailing columns
         const int acol_tau = c.acol0 + jc + pw;
@@ -329,8 +329,7 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
         if ((rc = dev_alloc(h, (void**)&h->sync_ws, panel_sync_ws_bytes()))) break;
         if (cudaMemset(h->sync_ws, 0, panel_sync_ws_bytes()) != cudaSuccess) { set_error("memset failed"); rc = MPQR_ECUDA; break; }
         // panel scratch only needed when a panel slice cannot live in shared memory
-        long rows_fit = (long)di.num_sms * 288;
-        if (m > rows_fit) {
+        if (m > 32768) {  // only the shared-memory fallback kernel (panel_legacy.cu) needs it
             h->scratch_rows = m;
             if ((rc = dev_alloc(h, (void**)&h->scratch, panel_scratch_bytes(m)))) break;
         }
@@ -473,6 +472,7 @@ int mpqr_set_profiling(mpqr_handle* h, int on) {
     h->prof_recs.clear();
     for (int c = 0; c < MPQR_NUM_KERNEL_CLASSES; ++c) h->prof_flops[c] = h->prof_bytes[c] = 0;
     h->prof = on != 0;
+    h->hook = {h, hook_begin, hook_end};
     return MPQR_OK;
 }
 
@@ -543,7 +543,7 @@ int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
     }
     unsigned host_ctr = 0;
     long scratch_rows = 0;
-    if (m - lam > (long)di.num_sms * 288) {
+    if (m - lam > 32768) {
         scratch_rows = m;
         if (cudaMalloc(&scratch, panel_scratch_bytes(m)) != cudaSuccess) {
             cudaFree(ws); cudaFree(pws);

@@ -49,6 +49,13 @@ size_t panel_sync_ws_bytes();
 // Scratch for the non-shared-memory-resident variant: rows x 128 floats.
 size_t panel_scratch_bytes(int max_rows);
 
+// optional per-launch event hook (internal.h implements it on the handle's profiler)
+struct ProfHook {
+    void* ctx;
+    void (*begin)(void* ctx, int cls, cudaStream_t st);
+    void (*end)(void* ctx, cudaStream_t st);
+};
+
 struct PanelArgs {
     float* A;      // packed master, (m+1) x lda
     long lda;
@@ -82,6 +89,7 @@ struct PanelArgs {
     long ws_rows;       // rows the workspace was sized for
     int force_b;        // 16 / 32: override the register-block width (tuning / tests)
     int force_rpt;      // > 0: override the rows per thread (tuning / tests)
+    const ProfHook* prof;  // optional: sub-classes 4 (block kernels), 5 (in-panel S/U), 6 (Gram/T/W)
 };
 size_t panel_ws_bytes(long max_rows);
 int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches);

@@ -51,8 +51,9 @@ struct mpqr_handle {
     struct ProfRec { int cls; cudaEvent_t e0, e1; };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
-    double prof_flops[MPQR_NUM_KERNEL_CLASSES] = {0, 0, 0, 0};
-    double prof_bytes[MPQR_NUM_KERNEL_CLASSES] = {0, 0, 0, 0};
+    double prof_flops[MPQR_NUM_KERNEL_CLASSES] = {};
+    double prof_bytes[MPQR_NUM_KERNEL_CLASSES] = {};
+    mpqr::ProfHook hook{};  // filled by mpqr_set_profiling
 
     std::vector<void*> allocs;
 };
@@ -91,6 +92,26 @@ struct ProfScope {
         ProfScope ps__(h, cls, st, flops, bytes);             \
         MPQR_TRY(call);                                       \
     } while (0)
+
+// ProfHook implementation on the handle (used by launch_panel for its sub-classes)
+inline void hook_begin(void* ctx, int cls, cudaStream_t st) {
+    mpqr_handle* h = (mpqr_handle*)ctx;
+    if (!h->prof) return;
+    cudaEvent_t e0, e1;
+    auto get = [&](cudaEvent_t* e) {
+        if (!h->prof_pool.empty()) { *e = h->prof_pool.back(); h->prof_pool.pop_back(); }
+        else cudaEventCreate(e);
+    };
+    get(&e0);
+    get(&e1);
+    cudaEventRecord(e0, st);
+    h->prof_recs.push_back({cls, e0, e1});
+}
+inline void hook_end(void* ctx, cudaStream_t st) {
+    mpqr_handle* h = (mpqr_handle*)ctx;
+    if (!h->prof || h->prof_recs.empty()) return;
+    cudaEventRecord(h->prof_recs.back().e1, st);
+}
 
 inline double tn_bytes(double M, double N, double K) { return 2.0 * K * (M + N) + 4.0 * M * N; }
 inline double nn_bytes(double M, double N, double K) { return 10.0 * M * N + 2.0 * K * (M + N); }

@@ -36,7 +36,7 @@ int sgemm_nn_store(const float* X, long ldx, const float* S, long lds, float* C,
 
 namespace {
 
-constexpr int NT = 512;
+constexpr int NT = 256;
 constexpr int NW = NT / 32;
 constexpr int CSMAX = 16;
 constexpr int SLD = 128;   // leading dimension of the S replicas
@@ -63,6 +63,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, unsigned ran
 __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
                  ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(remote_addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                   "r"(__float_as_uint(v.w)), "r"(remote_mbar) : "memory");
 }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
@@ -117,6 +122,56 @@ __device__ __forceinline__ void warp_transpose_reduce(float* acc, int lane) {
         tr_stage<4, 4>(acc, lane);
         tr_stage<2, 2>(acc, lane);
         acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+    }
+}
+
+// T = (striu(G) + I/2)^-1 in shared memory, all NT threads: 8 x 8 diagonal blocks by back
+// substitution from registers (x_c = 2, x_t = -2 sum_{u=t+1..c} G[t][u] x_u), then pairs of
+// blocks are merged, T12 = -T11 (G12 T22), 8 -> 16 -> 32.  gt: B x LD, strictly upper = G.
+template <int B, int LD>
+__device__ __forceinline__ void tinv_smem(float (*gt)[LD], float* xs, int tid) {
+    float xv[8];
+    const int b0 = tid & ~7, cc = tid & 7;
+    if (tid < B) {
+        float g[8][8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+#pragma unroll
+            for (int u2 = t + 1; u2 < 8; ++u2) g[t][u2] = gt[b0 + t][b0 + u2];
+#pragma unroll
+        for (int t = 7; t >= 0; --t) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int u2 = t + 1; u2 < 8; ++u2)
+                if (u2 <= cc) sacc = fmaf(g[t][u2], xv[u2], sacc);
+            xv[t] = (t == cc) ? 2.f : ((t < cc) ? -2.f * sacc : 0.f);
+        }
+    }
+    __syncthreads();  // every column has read G before anyone overwrites it
+    if (tid < B) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            if (t <= cc) gt[b0 + t][b0 + cc] = xv[t];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 8; h < B; h *= 2) {
+        // pairs of blocks [o, o+h) and [o+h, o+2h); B*h/2 <= NT outputs per matrix product
+        const int pr = tid / (h * h), e = tid - pr * h * h;
+        const int i = e / h, j = e - i * h, o = pr * 2 * h;
+        const bool on = tid < (B / (2 * h)) * h * h;
+        if (on) {
+            float sacc = 0.f;
+            for (int u2 = 0; u2 <= j; ++u2) sacc = fmaf(gt[o + i][o + h + u2], gt[o + h + u2][o + h + j], sacc);
+            xs[tid] = sacc;  // X = G12 T22, element (pr, i, j)
+        }
+        __syncthreads();
+        if (on) {
+            float sacc = 0.f;
+            for (int u2 = i; u2 < h; ++u2) sacc = fmaf(gt[o + i][o + u2], xs[pr * h * h + u2 * h + j], sacc);
+            gt[o + i][o + h + j] = -sacc;
+        }
+        __syncthreads();
     }
 }
 
@@ -185,7 +240,8 @@ __device__ __forceinline__ void store_row16(void* p, const float (&x)[B], int bw
     }
 }
 
-// dbg slots: 0 pass, 1 local reduce, 2 exchange wait, 3 gather+scalars, 4 load, 5 tail, 6 steps
+// dbg slots: 0 pass, 1 shuffle tree, 2 smem + CTA barrier, 3 CTA sum + send, 4 exchange wait, 5 gather+scalars,
+// 6 load, 7 tail, 8 steps, 9 CS, 10 RPT, 11 B
 #define PROF_MARK(slot)                     \
     if (prof) {                             \
         long long t__ = clock64();          \
@@ -200,8 +256,9 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
     __shared__ __align__(16) float prow[2][B];
     __shared__ __align__(16) float slot[2][CSMAX][B];
     __shared__ __align__(16) float pslot[2][B];
+    __shared__ __align__(16) float csumS[2][B];
     __shared__ __align__(16) float tauS[NW][B];
-    __shared__ float gt[B][B + 1];
+    __shared__ __align__(16) float gt[B][B + 4];
     __shared__ float diag[B];
     __shared__ __align__(8) uint64_t mbar[2];
 
@@ -214,7 +271,7 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
     const bool vecA = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
 
     const bool prof = (a.dbg != nullptr) && blockIdx.x == 0 && tid == 0;
-    long long pacc[7] = {0, 0, 0, 0, 0, 0, 0};
+    long long pacc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = prof ? clock64() : 0;
 
     float x[RPT][B];
@@ -228,7 +285,7 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
             for (int c = 0; c < B; ++c) x[u][c] = 0.f;
         }
     }
-    for (int idx = tid; idx < B * (B + 1); idx += NT) (&gt[0][0])[idx] = 0.f;
+    for (int idx = tid; idx < B * (B + 4); idx += NT) (&gt[0][0])[idx] = 0.f;
     if (a.zero_buf) {
         const int nthr = CS * NT;
         for (int idx = (int)crank * NT + tid; idx < a.zero_n; idx += nthr) a.zero_buf[idx] = 0.f;
@@ -243,125 +300,133 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
     } else {
         __syncthreads();
     }
-    PROF_MARK(4);
+    PROF_MARK(6);
 
     const uint32_t tx_bytes = (uint32_t)(CS + 1) * B * 4;
-    float tau[B];
-#pragma unroll
-    for (int j = 0; j < B; ++j) tau[j] = 0.f;
-    float smu = 0.f, vinv = 0.f;
-    const int mycol = (lane >> LB) & (B - 1);  // column this lane owns after the reduce
+    const int mypos = (lane >> LB) & (B - 1);  // position this lane owns after the transpose-reduce
 
-    // step s: apply reflector s-1 (s > 0), accumulate the dots of column s (s < kr)
-#pragma unroll
-    for (int s = 0; s <= B; ++s) {
-        if (s > kr) break;
+    // The step loop is ROLLED (a fully unrolled body is ~300 KB of straight-line SASS and the
+    // kernel then starves on instruction fetch: ncu showed 70 % stall_no_inst).  Registers
+    // cannot be indexed dynamically, so the block is ROTATED instead: the current column always
+    // sits at position 0, and the rank-1 update writes position p into p-1
+    // (x[p-1] = x[p] - v*tau[p], one FFMA does update + rotation); the finished column re-enters
+    // at position B-1.  After B steps every column is back at its own position.
+    // Position p at step s holds column (s + p) mod B: live for p < B - s, finished otherwise.
+#pragma unroll 1
+    for (int s = 0; s < B; ++s) {
+        const int par = s & 1;
+        const bool active = s < kr;  // ragged blocks: the remaining steps only rotate
+        // ---- dots of the current column with every position (norm, update coefficients, Gram)
         float acc[B];
+        float xs[RPT];
+        if (crank == 0 && tid == s) {
 #pragma unroll
-        for (int j = 0; j < B; ++j) acc[j] = 0.f;
+            for (int q = 0; q < B / 4; ++q)  // pivot row (row s is u = 0 of thread s), positions
+                *reinterpret_cast<float4*>(&prow[par][4 * q]) = make_float4(x[0][4 * q], x[0][4 * q + 1], x[0][4 * q + 2], x[0][4 * q + 3]);
+        }
 #pragma unroll
         for (int u = 0; u < RPT; ++u) {
             const int i = rbase + u * NT;
-            if (s > 0) {
-                const float xk = (i >= s - 1) ? x[u][s - 1] : 0.f;  // rows above hold R entries
-                const float vi = (i == s - 1) ? xk + smu : xk;
+            xs[u] = (i >= s) ? x[u][0] : 0.f;  // rows above the diagonal hold R entries
+            if (u == 0) {
 #pragma unroll
-                for (int j = s; j < B; ++j) x[u][j] = fmaf(-vi, tau[j], x[u][j]);
-                if (i >= s - 1) x[u][s - 1] = vi * vinv;  // w in place (unshifted)
-            }
-            if (s < B) {
-                const float xs = (i >= s) ? x[u][s] : 0.f;
+                for (int p2 = 0; p2 < B; ++p2) acc[p2] = xs[0] * x[0][p2];
+            } else {
 #pragma unroll
-                for (int j = 0; j < B; ++j) acc[j] = fmaf(xs, x[u][j], acc[j]);
+                for (int p2 = 0; p2 < B; ++p2) acc[p2] = fmaf(xs[u], x[u][p2], acc[p2]);
             }
         }
-        if (s == kr) break;
-        if (s < B) {  // (always true here; keeps x[..][s] indices in range for the compiler)
-            const int par = s & 1;
-            PROF_MARK(0);
-            warp_transpose_reduce<B>(acc, lane);
-            if (LB == 0 || (lane & 1) == 0) red[par][warp][mycol] = acc[0];
-            if (crank == 0 && tid == s) {
+        PROF_MARK(0);
+        warp_transpose_reduce<B>(acc, lane);
+        PROF_MARK(1);
+        if (LB == 0 || (lane & 1) == 0) red[par][warp][mypos] = acc[0];
+        if (CS > 1 && tid == 0) mbar_arrive_expect_tx(&mbar[par], tx_bytes);
+        __syncthreads();
+        PROF_MARK(2);
+        float g, pv;
+        if (CS > 1) {
+            if (warp == 0) {
+                // CTA sum (lane <-> position), then 16-byte remote stores: one lane per (peer, 4-position chunk)
+                float csum = 0.f;
 #pragma unroll
-                for (int j = 0; j < B; ++j) prow[par][j] = x[0][j];  // pivot row (row s is u = 0 of thread s)
-            }
-            if (CS > 1 && tid == 0) mbar_arrive_expect_tx(&mbar[par], tx_bytes);
-            __syncthreads();
-            float csum = 0.f;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) csum += red[par][w][lane & (B - 1)];
-            float g, p;
-            if (CS > 1) {
-                if (warp < CS) {
-                    const uint32_t rbar = map_to_cta(smem_addr(&mbar[par]), (unsigned)warp);
-                    if (B == 32) {
-                        st_async_f32(map_to_cta(smem_addr(&slot[par][crank][lane]), (unsigned)warp), csum, rbar);
-                        if (crank == 0)
-                            st_async_f32(map_to_cta(smem_addr(&pslot[par][lane]), (unsigned)warp), prow[par][lane], rbar);
-                    } else {
-                        if (lane < 16) st_async_f32(map_to_cta(smem_addr(&slot[par][crank][lane]), (unsigned)warp), csum, rbar);
-                        else if (crank == 0)
-                            st_async_f32(map_to_cta(smem_addr(&pslot[par][lane - 16]), (unsigned)warp), prow[par][lane - 16], rbar);
-                    }
-                }
-                PROF_MARK(1);
-                mbar_wait_cluster(&mbar[par], (uint32_t)((s >> 1) & 1));
-                PROF_MARK(2);
-                g = 0.f;
-                for (int c = 0; c < CS; ++c) g += slot[par][c][lane & (B - 1)];
-                p = pslot[par][lane & (B - 1)];
-            } else {
-                PROF_MARK(1);
-                g = csum;
-                p = prow[par][lane & (B - 1)];
-            }
-            // reflector scalars (every lane redundantly): MUFU.RSQ + one Newton step each
-            const float gk = __shfl_sync(0xffffffffu, g, s);
-            const float ak = __shfl_sync(0xffffffffu, p, s);
-            const bool skip = !(gk > 0.f);
-            const float rs = rsqrtf(skip ? 1.f : gk);
-            float mu = gk * rs;
-            mu = fmaf(0.5f * rs, fmaf(-mu, mu, gk), mu);  // sqrt(gk)
-            if (skip) mu = 0.f;
-            smu = (ak >= 0.f) ? mu : -mu;
-            const float vn2 = 2.f * mu * (mu + fabsf(ak));
-            float rv = rsqrtf(skip ? 1.f : vn2);
-            rv = rv * fmaf(-0.5f * vn2, rv * rv, 1.5f);  // 1/sqrt(vn2)
-            vinv = skip ? 0.f : rv;
-            const float inv2 = skip ? 0.f : 2.f * rv * rv;  // 2/vn2
-            const int col = lane & (B - 1);
-            const float t = fmaf(smu, p, g);
-            if (lane < B) tauS[warp][col] = (col > s && col < bw) ? t * inv2 : 0.f;
-            if (warp == 0 && lane < B) {
-                if (col < s) gt[col][s] = t * vinv;           // Gram entry y_col^T y_s
-                if (col == s) diag[s] = skip ? ak : -smu;     // R_ss
-            }
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < B / 4; ++q) {
-                if (4 * q + 3 > s) {
-                    const float4 t4 = *reinterpret_cast<const float4*>(&tauS[warp][4 * q]);
-                    tau[4 * q] = t4.x; tau[4 * q + 1] = t4.y; tau[4 * q + 2] = t4.z; tau[4 * q + 3] = t4.w;
+                for (int w = 0; w < NW; ++w) csum += red[par][w][lane & (B - 1)];
+                if (lane < B) csumS[par][lane] = csum;
+                __syncwarp();
+                constexpr int CH = B / 4;
+                for (int o = lane; o < CS * CH; o += 32) {
+                    const unsigned peer = (unsigned)(o / CH);
+                    const int ch = o % CH;
+                    const uint32_t rbar = map_to_cta(smem_addr(&mbar[par]), peer);
+                    st_async_v4(map_to_cta(smem_addr(&slot[par][crank][4 * ch]), peer),
+                                *reinterpret_cast<const float4*>(&csumS[par][4 * ch]), rbar);
+                    if (crank == 0)
+                        st_async_v4(map_to_cta(smem_addr(&pslot[par][4 * ch]), peer),
+                                    *reinterpret_cast<const float4*>(&prow[par][4 * ch]), rbar);
                 }
             }
             PROF_MARK(3);
+            mbar_wait_cluster(&mbar[par], (uint32_t)((s >> 1) & 1));
+            PROF_MARK(4);
+            float g0 = 0.f, g1 = 0.f;
+            for (int c = 0; c < CS; c += 2) {
+                g0 += slot[par][c][lane & (B - 1)];
+                g1 += slot[par][c + 1][lane & (B - 1)];
+            }
+            g = g0 + g1;
+            pv = pslot[par][lane & (B - 1)];
+        } else {
+            float csum = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) csum += red[par][w][lane & (B - 1)];
+            PROF_MARK(3);
+            g = csum;
+            pv = prow[par][lane & (B - 1)];
         }
+        // ---- reflector scalars (every lane redundantly): MUFU.RSQ + one Newton step each
+        const float gk = __shfl_sync(0xffffffffu, g, 0);
+        const float ak = __shfl_sync(0xffffffffu, pv, 0);
+        const bool skip = !(gk > 0.f) || !active;
+        const float rs = rsqrtf(skip ? 1.f : gk);
+        float mu = gk * rs;
+        mu = fmaf(0.5f * rs, fmaf(-mu, mu, gk), mu);  // sqrt(gk)
+        if (skip) mu = 0.f;
+        float smu = (ak >= 0.f) ? mu : -mu;
+        const float vn2 = 2.f * mu * (mu + fabsf(ak));
+        float rv = rsqrtf(skip ? 1.f : vn2);
+        rv = rv * fmaf(-0.5f * vn2, rv * rv, 1.5f);  // 1/sqrt(vn2)
+        const float vinv = skip ? 0.f : rv;
+        const float inv2 = skip ? 0.f : 2.f * rv * rv;  // 2/vn2
+        const int pos = lane & (B - 1);
+        const int col = (s + pos) & (B - 1);  // column held at this position
+        const float t = fmaf(smu, pv, g);
+        if (lane < B) tauS[warp][pos] = (pos >= 1 && pos < B - s && col < bw) ? t * inv2 : 0.f;
+        if (warp == 0 && lane < B) {
+            if (pos >= B - s) gt[col][s] = t * vinv;        // Gram entry y_col^T y_s (col < s)
+            if (pos == 0) diag[s] = skip ? ak : -smu;       // R_ss
+        }
+        __syncwarp();
+        // ---- rank-1 update fused with the rotation
+        float tau[B];
+#pragma unroll
+        for (int q = 0; q < B / 4; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(&tauS[warp][4 * q]);
+            tau[4 * q] = t4.x; tau[4 * q + 1] = t4.y; tau[4 * q + 2] = t4.z; tau[4 * q + 3] = t4.w;
+        }
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const int i = rbase + u * NT;
+            const float vi = (i == s) ? xs[u] + smu : xs[u];
+            const float fin = (i >= s && active) ? vi * vinv : x[u][0];  // w in place (unshifted); R entries above
+#pragma unroll
+            for (int p2 = 1; p2 < B; ++p2) x[u][p2 - 1] = fmaf(-vi, tau[p2], x[u][p2]);
+            x[u][B - 1] = fin;
+        }
+        PROF_MARK(5);
     }
     __syncthreads();
 
-    // ---- T of the block by the larft recurrence (warp 0), in place in gt
-    if (warp == 0) {
-        for (int c = 0; c < kr; ++c) {
-            float sacc = 0.f;
-            if (lane < c)
-                for (int u2 = lane; u2 < c; ++u2) sacc = fmaf(gt[lane][u2], gt[u2][c], sacc);
-            __syncwarp();
-            if (lane < c) gt[lane][c] = -2.f * sacc;
-            if (lane == c) gt[c][c] = 2.f;
-            __syncwarp();
-        }
-    }
-    __syncthreads();
+    // ---- T of the block, T = (striu(G) + I/2)^-1 (recursive doubling in shared memory)
+    tinv_smem<B, B + 4>(gt, &red[0][0][0], tid);
 
     // ---- outputs
     const bool want_w = a.W32.p || a.W16.p;
@@ -396,18 +461,38 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
         }
         if (a.Y32.p) store_row32<B>(a.Y32.p + (size_t)i * a.Y32.ld, x[u], bw, vecY32);
         if (a.Y16.p) store_row16<B>((char*)a.Y16.p + (size_t)i * a.Y16.ld * 2, x[u], bw, vecY16, a.bf16);
-        if (want_w) {
-            float w[B];
+    }
+    if (want_w) {
+        constexpr int WG = (RPT >= 2) ? 2 : 1;  // rows that share one sweep over T
 #pragma unroll
-            for (int c = 0; c < B; ++c) w[c] = 0.f;
+        for (int u0 = 0; u0 < RPT; u0 += WG) {
+            float w[WG][B];
+#pragma unroll
+            for (int g2 = 0; g2 < WG; ++g2)
+#pragma unroll
+                for (int c = 0; c < B; ++c) w[g2][c] = 0.f;
 #pragma unroll
             for (int t = 0; t < B; ++t) {
-                const float y = x[u][t];
 #pragma unroll
-                for (int c = t; c < B; ++c) w[c] = fmaf(y, gt[t][c], w[c]);
+                for (int q = t / 4; q < B / 4; ++q) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(&gt[t][4 * q]);  // zero below the diagonal
+#pragma unroll
+                    for (int g2 = 0; g2 < WG; ++g2) {
+                        const float y = x[u0 + g2][t];
+                        w[g2][4 * q] = fmaf(y, t4.x, w[g2][4 * q]);
+                        w[g2][4 * q + 1] = fmaf(y, t4.y, w[g2][4 * q + 1]);
+                        w[g2][4 * q + 2] = fmaf(y, t4.z, w[g2][4 * q + 2]);
+                        w[g2][4 * q + 3] = fmaf(y, t4.w, w[g2][4 * q + 3]);
+                    }
+                }
             }
-            if (a.W32.p) store_row32<B>(a.W32.p + (size_t)i * a.W32.ld, w, bw, vecW32);
-            if (a.W16.p) store_row16<B>((char*)a.W16.p + (size_t)i * a.W16.ld * 2, w, bw, vecW16, a.bf16);
+#pragma unroll
+            for (int g2 = 0; g2 < WG; ++g2) {
+                const int i = rbase + (u0 + g2) * NT;
+                if (i >= D) continue;
+                if (a.W32.p) store_row32<B>(a.W32.p + (size_t)i * a.W32.ld, w[g2], bw, vecW32);
+                if (a.W16.p) store_row16<B>((char*)a.W16.p + (size_t)i * a.W16.ld * 2, w[g2], bw, vecW16, a.bf16);
+            }
         }
     }
     // rows above the block are structurally zero in the compact outputs
@@ -440,18 +525,18 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
             a.T[(size_t)t * a.ldt + c] = (t <= c && c < kr) ? gt[t][c] : 0.f;
         }
     }
-    PROF_MARK(5);
+    PROF_MARK(7);
     if (prof) {
-        pacc[6] = kr;
-        for (int i = 0; i < 7; ++i) a.dbg[i] += pacc[i];
-        a.dbg[7] = CS; a.dbg[8] = RPT; a.dbg[9] = B;
+        pacc[8] = kr;
+        for (int i = 0; i < 9; ++i) a.dbg[i] += pacc[i];
+        a.dbg[9] = CS; a.dbg[10] = RPT; a.dbg[11] = B;
     }
     // shared memory must stay alive until no peer can signal into it any more
     if (CS > 1) cluster_sync_all();
 }
 
 // ------------------------------------------------------------------ level 1: in-panel update
-// S[rep][t][c] += sum_rows W[row][t] * A[row][c]   (FP32; B x ncols, rows split over the grid)
+// S'[rep][t][c] += sum_rows Y[row][t] * A[row][c]   (FP32; B x ncols, rows split over the grid)
 template <int B>
 __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict__ W, long ldw, const float* __restrict__ A,
                                                          long lda, int D, int ncols, float* __restrict__ Srep, int rows_per_cta) {
@@ -511,11 +596,13 @@ __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict_
     }
 }
 
-// A[row][c] -= sum_t Y[row][t] * S[t][c],  S = sum of the replicas
+// A[row][c] -= sum_t Y[row][t] * S[t][c],  S = T^T (sum of the replicas)   [Q_j^T A = A - Y T^T (Y^T A)]
 template <int B>
 __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict__ Y, long ldy, float* __restrict__ A, long lda,
-                                                         int D, int ncols, const float* __restrict__ Srep, int rows_per_cta) {
+                                                         int D, int ncols, const float* __restrict__ Srep,
+                                                         const float* __restrict__ Tj, int rows_per_cta) {
     extern __shared__ __align__(16) float sm[];
+    __shared__ float Ts[B][B + 1];
     const int tid = threadIdx.x, c = tid & 127, rg = tid >> 7;
     const int r0 = blockIdx.x * rows_per_cta;
     int nrows = D - r0;
@@ -523,7 +610,7 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
     if (nrows <= 0) return;
     const int c0 = blockIdx.y * 128;
     const bool on = (c0 + c) < ncols;
-    float s[B];
+    float sp[B];
 #pragma unroll
     for (int t = 0; t < B; ++t) {
         float v = 0.f;
@@ -531,14 +618,23 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
 #pragma unroll
             for (int rep = 0; rep < NREP; ++rep) v += __ldcg(&Srep[(size_t)rep * RMAX * SLD + t * SLD + c0 + c]);
         }
-        s[t] = v;
+        sp[t] = v;
     }
+    for (int idx = tid; idx < B * B; idx += 512) Ts[idx / B][idx % B] = Tj[idx];
     for (int idx = tid; idx < nrows * B; idx += 512) {
         int rr = idx / B, t = idx - rr * B;
         sm[idx] = Y[(size_t)(r0 + rr) * ldy + t];
     }
     __syncthreads();
     if (!on) return;
+    float s[B];
+#pragma unroll
+    for (int t = 0; t < B; ++t) {
+        float v = 0.f;
+#pragma unroll
+        for (int u2 = 0; u2 <= t; ++u2) v = fmaf(Ts[u2][t], sp[u2], v);
+        s[t] = v;
+    }
     float* Ac = A + (size_t)r0 * lda + c0 + c;
     for (int rr = rg; rr < nrows; rr += 16) {
         float av[4];
@@ -695,33 +791,34 @@ int launch_block_t(const BlockArgs& a, int CS, cudaStream_t stream) {
 int g_max_cs = 0;
 int max_cluster() {
     if (!g_max_cs) {
-        int a1, a2, a3, a4, a5;
-        prepare_kernel<16, 1>(&a1);
-        prepare_kernel<16, 2>(&a2);
-        prepare_kernel<16, 4>(&a3);
-        prepare_kernel<32, 1>(&a4);
-        prepare_kernel<32, 2>(&a5);
-        int mc = a1;
-        if (a2 < mc) mc = a2;
-        if (a3 < mc) mc = a3;
-        if (a4 < mc) mc = a4;
-        if (a5 < mc) mc = a5;
+        int v[7];
+        prepare_kernel<16, 1>(&v[0]);
+        prepare_kernel<16, 2>(&v[1]);
+        prepare_kernel<16, 4>(&v[2]);
+        prepare_kernel<16, 8>(&v[3]);
+        prepare_kernel<32, 1>(&v[4]);
+        prepare_kernel<32, 2>(&v[5]);
+        prepare_kernel<32, 4>(&v[6]);
+        int mc = v[0];
+        for (int i = 1; i < 7; ++i)
+            if (v[i] < mc) mc = v[i];
         g_max_cs = mc;
     }
     return g_max_cs;
 }
 
 // rows a block kernel of width B can hold
-long block_capacity(int B) { return (long)max_cluster() * NT * (B == 32 ? 2 : 4); }
+long block_capacity(int B) { return (long)max_cluster() * NT * (B == 32 ? 4 : 8); }
 
 // Picks (RPT, CS) for D rows; returns false if the block does not fit one cluster.
 bool pick_shape(int B, int D, int force_cs, int force_rpt, int* rpt, int* cs) {
     const int mc = max_cluster();
-    const int max_rpt = (B == 32) ? 2 : 4;
+    const int max_rpt = (B == 32) ? 4 : 8;
     if ((long)D > (long)mc * NT * max_rpt) return false;
     int R = 1, C = 1;
     if (D <= NT) { R = 1; C = 1; }
     else if (D <= 2 * NT) { R = 2; C = 1; }
+    else if (D <= 4 * NT) { R = 4; C = 1; }
     else {
         // prefer one row per thread and more CTAs: the exchange costs the same for any CS > 1
         R = 1;
@@ -749,11 +846,13 @@ bool pick_shape(int B, int D, int force_cs, int force_rpt, int* rpt, int* cs) {
 int launch_block(int B, const BlockArgs& a, int RPT, int CS, cudaStream_t st) {
     if (B == 32) {
         if (RPT == 1) return launch_block_t<32, 1>(a, CS, st);
-        return launch_block_t<32, 2>(a, CS, st);
+        if (RPT == 2) return launch_block_t<32, 2>(a, CS, st);
+        return launch_block_t<32, 4>(a, CS, st);
     }
     if (RPT == 1) return launch_block_t<16, 1>(a, CS, st);
     if (RPT == 2) return launch_block_t<16, 2>(a, CS, st);
-    return launch_block_t<16, 4>(a, CS, st);
+    if (RPT == 4) return launch_block_t<16, 4>(a, CS, st);
+    return launch_block_t<16, 8>(a, CS, st);
 }
 
 // workspace layout (floats): Y32p [rows x RMAX] | Wj [rows x 32] | Srep [NREP x RMAX x SLD] | G [RMAX x RMAX] |
@@ -778,7 +877,7 @@ Ws carve(float* ws, long rows) {
 }
 
 template <int B>
-int launch_su(const float* Wj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, int num_sms,
+int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, int num_sms,
               cudaStream_t st, long* launches) {
     static bool attr = false;
     const int max_rows = 256;
@@ -792,9 +891,9 @@ int launch_su(const float* Wj, const float* Yj, long ldy, float* Arest, long lda
         attr = true;
     }
     dim3 grid(ceil_div(D, rows), ceil_div(ncols, 128));
-    inpanel_s_kernel<B><<<grid, 512, smem_s, st>>>(Wj, B, Arest, lda, D, ncols, Srep, rows);
+    inpanel_s_kernel<B><<<grid, 512, smem_s, st>>>(Yj, ldy, Arest, lda, D, ncols, Srep, rows);
     MPQR_CUDA(cudaGetLastError());
-    inpanel_u_kernel<B><<<grid, 512, smem_u, st>>>(Yj, ldy, Arest, lda, D, ncols, Srep, rows);
+    inpanel_u_kernel<B><<<grid, 512, smem_u, st>>>(Yj, ldy, Arest, lda, D, ncols, Srep, Tj, rows);
     MPQR_CUDA(cudaGetLastError());
     if (launches) *launches += 2;
     return MPQR_OK;
@@ -840,7 +939,9 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         b.Y32 = {Y32l, a.ld32, zr}; b.W32 = {W32l, a.ld32, zr};
         b.Y16 = {Y16l, a.ldy16, zr}; b.W16 = {W16l, a.ldw16, zr};
         b.bf16 = a.bf16; b.T = a.T; b.ldt = a.ldt; b.dbg = a.dbg;
+        if (a.prof) a.prof->begin(a.prof->ctx, 4, stream);
         MPQR_TRY(launch_block(B, b, rpt, cs, stream));
+        if (a.prof) a.prof->end(a.prof->ctx, stream);
         if (a.dbg_caps) { a.dbg_caps[0] = max_cluster(); a.dbg_caps[1] = cs; a.dbg_caps[2] = rpt; }
         if (launches) *launches += 1;
         return MPQR_OK;
@@ -868,16 +969,20 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         BlockArgs b{};
         b.A = Ablk + (size_t)j0 * a.lda + j0; b.lda = a.lda; b.D = Dj; b.bw = bw;
         b.Y32 = {Yp + (size_t)j0 * ldyp + j0, ldyp, j0 + (Y32l ? zr : 0)};
-        if (nrest > 0) b.W32 = {w.Wj, B, 0};
+        if (nrest > 0) { b.T = w.Wj; b.ldt = B; }  // block T (B x B) for the in-panel update
         if (Y16l) b.Y16 = {Y16l + ((size_t)j0 * a.ldy16 + j0) * 2, a.ldy16, j0 + zr};
         b.bf16 = a.bf16; b.dbg = a.dbg;
         if (nrest > 0) { b.zero_buf = w.Srep; b.zero_n = NREP * RMAX * SLD; }
+        if (a.prof) a.prof->begin(a.prof->ctx, 4, stream);
         MPQR_TRY(launch_block(B, b, rpt, cs, stream));
+        if (a.prof) a.prof->end(a.prof->ctx, stream);
         if (launches) *launches += 1;
         if (nrest > 0) {
             float* Arest = b.A + bw;
+            if (a.prof) a.prof->begin(a.prof->ctx, 5, stream);
             if (B == 32) MPQR_TRY(launch_su<32>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, di.num_sms, stream, launches));
             else MPQR_TRY(launch_su<16>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, di.num_sms, stream, launches));
+            if (a.prof) a.prof->end(a.prof->ctx, stream);
         }
     }
     if (a.dbg_caps) { a.dbg_caps[0] = max_cluster(); a.dbg_caps[1] = cs; a.dbg_caps[2] = rpt; }
@@ -892,6 +997,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     const int Dz = D + zr;  // W is produced from the enclosing block's first row on (zero rows of Y give zero rows of W)
     float* Tdst = a.T ? a.T : w.T32;
     const int ldt = a.T ? a.ldt : RMAX;
+    if (a.prof) a.prof->begin(a.prof->ctx, 6, stream);
     if (mixed) {
         // Gram and W on tensor cores, from the 16-bit Y the trailing update uses
         MPQR_TRY(tc_gemm_tn(Y16l, a.ldy16, Y16l, a.ldy16, w.G, RMAX, pw, pw, D, a.bf16, 1, stream, launches));
@@ -909,6 +1015,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
             if (launches) *launches += 1;
         }
     }
+    if (a.prof) a.prof->end(a.prof->ctx, stream);
     return MPQR_OK;
 }
 

@@ -48,6 +48,21 @@ def run(m, n, r, prec, nb=0, reps=3, check=True):
         be = sampled_backward_error(A0[:, :n], A[:, :n], r=plan.r)
     print(f"{m}x{n} r={plan.r} nb={plan.nb} {prec}: {best:.2f} ms  {F / best / 1e9:.2f} TFLOP/s  launches={plan.last_launches} "
           f"bwd_err~{be:.2e}  all={['%.1f' % t for t in times]}", flush=True)
+    if os.environ.get("PROFILE") == "1":
+        import ctypes
+        L = pkg.lib()
+        L.mpqr_set_profiling(plan._h, 1)
+        pkg.fill_uniform(A.data_ptr(), lda, n, 0, m, 0, n, 1234, st)
+        plan.factor(A.data_ptr(), lda, st)
+        torch.cuda.synchronize()
+        names = ["panel(all)", "gemm_tn", "gemm_nn", "cast", "panel:block", "panel:S/U", "panel:G/T/W"]
+        out = []
+        for c in range(7):
+            ms, cnt, fl, by = ctypes.c_double(), ctypes.c_long(), ctypes.c_double(), ctypes.c_double()
+            L.mpqr_get_profile(plan._h, c, ctypes.byref(ms), ctypes.byref(cnt), ctypes.byref(fl), ctypes.byref(by))
+            out.append(f"{names[c]}={ms.value:.2f}ms/{cnt.value}")
+        print("   profile: " + "  ".join(out), flush=True)
+        L.mpqr_set_profiling(plan._h, 0)
     plan.close()
     del A
     torch.cuda.empty_cache()
