@@ -161,15 +161,23 @@ __device__ __forceinline__ void tinv_smem(float (*gt)[LD], float* xs, int tid) {
         const int i = e / h, j = e - i * h, o = pr * 2 * h;
         const bool on = tid < (B / (2 * h)) * h * h;
         if (on) {
-            float sacc = 0.f;
-            for (int u2 = 0; u2 <= j; ++u2) sacc = fmaf(gt[o + i][o + h + u2], gt[o + h + u2][o + h + j], sacc);
-            xs[tid] = sacc;  // X = G12 T22, element (pr, i, j)
+            float s0 = 0.f, s1 = 0.f;  // zeros below the diagonals: fixed trip counts
+#pragma unroll
+            for (int u2 = 0; u2 < h; u2 += 2) {
+                s0 = fmaf(gt[o + i][o + h + u2], gt[o + h + u2][o + h + j], s0);
+                s1 = fmaf(gt[o + i][o + h + u2 + 1], gt[o + h + u2 + 1][o + h + j], s1);
+            }
+            xs[tid] = s0 + s1;  // X = G12 T22, element (pr, i, j)
         }
         __syncthreads();
         if (on) {
-            float sacc = 0.f;
-            for (int u2 = i; u2 < h; ++u2) sacc = fmaf(gt[o + i][o + u2], xs[pr * h * h + u2 * h + j], sacc);
-            gt[o + i][o + h + j] = -sacc;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int u2 = 0; u2 < h; u2 += 2) {
+                s0 = fmaf(gt[o + i][o + u2], xs[pr * h * h + u2 * h + j], s0);
+                s1 = fmaf(gt[o + i][o + u2 + 1], xs[pr * h * h + (u2 + 1) * h + j], s1);
+            }
+            gt[o + i][o + h + j] = -(s0 + s1);
         }
         __syncthreads();
     }
@@ -345,20 +353,22 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
         PROF_MARK(2);
         float g, pv;
         if (CS > 1) {
-            if (warp == 0) {
-                // CTA sum (lane <-> position), then 16-byte remote stores: one lane per (peer, 4-position chunk)
-                float csum = 0.f;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) csum += red[par][w][lane & (B - 1)];
-                if (lane < B) csumS[par][lane] = csum;
-                __syncwarp();
+            {
+                // one lane per (peer, 4-position chunk): the lane sums its chunk over the warps and ships
+                // 16 bytes to the peer's slot (+ the pivot row chunk from CTA 0)
                 constexpr int CH = B / 4;
-                for (int o = lane; o < CS * CH; o += 32) {
+                const int o = warp * 32 + lane;
+                if (o < CS * CH) {
                     const unsigned peer = (unsigned)(o / CH);
                     const int ch = o % CH;
+                    float4 cs4 = *reinterpret_cast<const float4*>(&red[par][0][4 * ch]);
+#pragma unroll
+                    for (int w = 1; w < NW; ++w) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(&red[par][w][4 * ch]);
+                        cs4.x += r4.x; cs4.y += r4.y; cs4.z += r4.z; cs4.w += r4.w;
+                    }
                     const uint32_t rbar = map_to_cta(smem_addr(&mbar[par]), peer);
-                    st_async_v4(map_to_cta(smem_addr(&slot[par][crank][4 * ch]), peer),
-                                *reinterpret_cast<const float4*>(&csumS[par][4 * ch]), rbar);
+                    st_async_v4(map_to_cta(smem_addr(&slot[par][crank][4 * ch]), peer), cs4, rbar);
                     if (crank == 0)
                         st_async_v4(map_to_cta(smem_addr(&pslot[par][4 * ch]), peer),
                                     *reinterpret_cast<const float4*>(&prow[par][4 * ch]), rbar);
@@ -443,15 +453,9 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
             store_row32<B>(a.A + (size_t)(i + 1) * lda, x[u], bw, vecA);
         } else {
 #pragma unroll
-            for (int c = 0; c < B; ++c) {
-                if (c >= bw) continue;
-                if (i < c) {
-                    a.A[(size_t)i * lda + c] = x[u][c];
-                } else {
-                    a.A[(size_t)(i + 1) * lda + c] = x[u][c];
-                    if (i == c) a.A[(size_t)i * lda + c] = diag[c];
-                }
-            }
+            for (int c = 0; c < B; ++c)
+                if (c < bw) a.A[(size_t)(i + (i >= c ? 1 : 0)) * lda + c] = x[u][c];
+            a.A[(size_t)i * lda + i] = diag[i];  // i < bw: R_ii (the loop above put w_ii one row below)
         }
         // Y: zero strictly above the diagonal and for columns without reflector
         if (i < B) {
@@ -610,15 +614,17 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
     if (nrows <= 0) return;
     const int c0 = blockIdx.y * 128;
     const bool on = (c0 + c) < ncols;
-    float sp[B];
-#pragma unroll
-    for (int t = 0; t < B; ++t) {
+    // S' = sum of the replicas (B x 128 chunk), once per CTA
+    __shared__ float Sp[B][128];
+    __shared__ float S2[B][128];
+    for (int idx = tid; idx < B * 128; idx += 512) {
+        const int t = idx >> 7, cc = idx & 127;
         float v = 0.f;
-        if (on) {
+        if (c0 + cc < ncols) {
 #pragma unroll
-            for (int rep = 0; rep < NREP; ++rep) v += __ldcg(&Srep[(size_t)rep * RMAX * SLD + t * SLD + c0 + c]);
+            for (int rep = 0; rep < NREP; ++rep) v += __ldcg(&Srep[(size_t)rep * RMAX * SLD + t * SLD + c0 + cc]);
         }
-        sp[t] = v;
+        Sp[t][cc] = v;
     }
     for (int idx = tid; idx < B * B; idx += 512) Ts[idx / B][idx % B] = Tj[idx];
     for (int idx = tid; idx < nrows * B; idx += 512) {
@@ -626,15 +632,17 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
         sm[idx] = Y[(size_t)(r0 + rr) * ldy + t];
     }
     __syncthreads();
+    // S = T^T S': row group rg computes rows t = rg, rg+4, ... of its column
+    for (int t = rg; t < B; t += 4) {
+        float v = 0.f;
+        for (int u2 = 0; u2 <= t; ++u2) v = fmaf(Ts[u2][t], Sp[u2][c], v);
+        S2[t][c] = v;
+    }
+    __syncthreads();
     if (!on) return;
     float s[B];
 #pragma unroll
-    for (int t = 0; t < B; ++t) {
-        float v = 0.f;
-#pragma unroll
-        for (int u2 = 0; u2 <= t; ++u2) v = fmaf(Ts[u2][t], sp[u2], v);
-        s[t] = v;
-    }
+    for (int t = 0; t < B; ++t) s[t] = S2[t][c];
     float* Ac = A + (size_t)r0 * lda + c0 + c;
     for (int rr = rg; rr < nrows; rr += 16) {
         float av[4];
@@ -709,18 +717,26 @@ __global__ void __launch_bounds__(1024) tinv_kernel(const float* __restrict__ G,
         for (int idx = tid; idx < npairs * h * h; idx += 1024) {
             const int pr = idx / (h * h), e = idx - pr * h * h;
             const int i = e / h, j = e - i * h, o = pr * 2 * h;
-            float sacc = 0.f;
-            for (int u2 = 0; u2 <= j; ++u2) sacc = fmaf(Ts[(o + i) * TLD + o + h + u2], Ts[(o + h + u2) * TLD + o + h + j], sacc);
-            Xs[(pr * h + i) * 65 + j] = sacc;  // pr*h + i < 64 (npairs*h = R/2 <= 64)
+            float s0 = 0.f, s1 = 0.f;  // T22 is zero below its diagonal: fixed trip count, loads pipeline
+#pragma unroll 8
+            for (int u2 = 0; u2 < h; u2 += 2) {
+                s0 = fmaf(Ts[(o + i) * TLD + o + h + u2], Ts[(o + h + u2) * TLD + o + h + j], s0);
+                s1 = fmaf(Ts[(o + i) * TLD + o + h + u2 + 1], Ts[(o + h + u2 + 1) * TLD + o + h + j], s1);
+            }
+            Xs[(pr * h + i) * 65 + j] = s0 + s1;  // pr*h + i < 64 (npairs*h = R/2 <= 64)
         }
         __syncthreads();
         // T12 = -T11 * X
         for (int idx = tid; idx < npairs * h * h; idx += 1024) {
             const int pr = idx / (h * h), e = idx - pr * h * h;
             const int i = e / h, j = e - i * h, o = pr * 2 * h;
-            float sacc = 0.f;
-            for (int u2 = i; u2 < h; ++u2) sacc = fmaf(Ts[(o + i) * TLD + o + u2], Xs[(pr * h + u2) * 65 + j], sacc);
-            Ts[(o + i) * TLD + o + h + j] = -sacc;
+            float s0 = 0.f, s1 = 0.f;  // T11 is zero below its diagonal
+#pragma unroll 8
+            for (int u2 = 0; u2 < h; u2 += 2) {
+                s0 = fmaf(Ts[(o + i) * TLD + o + u2], Xs[(pr * h + u2) * 65 + j], s0);
+                s1 = fmaf(Ts[(o + i) * TLD + o + u2 + 1], Xs[(pr * h + u2 + 1) * 65 + j], s1);
+            }
+            Ts[(o + i) * TLD + o + h + j] = -(s0 + s1);
         }
         __syncthreads();
     }
@@ -888,6 +904,7 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
     const size_t smem_u = (size_t)rows * B * sizeof(float);
     if (!attr) {
         MPQR_CUDA(cudaFuncSetAttribute(inpanel_s_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 32 * 128 * 4));
+        MPQR_CUDA(cudaFuncSetAttribute(inpanel_u_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr = true;
     }
     dim3 grid(ceil_div(D, rows), ceil_div(ncols, 128));
