@@ -103,7 +103,7 @@ long mpqr_last_launch_count(const mpqr_handle* h);
  * mpqr_get_profile synchronises on the recorded events and returns totals accumulated since the
  * last mpqr_set_profiling(h, 1): device milliseconds, launches, algorithmic flops and
  * algorithmic HBM bytes (panel: 8*D*pw; NN: 10*M*N; TN: 2*K*(M+N)+4*M*N). */
-#define MPQR_NUM_KERNEL_CLASSES 7  /* 4..6: parts of class 0 (register-block kernels, in-panel updates, Gram/T/W) */
+#define MPQR_NUM_KERNEL_CLASSES 8  /* 4..7: parts of class 0 (register-block kernels, in-panel S, Gram/T/W, in-panel U) */
 int mpqr_set_profiling(mpqr_handle* h, int on);
 int mpqr_get_profile(mpqr_handle* h, int kernel_class, double* ms_total, long* launches, double* flops,
                      double* bytes);

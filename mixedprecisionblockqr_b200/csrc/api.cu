@@ -19,6 +19,7 @@
 //   The trailing update uses the identity  Q_panel^T A = A - Y (W^T A)  with W = Y T
 //   ("mind the transpose").
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "internal.h"
@@ -26,6 +27,7 @@
 namespace mpqr {
 
 static thread_local char g_err[512] = "";
+thread_local int g_sm_budget = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -155,6 +157,98 @@ using namespace mpqr;
 
 namespace {
 
+
+// ------------------------------------------------------------------ look-ahead resources
+// Two green contexts (CUDA 12.4+ driver API, resolved at run time so that libmpqr.so does not
+// link libcuda): a small cluster-capable SM partition for the panel chain and the rest of the
+// device for the far trailing update.  Streams created in a green context only use its SMs, so
+// the panel chain of outer block J+1 really runs WHILE block J's far update does.
+struct GreenApi {
+    CUresult (*DeviceGet)(CUdevice*, int);
+    CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType);
+    CUresult (*DevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+    CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+    CUresult (*GreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+    CUresult (*GreenCtxDestroy)(CUgreenCtx);
+    CUresult (*GreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int);
+    bool ok;
+};
+const GreenApi* green_api() {
+    static GreenApi api{};
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        auto get = [](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+        };
+        api.ok = get("cuDeviceGet", (void**)&api.DeviceGet) && get("cuDeviceGetDevResource", (void**)&api.DeviceGetDevResource) &&
+                 get("cuDevSmResourceSplitByCount", (void**)&api.DevSmResourceSplitByCount) &&
+                 get("cuDevResourceGenerateDesc", (void**)&api.DevResourceGenerateDesc) &&
+                 get("cuGreenCtxCreate", (void**)&api.GreenCtxCreate) && get("cuGreenCtxDestroy", (void**)&api.GreenCtxDestroy) &&
+                 get("cuGreenCtxStreamCreate", (void**)&api.GreenCtxStreamCreate);
+        if (!api.ok) cudaGetLastError();
+    }
+    return &api;
+}
+
+// Best effort: on any failure the handle simply keeps the single-stream driver.
+void overlap_init(mpqr_handle* h, int panel_sms) {
+    const GreenApi* g = green_api();
+    if (!g->ok) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    CUdevice cudev;
+    CUdevResource full, grp[1], rem;
+    unsigned int n = 1;
+    if (g->DeviceGet(&cudev, dev) != CUDA_SUCCESS) return;
+    if (g->DeviceGetDevResource(cudev, &full, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return;
+    if (g->DevSmResourceSplitByCount(grp, &n, &full, &rem, CU_DEV_SM_RESOURCE_SPLIT_MAX_POTENTIAL_CLUSTER_SIZE,
+                                     (unsigned)panel_sms) != CUDA_SUCCESS || n < 1 || rem.sm.smCount < 32)
+        return;
+    CUdevResourceDesc dP, dU;
+    if (g->DevResourceGenerateDesc(&dP, &grp[0], 1) != CUDA_SUCCESS) return;
+    if (g->DevResourceGenerateDesc(&dU, &rem, 1) != CUDA_SUCCESS) return;
+    CUgreenCtx gP = nullptr, gU = nullptr;
+    if (g->GreenCtxCreate(&gP, dP, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
+    if (g->GreenCtxCreate(&gU, dU, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { g->GreenCtxDestroy(gP); return; }
+    CUstream sP = nullptr, sU = nullptr;
+    if (g->GreenCtxStreamCreate(&sP, gP, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS ||
+        g->GreenCtxStreamCreate(&sU, gU, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+        if (sP) cudaStreamDestroy((cudaStream_t)sP);
+        g->GreenCtxDestroy(gP); g->GreenCtxDestroy(gU);
+        return;
+    }
+    auto& o = h->ov;
+    o.gP = gP; o.gU = gU; o.sP = (cudaStream_t)sP; o.sU = (cudaStream_t)sU;
+    o.nsmP = (int)grp[0].sm.smCount; o.nsmU = (int)rem.sm.smCount;
+    const int nblk = ceil_div(h->kmax, h->nb);
+    o.ev_bp.resize(nblk); o.ev_fn.resize(nblk);
+    for (int i = 0; i < nblk; ++i) {
+        cudaEventCreateWithFlags(&o.ev_bp[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&o.ev_fn[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&o.ev_start, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&o.ev_endP, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&o.ev_endU, cudaEventDisableTiming);
+    o.on = true;
+}
+
+void overlap_destroy(mpqr_handle* h) {
+    auto& o = h->ov;
+    if (!o.gP) return;
+    for (auto e : o.ev_bp) cudaEventDestroy(e);
+    for (auto e : o.ev_fn) cudaEventDestroy(e);
+    if (o.ev_start) cudaEventDestroy(o.ev_start);
+    if (o.ev_endP) cudaEventDestroy(o.ev_endP);
+    if (o.ev_endU) cudaEventDestroy(o.ev_endU);
+    if (o.sP) cudaStreamDestroy(o.sP);
+    if (o.sU) cudaStreamDestroy(o.sU);
+    const GreenApi* g = green_api();
+    if (g->ok) { g->GreenCtxDestroy((CUgreenCtx)o.gP); g->GreenCtxDestroy((CUgreenCtx)o.gU); }
+    o = mpqr_handle::Overlap();
+}
+
 int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     const int m = h->m, n = h->n, r = h->r;
     for (int lam = 0, p = 0; lam < h->kmax; lam += r, ++p) {
@@ -197,16 +291,61 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     // operand shadow of the whole matrix
     PROF(3, 0, 6.0 * m * n, convert_f32_to_16(A, lda, h->Ah, h->ldh, m, n, bf, st));
     h->launches += 1;
-    for (int c0 = 0; c0 < h->kmax; c0 += nb) {
-        const int c1 = (c0 + nb < h->kmax) ? c0 + nb : h->kmax;
+    const int nblk = ceil_div(h->kmax, nb);
+    auto ctx_of = [&](int b, int c0) {
         BlockCtx c{};
         c.A = A; c.lda = lda; c.acol0 = c0; c.Ah = h->Ah; c.ldh = h->ldh;
         c.Y16 = at16(h->Ah, h->ldh, c0, c0); c.ldy = h->ldh;  // Y lives in the shadow's dead columns
-        c.W16 = h->keep_wy ? (void*)at16(h->W16, h->ldw16, c0, c0) : h->W16;
+        void* wbuf = (h->W16b && (b & 1)) ? h->W16b : h->W16;
+        c.W16 = h->keep_wy ? (void*)at16(h->W16, h->ldw16, c0, c0) : wbuf;
         c.ldw = h->ldw16;
-        MPQR_TRY(block_phase(h, c, c0, c1, c1 == n, st));
-        MPQR_TRY(far_update(h, c, c0, c1, c1, n - c1, st));
+        return c;
+    };
+    if (!h->ov.on || nblk < 3 || h->prof) {
+        for (int c0 = 0, b = 0; c0 < h->kmax; c0 += nb, ++b) {
+            const int c1 = (c0 + nb < h->kmax) ? c0 + nb : h->kmax;
+            BlockCtx c = ctx_of(b, c0);
+            MPQR_TRY(block_phase(h, c, c0, c1, c1 == n, st));
+            MPQR_TRY(far_update(h, c, c0, c1, c1, n - c1, st));
+        }
+        return MPQR_OK;
     }
+    // Look-ahead schedule.  sP (panel partition): block_phase(J).  sU (update partition): the far
+    // update of block J, next outer block's columns first (far_next) so that block_phase(J+1)
+    // can start while the rest of the trailing matrix (far_rest) is still being updated.
+    //   sP:  bp(0)        | wait fn(0) | bp(1)         | wait fn(1) | bp(2) ...
+    //   sU:  wait bp(0) | fn(0) fr(0)            | wait bp(1) | fn(1) fr(1) ...
+    auto& o = h->ov;
+    MPQR_CUDA(cudaEventRecord(o.ev_start, st));
+    MPQR_CUDA(cudaStreamWaitEvent(o.sP, o.ev_start, 0));
+    MPQR_CUDA(cudaStreamWaitEvent(o.sU, o.ev_start, 0));
+    for (int c0 = 0, b = 0; c0 < h->kmax; c0 += nb, ++b) {
+        const int c1 = (c0 + nb < h->kmax) ? c0 + nb : h->kmax;
+        BlockCtx c = ctx_of(b, c0);
+        if (b > 0) MPQR_CUDA(cudaStreamWaitEvent(o.sP, o.ev_fn[b - 1], 0));
+        {
+            SmBudget budget(o.nsmP);
+            MPQR_TRY(block_phase(h, c, c0, c1, c1 == n, o.sP));
+        }
+        MPQR_CUDA(cudaEventRecord(o.ev_bp[b], o.sP));
+        const int nfar = n - c1;
+        if (nfar > 0) {
+            BlockCtx cu = c;
+            cu.S32 = h->S32u; cu.S16 = h->S16u;
+            const int nnext = nfar < nb ? nfar : nb;
+            SmBudget budget(o.nsmU);
+            MPQR_CUDA(cudaStreamWaitEvent(o.sU, o.ev_bp[b], 0));
+            MPQR_TRY(far_update(h, cu, c0, c1, c1, nnext, o.sU));
+            MPQR_CUDA(cudaEventRecord(o.ev_fn[b], o.sU));
+            MPQR_TRY(far_update(h, cu, c0, c1, c1 + nnext, nfar - nnext, o.sU));
+        } else {
+            MPQR_CUDA(cudaEventRecord(o.ev_fn[b], o.sP));
+        }
+    }
+    MPQR_CUDA(cudaEventRecord(o.ev_endP, o.sP));
+    MPQR_CUDA(cudaEventRecord(o.ev_endU, o.sU));
+    MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_endP, 0));
+    MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_endU, 0));
     return MPQR_OK;
 }
 
@@ -231,6 +370,8 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
     const int m = h->m, n = h->n, r = h->r;
     const int bf = h->prec == 2;
     const int Dblk = m - c0;
+    float* S32 = c.S32 ? c.S32 : h->S32;
+    void* S16 = c.S16 ? c.S16 : h->S16;
     for (int lam = c0; lam < c1; lam += r) {
         const int p = lam / r;
         const int pw = (lam + r < c1) ? r : c1 - lam;
@@ -252,23 +393,23 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             const void* Wp = (char*)c.W16 + ((size_t)jc * c.ldw + jc) * 2;
             const void* Yp = (char*)c.Y16 + ((size_t)jc * c.ldy + jc) * 2;
             PROF(1, 2.0 * pw * nin * D, tn_bytes(pw, nin, D),
-                 tc_gemm_tn(Wp, c.ldw, at16(c.Ah, c.ldh, lam, acol_tau), c.ldh, h->S32, h->lds32, pw, nin, D, bf, 1, st, &h->launches));
-            PROF(3, 0, 6.0 * pw * nin, convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, pw, nin, bf, st));
+                 tc_gemm_tn(Wp, c.ldw, at16(c.Ah, c.ldh, lam, acol_tau), c.ldh, S32, h->lds32, pw, nin, D, bf, 1, st, &h->launches));
+            PROF(3, 0, 6.0 * pw * nin, convert_f32_to_16(S32, h->lds32, S16, h->lds16, pw, nin, bf, st));
             h->launches += 1;
             // A[lam:, tau:c1] -= Y_p S   (+ shadow)
             PROF(2, 2.0 * D * nin * pw, nn_bytes(D, nin, pw),
-                 tc_gemm_nn(Yp, c.ldy, h->S16, h->lds16, c.A + (size_t)lam * c.lda + acol_tau, c.lda,
+                 tc_gemm_nn(Yp, c.ldy, S16, h->lds16, c.A + (size_t)lam * c.lda + acol_tau, c.lda,
                             at16(c.Ah, c.ldh, lam, acol_tau), c.ldh, D, nin, pw, bf, end_is_matrix_end, st, &h->launches));
         }
         if (jc > 0) {
             // WY accumulation: X = Y_prev^T W_p ; W_p -= W_prev X   (rows c0..m)
             const void* Wp = (char*)c.W16 + (size_t)jc * 2;
             PROF(1, 2.0 * jc * pw * Dblk, tn_bytes(jc, pw, Dblk),
-                 tc_gemm_tn(c.Y16, c.ldy, Wp, c.ldw, h->S32, h->lds32, jc, pw, Dblk, bf, 1, st, &h->launches));
-            PROF(3, 0, 6.0 * jc * pw, convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, jc, pw, bf, st));
+                 tc_gemm_tn(c.Y16, c.ldy, Wp, c.ldw, S32, h->lds32, jc, pw, Dblk, bf, 1, st, &h->launches));
+            PROF(3, 0, 6.0 * jc * pw, convert_f32_to_16(S32, h->lds32, S16, h->lds16, jc, pw, bf, st));
             h->launches += 1;
             PROF(2, 2.0 * Dblk * pw * jc, nn_bytes(Dblk, pw, jc),
-                 tc_gemm_nn(c.W16, c.ldw, h->S16, h->lds16, h->Wblk32 + jc, h->ldwb, (void*)Wp, c.ldw, Dblk, pw, jc, bf, 1, st, &h->launches));
+                 tc_gemm_nn(c.W16, c.ldw, S16, h->lds16, h->Wblk32 + jc, h->ldwb, (void*)Wp, c.ldw, Dblk, pw, jc, bf, 1, st, &h->launches));
         }
     }
     return MPQR_OK;
@@ -278,12 +419,14 @@ int far_update(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int afar, int 
     if (nfar <= 0) return MPQR_OK;
     const int bf = h->prec == 2;
     const int Dblk = h->m - c0, kb = c1 - c0;
+    float* S32 = c.S32 ? c.S32 : h->S32;
+    void* S16 = c.S16 ? c.S16 : h->S16;
     PROF(1, 2.0 * kb * nfar * Dblk, tn_bytes(kb, nfar, Dblk),
-         tc_gemm_tn(c.W16, c.ldw, at16(c.Ah, c.ldh, c0, afar), c.ldh, h->S32, h->lds32, kb, nfar, Dblk, bf, 1, st, &h->launches));
-    PROF(3, 0, 6.0 * kb * nfar, convert_f32_to_16(h->S32, h->lds32, h->S16, h->lds16, kb, nfar, bf, st));
+         tc_gemm_tn(c.W16, c.ldw, at16(c.Ah, c.ldh, c0, afar), c.ldh, S32, h->lds32, kb, nfar, Dblk, bf, 1, st, &h->launches));
+    PROF(3, 0, 6.0 * kb * nfar, convert_f32_to_16(S32, h->lds32, S16, h->lds16, kb, nfar, bf, st));
     h->launches += 1;
     PROF(2, 2.0 * Dblk * nfar * kb, nn_bytes(Dblk, nfar, kb),
-         tc_gemm_nn(c.Y16, c.ldy, h->S16, h->lds16, c.A + (size_t)c0 * c.lda + afar, c.lda, at16(c.Ah, c.ldh, c0, afar), c.ldh,
+         tc_gemm_nn(c.Y16, c.ldy, S16, h->lds16, c.A + (size_t)c0 * c.lda + afar, c.lda, at16(c.Ah, c.ldh, c0, afar), c.ldh,
                     Dblk, nfar, kb, bf, 1, st, &h->launches));
     return MPQR_OK;
 }
@@ -359,6 +502,19 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
             if ((rc = dev_alloc(h, (void**)&h->Wblk32, (size_t)m * h->ldwb * sizeof(float)))) break;
             h->lds16 = h->lds32;
             if ((rc = dev_alloc(h, &h->S16, (size_t)h->sk * h->lds16 * 2))) break;
+            const char* env = getenv("MPQR_OVERLAP");
+            const bool want_overlap = (env && env[0] == '1') && ceil_div(h->kmax, h->nb) >= 3;
+            if (want_overlap) {
+                const char* ps = getenv("MPQR_PANEL_SMS");
+                int panel_sms = ps ? atoi(ps) : 16;
+                if (panel_sms < 16) panel_sms = 16;
+                overlap_init(h, panel_sms);
+                if (h->ov.on) {
+                    if ((rc = dev_alloc(h, (void**)&h->S32u, (size_t)h->sk * h->lds32 * sizeof(float)))) break;
+                    if ((rc = dev_alloc(h, &h->S16u, (size_t)h->sk * h->lds16 * 2))) break;
+                    if (!h->keep_wy && (rc = dev_alloc(h, &h->W16b, (size_t)m * h->ldw16 * 2))) break;
+                }
+            }
         }
     } while (0);
     if (rc != MPQR_OK) {
@@ -372,6 +528,7 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
 int mpqr_destroy(mpqr_handle* h) {
     if (!h) return MPQR_OK;
     mg_destroy(h->mg);
+    overlap_destroy(h);
     for (void* p : h->allocs) cudaFree(p);
     for (auto& r : h->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : h->prof_pool) cudaEventDestroy(e);

@@ -40,6 +40,17 @@ struct DeviceInfo {
 };
 int get_device_info(DeviceInfo* out);
 
+// SM budget of the stream the host is currently issuing into (green-context partitions of the
+// look-ahead driver, api.cu).  0 = the whole device.  Persistent-kernel grids and split-K factors
+// are sized from sm_count(), not from the device attribute.
+extern thread_local int g_sm_budget;
+struct SmBudget {
+    int prev;
+    explicit SmBudget(int n) : prev(g_sm_budget) { g_sm_budget = n; }
+    ~SmBudget() { g_sm_budget = prev; }
+};
+inline int sm_count(const DeviceInfo& di) { return g_sm_budget > 0 ? g_sm_budget : di.num_sms; }
+
 // ------------------------------------------------------------------ panel factorisation
 constexpr int kPanelMaxWidth = 128;
 

@@ -108,7 +108,7 @@ int tn_any(const TI* X, long ldx, const TI* Z, long ldz, float* S, long lds, int
     int tiles = ceil_div(M, BM) * ceil_div(N, BN);
     int splits = 1;
     if (K > 4 * BK) {
-        int want = ceil_div(4 * di.num_sms, tiles);
+        int want = ceil_div(4 * sm_count(di), tiles);
         int maxs = ceil_div(K, 8 * BK);
         splits = want < 1 ? 1 : (want > maxs ? maxs : want);
     }

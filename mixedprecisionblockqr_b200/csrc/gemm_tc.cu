@@ -512,8 +512,8 @@ int tc_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long 
     const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
     const int kblocks = ceil_div(K, BK);
     int splits = 1;
-    if (tiles < di.num_sms && kblocks >= 8) {
-        splits = di.num_sms / tiles;
+    if (tiles < sm_count(di) && kblocks >= 8) {
+        splits = sm_count(di) / tiles;
         int maxs = kblocks / 4;
         if (splits > maxs) splits = maxs;
         if (splits < 1) splits = 1;
@@ -523,7 +523,7 @@ int tc_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long 
     if (p.splits > 1)
         MPQR_CUDA(cudaMemset2DAsync(S, lds * sizeof(float), 0, (size_t)N * sizeof(float), M, stream));
     int total = tiles * p.splits;
-    int grid = total < di.num_sms ? total : di.num_sms;
+    int grid = total < sm_count(di) ? total : sm_count(di);
     int rc = (BN == 256) ? launch<256, true, 0>(tA, tB, tC, tC, p, bf16 ? 1 : 0, grid, stream)
                          : launch<128, true, 0>(tA, tB, tC, tC, p, bf16 ? 1 : 0, grid, stream);
     if (rc == MPQR_OK && launches) *launches += 1;
@@ -561,7 +561,7 @@ static int tc_gemm_nn_impl(const void* X, long ldx, const void* S16, long lds16,
         tH = tC;
     }
     const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
-    int grid = tiles < di.num_sms ? tiles : di.num_sms;
+    int grid = tiles < sm_count(di) ? tiles : sm_count(di);
     int rc;
     if (store) rc = (BN == 256) ? launch<256, false, 2>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream)
                                 : launch<128, false, 2>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream);

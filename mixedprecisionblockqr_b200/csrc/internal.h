@@ -43,6 +43,20 @@ struct mpqr_handle {
     void* Qh = nullptr;  // m x ldqh shadow of Q (form_q)
     long ldqh = 0;
 
+    // look-ahead driver (api.cu): two green-context SM partitions with one stream each
+    struct Overlap {
+        bool on = false;
+        void* gP = nullptr;  // CUgreenCtx: panel partition
+        void* gU = nullptr;  // CUgreenCtx: update partition
+        cudaStream_t sP = nullptr, sU = nullptr;
+        int nsmP = 0, nsmU = 0;
+        std::vector<cudaEvent_t> ev_bp, ev_fn;
+        cudaEvent_t ev_start = nullptr, ev_endP = nullptr, ev_endU = nullptr;
+    } ov;
+    float* S32u = nullptr;  // scratch of the update stream (same shape as S32 / S16)
+    void* S16u = nullptr;
+    void* W16b = nullptr;   // second W buffer (blocks alternate) when the look-ahead driver is on
+
     // multi-GPU (mg.cu)
     void* mg = nullptr;
 
@@ -131,6 +145,8 @@ struct BlockCtx {
     long ldy;
     void* W16;     // W of the block: element (row c0, block column 0)
     long ldw;
+    float* S32;    // GEMM scratch of the issuing stream (null: the handle's)
+    void* S16;
 };
 // panels + in-block updates + WY accumulation of block [c0, c1); `ncols_in` = columns of A
 // (starting at acol0) that belong to the block's own panel region (= c1 - c0)

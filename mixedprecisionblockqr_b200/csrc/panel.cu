@@ -541,6 +541,9 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
 
 // ------------------------------------------------------------------ level 1: in-panel update
 // S'[rep][t][c] += sum_rows Y[row][t] * A[row][c]   (FP32; B x ncols, rows split over the grid)
+// 512 threads = 4 row groups x 128 columns; RB rows in flight per thread (memory-level parallelism
+// is what bounds these skinny passes: 512 x RB x 4 B in flight per SM).
+constexpr int SU_RB = 8;
 template <int B>
 __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict__ W, long ldw, const float* __restrict__ A,
                                                          long lda, int D, int ncols, float* __restrict__ Srep, int rows_per_cta) {
@@ -551,6 +554,15 @@ __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict_
     if (nrows > rows_per_cta) nrows = rows_per_cta;
     if (nrows <= 0) return;
     const int c0 = blockIdx.y * 128;
+    const bool on = (c0 + c) < ncols;
+    const float* Ac = A + (size_t)r0 * lda + c0 + c;
+    // first batch of A goes out before the Y chunk is staged (overlaps the two global latencies)
+    float av[SU_RB];
+#pragma unroll
+    for (int u = 0; u < SU_RB; ++u) {
+        const int r2 = rg + 4 * u;
+        av[u] = (on && r2 < nrows) ? __ldg(Ac + (size_t)r2 * lda) : 0.f;
+    }
     for (int idx = tid; idx < nrows * B; idx += 512) {
         int rr = idx / B, t = idx - rr * B;
         sm[idx] = W[(size_t)(r0 + rr) * ldw + t];
@@ -559,17 +571,15 @@ __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict_
     float acc[B];
 #pragma unroll
     for (int t = 0; t < B; ++t) acc[t] = 0.f;
-    const bool on = (c0 + c) < ncols;
-    const float* Ac = A + (size_t)r0 * lda + c0 + c;
-    for (int rr = rg; rr < nrows; rr += 16) {
-        float av[4];
+    for (int rr = rg; rr < nrows; rr += 4 * SU_RB) {
+        float nx[SU_RB];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int r2 = rr + 4 * u;
-            av[u] = (on && r2 < nrows) ? Ac[(size_t)r2 * lda] : 0.f;
+        for (int u = 0; u < SU_RB; ++u) {  // next batch in flight while this one is consumed
+            const int r2 = rr + 4 * SU_RB + 4 * u;
+            nx[u] = (on && r2 < nrows) ? __ldg(Ac + (size_t)r2 * lda) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < SU_RB; ++u) {
             const int r2 = rr + 4 * u;
             if (r2 < nrows) {
                 const float* wr = sm + r2 * B;
@@ -583,8 +593,10 @@ __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict_
                 }
             }
         }
+#pragma unroll
+        for (int u = 0; u < SU_RB; ++u) av[u] = nx[u];
     }
-    __syncthreads();  // W chunk no longer needed: reuse shared memory for the row-group reduction
+    __syncthreads();  // Y chunk no longer needed: reuse shared memory for the row-group reduction
     if (rg > 0) {
 #pragma unroll
         for (int t = 0; t < B; ++t) sm[((rg - 1) * B + t) * 128 + c] = acc[t];
@@ -607,6 +619,8 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
                                                          const float* __restrict__ Tj, int rows_per_cta) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float Ts[B][B + 1];
+    __shared__ float Sp[B][128];
+    __shared__ float S2[B][128];
     const int tid = threadIdx.x, c = tid & 127, rg = tid >> 7;
     const int r0 = blockIdx.x * rows_per_cta;
     int nrows = D - r0;
@@ -614,9 +628,14 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
     if (nrows <= 0) return;
     const int c0 = blockIdx.y * 128;
     const bool on = (c0 + c) < ncols;
+    float* Ac = A + (size_t)r0 * lda + c0 + c;
+    float av[SU_RB];
+#pragma unroll
+    for (int u = 0; u < SU_RB; ++u) {  // first batch of A in flight during the prologue
+        const int r2 = rg + 4 * u;
+        av[u] = (on && r2 < nrows) ? Ac[(size_t)r2 * lda] : 0.f;
+    }
     // S' = sum of the replicas (B x 128 chunk), once per CTA
-    __shared__ float Sp[B][128];
-    __shared__ float S2[B][128];
     for (int idx = tid; idx < B * 128; idx += 512) {
         const int t = idx >> 7, cc = idx & 127;
         float v = 0.f;
@@ -632,42 +651,47 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
         sm[idx] = Y[(size_t)(r0 + rr) * ldy + t];
     }
     __syncthreads();
-    // S = T^T S': row group rg computes rows t = rg, rg+4, ... of its column
+    // S = T^T S': row group rg computes rows t = rg, rg+4, ... of its column (T is zero below its diagonal)
     for (int t = rg; t < B; t += 4) {
-        float v = 0.f;
-        for (int u2 = 0; u2 <= t; ++u2) v = fmaf(Ts[u2][t], Sp[u2][c], v);
-        S2[t][c] = v;
+        float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+        for (int u2 = 0; u2 < B; u2 += 2) {
+            v0 = fmaf(Ts[u2][t], Sp[u2][c], v0);
+            v1 = fmaf(Ts[u2 + 1][t], Sp[u2 + 1][c], v1);
+        }
+        S2[t][c] = v0 + v1;
     }
     __syncthreads();
     if (!on) return;
     float s[B];
 #pragma unroll
     for (int t = 0; t < B; ++t) s[t] = S2[t][c];
-    float* Ac = A + (size_t)r0 * lda + c0 + c;
-    for (int rr = rg; rr < nrows; rr += 16) {
-        float av[4];
+    for (int rr = rg; rr < nrows; rr += 4 * SU_RB) {
+        float nx[SU_RB];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int r2 = rr + 4 * u;
-            av[u] = (r2 < nrows) ? Ac[(size_t)r2 * lda] : 0.f;
+        for (int u = 0; u < SU_RB; ++u) {
+            const int r2 = rr + 4 * SU_RB + 4 * u;
+            nx[u] = (r2 < nrows) ? Ac[(size_t)r2 * lda] : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < SU_RB; ++u) {
             const int r2 = rr + 4 * u;
             if (r2 < nrows) {
                 const float* yr = sm + r2 * B;
-                float d = 0.f;
+                float d0 = 0.f, d1 = 0.f;
 #pragma unroll
                 for (int q = 0; q < B / 4; ++q) {
                     const float4 y4 = *reinterpret_cast<const float4*>(yr + 4 * q);
-                    d = fmaf(y4.x, s[4 * q], d);
-                    d = fmaf(y4.y, s[4 * q + 1], d);
-                    d = fmaf(y4.z, s[4 * q + 2], d);
-                    d = fmaf(y4.w, s[4 * q + 3], d);
+                    d0 = fmaf(y4.x, s[4 * q], d0);
+                    d1 = fmaf(y4.y, s[4 * q + 1], d1);
+                    d0 = fmaf(y4.z, s[4 * q + 2], d0);
+                    d1 = fmaf(y4.w, s[4 * q + 3], d1);
                 }
-                Ac[(size_t)r2 * lda] = av[u] - d;
+                Ac[(size_t)r2 * lda] = av[u] - (d0 + d1);
             }
         }
+#pragma unroll
+        for (int u = 0; u < SU_RB; ++u) av[u] = nx[u];
     }
 }
 
@@ -711,32 +735,59 @@ __global__ void __launch_bounds__(1024) tinv_kernel(const float* __restrict__ G,
     }
     __syncthreads();
     for (int h = 16; h < R; h *= 2) {
-        // pairs (p): blocks [o, o+h) and [o+h, o+2h)
+        // pairs: blocks [o, o+h) and [o+h, o+2h).  Each thread owns a 4 x 4 tile of the h x h products
+        // (shared memory bandwidth bounds this kernel: 0.5 LDS per FMA instead of 2).
         const int npairs = R / (2 * h);
-        // X = G12 * T22   (h x h per pair)
-        for (int idx = tid; idx < npairs * h * h; idx += 1024) {
-            const int pr = idx / (h * h), e = idx - pr * h * h;
-            const int i = e / h, j = e - i * h, o = pr * 2 * h;
-            float s0 = 0.f, s1 = 0.f;  // T22 is zero below its diagonal: fixed trip count, loads pipeline
-#pragma unroll 8
-            for (int u2 = 0; u2 < h; u2 += 2) {
-                s0 = fmaf(Ts[(o + i) * TLD + o + h + u2], Ts[(o + h + u2) * TLD + o + h + j], s0);
-                s1 = fmaf(Ts[(o + i) * TLD + o + h + u2 + 1], Ts[(o + h + u2 + 1) * TLD + o + h + j], s1);
+        const int tpr = h / 4;                 // tiles per row/column of one product
+        const int ntiles = npairs * tpr * tpr;  // <= (R/2h) * h*h/16 = R*h/32 <= 256
+        const bool on = tid < ntiles;
+        const int pr = tid / (tpr * tpr), e = tid - pr * tpr * tpr;
+        const int i0 = 4 * (e / tpr), j0 = 4 * (e % tpr), o = pr * 2 * h;
+        float acc[4][4];
+        if (on) {
+            // X = G12 * T22 (T22 zero below its diagonal: fixed trip count)
+#pragma unroll
+            for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) acc[a2][b2] = 0.f;
+            for (int u2 = 0; u2 < h; ++u2) {
+                float ga[4], tb[4];
+#pragma unroll
+                for (int a2 = 0; a2 < 4; ++a2) ga[a2] = Ts[(o + i0 + a2) * TLD + o + h + u2];
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) tb[b2] = Ts[(o + h + u2) * TLD + o + h + j0 + b2];
+#pragma unroll
+                for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; ++b2) acc[a2][b2] = fmaf(ga[a2], tb[b2], acc[a2][b2]);
             }
-            Xs[(pr * h + i) * 65 + j] = s0 + s1;  // pr*h + i < 64 (npairs*h = R/2 <= 64)
+#pragma unroll
+            for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) Xs[(pr * h + i0 + a2) * 65 + j0 + b2] = acc[a2][b2];  // pr*h + i < 64
         }
         __syncthreads();
-        // T12 = -T11 * X
-        for (int idx = tid; idx < npairs * h * h; idx += 1024) {
-            const int pr = idx / (h * h), e = idx - pr * h * h;
-            const int i = e / h, j = e - i * h, o = pr * 2 * h;
-            float s0 = 0.f, s1 = 0.f;  // T11 is zero below its diagonal
-#pragma unroll 8
-            for (int u2 = 0; u2 < h; u2 += 2) {
-                s0 = fmaf(Ts[(o + i) * TLD + o + u2], Xs[(pr * h + u2) * 65 + j], s0);
-                s1 = fmaf(Ts[(o + i) * TLD + o + u2 + 1], Xs[(pr * h + u2 + 1) * 65 + j], s1);
+        if (on) {
+            // T12 = -T11 * X (T11 zero below its diagonal)
+#pragma unroll
+            for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) acc[a2][b2] = 0.f;
+            for (int u2 = 0; u2 < h; ++u2) {
+                float ta[4], xb[4];
+#pragma unroll
+                for (int a2 = 0; a2 < 4; ++a2) ta[a2] = Ts[(o + i0 + a2) * TLD + o + u2];
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) xb[b2] = Xs[(pr * h + u2) * 65 + j0 + b2];
+#pragma unroll
+                for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; ++b2) acc[a2][b2] = fmaf(ta[a2], xb[b2], acc[a2][b2]);
             }
-            Ts[(o + i) * TLD + o + h + j] = -(s0 + s1);
+#pragma unroll
+            for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) Ts[(o + i0 + a2) * TLD + o + h + j0 + b2] = -acc[a2][b2];
         }
         __syncthreads();
     }
@@ -894,7 +945,7 @@ Ws carve(float* ws, long rows) {
 
 template <int B>
 int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, int num_sms,
-              cudaStream_t st, long* launches) {
+              cudaStream_t st, long* launches, const ProfHook* prof) {
     static bool attr = false;
     const int max_rows = 256;
     int rows = ceil_div(D, num_sms);
@@ -908,10 +959,13 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
         attr = true;
     }
     dim3 grid(ceil_div(D, rows), ceil_div(ncols, 128));
+    if (prof) prof->begin(prof->ctx, 5, st);
     inpanel_s_kernel<B><<<grid, 512, smem_s, st>>>(Yj, ldy, Arest, lda, D, ncols, Srep, rows);
     MPQR_CUDA(cudaGetLastError());
+    if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st); }
     inpanel_u_kernel<B><<<grid, 512, smem_u, st>>>(Yj, ldy, Arest, lda, D, ncols, Srep, Tj, rows);
     MPQR_CUDA(cudaGetLastError());
+    if (prof) prof->end(prof->ctx, st);
     if (launches) *launches += 2;
     return MPQR_OK;
 }
@@ -996,10 +1050,8 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         if (launches) *launches += 1;
         if (nrest > 0) {
             float* Arest = b.A + bw;
-            if (a.prof) a.prof->begin(a.prof->ctx, 5, stream);
-            if (B == 32) MPQR_TRY(launch_su<32>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, di.num_sms, stream, launches));
-            else MPQR_TRY(launch_su<16>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, di.num_sms, stream, launches));
-            if (a.prof) a.prof->end(a.prof->ctx, stream);
+            if (B == 32) MPQR_TRY(launch_su<32>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, sm_count(di), stream, launches, a.prof));
+            else MPQR_TRY(launch_su<16>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, sm_count(di), stream, launches, a.prof));
         }
     }
     if (a.dbg_caps) { a.dbg_caps[0] = max_cluster(); a.dbg_caps[1] = cs; a.dbg_caps[2] = rpt; }

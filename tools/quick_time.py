@@ -55,9 +55,9 @@ def run(m, n, r, prec, nb=0, reps=3, check=True):
         pkg.fill_uniform(A.data_ptr(), lda, n, 0, m, 0, n, 1234, st)
         plan.factor(A.data_ptr(), lda, st)
         torch.cuda.synchronize()
-        names = ["panel(all)", "gemm_tn", "gemm_nn", "cast", "panel:block", "panel:S/U", "panel:G/T/W"]
+        names = ["panel(all)", "gemm_tn", "gemm_nn", "cast", "panel:block", "panel:S", "panel:G/T/W", "panel:U"]
         out = []
-        for c in range(7):
+        for c in range(8):
             ms, cnt, fl, by = ctypes.c_double(), ctypes.c_long(), ctypes.c_double(), ctypes.c_double()
             L.mpqr_get_profile(plan._h, c, ctypes.byref(ms), ctypes.byref(cnt), ctypes.byref(fl), ctypes.byref(by))
             out.append(f"{names[c]}={ms.value:.2f}ms/{cnt.value}")
