@@ -51,6 +51,21 @@ struct SmBudget {
 };
 inline int sm_count(const DeviceInfo& di) { return g_sm_budget > 0 ? g_sm_budget : di.num_sms; }
 
+// Programmatic dependent launch (PDL): every kernel of the factorisation chain lets its successor
+// become resident at once (launch_dependents) and waits for its predecessor's completion and
+// memory flush (wait) only after its own set-up, so launch latency and prologues overlap the
+// predecessor's tail.  Host side: launch with pdl_attr() through cudaLaunchKernelEx.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+inline cudaLaunchAttribute pdl_attr() {
+    cudaLaunchAttribute a{};
+    a.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    a.val.programmaticStreamSerializationAllowed = 1;
+    return a;
+}
+
 // ------------------------------------------------------------------ panel factorisation
 constexpr int kPanelMaxWidth = 128;
 

@@ -221,10 +221,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, C_::TMEM_COLS);
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // barrier init / TMEM allocation / descriptor prefetch overlapped the predecessor's tail
 
     auto decode = [&](int w, int& mb, int& nb, int& kb0, int& kb1) {
         int tile = w / p.splits, ks = w - tile * p.splits;
@@ -465,8 +467,11 @@ int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, 
                                        C_::SMEM_BYTES));
         attr = true;
     }
-    tc_gemm_kernel<BN, kAMN, kEpi><<<grid, NTHREADS, C_::SMEM_BYTES, stream>>>(tA, tB, tC, tH, p, fmt16);
-    MPQR_CUDA(cudaGetLastError());
+    cudaLaunchAttribute pat[1] = {pdl_attr()};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.stream = stream; cfg.attrs = pat; cfg.numAttrs = 1;
+    cfg.dynamicSmemBytes = C_::SMEM_BYTES;
+    MPQR_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, kAMN, kEpi>, tA, tB, tC, tH, p, fmt16));
     return MPQR_OK;
 }
 

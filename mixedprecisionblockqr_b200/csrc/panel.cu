@@ -75,10 +75,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+// The awaited data are st.async writes into THIS CTA's shared memory, completed through the barrier's
+// tx-count: the default (CTA-scope acquire) wait is sufficient and avoids the L1 invalidate (CCTL.IVALL)
+// that a cluster-scope acquire emits on every step.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
         "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}"
         ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
@@ -282,6 +285,18 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
     long long pacc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = prof ? clock64() : 0;
 
+    pdl_launch_dependents();
+    for (int idx = tid; idx < B * (B + 4); idx += NT) (&gt[0][0])[idx] = 0.f;
+    if (CS > 1) {
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster_sync_all();  // peers must not signal a barrier that is not initialised yet
+    }
+    pdl_wait();  // everything above overlapped the predecessor's tail; its results are visible from here on
+
     float x[RPT][B];
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
@@ -293,21 +308,11 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
             for (int c = 0; c < B; ++c) x[u][c] = 0.f;
         }
     }
-    for (int idx = tid; idx < B * (B + 4); idx += NT) (&gt[0][0])[idx] = 0.f;
     if (a.zero_buf) {
         const int nthr = CS * NT;
         for (int idx = (int)crank * NT + tid; idx < a.zero_n; idx += nthr) a.zero_buf[idx] = 0.f;
     }
-    if (CS > 1) {
-        if (tid == 0) {
-            mbar_init(&mbar[0], 1);
-            mbar_init(&mbar[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        cluster_sync_all();  // peers must not signal a barrier that is not initialised yet
-    } else {
-        __syncthreads();
-    }
+    __syncthreads();
     PROF_MARK(6);
 
     const uint32_t tx_bytes = (uint32_t)(CS + 1) * B * 4;
@@ -543,10 +548,13 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
 // S'[rep][t][c] += sum_rows Y[row][t] * A[row][c]   (FP32; B x ncols, rows split over the grid)
 // 512 threads = 4 row groups x 128 columns; RB rows in flight per thread (memory-level parallelism
 // is what bounds these skinny passes: 512 x RB x 4 B in flight per SM).
-constexpr int SU_RB = 8;
+// rows in flight per thread: the loops are latency-bound (one round trip per batch), so a CTA's rows
+// should be covered in about two batches
+template <int B> struct SuRb { static constexpr int value = (B == 16) ? 32 : 16; };
 template <int B>
 __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict__ W, long ldw, const float* __restrict__ A,
                                                          long lda, int D, int ncols, float* __restrict__ Srep, int rows_per_cta) {
+    constexpr int SU_RB = SuRb<B>::value;
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, c = tid & 127, rg = tid >> 7;
     const int r0 = blockIdx.x * rows_per_cta;
@@ -556,6 +564,8 @@ __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict_
     const int c0 = blockIdx.y * 128;
     const bool on = (c0 + c) < ncols;
     const float* Ac = A + (size_t)r0 * lda + c0 + c;
+    pdl_launch_dependents();
+    pdl_wait();
     // first batch of A goes out before the Y chunk is staged (overlaps the two global latencies)
     float av[SU_RB];
 #pragma unroll
@@ -617,8 +627,9 @@ template <int B>
 __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict__ Y, long ldy, float* __restrict__ A, long lda,
                                                          int D, int ncols, const float* __restrict__ Srep,
                                                          const float* __restrict__ Tj, int rows_per_cta) {
+    constexpr int SU_RB = SuRb<B>::value;
     extern __shared__ __align__(16) float sm[];
-    __shared__ float Ts[B][B + 1];
+    __shared__ __align__(16) float Ts[B][B + 4];
     __shared__ float Sp[B][128];
     __shared__ float S2[B][128];
     const int tid = threadIdx.x, c = tid & 127, rg = tid >> 7;
@@ -629,6 +640,8 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
     const int c0 = blockIdx.y * 128;
     const bool on = (c0 + c) < ncols;
     float* Ac = A + (size_t)r0 * lda + c0 + c;
+    pdl_launch_dependents();
+    pdl_wait();
     float av[SU_RB];
 #pragma unroll
     for (int u = 0; u < SU_RB; ++u) {  // first batch of A in flight during the prologue
@@ -651,15 +664,27 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
         sm[idx] = Y[(size_t)(r0 + rr) * ldy + t];
     }
     __syncthreads();
-    // S = T^T S': row group rg computes rows t = rg, rg+4, ... of its column (T is zero below its diagonal)
-    for (int t = rg; t < B; t += 4) {
-        float v0 = 0.f, v1 = 0.f;
+    // S = T^T S': row group rg computes B/4 consecutive rows t of its column; T is zero below its
+    // diagonal, so the sum runs over all u2 with 16-byte broadcast reads of T (shared-memory bandwidth bound)
+    {
+        constexpr int TQ = B / 4;
+        float v[TQ];
 #pragma unroll
-        for (int u2 = 0; u2 < B; u2 += 2) {
-            v0 = fmaf(Ts[u2][t], Sp[u2][c], v0);
-            v1 = fmaf(Ts[u2 + 1][t], Sp[u2 + 1][c], v1);
+        for (int q = 0; q < TQ; ++q) v[q] = 0.f;
+#pragma unroll 4
+        for (int u2 = 0; u2 < B; ++u2) {
+            const float sp = Sp[u2][c];
+#pragma unroll
+            for (int q = 0; q < TQ; q += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(&Ts[u2][rg * TQ + q]);
+                v[q] = fmaf(t4.x, sp, v[q]);
+                v[q + 1] = fmaf(t4.y, sp, v[q + 1]);
+                v[q + 2] = fmaf(t4.z, sp, v[q + 2]);
+                v[q + 3] = fmaf(t4.w, sp, v[q + 3]);
+            }
         }
-        S2[t][c] = v0 + v1;
+#pragma unroll
+        for (int q = 0; q < TQ; ++q) S2[rg * TQ + q][c] = v[q];
     }
     __syncthreads();
     if (!on) return;
@@ -695,6 +720,207 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
     }
 }
 
+// ---- vectorised in-panel kernels (16-byte aligned A_rest, ncols % 4 == 0): one thread owns FOUR
+// columns and all B reflectors, i.e. 4*B FMAs per 16-byte load and B/4 broadcast LDS.128 (the
+// one-column kernels above issue ~5x more instructions per FMA and are kept for unaligned shapes).
+// The last CTA to finish (ticket counter) folds the replicas and applies T^T once, so that the
+// update kernel starts from the final S = T^T (Y^T A_rest).
+template <int B> struct Su4 {
+    static constexpr int NTHR = (B == 16) ? 512 : 256;
+    static constexpr int RB = 8;  // rows in flight per thread
+};
+
+template <int B>
+__global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* __restrict__ Y, long ldy, const float* __restrict__ A,
+                                                                  long lda, int D, int ncols, float* __restrict__ Srep,
+                                                                  unsigned* __restrict__ counter, const float* __restrict__ Tj,
+                                                                  float* __restrict__ Sfin, int rows_per_cta, int ysm_floats) {
+    constexpr int NTHR = Su4<B>::NTHR, NWARP = NTHR / 32, RB = Su4<B>::RB;
+    extern __shared__ __align__(16) float sm[];
+    float* ysm = sm;               // rows_per_cta x B  (later: T, B x (B+4))
+    float* red = sm + ysm_floats;  // B x 128           (later: S')
+    __shared__ unsigned ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = blockIdx.x * rows_per_cta;
+    int nrows = D - r0;
+    if (nrows > rows_per_cta) nrows = rows_per_cta;
+    const int c0 = blockIdx.y * 128, col = c0 + 4 * lane;
+    const bool on = col < ncols;
+    pdl_launch_dependents();
+    pdl_wait();
+    const float* Ap = A + (size_t)r0 * lda + col;
+    float4 a4[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {  // first batch in flight while Y is staged
+        const int r2 = warp + u * NWARP;
+        a4[u] = (on && r2 < nrows) ? __ldg(reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int idx = tid; idx < nrows * B; idx += NTHR) {
+        const int rr = idx / B, t = idx - rr * B;
+        ysm[idx] = Y[(size_t)(r0 + rr) * ldy + t];
+    }
+    __syncthreads();
+    float acc[B][4];
+#pragma unroll
+    for (int t = 0; t < B; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+    for (int rb = warp; rb < nrows; rb += NWARP * RB) {
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const int r2 = rb + u * NWARP;
+            if (r2 < nrows) {
+                const float* yr = ysm + r2 * B;
+#pragma unroll
+                for (int q = 0; q < B / 4; ++q) {
+                    const float4 y4 = *reinterpret_cast<const float4*>(yr + 4 * q);
+                    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        acc[4 * q + k][0] = fmaf(yv[k], a4[u].x, acc[4 * q + k][0]);
+                        acc[4 * q + k][1] = fmaf(yv[k], a4[u].y, acc[4 * q + k][1]);
+                        acc[4 * q + k][2] = fmaf(yv[k], a4[u].z, acc[4 * q + k][2]);
+                        acc[4 * q + k][3] = fmaf(yv[k], a4[u].w, acc[4 * q + k][3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const int r2 = rb + NWARP * RB + u * NWARP;
+            a4[u] = (on && r2 < nrows) ? __ldg(reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    // cross-warp tree through shared memory (conflict-free 16-byte slots), then warp 0 adds the
+    // CTA's partial S' into its replica
+    __syncthreads();  // Y chunk no longer needed
+    for (int half = NWARP / 2; half >= 1; half >>= 1) {
+        if (warp >= half && warp < 2 * half) {
+            float4* dst = reinterpret_cast<float4*>(sm) + ((size_t)(warp - half) * B) * 32 + lane;
+#pragma unroll
+            for (int t = 0; t < B; ++t) dst[t * 32] = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+        }
+        __syncthreads();
+        if (warp < half) {
+            const float4* src = reinterpret_cast<const float4*>(sm) + ((size_t)warp * B) * 32 + lane;
+#pragma unroll
+            for (int t = 0; t < B; ++t) {
+                const float4 v = src[t * 32];
+                acc[t][0] += v.x; acc[t][1] += v.y; acc[t][2] += v.z; acc[t][3] += v.w;
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 0 && on) {
+        float* S = Srep + (size_t)(blockIdx.x % NREP) * RMAX * SLD + col;
+#pragma unroll
+        for (int t = 0; t < B; ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(&S[t * SLD + k], acc[t][k]);
+    }
+    // ---- last CTA: S = T^T (sum of the replicas)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) ticket = atomicAdd(counter, 1u);
+    __syncthreads();
+    if (ticket != gridDim.x * gridDim.y - 1) return;
+    __threadfence();
+    float* Ts = ysm;  // B x (B + 4)
+    for (int idx = tid; idx < B * 128; idx += NTHR) {
+        const int t = idx >> 7, cc = idx & 127;
+        float v = 0.f;
+        if (cc < ncols) {
+#pragma unroll
+            for (int rep = 0; rep < NREP; ++rep) v += __ldcg(&Srep[(size_t)rep * RMAX * SLD + t * SLD + cc]);
+        }
+        red[idx] = v;
+    }
+    for (int idx = tid; idx < B * B; idx += NTHR) Ts[(idx / B) * (B + 4) + (idx % B)] = Tj[idx];
+    __syncthreads();
+    {
+        constexpr int NG = NTHR / 128, TQ = B / NG;  // thread: column cc, TQ consecutive rows t of S
+        const int cc = tid & 127, tg = tid >> 7;
+        float v[TQ];
+#pragma unroll
+        for (int q = 0; q < TQ; ++q) v[q] = 0.f;
+#pragma unroll 4
+        for (int u2 = 0; u2 < B; ++u2) {  // T is zero below its diagonal
+            const float sp = red[u2 * 128 + cc];
+#pragma unroll
+            for (int q = 0; q < TQ; q += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(&Ts[u2 * (B + 4) + tg * TQ + q]);
+                v[q] = fmaf(t4.x, sp, v[q]);
+                v[q + 1] = fmaf(t4.y, sp, v[q + 1]);
+                v[q + 2] = fmaf(t4.z, sp, v[q + 2]);
+                v[q + 3] = fmaf(t4.w, sp, v[q + 3]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < TQ; ++q) Sfin[(size_t)(tg * TQ + q) * SLD + cc] = v[q];
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* __restrict__ Y, long ldy, float* __restrict__ A, long lda,
+                                                                  int D, int ncols, const float* __restrict__ Sfin, int rows_per_cta) {
+    constexpr int NTHR = Su4<B>::NTHR, NWARP = NTHR / 32, RB = Su4<B>::RB;
+    extern __shared__ __align__(16) float sm[];
+    float* ysm = sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = blockIdx.x * rows_per_cta;
+    int nrows = D - r0;
+    if (nrows > rows_per_cta) nrows = rows_per_cta;
+    const int c0 = blockIdx.y * 128, col = c0 + 4 * lane;
+    const bool on = col < ncols;
+    pdl_launch_dependents();
+    pdl_wait();
+    float* Ap = A + (size_t)r0 * lda + col;
+    float4 a4[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+        const int r2 = warp + u * NWARP;
+        a4[u] = (on && r2 < nrows) ? *reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float sv[B][4];
+#pragma unroll
+    for (int t = 0; t < B; ++t) {
+        const float4 s4 = on ? __ldcg(reinterpret_cast<const float4*>(Sfin + (size_t)t * SLD + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sv[t][0] = s4.x; sv[t][1] = s4.y; sv[t][2] = s4.z; sv[t][3] = s4.w;
+    }
+    for (int idx = tid; idx < nrows * B; idx += NTHR) {
+        const int rr = idx / B, t = idx - rr * B;
+        ysm[idx] = Y[(size_t)(r0 + rr) * ldy + t];
+    }
+    __syncthreads();
+    if (!on) return;
+    for (int rb = warp; rb < nrows; rb += NWARP * RB) {
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const int r2 = rb + u * NWARP;
+            if (r2 < nrows) {
+                const float* yr = ysm + r2 * B;
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int q = 0; q < B / 4; ++q) {
+                    const float4 y4 = *reinterpret_cast<const float4*>(yr + 4 * q);
+                    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        d[0] = fmaf(yv[k], sv[4 * q + k][0], d[0]);
+                        d[1] = fmaf(yv[k], sv[4 * q + k][1], d[1]);
+                        d[2] = fmaf(yv[k], sv[4 * q + k][2], d[2]);
+                        d[3] = fmaf(yv[k], sv[4 * q + k][3], d[3]);
+                    }
+                }
+                *reinterpret_cast<float4*>(Ap + (size_t)r2 * lda) = make_float4(a4[u].x - d[0], a4[u].y - d[1], a4[u].z - d[2], a4[u].w - d[3]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const int r2 = rb + NWARP * RB + u * NWARP;
+            a4[u] = (r2 < nrows) ? *reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ level 2: T = (striu(G) + I/2)^-1
 // One CTA, recursive doubling: the 16 x 16 diagonal blocks are inverted column by column, then
 // T12 = -T11 (G12 T22) merges pairs of blocks (16 -> 32 -> 64 -> 128).  G is read from global
@@ -706,6 +932,8 @@ __global__ void __launch_bounds__(1024) tinv_kernel(const float* __restrict__ G,
     float* Ts = sm;               // RMAX x TLD
     float* Xs = sm + RMAX * TLD;  // 64 x 65 temp
     const int tid = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     int R = 16;
     while (R < pw) R *= 2;
     for (int idx = tid; idx < R * R; idx += 1024) {
@@ -840,7 +1068,7 @@ int launch_block_t(const BlockArgs& a, int CS, cudaStream_t stream) {
     cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     int na = 0;
     if (CS > 1) {
         at[na].id = cudaLaunchAttributeClusterDimension;
@@ -849,6 +1077,7 @@ int launch_block_t(const BlockArgs& a, int CS, cudaStream_t stream) {
         at[na].val.clusterDim.z = 1;
         ++na;
     }
+    at[na++] = pdl_attr();
     cfg.attrs = at;
     cfg.numAttrs = na;
     MPQR_CUDA(cudaLaunchKernelEx(&cfg, panel_block_kernel<B, RPT>, a, CS));
@@ -927,7 +1156,8 @@ int launch_block(int B, const BlockArgs& a, int RPT, int CS, cudaStream_t st) {
 struct Ws {
     float* Y32p;
     float* Wj;
-    float* Srep;
+    float* Srep;     // NREP replicas | 4 floats (ticket counter) : cleared together by the block kernel
+    float* Sfin;     // RMAX x SLD: S = T^T (Y^T A_rest)
     float* G;
     float* T32;
     void* T16;
@@ -937,34 +1167,65 @@ Ws carve(float* ws, long rows) {
     w.Y32p = ws;
     w.Wj = w.Y32p + (size_t)rows * RMAX;
     w.Srep = w.Wj + (size_t)rows * 32;
-    w.G = w.Srep + (size_t)NREP * RMAX * SLD;
+    w.Sfin = w.Srep + (size_t)NREP * RMAX * SLD + 4;
+    w.G = w.Sfin + (size_t)RMAX * SLD;
     w.T32 = w.G + (size_t)RMAX * RMAX;
     w.T16 = (void*)(w.T32 + (size_t)RMAX * RMAX);
     return w;
 }
 
+int launch_tinv(const float* G, long ldg, int pw, float* T32, int ldt, void* T16, long ldt16, int bf16, size_t smem, cudaStream_t st) {
+    cudaLaunchAttribute pat[1] = {pdl_attr()};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(1024); cfg.stream = st; cfg.attrs = pat; cfg.numAttrs = 1;
+    cfg.dynamicSmemBytes = smem;
+    MPQR_CUDA(cudaLaunchKernelEx(&cfg, tinv_kernel, G, ldg, pw, T32, ldt, T16, ldt16, bf16));
+    return MPQR_OK;
+}
+
 template <int B>
-int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, int num_sms,
-              cudaStream_t st, long* launches, const ProfHook* prof) {
+int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, float* Sfin,
+              int num_sms, cudaStream_t st, long* launches, const ProfHook* prof) {
     static bool attr = false;
     const int max_rows = 256;
     int rows = ceil_div(D, num_sms);
     rows = round_up(rows < 16 ? 16 : rows, 16);
     if (rows > max_rows) rows = max_rows;
-    const size_t smem_s = (size_t)((rows * B > 3 * B * 128) ? rows * B : 3 * B * 128) * sizeof(float);
-    const size_t smem_u = (size_t)rows * B * sizeof(float);
     if (!attr) {
         MPQR_CUDA(cudaFuncSetAttribute(inpanel_s_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 32 * 128 * 4));
         MPQR_CUDA(cudaFuncSetAttribute(inpanel_u_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        MPQR_CUDA(cudaFuncSetAttribute(inpanel_s4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        MPQR_CUDA(cudaFuncSetAttribute(inpanel_u4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr = true;
     }
     dim3 grid(ceil_div(D, rows), ceil_div(ncols, 128));
+    cudaLaunchAttribute pat[1] = {pdl_attr()};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.stream = st; cfg.attrs = pat; cfg.numAttrs = 1;
+    const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(Arest) & 15) == 0) && ((ncols & 3) == 0) && ncols <= 128;
     if (prof) prof->begin(prof->ctx, 5, st);
-    inpanel_s_kernel<B><<<grid, 512, smem_s, st>>>(Yj, ldy, Arest, lda, D, ncols, Srep, rows);
-    MPQR_CUDA(cudaGetLastError());
-    if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st); }
-    inpanel_u_kernel<B><<<grid, 512, smem_u, st>>>(Yj, ldy, Arest, lda, D, ncols, Srep, Tj, rows);
-    MPQR_CUDA(cudaGetLastError());
+    if (vec) {
+        int ysm_floats = rows * B;
+        if (ysm_floats < B * (B + 4)) ysm_floats = B * (B + 4);
+        cfg.blockDim = dim3(Su4<B>::NTHR);
+        size_t s4_floats = (size_t)ysm_floats + B * 128;
+        const size_t tree_floats = (size_t)(Su4<B>::NTHR / 32) * B * 64;
+        if (s4_floats < tree_floats) s4_floats = tree_floats;
+        cfg.dynamicSmemBytes = s4_floats * sizeof(float);
+        unsigned* counter = reinterpret_cast<unsigned*>(Srep + (size_t)NREP * RMAX * SLD);
+        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_s4_kernel<B>, Yj, ldy, (const float*)Arest, lda, D, ncols, Srep, counter, Tj, Sfin, rows,
+                                     ysm_floats));
+        if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st); }
+        cfg.dynamicSmemBytes = (size_t)rows * B * sizeof(float);
+        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_u4_kernel<B>, Yj, ldy, Arest, lda, D, ncols, (const float*)Sfin, rows));
+    } else {
+        cfg.blockDim = dim3(512);
+        cfg.dynamicSmemBytes = (size_t)((rows * B > 3 * B * 128) ? rows * B : 3 * B * 128) * sizeof(float);
+        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_s_kernel<B>, Yj, ldy, (const float*)Arest, lda, D, ncols, Srep, rows));
+        if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st); }
+        cfg.dynamicSmemBytes = (size_t)rows * B * sizeof(float);
+        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_u_kernel<B>, Yj, ldy, Arest, lda, D, ncols, (const float*)Srep, Tj, rows));
+    }
     if (prof) prof->end(prof->ctx, st);
     if (launches) *launches += 2;
     return MPQR_OK;
@@ -973,7 +1234,7 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
 }  // namespace
 
 size_t panel_ws_bytes(long max_rows) {
-    return ((size_t)max_rows * (RMAX + 32) + (size_t)NREP * RMAX * SLD + 2 * (size_t)RMAX * RMAX) * sizeof(float) +
+    return ((size_t)max_rows * (RMAX + 32) + (size_t)(NREP + 1) * RMAX * SLD + 4 + 2 * (size_t)RMAX * RMAX) * sizeof(float) +
            (size_t)RMAX * RMAX * 2 + 256;
 }
 
@@ -1043,15 +1304,15 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         if (nrest > 0) { b.T = w.Wj; b.ldt = B; }  // block T (B x B) for the in-panel update
         if (Y16l) b.Y16 = {Y16l + ((size_t)j0 * a.ldy16 + j0) * 2, a.ldy16, j0 + zr};
         b.bf16 = a.bf16; b.dbg = a.dbg;
-        if (nrest > 0) { b.zero_buf = w.Srep; b.zero_n = NREP * RMAX * SLD; }
+        if (nrest > 0) { b.zero_buf = w.Srep; b.zero_n = NREP * RMAX * SLD + 4; }
         if (a.prof) a.prof->begin(a.prof->ctx, 4, stream);
         MPQR_TRY(launch_block(B, b, rpt, cs, stream));
         if (a.prof) a.prof->end(a.prof->ctx, stream);
         if (launches) *launches += 1;
         if (nrest > 0) {
             float* Arest = b.A + bw;
-            if (B == 32) MPQR_TRY(launch_su<32>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, sm_count(di), stream, launches, a.prof));
-            else MPQR_TRY(launch_su<16>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, sm_count(di), stream, launches, a.prof));
+            if (B == 32) MPQR_TRY(launch_su<32>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, w.Sfin, sm_count(di), stream, launches, a.prof));
+            else MPQR_TRY(launch_su<16>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, w.Sfin, sm_count(di), stream, launches, a.prof));
         }
     }
     if (a.dbg_caps) { a.dbg_caps[0] = max_cluster(); a.dbg_caps[1] = cs; a.dbg_caps[2] = rpt; }
@@ -1070,14 +1331,12 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     if (mixed) {
         // Gram and W on tensor cores, from the 16-bit Y the trailing update uses
         MPQR_TRY(tc_gemm_tn(Y16l, a.ldy16, Y16l, a.ldy16, w.G, RMAX, pw, pw, D, a.bf16, 1, stream, launches));
-        tinv_kernel<<<1, 1024, tsmem, stream>>>(w.G, RMAX, pw, Tdst, ldt, w.T16, RMAX, a.bf16);
-        MPQR_CUDA(cudaGetLastError());
+        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, w.T16, RMAX, a.bf16, tsmem, stream));
         if (launches) *launches += 1;
         MPQR_TRY(tc_gemm_nn_store(a.Y16, a.ldy16, w.T16, RMAX, a.W32, a.ld32, a.W16, a.ldw16, Dz, pw, pw, a.bf16, stream, launches));
     } else {
         MPQR_TRY(sgemm_tn(Yp, ldyp, Yp, ldyp, w.G, RMAX, pw, pw, D, stream, launches));
-        tinv_kernel<<<1, 1024, tsmem, stream>>>(w.G, RMAX, pw, Tdst, ldt, nullptr, 0, 0);
-        MPQR_CUDA(cudaGetLastError());
+        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, nullptr, 0, 0, tsmem, stream));
         if (launches) *launches += 1;
         if (a.W32) {
             MPQR_TRY(sgemm_nn_store(a.Y32, a.ld32, Tdst, ldt, a.W32, a.ld32, Dz, pw, pw, stream));
