@@ -214,7 +214,6 @@ def main_native(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    plan.set_profiling(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -223,9 +222,20 @@ def main_native(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    # Per-kernel-class breakdown: ONE more step of the same workload with the library's per-launch
+    # CUDA events switched on (they serialise the streams and cost ~2 us per launch, so they are
+    # kept out of the region `value` is computed from); prof_ms is that step's own duration.
+    plan.set_profiling(True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    p0.record()
+    step()
+    p1.record()
+    barrier()
+    prof_ms = p0.elapsed_time(p1)
     prof = plan.profile()
     plan.set_profiling(False)
-    launches = plan.last_launches * args.steps
+    launches = plan.last_launches * args.steps   # kernels launched inside the timed region (the profiled step is extra)
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -293,10 +303,13 @@ def main_native(args):
         return
 
     # ---- roofline per kernel class (CUDA events recorded inside the library on the launch stream)
-    by_kernel, total_kernel_ms = {}, sum(v["ms"] for v in prof.values()) or 1.0
+    # classes panel_* are the parts of "panel"; shares are taken over the leaf classes only
+    leaves = [k for k in prof if k != "panel"] if any(prof[k]["launches"] for k in prof if k.startswith("panel_")) else list(prof)
+    by_kernel, total_kernel_ms = {}, sum(prof[k]["ms"] for k in leaves) or 1.0
     traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
-    for name, v in prof.items():
+    for name in leaves:
+        v = prof[name]
         if v["launches"] == 0:
             continue
         avg_ms = v["ms"] / v["launches"]
@@ -310,14 +323,14 @@ def main_native(args):
             by_kernel[name] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                "frac": ach / peaks["hbm_gbs"], "traffic": traffic.get(name)}
         by_kernel[name].update({"share_of_kernel_time": v["ms"] / total_kernel_ms, "avg_launch_ms": avg_ms,
-                                "launches_per_step": v["launches"] / args.steps})
+                                "launches_per_step": v["launches"], "algorithmic_bytes_per_launch": v["bytes"] / v["launches"]})
     dominant = max(by_kernel, key=lambda k: by_kernel[k]["share_of_kernel_time"])
     roofline = dict(by_kernel[dominant])
     roofline["kernel"] = dominant
     roofline["peak_source"] = peaks["source"] + (", sustained bf16 cuBLAS" if roofline["bound"] == "tensor" else ", copy bandwidth")
     # whole-QR roofline: every class at its own bound (SURVEY 8d T_roof)
-    t_roof = sum(max(v["flops"] / (peaks["tc_sustained"] * 1e12) if k in ("gemm_tn", "gemm_nn") else 0.0,
-                     v["bytes"] / (peaks["hbm_gbs"] * 1e9)) for k, v in prof.items()) / args.steps
+    t_roof = sum(max(prof[k]["flops"] / (peaks["tc_sustained"] * 1e12) if k in ("gemm_tn", "gemm_nn") else 0.0,
+                     prof[k]["bytes"] / (peaks["hbm_gbs"] * 1e9)) for k in leaves)
     whole = {"t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / ms_per_step,
              "frac_of_tensor_peak": value / peaks["tc_sustained"]}
 
@@ -336,6 +349,7 @@ def main_native(args):
                    "flop_model": "2mn^2-2n^3/3 (m>=n) / 2m^2n-2m^3/3 (m<n)"},
         "backward_error_sampled": be, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "roofline": roofline, "roofline_by_kernel": by_kernel, "whole_qr_roofline": whole, "cpu_baseline": cpu_baseline,
+        "profiled_step_ms": prof_ms,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -141,7 +141,8 @@ class BlockQR:
     def panel_T(self, panel, dT_ptr, ldt, stream=0):
         check(lib().mpqr_get_panel_T(self._h, panel, dT_ptr, ldt, stream), "mpqr_get_panel_T")
 
-    KERNEL_CLASSES = ("panel", "gemm_tn", "gemm_nn", "cast")
+    # classes 4..7 are parts of class 0 ("panel" = register-block kernels + in-panel updates + Gram/T/W)
+    KERNEL_CLASSES = ("panel", "gemm_tn", "gemm_nn", "cast", "panel_block", "panel_s", "panel_gtw", "panel_u")
 
     def set_profiling(self, on):
         check(lib().mpqr_set_profiling(self._h, int(on)), "mpqr_set_profiling")

@@ -78,7 +78,7 @@ size_t panel_scratch_bytes(int max_rows);
 // optional per-launch event hook (internal.h implements it on the handle's profiler)
 struct ProfHook {
     void* ctx;
-    void (*begin)(void* ctx, int cls, cudaStream_t st);
+    void (*begin)(void* ctx, int cls, cudaStream_t st, double flops, double bytes);
     void (*end)(void* ctx, cudaStream_t st);
 };
 
@@ -115,7 +115,7 @@ struct PanelArgs {
     long ws_rows;       // rows the workspace was sized for
     int force_b;        // 16 / 32: override the register-block width (tuning / tests)
     int force_rpt;      // > 0: override the rows per thread (tuning / tests)
-    const ProfHook* prof;  // optional: sub-classes 4 (block kernels), 5 (in-panel S/U), 6 (Gram/T/W)
+    const ProfHook* prof;  // optional: sub-classes 4 (block kernels), 5 (in-panel S), 6 (Gram/T/W), 7 (in-panel U)
 };
 size_t panel_ws_bytes(long max_rows);
 int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches);

@@ -108,7 +108,7 @@ struct ProfScope {
     } while (0)
 
 // ProfHook implementation on the handle (used by launch_panel for its sub-classes)
-inline void hook_begin(void* ctx, int cls, cudaStream_t st) {
+inline void hook_begin(void* ctx, int cls, cudaStream_t st, double flops, double bytes) {
     mpqr_handle* h = (mpqr_handle*)ctx;
     if (!h->prof) return;
     cudaEvent_t e0, e1;
@@ -120,6 +120,8 @@ inline void hook_begin(void* ctx, int cls, cudaStream_t st) {
     get(&e1);
     cudaEventRecord(e0, st);
     h->prof_recs.push_back({cls, e0, e1});
+    h->prof_flops[cls] += flops;
+    h->prof_bytes[cls] += bytes;
 }
 inline void hook_end(void* ctx, cudaStream_t st) {
     mpqr_handle* h = (mpqr_handle*)ctx;

@@ -1203,7 +1203,7 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.stream = st; cfg.attrs = pat; cfg.numAttrs = 1;
     const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(Arest) & 15) == 0) && ((ncols & 3) == 0) && ncols <= 128;
-    if (prof) prof->begin(prof->ctx, 5, st);
+    if (prof) prof->begin(prof->ctx, 5, st, 2.0 * D * ncols * B, 4.0 * D * (ncols + B));
     if (vec) {
         int ysm_floats = rows * B;
         if (ysm_floats < B * (B + 4)) ysm_floats = B * (B + 4);
@@ -1215,14 +1215,14 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
         unsigned* counter = reinterpret_cast<unsigned*>(Srep + (size_t)NREP * RMAX * SLD);
         MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_s4_kernel<B>, Yj, ldy, (const float*)Arest, lda, D, ncols, Srep, counter, Tj, Sfin, rows,
                                      ysm_floats));
-        if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st); }
+        if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st, 2.0 * D * ncols * B, 4.0 * D * (2 * ncols + B)); }
         cfg.dynamicSmemBytes = (size_t)rows * B * sizeof(float);
         MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_u4_kernel<B>, Yj, ldy, Arest, lda, D, ncols, (const float*)Sfin, rows));
     } else {
         cfg.blockDim = dim3(512);
         cfg.dynamicSmemBytes = (size_t)((rows * B > 3 * B * 128) ? rows * B : 3 * B * 128) * sizeof(float);
         MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_s_kernel<B>, Yj, ldy, (const float*)Arest, lda, D, ncols, Srep, rows));
-        if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st); }
+        if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st, 2.0 * D * ncols * B, 4.0 * D * (2 * ncols + B)); }
         cfg.dynamicSmemBytes = (size_t)rows * B * sizeof(float);
         MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_u_kernel<B>, Yj, ldy, Arest, lda, D, ncols, (const float*)Srep, Tj, rows));
     }
@@ -1271,7 +1271,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         b.Y32 = {Y32l, a.ld32, zr}; b.W32 = {W32l, a.ld32, zr};
         b.Y16 = {Y16l, a.ldy16, zr}; b.W16 = {W16l, a.ldw16, zr};
         b.bf16 = a.bf16; b.T = a.T; b.ldt = a.ldt; b.dbg = a.dbg;
-        if (a.prof) a.prof->begin(a.prof->ctx, 4, stream);
+        if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 4.0 * D * pw * pw, 20.0 * D * pw);
         MPQR_TRY(launch_block(B, b, rpt, cs, stream));
         if (a.prof) a.prof->end(a.prof->ctx, stream);
         if (a.dbg_caps) { a.dbg_caps[0] = max_cluster(); a.dbg_caps[1] = cs; a.dbg_caps[2] = rpt; }
@@ -1305,7 +1305,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         if (Y16l) b.Y16 = {Y16l + ((size_t)j0 * a.ldy16 + j0) * 2, a.ldy16, j0 + zr};
         b.bf16 = a.bf16; b.dbg = a.dbg;
         if (nrest > 0) { b.zero_buf = w.Srep; b.zero_n = NREP * RMAX * SLD + 4; }
-        if (a.prof) a.prof->begin(a.prof->ctx, 4, stream);
+        if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 4.0 * Dj * bw * bw, 14.0 * Dj * bw);
         MPQR_TRY(launch_block(B, b, rpt, cs, stream));
         if (a.prof) a.prof->end(a.prof->ctx, stream);
         if (launches) *launches += 1;
@@ -1327,7 +1327,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     const int Dz = D + zr;  // W is produced from the enclosing block's first row on (zero rows of Y give zero rows of W)
     float* Tdst = a.T ? a.T : w.T32;
     const int ldt = a.T ? a.ldt : RMAX;
-    if (a.prof) a.prof->begin(a.prof->ctx, 6, stream);
+    if (a.prof) a.prof->begin(a.prof->ctx, 6, stream, 4.0 * D * pw * pw, 10.0 * D * pw);
     if (mixed) {
         // Gram and W on tensor cores, from the 16-bit Y the trailing update uses
         MPQR_TRY(tc_gemm_tn(Y16l, a.ldy16, Y16l, a.ldy16, w.G, RMAX, pw, pw, D, a.bf16, 1, stream, launches));

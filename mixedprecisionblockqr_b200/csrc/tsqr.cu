@@ -80,7 +80,7 @@ extern "C" int mpqr_tsqr_device(const float* dA, long lda, long m, int n, float*
     const long HMAX = 32768;
     const int r = n < 128 ? n : 128;
     // single block: plain blocked QR
-    long nblk = m / HMAX;
+    long nblk = (m + HMAX - 1) / HMAX;  // block height <= HMAX: panels stay in the register-resident kernel
     if (nblk < 1 || m < 2L * n) nblk = 1;
     long hrows = (m + nblk - 1) / nblk;
     if (hrows < n) { nblk = 1; hrows = m; }

@@ -52,3 +52,20 @@ def test_argument_validation_messages():
 def test_flop_formula():
     assert pkg.householder_flops(32768, 32768) == pytest.approx(4.691e13, rel=1e-3)
     assert pkg.householder_flops(4096, 16384) > 0
+
+
+REF_SYMBOLS = {  # C++-mangled names of the reference drivers, Cuda/qr.cuh:129-137
+    "dev_mixed_precision_block_qr": "_Z28dev_mixed_precision_block_qrPfS_iii",
+    "dev_block_qr_wy": "_Z15dev_block_qr_wyPfS_iii",
+    "dev_block_qr": "_Z12dev_block_qrPfS_iii",
+}
+
+
+def test_reference_symbol_shim_exports():
+    """libmpqr_refshim.so defines the reference's own driver symbols (drop-in at link level)."""
+    import ctypes
+    shim = os.path.join(ROOT, "mixedprecisionblockqr_b200", "libmpqr_refshim.so")
+    assert os.path.exists(shim), "run python -m mixedprecisionblockqr_b200.build"
+    L = ctypes.CDLL(shim)
+    for sym in REF_SYMBOLS.values():
+        assert hasattr(L, sym), sym

@@ -89,3 +89,26 @@ def test_python_fixtures_match_lapack():
         _, Rl = np.linalg.qr(A.astype(np.float64), mode="complete")
         assert np.allclose(np.abs(R), np.abs(Rl), atol=2e-4 * max(1, np.abs(A).max()))
         assert np.allclose(Q.astype(np.float64) @ R, A, atol=2e-4 * max(1, np.abs(A).max()))
+
+
+def test_reference_symbol_shim_matches_oracle():
+    """Calls the reference's mangled driver symbols in libmpqr_refshim.so exactly as Cuda/qr.cu:1879 /
+    :1826 do (A packed (m+1) x n zero-padded, Q = identity) and checks the reference's pass criteria."""
+    import ctypes
+    import os
+    from test_abi import REF_SYMBOLS, ROOT
+    L = ctypes.CDLL(os.path.join(ROOT, "mixedprecisionblockqr_b200", "libmpqr_refshim.so"))
+    m, n, r = 240, 160, 16
+    A = oracle.uniform_matrix(m, n, 4242)
+    Pref, _ = oracle.block_qr(A, r, want_q=False)
+    for name, bits, tol in (("dev_mixed_precision_block_qr", 11, 40 * 2.0 ** -11), ("dev_block_qr_wy", 23, 5e-5), ("dev_block_qr", 23, 5e-5)):
+        fn = getattr(L, REF_SYMBOLS[name])
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        fn.restype = None
+        P = oracle.pack(A)
+        Q = np.eye(m, dtype=np.float32)
+        fn(P.ctypes.data, Q.ctypes.data, m, n, r)
+        R = oracle.strip_R(P)
+        assert oracle.backward_error(A, R, Q) <= m * 2.0 ** -bits
+        assert oracle.q_error_max(Q) <= m * 2.0 ** -bits
+        assert np.abs(np.abs(R) - np.abs(oracle.strip_R(Pref))).max() <= tol * np.abs(Pref).max()

@@ -43,7 +43,7 @@ def test_tsqr_shapes(m, n):
     Ad = A.astype(np.float64)
     assert np.linalg.norm(Ad - Q.astype(np.float64) @ R) / np.linalg.norm(Ad) <= 5e-6
     assert np.linalg.norm(Q.astype(np.float64).T @ Q - np.eye(n)) <= 5e-5
-    if m // 4 >= n:
+    if m // 4 >= n and m <= 8192:   # the oracle mirrors ca_qr.py's dense per-block Q (O(m^2)): small cases only
         _, Ro = oracle.tsqr(A, 4)
         assert np.abs(np.abs(R) - np.abs(Ro)).max() <= 2e-5 * np.abs(Ro).max()
 
