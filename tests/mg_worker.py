@@ -11,6 +11,22 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mixedprecisionblockqr_b200 as pkg  # noqa: E402
 
 
+def sampled_backward_error(A0, P, r, k=16):
+    """||(A - QR) X||_F / (||A||_F sqrt(k)), Gaussian X, FP64, from the packed factor (GPU tensors)."""
+    m, n = A0.shape
+    g = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.randn(n, k, device="cuda", dtype=torch.float64, generator=g)
+    AX = A0.double() @ X
+    kmax = min(m, n)
+    Z = torch.triu(P[:m].double()) @ X
+    for lam in range(((kmax - 1) // r) * r, -1, -r):
+        pw = min(r, kmax - lam)
+        Y = torch.tril(P[lam + 1:m + 1, lam:lam + pw].double())
+        Tinv = torch.triu(Y.T @ Y, 1) + 0.5 * torch.eye(pw, device="cuda", dtype=torch.float64)
+        Z[lam:] -= Y @ torch.linalg.solve_triangular(Tinv, Y.T @ Z[lam:], upper=True)
+    return (torch.linalg.norm(AX - Z) / (torch.linalg.norm(A0.double()) * k ** 0.5)).item()
+
+
 def main():
     m, n, r, nb = [int(x) for x in sys.argv[1:5]]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -43,9 +59,17 @@ def main():
         single.factor(ref.data_ptr(), n, st)
         torch.cuda.synchronize()
         Pref = ref.cpu().numpy()
-        d = np.abs(P - Pref).max() / np.abs(Pref).max()
-        print(f"mg({world}) vs single-GPU packed factor: rel max diff {d:.3e}")
-        ok = d <= 1e-5   # same kernels, same operand order -> identical up to split-K atomics order
+        # Two FP16-operand factorisations that differ only in rounding (here: split-K reduce-add order,
+        # and Y/W staged in NCCL buffers instead of the shadow) agree in |R| at FP16-GEMM error level, not
+        # bit for bit, and a tiny pivot may flip its sign; so the criteria are the reference's own: backward
+        # error of the multi-GPU factor, and elementwise |R| against the single-GPU factor.
+        Rm, Rs = np.triu(np.abs(P[:m])), np.triu(np.abs(Pref[:m]))
+        d = np.abs(Rm - Rs).max() / Rs.max()
+        be = sampled_backward_error(full[:m], torch.from_numpy(P).cuda(), plan.r)
+        bes = sampled_backward_error(full[:m], ref, plan.r)
+        print(f"mg({world}) vs single-GPU: |R| rel max diff {d:.3e}; sampled backward error mg {be:.3e} single {bes:.3e}")
+        eps = 2.0 ** -11
+        ok = d <= 40 * eps and be <= 12 * eps and be <= 2.0 * bes + 1e-4
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
