@@ -57,6 +57,12 @@ struct mpqr_handle {
     void* S16u = nullptr;
     void* W16b = nullptr;   // second W buffer (blocks alternate) when the look-ahead driver is on
 
+    // host sink (mpqr_block_qr_host): finished column blocks are copied back while later blocks compute
+    float* sink_host = nullptr;
+    size_t sink_pitch = 0;  // bytes
+    cudaStream_t sink_stream = nullptr;
+    std::vector<cudaEvent_t> sink_ev;
+
     // multi-GPU (mg.cu)
     void* mg = nullptr;
 
