@@ -1187,15 +1187,18 @@ template <int B>
 int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, float* Sfin,
               int num_sms, cudaStream_t st, long* launches, const ProfHook* prof) {
     static bool attr = false;
-    const int max_rows = 256;
-    int rows = ceil_div(D, num_sms);
+    // one wave of CTAs over the SMs this stream may use (up to 512 rows = 32 KB of staged Y per CTA);
+    // taller blocks take k balanced waves
+    const int max_rows = 512;
+    const int waves = ceil_div(D, max_rows * num_sms);
+    int rows = ceil_div(D, waves * num_sms);
     rows = round_up(rows < 16 ? 16 : rows, 16);
     if (rows > max_rows) rows = max_rows;
     if (!attr) {
-        MPQR_CUDA(cudaFuncSetAttribute(inpanel_s_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 32 * 128 * 4));
-        MPQR_CUDA(cudaFuncSetAttribute(inpanel_u_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        MPQR_CUDA(cudaFuncSetAttribute(inpanel_s_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        MPQR_CUDA(cudaFuncSetAttribute(inpanel_u_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         MPQR_CUDA(cudaFuncSetAttribute(inpanel_s4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        MPQR_CUDA(cudaFuncSetAttribute(inpanel_u4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        MPQR_CUDA(cudaFuncSetAttribute(inpanel_u4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr = true;
     }
     dim3 grid(ceil_div(D, rows), ceil_div(ncols, 128));
