@@ -193,60 +193,100 @@ const GreenApi* green_api() {
 }
 
 // Best effort: on any failure the handle simply keeps the single-stream driver.
-void overlap_init(mpqr_handle* h, int panel_sms) {
+// `sizes`: panel-partition SM counts to prepare (each with the rest of the device as its update partition).
+void overlap_init(mpqr_handle* h, const int* sizes, int nsizes) {
     const GreenApi* g = green_api();
     if (!g->ok) return;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return;
     CUdevice cudev;
-    CUdevResource full, grp[1], rem;
-    unsigned int n = 1;
+    CUdevResource full;
     if (g->DeviceGet(&cudev, dev) != CUDA_SUCCESS) return;
     if (g->DeviceGetDevResource(cudev, &full, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return;
-    if (g->DevSmResourceSplitByCount(grp, &n, &full, &rem, CU_DEV_SM_RESOURCE_SPLIT_MAX_POTENTIAL_CLUSTER_SIZE,
-                                     (unsigned)panel_sms) != CUDA_SUCCESS || n < 1 || rem.sm.smCount < 32)
-        return;
-    CUdevResourceDesc dP, dU;
-    if (g->DevResourceGenerateDesc(&dP, &grp[0], 1) != CUDA_SUCCESS) return;
-    if (g->DevResourceGenerateDesc(&dU, &rem, 1) != CUDA_SUCCESS) return;
-    CUgreenCtx gP = nullptr, gU = nullptr;
-    if (g->GreenCtxCreate(&gP, dP, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
-    if (g->GreenCtxCreate(&gU, dU, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { g->GreenCtxDestroy(gP); return; }
-    CUstream sP = nullptr, sU = nullptr;
-    if (g->GreenCtxStreamCreate(&sP, gP, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS ||
-        g->GreenCtxStreamCreate(&sU, gU, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
-        if (sP) cudaStreamDestroy((cudaStream_t)sP);
-        g->GreenCtxDestroy(gP); g->GreenCtxDestroy(gU);
-        return;
-    }
     auto& o = h->ov;
-    o.gP = gP; o.gU = gU; o.sP = (cudaStream_t)sP; o.sU = (cudaStream_t)sU;
-    o.nsmP = (int)grp[0].sm.smCount; o.nsmU = (int)rem.sm.smCount;
+    o.nsm_full = (int)full.sm.smCount;
+    for (int k = 0; k < nsizes; ++k) {
+        CUdevResource grp[1], rem;
+        unsigned int n = 1;
+        if (g->DevSmResourceSplitByCount(grp, &n, &full, &rem, CU_DEV_SM_RESOURCE_SPLIT_MAX_POTENTIAL_CLUSTER_SIZE,
+                                         (unsigned)sizes[k]) != CUDA_SUCCESS || n < 1 || rem.sm.smCount < 16)
+            continue;
+        CUdevResourceDesc dP, dU;
+        if (g->DevResourceGenerateDesc(&dP, &grp[0], 1) != CUDA_SUCCESS) continue;
+        if (g->DevResourceGenerateDesc(&dU, &rem, 1) != CUDA_SUCCESS) continue;
+        CUgreenCtx gP = nullptr, gU = nullptr;
+        if (g->GreenCtxCreate(&gP, dP, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) continue;
+        if (g->GreenCtxCreate(&gU, dU, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { g->GreenCtxDestroy(gP); continue; }
+        CUstream sP = nullptr, sU = nullptr;
+        if (g->GreenCtxStreamCreate(&sP, gP, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS ||
+            g->GreenCtxStreamCreate(&sU, gU, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+            if (sP) cudaStreamDestroy((cudaStream_t)sP);
+            g->GreenCtxDestroy(gP); g->GreenCtxDestroy(gU);
+            continue;
+        }
+        mpqr_handle::Overlap::Pair pr;
+        pr.gP = gP; pr.gU = gU; pr.sP = (cudaStream_t)sP; pr.sU = (cudaStream_t)sU;
+        pr.nsmP = (int)grp[0].sm.smCount; pr.nsmU = (int)rem.sm.smCount;
+        o.pairs.push_back(pr);
+    }
+    if (o.pairs.empty()) return;
+    if (cudaStreamCreateWithFlags(&o.sF, cudaStreamNonBlocking) != cudaSuccess) { o.sF = nullptr; }
     const int nblk = ceil_div(h->kmax, h->nb);
-    o.ev_bp.resize(nblk); o.ev_fn.resize(nblk);
+    o.ev_bp.resize(nblk); o.ev_fn.resize(nblk); o.ev_fr.resize(nblk);
     for (int i = 0; i < nblk; ++i) {
         cudaEventCreateWithFlags(&o.ev_bp[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&o.ev_fn[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&o.ev_fr[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&o.ev_start, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&o.ev_endP, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&o.ev_endU, cudaEventDisableTiming);
-    o.on = true;
+    cudaEventCreateWithFlags(&o.ev_end, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&o.ev_accdone, cudaEventDisableTiming);
+    o.ev_acc.resize(ceil_div(h->nb, h->r) + 1);
+    for (auto& e : o.ev_acc) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    const char* trc = getenv("MPQR_TRACE");
+    o.trace = trc && trc[0] == '1';
+    if (o.trace) {
+        o.tr.resize(nblk);
+        for (auto& t : o.tr) { cudaEventCreate(&t.b0); cudaEventCreate(&t.b1); cudaEventCreate(&t.f0); cudaEventCreate(&t.f1); cudaEventCreate(&t.f2); t.psm = 0; }
+    }
+    o.on = o.sF != nullptr;
 }
 
 void overlap_destroy(mpqr_handle* h) {
     auto& o = h->ov;
-    if (!o.gP) return;
     for (auto e : o.ev_bp) cudaEventDestroy(e);
     for (auto e : o.ev_fn) cudaEventDestroy(e);
+    for (auto e : o.ev_fr) cudaEventDestroy(e);
     if (o.ev_start) cudaEventDestroy(o.ev_start);
-    if (o.ev_endP) cudaEventDestroy(o.ev_endP);
-    if (o.ev_endU) cudaEventDestroy(o.ev_endU);
-    if (o.sP) cudaStreamDestroy(o.sP);
-    if (o.sU) cudaStreamDestroy(o.sU);
+    if (o.ev_end) cudaEventDestroy(o.ev_end);
+    if (o.ev_accdone) cudaEventDestroy(o.ev_accdone);
+    for (auto e : o.ev_acc) cudaEventDestroy(e);
+    if (o.sF) cudaStreamDestroy(o.sF);
     const GreenApi* g = green_api();
-    if (g->ok) { g->GreenCtxDestroy((CUgreenCtx)o.gP); g->GreenCtxDestroy((CUgreenCtx)o.gU); }
+    for (auto& pr : o.pairs) {
+        if (pr.sP) cudaStreamDestroy(pr.sP);
+        if (pr.sU) cudaStreamDestroy(pr.sU);
+        if (g->ok) { g->GreenCtxDestroy((CUgreenCtx)pr.gP); g->GreenCtxDestroy((CUgreenCtx)pr.gU); }
+    }
     o = mpqr_handle::Overlap();
+}
+
+// Cost model of the look-ahead driver (B200 measurements of round 1).  Times in ms.
+//   panel chain of one r-wide panel on the whole device: 0.15 + 0.0116 * D/1024   (D <= 16384, 32-column register blocks)
+//                                                        0.33 + 0.0122 * (D - 16384)/1024 + 0.19  (taller: 16-column blocks)
+//   the chain is latency-bound, but its device-wide kernels slow down on a small partition:  x (1 + 22 / SMs)
+//   far update: 4 D N' kb flops at ~6.6 TFLOP/s per SM (measured: 4.1e12 flop in 6.2 ms on 100 SMs)
+double model_bp_ms(const mpqr_handle* h, int c0, int c1) {
+    double t = 0;
+    for (int lam = c0; lam < c1; lam += h->r) {
+        const double D = h->m - lam;
+        t += (D <= 16384) ? 0.15 + 0.0116 * D / 1024.0 : 0.52 + 0.0122 * (D - 16384) / 1024.0;
+    }
+    return t * (h->r / 128.0 < 0.25 ? 0.25 : h->r / 128.0);
+}
+double model_far_ms(const mpqr_handle* h, int c0, int c1, int ncols, int sms) {
+    const double flops = 4.0 * (double)(h->m - c0) * (double)ncols * (double)(c1 - c0);
+    return flops / (6.6e12 * sms) * 1e3;
 }
 
 int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
@@ -326,43 +366,89 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         if (h->kmax < n) MPQR_TRY(emit(nblk, h->kmax, n, st));  // wide matrices: the columns right of the last reflector
         return MPQR_OK;
     }
-    // Look-ahead schedule.  sP (panel partition): block_phase(J).  sU (update partition): the far
-    // update of block J, next outer block's columns first (far_next) so that block_phase(J+1)
-    // can start while the rest of the trailing matrix (far_rest) is still being updated.
-    //   sP:  bp(0)        | wait fn(0) | bp(1)         | wait fn(1) | bp(2) ...
-    //   sU:  wait bp(0) | fn(0) fr(0)            | wait bp(1) | fn(1) fr(1) ...
+    // Look-ahead schedule.  Interval b = { far_next(b), far_rest(b) on an update partition ; block_phase(b+1) on
+    // the matching panel partition }: the next outer block's columns are updated first (far_next) so that its
+    // panel chain runs WHILE the rest of the trailing matrix is still being updated.  Per interval the
+    // partition pair (or the whole device, serially) is chosen by the cost model above; everything is
+    // ordered by events, so consecutive intervals may use different partitions.
+    //   bp(b+1) waits fn(b);  fn(b) waits bp(b) and fr(b-1);  fr(b) follows fn(b) in its stream.
     auto& o = h->ov;
     MPQR_CUDA(cudaEventRecord(o.ev_start, st));
-    MPQR_CUDA(cudaStreamWaitEvent(o.sP, o.ev_start, 0));
-    MPQR_CUDA(cudaStreamWaitEvent(o.sU, o.ev_start, 0));
+    const char* fix = getenv("MPQR_PANEL_SMS");
+    const int fixed_sms = fix ? atoi(fix) : 0;
+    // interval b-1 decided where block_phase(b) runs; block 0 runs on the whole device
+    cudaStream_t s_bp = o.sF, s_uprev = nullptr;
+    int nsm_bp = o.nsm_full, nsm_uprev = 0;
+    MPQR_CUDA(cudaStreamWaitEvent(s_bp, o.ev_start, 0));
     for (int c0 = 0, b = 0; c0 < h->kmax; c0 += nb, ++b) {
         const int c1 = (c0 + nb < h->kmax) ? c0 + nb : h->kmax;
         BlockCtx c = ctx_of(b, c0);
-        if (b > 0) MPQR_CUDA(cudaStreamWaitEvent(o.sP, o.ev_fn[b - 1], 0));
-        {
-            SmBudget budget(o.nsmP);
-            MPQR_TRY(block_phase(h, c, c0, c1, c1 == n, o.sP));
+        // WY accumulation of this block: on the update partition of the previous interval (it idles once its
+        // far update is done), unless that interval ran serially on the whole device
+        const bool defer_acc = s_uprev && s_uprev != s_bp && !getenv("MPQR_NO_DEFER_ACC");
+        if (defer_acc) {
+            c.acc_stream = s_uprev; c.acc_sms = nsm_uprev == o.nsm_full ? 0 : nsm_uprev;
+            c.acc_S32 = h->S32u; c.acc_S16 = h->S16u; c.acc_ev = o.ev_acc.data();
         }
-        MPQR_CUDA(cudaEventRecord(o.ev_bp[b], o.sP));
-        MPQR_TRY(emit(b, c0, c1, o.sP));
+        if (b > 0) MPQR_CUDA(cudaStreamWaitEvent(s_bp, o.ev_fn[b - 1], 0));
+        if (o.trace) { cudaEventRecord(o.tr[b].b0, s_bp); o.tr[b].psm = nsm_bp; }
+        {
+            SmBudget budget(nsm_bp == o.nsm_full ? 0 : nsm_bp);
+            MPQR_TRY(block_phase(h, c, c0, c1, c1 == n, s_bp));
+        }
+        if (o.trace) cudaEventRecord(o.tr[b].b1, s_bp);
+        MPQR_CUDA(cudaEventRecord(o.ev_bp[b], s_bp));
+        if (defer_acc) MPQR_CUDA(cudaEventRecord(o.ev_accdone, s_uprev));
+        MPQR_TRY(emit(b, c0, c1, s_bp));
         const int nfar = n - c1;
+        // ---- choose the partition of interval b
+        const int nnext = nfar < nb ? nfar : nb;
+        const int c2 = (c1 + nb < h->kmax) ? c1 + nb : h->kmax;
+        const bool has_next = c1 < h->kmax;
+        int best = -1;  // -1: whole device, serial
+        if (has_next && nfar - nnext > 0) {
+            const double bp_full = model_bp_ms(h, c1, c2);
+            double best_t = bp_full + model_far_ms(h, c0, c1, nfar - nnext, o.nsm_full);
+            for (size_t k = 0; k < o.pairs.size(); ++k) {
+                if (fixed_sms > 0 && o.pairs[k].nsmP != fixed_sms) continue;
+                const double tb = bp_full * (1.0 + 22.0 / o.pairs[k].nsmP);
+                const double tf = model_far_ms(h, c0, c1, nfar - nnext, o.pairs[k].nsmU);
+                const double t = tb > tf ? tb : tf;
+                if (t < best_t || (fixed_sms > 0 && best < 0)) { best_t = t; best = (int)k; }
+            }
+        }
+        cudaStream_t s_u = best >= 0 ? o.pairs[best].sU : o.sF;
+        const int nsm_u = best >= 0 ? o.pairs[best].nsmU : o.nsm_full;
         if (nfar > 0) {
             BlockCtx cu = c;
             cu.S32 = h->S32u; cu.S16 = h->S16u;
-            const int nnext = nfar < nb ? nfar : nb;
-            SmBudget budget(o.nsmU);
-            MPQR_CUDA(cudaStreamWaitEvent(o.sU, o.ev_bp[b], 0));
-            MPQR_TRY(far_update(h, cu, c0, c1, c1, nnext, o.sU));
-            MPQR_CUDA(cudaEventRecord(o.ev_fn[b], o.sU));
-            MPQR_TRY(far_update(h, cu, c0, c1, c1 + nnext, nfar - nnext, o.sU));
+            cu.acc_stream = nullptr;
+            SmBudget budget(nsm_u == o.nsm_full ? 0 : nsm_u);
+            MPQR_CUDA(cudaStreamWaitEvent(s_u, o.ev_bp[b], 0));
+            if (defer_acc) MPQR_CUDA(cudaStreamWaitEvent(s_u, o.ev_accdone, 0));
+            if (b > 0) MPQR_CUDA(cudaStreamWaitEvent(s_u, o.ev_fr[b - 1], 0));
+            if (o.trace) cudaEventRecord(o.tr[b].f0, s_u);
+            MPQR_TRY(far_update(h, cu, c0, c1, c1, nnext, s_u));
+            if (o.trace) cudaEventRecord(o.tr[b].f1, s_u);
+            MPQR_CUDA(cudaEventRecord(o.ev_fn[b], s_u));
+            MPQR_TRY(far_update(h, cu, c0, c1, c1 + nnext, nfar - nnext, s_u));
+            if (o.trace) cudaEventRecord(o.tr[b].f2, s_u);
+            MPQR_CUDA(cudaEventRecord(o.ev_fr[b], s_u));
         } else {
-            MPQR_CUDA(cudaEventRecord(o.ev_fn[b], o.sP));
+            if (defer_acc) MPQR_CUDA(cudaStreamWaitEvent(s_bp, o.ev_accdone, 0));
+            MPQR_CUDA(cudaEventRecord(o.ev_fn[b], s_bp));
+            MPQR_CUDA(cudaEventRecord(o.ev_fr[b], s_bp));
         }
+        // where the next block_phase runs
+        s_bp = best >= 0 ? o.pairs[best].sP : o.sF;
+        nsm_bp = best >= 0 ? o.pairs[best].nsmP : o.nsm_full;
+        s_uprev = best >= 0 ? s_u : nullptr;
+        nsm_uprev = nsm_u;
     }
-    MPQR_CUDA(cudaEventRecord(o.ev_endP, o.sP));
-    MPQR_CUDA(cudaEventRecord(o.ev_endU, o.sU));
-    MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_endP, 0));
-    MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_endU, 0));
+    // join: the last ev_fr / ev_bp cover everything (fr(b) follows fn(b); bp(last) waited fn(last-1))
+    MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_fr[nblk - 1], 0));
+    MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_bp[nblk - 1], 0));
+    for (int b = 0; b + 1 < nblk; ++b) MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_fr[b], 0));
     if (h->kmax < n) MPQR_TRY(emit(nblk, h->kmax, n, st));
     return MPQR_OK;
 }
@@ -422,12 +508,26 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         if (jc > 0) {
             // WY accumulation: X = Y_prev^T W_p ; W_p -= W_prev X   (rows c0..m)
             const void* Wp = (char*)c.W16 + (size_t)jc * 2;
-            PROF(1, 2.0 * jc * pw * Dblk, tn_bytes(jc, pw, Dblk),
-                 tc_gemm_tn(c.Y16, c.ldy, Wp, c.ldw, S32, h->lds32, jc, pw, Dblk, bf, 1, st, &h->launches));
-            PROF(3, 0, 6.0 * jc * pw, convert_f32_to_16(S32, h->lds32, S16, h->lds16, jc, pw, bf, st));
-            h->launches += 1;
-            PROF(2, 2.0 * Dblk * pw * jc, nn_bytes(Dblk, pw, jc),
-                 tc_gemm_nn(c.W16, c.ldw, S16, h->lds16, h->Wblk32 + jc, h->ldwb, (void*)Wp, c.ldw, Dblk, pw, jc, bf, 1, st, &h->launches));
+            cudaStream_t st_panel = st;
+            float* aS32 = S32;
+            void* aS16 = S16;
+            if (c.acc_stream) {
+                // W_p is modified in place: wait until this panel's in-block update has consumed it
+                cudaEvent_t ev = c.acc_ev[jc / r];
+                MPQR_CUDA(cudaEventRecord(ev, st_panel));
+                MPQR_CUDA(cudaStreamWaitEvent(c.acc_stream, ev, 0));
+                aS32 = c.acc_S32; aS16 = c.acc_S16;
+            }
+            {
+                cudaStream_t st = c.acc_stream ? c.acc_stream : st_panel;  // (PROF records on `st`)
+                SmBudget budget(c.acc_stream ? c.acc_sms : g_sm_budget);
+                PROF(1, 2.0 * jc * pw * Dblk, tn_bytes(jc, pw, Dblk),
+                     tc_gemm_tn(c.Y16, c.ldy, Wp, c.ldw, aS32, h->lds32, jc, pw, Dblk, bf, 1, st, &h->launches));
+                PROF(3, 0, 6.0 * jc * pw, convert_f32_to_16(aS32, h->lds32, aS16, h->lds16, jc, pw, bf, st));
+                h->launches += 1;
+                PROF(2, 2.0 * Dblk * pw * jc, nn_bytes(Dblk, pw, jc),
+                     tc_gemm_nn(c.W16, c.ldw, aS16, h->lds16, h->Wblk32 + jc, h->ldwb, (void*)Wp, c.ldw, Dblk, pw, jc, bf, 1, st, &h->launches));
+            }
         }
     }
     return MPQR_OK;
@@ -527,10 +627,8 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
             const int nblk_outer = ceil_div(h->kmax, h->nb);
             const bool want_overlap = env ? (env[0] == '1' && nblk_outer >= 3) : (nblk_outer >= 12);
             if (want_overlap) {
-                const char* ps = getenv("MPQR_PANEL_SMS");
-                int panel_sms = ps ? atoi(ps) : 80;
-                if (panel_sms < 16) panel_sms = 16;
-                overlap_init(h, panel_sms);
+                const int sizes[5] = {32, 48, 64, 80, 112};
+                overlap_init(h, sizes, 5);
                 if (h->ov.on) {
                     if ((rc = dev_alloc(h, (void**)&h->S32u, (size_t)h->sk * h->lds32 * sizeof(float)))) break;
                     if ((rc = dev_alloc(h, &h->S16u, (size_t)h->sk * h->lds16 * 2))) break;
@@ -765,6 +863,27 @@ int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
         rc = MPQR_ECUDA;
     }
     return rc;
+}
+
+// MPQR_TRACE=1: per-interval timeline of the last look-ahead factorisation (tools/quick_time.py TRACE=1)
+int mpqr_debug_dump_trace(mpqr_handle* h) {
+    if (!h || !h->ov.on || !h->ov.trace) return MPQR_ESTATE;
+    cudaDeviceSynchronize();
+    auto& o = h->ov;
+    const int nblk = (int)o.tr.size();
+    fprintf(stderr, "# b  panelSMs  t0(bp)  bp_ms  | t0(fn)  fn_ms  fr_ms   (times relative to bp(0) start)\n");
+    for (int b = 0; b < nblk; ++b) {
+        float tb0 = 0, bp = 0, tf0 = -1, fn = -1, fr = -1;
+        cudaEventElapsedTime(&tb0, o.tr[0].b0, o.tr[b].b0);
+        cudaEventElapsedTime(&bp, o.tr[b].b0, o.tr[b].b1);
+        if (b + 1 < nblk || h->n > h->kmax) {
+            if (cudaEventElapsedTime(&tf0, o.tr[0].b0, o.tr[b].f0) != cudaSuccess) { cudaGetLastError(); tf0 = -1; }
+            if (cudaEventElapsedTime(&fn, o.tr[b].f0, o.tr[b].f1) != cudaSuccess) { cudaGetLastError(); fn = -1; }
+            if (cudaEventElapsedTime(&fr, o.tr[b].f1, o.tr[b].f2) != cudaSuccess) { cudaGetLastError(); fr = -1; }
+        }
+        fprintf(stderr, "%3d  %4d  %8.2f %7.2f | %8.2f %6.2f %7.2f\n", b, o.tr[b].psm, tb0, bp, tf0, fn, fr);
+    }
+    return MPQR_OK;
 }
 
 // Tuning/profiling hook (tools/panel_probe.py; not part of the public header): runs the panel

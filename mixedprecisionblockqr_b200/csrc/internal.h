@@ -44,14 +44,25 @@ struct mpqr_handle {
     long ldqh = 0;
 
     // look-ahead driver (api.cu): two green-context SM partitions with one stream each
+    // Several (panel, update) SM partitions are kept ready; the driver picks one per outer block.
     struct Overlap {
         bool on = false;
-        void* gP = nullptr;  // CUgreenCtx: panel partition
-        void* gU = nullptr;  // CUgreenCtx: update partition
-        cudaStream_t sP = nullptr, sU = nullptr;
-        int nsmP = 0, nsmU = 0;
-        std::vector<cudaEvent_t> ev_bp, ev_fn;
-        cudaEvent_t ev_start = nullptr, ev_endP = nullptr, ev_endU = nullptr;
+        struct Pair {
+            void* gP = nullptr;  // CUgreenCtx: panel partition
+            void* gU = nullptr;  // CUgreenCtx: update partition
+            cudaStream_t sP = nullptr, sU = nullptr;
+            int nsmP = 0, nsmU = 0;
+        };
+        std::vector<Pair> pairs;
+        cudaStream_t sF = nullptr;  // whole-device stream (intervals that are not worth splitting)
+        int nsm_full = 0;
+        std::vector<cudaEvent_t> ev_bp, ev_fn, ev_fr;
+        cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_accdone = nullptr;
+        std::vector<cudaEvent_t> ev_acc;  // per panel of an outer block: in-block update done -> WY accumulation may start
+        // MPQR_TRACE=1: timed events around block_phase / far_next / far_rest of every interval
+        bool trace = false;
+        struct Tr { cudaEvent_t b0, b1, f0, f1, f2; int psm; };
+        std::vector<Tr> tr;
     } ov;
     float* S32u = nullptr;  // scratch of the update stream (same shape as S32 / S16)
     void* S16u = nullptr;
@@ -155,6 +166,14 @@ struct BlockCtx {
     long ldw;
     float* S32;    // GEMM scratch of the issuing stream (null: the handle's)
     void* S16;
+    // Optional: run the WY accumulation of the block (W_p <- W_p - W_prev (Y_prev^T W_p), only needed by
+    // the FAR update) on another stream / SM partition, off the panel chain.  The look-ahead driver points
+    // it at the update partition, which idles while the schedule is panel-bound.
+    cudaStream_t acc_stream;   // null: accumulate in line
+    int acc_sms;               // SM budget of acc_stream (0 = whole device)
+    float* acc_S32;            // its GEMM scratch
+    void* acc_S16;
+    cudaEvent_t* acc_ev;       // >= (c1 - c0) / r events
 };
 // panels + in-block updates + WY accumulation of block [c0, c1); `ncols_in` = columns of A
 // (starting at acol0) that belong to the block's own panel region (= c1 - c0)

@@ -48,6 +48,8 @@ def run(m, n, r, prec, nb=0, reps=3, check=True):
         be = sampled_backward_error(A0[:, :n], A[:, :n], r=plan.r)
     print(f"{m}x{n} r={plan.r} nb={plan.nb} {prec}: {best:.2f} ms  {F / best / 1e9:.2f} TFLOP/s  launches={plan.last_launches} "
           f"bwd_err~{be:.2e}  all={['%.1f' % t for t in times]}", flush=True)
+    if os.environ.get("MPQR_TRACE") == "1":
+        pkg.lib().mpqr_debug_dump_trace(plan._h)
     if os.environ.get("PROFILE") == "1":
         import ctypes
         L = pkg.lib()
