@@ -26,6 +26,8 @@
 // Conventions mirrored from the reference: sign = (u0 >= 0) ? +1 : -1
 // (:229-235); zero column => reflector skipped (:242-244); unit vector w (beta = 2) stored
 // one row below the diagonal (:283-285); R_kk = -sign*||u||.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mpqr {
@@ -260,61 +262,43 @@ __device__ __forceinline__ void store_row16(void* p, const float (&x)[B], int bw
         tprev = t__;                        \
     }
 
+// The reflector steps of one B-column register block (rows rbase + u*NT of the cluster's slab; the
+// block's diagonal sits at row `roff` of the slab: 0, or 16 for the second half of a double block).
+template <int B>
+struct StepMem {
+    float (*red)[NW][B];
+    float (*prow)[B];
+    float (*slot)[CSMAX][B];
+    float (*pslot)[B];
+    float (*tauS)[B];
+    float (*gt)[B + 4];
+    float* diag;
+    uint64_t* mbar;
+};
+struct StepCtx {
+    int tid, lane, warp, CS, rbase, bw, kr, roff;
+    unsigned crank;
+    bool prof;
+    long long* pacc;
+    long long* tprev_p;
+};
+
 template <int B, int RPT>
-__global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS) {
+__device__ __forceinline__ void factor_steps(float (&x)[RPT][B], const StepMem<B>& M, const StepCtx& c) {
     constexpr int LB = (B == 32) ? 0 : 1;  // lane -> column shift after the transpose-reduce
-    __shared__ __align__(16) float red[2][NW][B];
-    __shared__ __align__(16) float prow[2][B];
-    __shared__ __align__(16) float slot[2][CSMAX][B];
-    __shared__ __align__(16) float pslot[2][B];
-    __shared__ __align__(16) float csumS[2][B];
-    __shared__ __align__(16) float tauS[NW][B];
-    __shared__ __align__(16) float gt[B][B + 4];
-    __shared__ float diag[B];
-    __shared__ __align__(8) uint64_t mbar[2];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned crank = (CS > 1) ? cluster_ctarank() : 0u;
-    const int D = a.D, bw = a.bw;
-    const int kr = bw < D ? bw : D;  // reflectors of this block
-    const int rbase = (int)crank * (NT * RPT) + tid;  // row of u = 0; row(u) = rbase + u*NT
-    const long lda = a.lda;
-    const bool vecA = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
-
-    const bool prof = (a.dbg != nullptr) && blockIdx.x == 0 && tid == 0;
-    long long pacc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long tprev = prof ? clock64() : 0;
-
-    pdl_launch_dependents();
-    for (int idx = tid; idx < B * (B + 4); idx += NT) (&gt[0][0])[idx] = 0.f;
-    if (CS > 1) {
-        if (tid == 0) {
-            mbar_init(&mbar[0], 1);
-            mbar_init(&mbar[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        cluster_sync_all();  // peers must not signal a barrier that is not initialised yet
-    }
-    pdl_wait();  // everything above overlapped the predecessor's tail; its results are visible from here on
-
-    float x[RPT][B];
-#pragma unroll
-    for (int u = 0; u < RPT; ++u) {
-        const int i = rbase + u * NT;
-        if (i < D) {
-            load_row<B>(a.A + (size_t)i * lda, x[u], bw, vecA);
-        } else {
-#pragma unroll
-            for (int c = 0; c < B; ++c) x[u][c] = 0.f;
-        }
-    }
-    if (a.zero_buf) {
-        const int nthr = CS * NT;
-        for (int idx = (int)crank * NT + tid; idx < a.zero_n; idx += nthr) a.zero_buf[idx] = 0.f;
-    }
-    __syncthreads();
-    PROF_MARK(6);
-
+    float (*red)[NW][B] = M.red;
+    float (*prow)[B] = M.prow;
+    float (*slot)[CSMAX][B] = M.slot;
+    float (*pslot)[B] = M.pslot;
+    float (*tauS)[B] = M.tauS;
+    float (*gt)[B + 4] = M.gt;
+    float* diag = M.diag;
+    uint64_t* mbar = M.mbar;
+    const int tid = c.tid, lane = c.lane, warp = c.warp, CS = c.CS, rbase = c.rbase, bw = c.bw, kr = c.kr, roff = c.roff;
+    const unsigned crank = c.crank;
+    const bool prof = c.prof;
+    long long* pacc = c.pacc;
+    long long& tprev = *c.tprev_p;
     const uint32_t tx_bytes = (uint32_t)(CS + 1) * B * 4;
     const int mypos = (lane >> LB) & (B - 1);  // position this lane owns after the transpose-reduce
 
@@ -332,7 +316,7 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
         // ---- dots of the current column with every position (norm, update coefficients, Gram)
         float acc[B];
         float xs[RPT];
-        if (crank == 0 && tid == s) {
+        if (crank == 0 && tid == s + roff) {
 #pragma unroll
             for (int q = 0; q < B / 4; ++q)  // pivot row (row s is u = 0 of thread s), positions
                 *reinterpret_cast<float4*>(&prow[par][4 * q]) = make_float4(x[0][4 * q], x[0][4 * q + 1], x[0][4 * q + 2], x[0][4 * q + 3]);
@@ -340,7 +324,7 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
 #pragma unroll
         for (int u = 0; u < RPT; ++u) {
             const int i = rbase + u * NT;
-            xs[u] = (i >= s) ? x[u][0] : 0.f;  // rows above the diagonal hold R entries
+            xs[u] = (i >= s + roff) ? x[u][0] : 0.f;  // rows above the diagonal hold R entries
             if (u == 0) {
 #pragma unroll
                 for (int p2 = 0; p2 < B; ++p2) acc[p2] = xs[0] * x[0][p2];
@@ -430,13 +414,73 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
 #pragma unroll
         for (int u = 0; u < RPT; ++u) {
             const int i = rbase + u * NT;
-            const float vi = (i == s) ? xs[u] + smu : xs[u];
-            const float fin = (i >= s && active) ? vi * vinv : x[u][0];  // w in place (unshifted); R entries above
+            const float vi = (i == s + roff) ? xs[u] + smu : xs[u];
+            const float fin = (i >= s + roff && active) ? vi * vinv : x[u][0];  // w in place (unshifted); R entries above
 #pragma unroll
             for (int p2 = 1; p2 < B; ++p2) x[u][p2 - 1] = fmaf(-vi, tau[p2], x[u][p2]);
             x[u][B - 1] = fin;
         }
         PROF_MARK(5);
+    }
+    }
+
+template <int B, int RPT>
+__global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS) {
+    __shared__ __align__(16) float red[2][NW][B];
+    __shared__ __align__(16) float prow[2][B];
+    __shared__ __align__(16) float slot[2][CSMAX][B];
+    __shared__ __align__(16) float pslot[2][B];
+    __shared__ __align__(16) float tauS[NW][B];
+    __shared__ __align__(16) float gt[B][B + 4];
+    __shared__ float diag[B];
+    __shared__ __align__(8) uint64_t mbar[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned crank = (CS > 1) ? cluster_ctarank() : 0u;
+    const int D = a.D, bw = a.bw;
+    const int kr = bw < D ? bw : D;  // reflectors of this block
+    const int rbase = (int)crank * (NT * RPT) + tid;  // row of u = 0; row(u) = rbase + u*NT
+    const long lda = a.lda;
+    const bool vecA = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
+
+    const bool prof = (a.dbg != nullptr) && blockIdx.x == 0 && tid == 0;
+    long long pacc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = prof ? clock64() : 0;
+
+    pdl_launch_dependents();
+    for (int idx = tid; idx < B * (B + 4); idx += NT) (&gt[0][0])[idx] = 0.f;
+    if (CS > 1) {
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster_sync_all();  // peers must not signal a barrier that is not initialised yet
+    }
+    pdl_wait();  // everything above overlapped the predecessor's tail; its results are visible from here on
+
+    float x[RPT][B];
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const int i = rbase + u * NT;
+        if (i < D) {
+            load_row<B>(a.A + (size_t)i * lda, x[u], bw, vecA);
+        } else {
+#pragma unroll
+            for (int c = 0; c < B; ++c) x[u][c] = 0.f;
+        }
+    }
+    if (a.zero_buf) {
+        const int nthr = CS * NT;
+        for (int idx = (int)crank * NT + tid; idx < a.zero_n; idx += nthr) a.zero_buf[idx] = 0.f;
+    }
+    __syncthreads();
+    PROF_MARK(6);
+
+    {
+        StepMem<B> M{red, prow, slot, pslot, tauS, gt, diag, mbar};
+        StepCtx sc{tid, lane, warp, CS, rbase, bw, kr, 0, crank, prof, pacc, &tprev};
+        factor_steps<B, RPT>(x, M, sc);
     }
     __syncthreads();
 
@@ -541,6 +585,249 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
         a.dbg[9] = CS; a.dbg[10] = RPT; a.dbg[11] = B;
     }
     // shared memory must stay alive until no peer can signal into it any more
+    if (CS > 1) cluster_sync_all();
+}
+
+// ------------------------------------------------------------------ double block (tall panels)
+// For D > 16384 a 32-column block does not fit the cluster's registers.  panel_dblock_kernel factors
+// 32 columns as two 16-column halves in ONE launch: half A lives in registers, half B is staged in
+// shared memory (<= 2048 rows x 64 B per CTA) and touched once, by the block update between the
+// halves  B -= Y_A T_A^T (Y_A^T B)  (partial 16 x 16 products reduced by a warp transpose-reduce, a
+// shared-memory stage and ONE DSMEM all-gather), after which B moves into the registers and is
+// factored with its diagonal at slab row 16.  Compared with two 16-column launches this saves one
+// launch's fixed cost and the device-wide in-panel update pair between the halves; the update of
+// the rest of the panel then runs once per 32 columns with T_32 = [[T_A, -T_A (Y_A^T Y_B) T_B], [0, T_B]],
+// whose cross term the in-panel S kernel accumulates on the side.
+template <int RPT>
+__device__ __forceinline__ void emit_half(float (&x)[RPT][16], const BlockArgs& a, int D, int rbase, int roff, int coloff, int bwh,
+                                          const float* diag, bool vecA, bool vecY32, bool vecY16) {
+    constexpr int B = 16;
+    const long lda = a.lda;
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const int i = rbase + u * NT;
+        if (i >= D) continue;
+        if (i >= roff + B) {
+            store_row32<B>(a.A + (size_t)(i + 1) * lda + coloff, x[u], bwh, vecA);
+        } else {
+#pragma unroll
+            for (int c = 0; c < B; ++c)
+                if (c < bwh) a.A[(size_t)(i + (i >= c + roff ? 1 : 0)) * lda + coloff + c] = x[u][c];
+            if (i >= roff && i - roff < bwh) a.A[(size_t)i * lda + coloff + (i - roff)] = diag[i - roff];
+#pragma unroll
+            for (int c = 0; c < B; ++c)
+                if (i < c + roff) x[u][c] = 0.f;  // Y: zero above the diagonal
+        }
+        if (a.Y32.p) store_row32<B>(a.Y32.p + (size_t)i * a.Y32.ld + coloff, x[u], bwh, vecY32);
+        if (a.Y16.p) store_row16<B>((char*)a.Y16.p + ((size_t)i * a.Y16.ld + coloff) * 2, x[u], bwh, vecY16, a.bf16);
+    }
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(NT, 1) panel_dblock_kernel(BlockArgs a, int CS) {
+    constexpr int B = 16;
+    __shared__ __align__(16) float red[2][NW][B];
+    __shared__ __align__(16) float prow[2][B];
+    __shared__ __align__(16) float slot[2][CSMAX][B];
+    __shared__ __align__(16) float pslot[2][B];
+    __shared__ __align__(16) float tauS[NW][B];
+    __shared__ __align__(16) float gt[B][B + 4];
+    __shared__ __align__(16) float TA[B][B + 4];
+    __shared__ float diag[B];
+    __shared__ __align__(16) float redw[NW][64];
+    __shared__ __align__(16) float csumAll[256];
+    __shared__ __align__(16) float slotX[CSMAX][256];
+    __shared__ __align__(16) float Sfull[256];
+    __shared__ __align__(16) float Ssm[B][B];
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ __align__(8) uint64_t mbarX;
+    extern __shared__ __align__(16) float Bsm[];  // (NT * RPT) rows x 16 floats; 16-byte chunk q of row r at q ^ ((r >> 1) & 3)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned crank = (CS > 1) ? cluster_ctarank() : 0u;
+    const int D = a.D, bw2 = a.bw - B;
+    const int rbase = (int)crank * (NT * RPT) + tid;
+    const long lda = a.lda;
+    const bool vecA = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
+    const bool vecY32 = a.Y32.p && ((a.Y32.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y32.p) & 15) == 0);
+    const bool vecY16 = a.Y16.p && ((a.Y16.ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.Y16.p) & 15) == 0);
+    long long pacc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = 0;
+
+    pdl_launch_dependents();
+    for (int idx = tid; idx < B * (B + 4); idx += NT) (&gt[0][0])[idx] = 0.f;
+    if (CS > 1) {
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            mbar_init(&mbarX, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster_sync_all();
+    }
+    pdl_wait();
+
+    float x[RPT][B];
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const int i = rbase + u * NT, lr = u * NT + tid;
+        float b[B];
+        if (i < D) {
+            load_row<B>(a.A + (size_t)i * lda, x[u], B, vecA);
+            load_row<B>(a.A + (size_t)i * lda + B, b, bw2, vecA);
+        } else {
+#pragma unroll
+            for (int c = 0; c < B; ++c) { x[u][c] = 0.f; b[c] = 0.f; }
+        }
+        float4* dst = reinterpret_cast<float4*>(Bsm + (size_t)lr * B);
+        const int sw = (lr >> 1) & 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q ^ sw] = make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+    }
+    if (a.zero_buf) {
+        const int nthr = CS * NT;
+        for (int idx = (int)crank * NT + tid; idx < a.zero_n; idx += nthr) a.zero_buf[idx] = 0.f;
+    }
+    __syncthreads();
+
+    StepMem<B> M{red, prow, slot, pslot, tauS, gt, diag, mbar};
+    // ---- half A
+    {
+        StepCtx sc{tid, lane, warp, CS, rbase, B, (B < D ? B : D), 0, crank, false, pacc, &tprev};
+        factor_steps<B, RPT>(x, M, sc);
+    }
+    __syncthreads();
+    tinv_smem<B, B + 4>(gt, &red[0][0][0], tid);
+    for (int idx = tid; idx < B * (B + 4); idx += NT) (&TA[0][0])[idx] = (&gt[0][0])[idx];
+    emit_half<RPT>(x, a, D, rbase, 0, 0, B, diag, vecA, vecY32, vecY16);  // x becomes Y_A (zero above the diagonal)
+    __syncthreads();
+
+    // ---- S' = Y_A^T B, four 16 x 4 column chunks
+    for (int p4 = 0; p4 < 4; ++p4) {
+        float acc[64];
+#pragma unroll
+        for (int e = 0; e < 64; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const int lr = u * NT + tid;
+            const float4 b4 = reinterpret_cast<const float4*>(Bsm + (size_t)lr * B)[p4 ^ ((lr >> 1) & 3)];
+#pragma unroll
+            for (int t = 0; t < B; ++t) {
+                acc[4 * t] = fmaf(x[u][t], b4.x, acc[4 * t]);
+                acc[4 * t + 1] = fmaf(x[u][t], b4.y, acc[4 * t + 1]);
+                acc[4 * t + 2] = fmaf(x[u][t], b4.z, acc[4 * t + 2]);
+                acc[4 * t + 3] = fmaf(x[u][t], b4.w, acc[4 * t + 3]);
+            }
+        }
+        tr_stage<64, 16>(acc, lane);
+        tr_stage<32, 8>(acc, lane);
+        tr_stage<16, 4>(acc, lane);
+        tr_stage<8, 2>(acc, lane);
+        tr_stage<4, 1>(acc, lane);  // lane l now holds the warp sums of entries 2l, 2l+1
+        redw[warp][2 * lane] = acc[0];
+        redw[warp][2 * lane + 1] = acc[1];
+        __syncthreads();
+        if (tid < 64) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) v += redw[w][tid];
+            csumAll[p4 * 64 + tid] = v;  // entry (t, k) of chunk p4 = S'[t][4 p4 + k], at t*4 + k
+        }
+        __syncthreads();
+    }
+    if (CS > 1) {
+        if (tid == 0) mbar_arrive_expect_tx(&mbarX, (uint32_t)CS * 1024u);
+        for (int o = tid; o < CS * 64; o += NT) {
+            const unsigned peer = (unsigned)(o >> 6);
+            const int ch = o & 63;
+            st_async_v4(map_to_cta(smem_addr(&slotX[crank][4 * ch]), peer), *reinterpret_cast<const float4*>(&csumAll[4 * ch]),
+                        map_to_cta(smem_addr(&mbarX), peer));
+        }
+        mbar_wait_cluster(&mbarX, 0);
+        float v = 0.f;
+        for (int cc = 0; cc < CS; ++cc) v += slotX[cc][tid];
+        Sfull[tid] = v;
+    } else {
+        Sfull[tid] = csumAll[tid];
+    }
+    __syncthreads();
+    {   // S = T_A^T S'   (thread <-> entry (t, c))
+        const int t = tid >> 4, cidx = tid & 15;
+        float v = 0.f;
+#pragma unroll
+        for (int u2 = 0; u2 < B; ++u2)
+            if (u2 <= t) v = fmaf(TA[u2][t], Sfull[(cidx >> 2) * 64 + u2 * 4 + (cidx & 3)], v);
+        Ssm[t][cidx] = v;
+    }
+    __syncthreads();
+    // ---- B -= Y_A S, two rows at a time, straight into the registers (Y_A is not needed afterwards)
+#pragma unroll
+    for (int u0 = 0; u0 < RPT; u0 += 2) {
+        constexpr int RG = (RPT >= 2) ? 2 : 1;
+        float b[RG][B], y[RG][B];
+#pragma unroll
+        for (int g2 = 0; g2 < RG; ++g2) {
+            const int lr = (u0 + g2) * NT + tid;
+            const float4* src = reinterpret_cast<const float4*>(Bsm + (size_t)lr * B);
+            const int sw = (lr >> 1) & 3;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 v4 = src[q ^ sw];
+                b[g2][4 * q] = v4.x; b[g2][4 * q + 1] = v4.y; b[g2][4 * q + 2] = v4.z; b[g2][4 * q + 3] = v4.w;
+            }
+#pragma unroll
+            for (int c = 0; c < B; ++c) y[g2][c] = x[u0 + g2][c];
+        }
+#pragma unroll
+        for (int t = 0; t < B; ++t) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 s4 = *reinterpret_cast<const float4*>(&Ssm[t][4 * q]);
+#pragma unroll
+                for (int g2 = 0; g2 < RG; ++g2) {
+                    b[g2][4 * q] = fmaf(-y[g2][t], s4.x, b[g2][4 * q]);
+                    b[g2][4 * q + 1] = fmaf(-y[g2][t], s4.y, b[g2][4 * q + 1]);
+                    b[g2][4 * q + 2] = fmaf(-y[g2][t], s4.z, b[g2][4 * q + 2]);
+                    b[g2][4 * q + 3] = fmaf(-y[g2][t], s4.w, b[g2][4 * q + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int g2 = 0; g2 < RG; ++g2)
+#pragma unroll
+            for (int c = 0; c < B; ++c) x[u0 + g2][c] = b[g2][c];
+    }
+    for (int idx = tid; idx < B * (B + 4); idx += NT) (&gt[0][0])[idx] = 0.f;
+    __syncthreads();
+
+    // ---- half B: diagonal at slab row 16
+    const int kr2 = (D - B) < bw2 ? (D - B > 0 ? D - B : 0) : bw2;
+    {
+        StepCtx sc{tid, lane, warp, CS, rbase, bw2, kr2, B, crank, false, pacc, &tprev};
+        factor_steps<B, RPT>(x, M, sc);
+    }
+    __syncthreads();
+    tinv_smem<B, B + 4>(gt, &red[0][0][0], tid);
+    emit_half<RPT>(x, a, D, rbase, B, B, bw2, diag, vecA, vecY32, vecY16);
+    // rows above the block are structurally zero in the compact outputs
+    {
+        const int gtid = (int)crank * NT + tid, nthr = CS * NT, bw = a.bw;
+        if (a.Y32.p)
+            for (long idx = gtid; idx < (long)a.Y32.zrows * bw; idx += nthr) {
+                long rr = idx / bw; int c = (int)(idx - rr * bw);
+                a.Y32.p[(rr - a.Y32.zrows) * a.Y32.ld + c] = 0.f;
+            }
+        if (a.Y16.p)
+            for (long idx = gtid; idx < (long)a.Y16.zrows * bw; idx += nthr) {
+                long rr = idx / bw; int c = (int)(idx - rr * bw);
+                store16(a.Y16.p, (rr - a.Y16.zrows) * a.Y16.ld + c, 0.f, a.bf16);
+            }
+    }
+    if (a.T && crank == 0) {  // [T_A | T_B], 16 x 16 each, ld 16
+        const int t = tid >> 4, c = tid & 15;
+        a.T[tid] = (t <= c) ? TA[t][c] : 0.f;
+        a.T[256 + tid] = (t <= c && c < kr2) ? gt[t][c] : 0.f;
+    }
     if (CS > 1) cluster_sync_all();
 }
 
@@ -734,7 +1021,10 @@ template <int B>
 __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* __restrict__ Y, long ldy, const float* __restrict__ A,
                                                                   long lda, int D, int ncols, float* __restrict__ Srep,
                                                                   unsigned* __restrict__ counter, const float* __restrict__ Tj,
-                                                                  float* __restrict__ Sfin, int rows_per_cta, int ysm_floats) {
+                                                                  float* __restrict__ Sfin, int rows_per_cta, int ysm_floats,
+                                                                  float* __restrict__ Cacc) {
+    // Cacc != null (B == 32 after a double block): Tj = [T_A | T_B] (16 x 16 each); this kernel also accumulates the
+    // cross Gram C = Y_A^T Y_B and its last CTA assembles T_32 = [[T_A, -T_A C T_B], [0, T_B]].
     constexpr int NTHR = Su4<B>::NTHR, NWARP = NTHR / 32, RB = Su4<B>::RB;
     extern __shared__ __align__(16) float sm[];
     float* ysm = sm;               // rows_per_cta x B  (later: T, B x (B+4))
@@ -760,6 +1050,17 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
         ysm[idx] = Y[(size_t)(r0 + rr) * ldy + t];
     }
     __syncthreads();
+    if (B == 32 && Cacc && blockIdx.y == 0) {  // NTHR == 256: thread <-> entry (ta, tb) of C
+        const int ta = tid >> 4, tb = tid & 15;
+        float c0 = 0.f, c1 = 0.f;
+        int r2 = 0;
+        for (; r2 + 1 < nrows; r2 += 2) {
+            c0 = fmaf(ysm[r2 * B + ta], ysm[r2 * B + 16 + tb], c0);
+            c1 = fmaf(ysm[(r2 + 1) * B + ta], ysm[(r2 + 1) * B + 16 + tb], c1);
+        }
+        if (r2 < nrows) c0 = fmaf(ysm[r2 * B + ta], ysm[r2 * B + 16 + tb], c0);
+        atomicAdd(&Cacc[tid], c0 + c1);
+    }
     float acc[B][4];
 #pragma unroll
     for (int t = 0; t < B; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
@@ -833,7 +1134,29 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
         }
         red[idx] = v;
     }
-    for (int idx = tid; idx < B * B; idx += NTHR) Ts[(idx / B) * (B + 4) + (idx % B)] = Tj[idx];
+    if (B == 32 && Cacc) {
+        // T_32 from T_A, T_B and C: X = C T_B, T_AB = -T_A X  (thread <-> entry (i, j); NTHR == 256)
+        float* Xs = red + B * 128;          // 16 x 16 scratch behind S' (the dynamic buffer has room: see launch)
+        float* Cs = Xs + 256;
+        const int i2 = tid >> 4, j2 = tid & 15;
+        Cs[tid] = __ldcg(&Cacc[tid]);
+        for (int idx = tid; idx < B * (B + 4); idx += NTHR) Ts[idx] = 0.f;
+        __syncthreads();
+        Ts[i2 * (B + 4) + j2] = Tj[tid];                    // T_A
+        Ts[(16 + i2) * (B + 4) + 16 + j2] = Tj[256 + tid];  // T_B
+        __syncthreads();
+        float xv = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) xv = fmaf(Cs[i2 * 16 + k], Ts[(16 + k) * (B + 4) + 16 + j2], xv);
+        Xs[tid] = xv;
+        __syncthreads();
+        float tv = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) tv = fmaf(Ts[i2 * (B + 4) + k], Xs[k * 16 + j2], tv);
+        Ts[i2 * (B + 4) + 16 + j2] = -tv;
+    } else {
+        for (int idx = tid; idx < B * B; idx += NTHR) Ts[(idx / B) * (B + 4) + (idx % B)] = Tj[idx];
+    }
     __syncthreads();
     {
         constexpr int NG = NTHR / 128, TQ = B / NG;  // thread: column cc, TQ consecutive rows t of S
@@ -1084,6 +1407,42 @@ int launch_block_t(const BlockArgs& a, int CS, cudaStream_t stream) {
     return MPQR_OK;
 }
 
+template <int RPT>
+int launch_dblock_t(const BlockArgs& a, int CS, cudaStream_t stream) {
+    static bool attr = false;
+    const size_t smem = (size_t)NT * RPT * 16 * sizeof(float);
+    if (!attr) {
+        MPQR_CUDA(cudaFuncSetAttribute(panel_dblock_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaFuncSetAttribute(panel_dblock_kernel<RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        attr = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CS);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (CS > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = CS;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    at[na++] = pdl_attr();
+    cfg.attrs = at;
+    cfg.numAttrs = na;
+    MPQR_CUDA(cudaLaunchKernelEx(&cfg, panel_dblock_kernel<RPT>, a, CS));
+    return MPQR_OK;
+}
+int launch_dblock(const BlockArgs& a, int RPT, int CS, cudaStream_t st) {
+    if (RPT == 1) return launch_dblock_t<1>(a, CS, st);
+    if (RPT == 2) return launch_dblock_t<2>(a, CS, st);
+    if (RPT == 4) return launch_dblock_t<4>(a, CS, st);
+    return launch_dblock_t<8>(a, CS, st);
+}
+
 int g_max_cs = 0;
 int max_cluster() {
     if (!g_max_cs) {
@@ -1167,7 +1526,7 @@ Ws carve(float* ws, long rows) {
     w.Y32p = ws;
     w.Wj = w.Y32p + (size_t)rows * RMAX;
     w.Srep = w.Wj + (size_t)rows * 32;
-    w.Sfin = w.Srep + (size_t)NREP * RMAX * SLD + 4;
+    w.Sfin = w.Srep + (size_t)NREP * RMAX * SLD + 4 + 256;  // (+ ticket counter + 16 x 16 cross-Gram accumulator)
     w.G = w.Sfin + (size_t)RMAX * SLD;
     w.T32 = w.G + (size_t)RMAX * RMAX;
     w.T16 = (void*)(w.T32 + (size_t)RMAX * RMAX);
@@ -1185,7 +1544,7 @@ int launch_tinv(const float* G, long ldg, int pw, float* T32, int ldt, void* T16
 
 template <int B>
 int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, float* Sfin,
-              int num_sms, cudaStream_t st, long* launches, const ProfHook* prof) {
+              int num_sms, cudaStream_t st, long* launches, const ProfHook* prof, bool pair = false) {
     static bool attr = false;
     // one wave of CTAs over the SMs this stream may use (up to 512 rows = 32 KB of staged Y per CTA);
     // taller blocks take k balanced waves
@@ -1211,13 +1570,14 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
         int ysm_floats = rows * B;
         if (ysm_floats < B * (B + 4)) ysm_floats = B * (B + 4);
         cfg.blockDim = dim3(Su4<B>::NTHR);
-        size_t s4_floats = (size_t)ysm_floats + B * 128;
+        size_t s4_floats = (size_t)ysm_floats + B * 128 + 512;  // (+ scratch of the T_32 assembly)
         const size_t tree_floats = (size_t)(Su4<B>::NTHR / 32) * B * 64;
         if (s4_floats < tree_floats) s4_floats = tree_floats;
         cfg.dynamicSmemBytes = s4_floats * sizeof(float);
         unsigned* counter = reinterpret_cast<unsigned*>(Srep + (size_t)NREP * RMAX * SLD);
+        float* Cacc = pair ? Srep + (size_t)NREP * RMAX * SLD + 4 : nullptr;
         MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_s4_kernel<B>, Yj, ldy, (const float*)Arest, lda, D, ncols, Srep, counter, Tj, Sfin, rows,
-                                     ysm_floats));
+                                     ysm_floats, Cacc));
         if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st, 2.0 * D * ncols * B, 4.0 * D * (2 * ncols + B)); }
         cfg.dynamicSmemBytes = (size_t)rows * B * sizeof(float);
         MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_u4_kernel<B>, Yj, ldy, Arest, lda, D, ncols, (const float*)Sfin, rows));
@@ -1237,7 +1597,7 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
 }  // namespace
 
 size_t panel_ws_bytes(long max_rows) {
-    return ((size_t)max_rows * (RMAX + 32) + (size_t)(NREP + 1) * RMAX * SLD + 4 + 2 * (size_t)RMAX * RMAX) * sizeof(float) +
+    return ((size_t)max_rows * (RMAX + 32) + (size_t)(NREP + 1) * RMAX * SLD + 4 + 256 + 2 * (size_t)RMAX * RMAX) * sizeof(float) +
            (size_t)RMAX * RMAX * 2 + 256;
 }
 
@@ -1294,29 +1654,42 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     // FP32 Y of the whole panel: caller's array if given, else the workspace
     float* Yp = Y32l ? Y32l : w.Y32p;
     const long ldyp = Y32l ? a.ld32 : RMAX;
-    for (int jb = 0; jb < nblk; ++jb) {
-        const int j0 = jb * B;
-        const int bw = (j0 + B < pw) ? B : pw - j0;
+    // MPQR_DBLOCK=1 (experimental, off by default): 16-column register blocks of tall panels are taken two at
+    // a time by panel_dblock_kernel, 32 columns per launch, and the in-panel update runs once per 32 columns.
+    // Round 1 measurement (B200, 32768^2): 88 us per double block against 2 x 41 us + one update pair (25 us);
+    // the in-kernel update between the halves still costs ~30 us, so the whole factorisation is 159 ms
+    // against 150 ms with single blocks.
+    const char* dbl_env = getenv("MPQR_DBLOCK");
+    // (its in-panel update needs the vectorised kernels: 16-byte aligned rows and widths that are multiples of 4)
+    const bool use_dblock = (B == 16) && dbl_env && dbl_env[0] == '1' && ((a.lda & 3) == 0) && ((pw & 3) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(Ablk) & 15) == 0);
+    for (int j0 = 0; j0 < pw;) {
         const int Dj = D - j0;
         if (Dj <= 0) break;
+        const bool dbl = use_dblock && (pw - j0 > B) && (Dj > 2 * B);
+        const int BW = dbl ? 2 * B : B;  // columns of this launch
+        const int bw = (j0 + BW < pw) ? BW : pw - j0;
         if (!pick_shape(B, Dj, a.force_cs, a.force_rpt, &rpt, &cs)) { set_error("panel: sizing error D=%d", Dj); return MPQR_EINVAL; }
         const int nrest = pw - (j0 + bw);
         BlockArgs b{};
         b.A = Ablk + (size_t)j0 * a.lda + j0; b.lda = a.lda; b.D = Dj; b.bw = bw;
         b.Y32 = {Yp + (size_t)j0 * ldyp + j0, ldyp, j0 + (Y32l ? zr : 0)};
-        if (nrest > 0) { b.T = w.Wj; b.ldt = B; }  // block T (B x B) for the in-panel update
+        if (nrest > 0) { b.T = w.Wj; b.ldt = B; }  // block T for the in-panel update ([T_A | T_B] after a double block)
         if (Y16l) b.Y16 = {Y16l + ((size_t)j0 * a.ldy16 + j0) * 2, a.ldy16, j0 + zr};
         b.bf16 = a.bf16; b.dbg = a.dbg;
-        if (nrest > 0) { b.zero_buf = w.Srep; b.zero_n = NREP * RMAX * SLD + 4; }
+        if (nrest > 0) { b.zero_buf = w.Srep; b.zero_n = NREP * RMAX * SLD + 4 + 256; }
         if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 4.0 * Dj * bw * bw, 14.0 * Dj * bw);
-        MPQR_TRY(launch_block(B, b, rpt, cs, stream));
+        if (dbl) MPQR_TRY(launch_dblock(b, rpt, cs, stream));
+        else MPQR_TRY(launch_block(B, b, rpt, cs, stream));
         if (a.prof) a.prof->end(a.prof->ctx, stream);
         if (launches) *launches += 1;
         if (nrest > 0) {
             float* Arest = b.A + bw;
-            if (B == 32) MPQR_TRY(launch_su<32>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, w.Sfin, sm_count(di), stream, launches, a.prof));
+            if (dbl) MPQR_TRY(launch_su<32>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, w.Sfin, sm_count(di), stream, launches, a.prof, true));
+            else if (B == 32) MPQR_TRY(launch_su<32>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, w.Sfin, sm_count(di), stream, launches, a.prof));
             else MPQR_TRY(launch_su<16>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, w.Sfin, sm_count(di), stream, launches, a.prof));
         }
+        j0 += bw;
     }
     if (a.dbg_caps) { a.dbg_caps[0] = max_cluster(); a.dbg_caps[1] = cs; a.dbg_caps[2] = rpt; }
     if (!need_t) return MPQR_OK;

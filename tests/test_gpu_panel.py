@@ -72,3 +72,10 @@ def test_panel_zero_column_and_signs():
     V = np.array([[0.0], [0.0], [2.0]], np.float32)
     P, _, _, _ = panel_factor(oracle.pack(V), 0, 1)
     assert np.allclose(P[:, 0], [-2, 1 / np.sqrt(2), 0, 1 / np.sqrt(2)], atol=1e-6)
+
+
+def test_panel_double_block_kernel(monkeypatch):
+    # experimental 32-column launch for tall panels (two 16-column halves, second half staged in shared memory)
+    monkeypatch.setenv("MPQR_DBLOCK", "1")
+    _check_panel(20000, 128, 0, 128, seed=77, tol=5e-5)
+    _check_panel(18000, 80, 16, 52, seed=78, tol=5e-5)   # ragged second half (32 + 16 + 4)
