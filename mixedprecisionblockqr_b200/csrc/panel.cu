@@ -253,6 +253,72 @@ __device__ __forceinline__ void store_row16(void* p, const float (&x)[B], int bw
     }
 }
 
+// ---- warp-cooperative, coalesced transfers between global rows and "one row per lane" registers.
+// A lane that moves its own row touches 32 different cache lines per instruction (a 64-byte row
+// segment per lane): ncu showed 10 us of load + 10 us of stores per 16-column block at D = 32768,
+// i.e. 32 GB/s per SM.  Here CH lanes share a row (CH = 16-byte chunks per row), so one
+// instruction covers 32/CH whole rows; the transposition to/from the row-per-lane layout goes through
+// a warp-private shared tile whose chunks are XOR-swizzled (conflict-free both ways).
+//   tile: 32 * CH uint4 per warp.   g: element (first row of the group, first column), pitch in BYTES.
+template <int CH>
+__device__ __forceinline__ int tile_swz(int row) { return (row / (8 / CH)) % CH; }
+
+template <int CH>
+__device__ __forceinline__ void warp_tile_in(const char* g, size_t pitch, int nvalid, uint4 (&v)[CH], uint4* tile, int lane) {
+    constexpr int RPI = 32 / CH;  // rows per instruction
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        const int r = k * RPI + lane / CH, q = lane % CH;
+        uint4 t = make_uint4(0u, 0u, 0u, 0u);
+        if (r < nvalid) t = __ldg(reinterpret_cast<const uint4*>(g + (size_t)r * pitch) + q);
+        tile[r * CH + (q ^ tile_swz<CH>(r))] = t;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < CH; ++q) v[q] = tile[lane * CH + (q ^ tile_swz<CH>(lane))];
+    __syncwarp();
+}
+template <int CH>
+__device__ __forceinline__ void warp_tile_out(char* g, size_t pitch, int nvalid, const uint4 (&v)[CH], uint4* tile, int lane) {
+    constexpr int RPI = 32 / CH;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) tile[lane * CH + (q ^ tile_swz<CH>(lane))] = v[q];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        const int r = k * RPI + lane / CH, q = lane % CH;
+        if (r < nvalid) reinterpret_cast<uint4*>(g + (size_t)r * pitch)[q] = tile[r * CH + (q ^ tile_swz<CH>(r))];
+    }
+    __syncwarp();
+}
+template <int B>
+__device__ __forceinline__ void rows_in_f32(const float* g, long ld, int nvalid, float (&x)[B], uint4* tile, int lane) {
+    uint4 v[B / 4];
+    warp_tile_in<B / 4>(reinterpret_cast<const char*>(g), (size_t)ld * 4, nvalid, v, tile, lane);
+#pragma unroll
+    for (int q = 0; q < B / 4; ++q) {
+        x[4 * q] = __uint_as_float(v[q].x); x[4 * q + 1] = __uint_as_float(v[q].y);
+        x[4 * q + 2] = __uint_as_float(v[q].z); x[4 * q + 3] = __uint_as_float(v[q].w);
+    }
+}
+template <int B>
+__device__ __forceinline__ void rows_out_f32(float* g, long ld, int nvalid, const float (&x)[B], uint4* tile, int lane) {
+    uint4 v[B / 4];
+#pragma unroll
+    for (int q = 0; q < B / 4; ++q)
+        v[q] = make_uint4(__float_as_uint(x[4 * q]), __float_as_uint(x[4 * q + 1]), __float_as_uint(x[4 * q + 2]), __float_as_uint(x[4 * q + 3]));
+    warp_tile_out<B / 4>(reinterpret_cast<char*>(g), (size_t)ld * 4, nvalid, v, tile, lane);
+}
+template <int B>
+__device__ __forceinline__ void rows_out_16(void* g, long ld, int nvalid, const float (&x)[B], uint4* tile, int lane, int bf16) {
+    uint4 v[B / 8];
+#pragma unroll
+    for (int q = 0; q < B / 8; ++q)
+        v[q] = make_uint4(pack16(x[8 * q], x[8 * q + 1], bf16), pack16(x[8 * q + 2], x[8 * q + 3], bf16),
+                          pack16(x[8 * q + 4], x[8 * q + 5], bf16), pack16(x[8 * q + 6], x[8 * q + 7], bf16));
+    warp_tile_out<B / 8>(reinterpret_cast<char*>(g), (size_t)ld * 2, nvalid, v, tile, lane);
+}
+
 // dbg slots: 0 pass, 1 shuffle tree, 2 smem + CTA barrier, 3 CTA sum + send, 4 exchange wait, 5 gather+scalars,
 // 6 load, 7 tail, 8 steps, 9 CS, 10 RPT, 11 B
 #define PROF_MARK(slot)                     \
@@ -434,6 +500,7 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
     __shared__ __align__(16) float gt[B][B + 4];
     __shared__ float diag[B];
     __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ __align__(16) uint4 tiles[NW][32 * (B / 4)];  // warp-private transposition tiles (coalesced I/O)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned crank = (CS > 1) ? cluster_ctarank() : 0u;
@@ -460,10 +527,14 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
     pdl_wait();  // everything above overlapped the predecessor's tail; its results are visible from here on
 
     float x[RPT][B];
+    const int wrow0 = rbase - lane;  // first row of this warp's 32-row group for u = 0
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
         const int i = rbase + u * NT;
-        if (i < D) {
+        if (vecA && bw == B) {
+            const int g0 = wrow0 + u * NT;
+            rows_in_f32<B>(a.A + (size_t)g0 * lda, lda, D - g0, x[u], tiles[warp], lane);  // rows >= D read as zero
+        } else if (i < D) {
             load_row<B>(a.A + (size_t)i * lda, x[u], bw, vecA);
         } else {
 #pragma unroll
@@ -496,15 +567,20 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
         const int i = rbase + u * NT;
-        if (i >= D) continue;
+        const int g0 = wrow0 + u * NT;          // first row of the warp's group
+        const bool full = (bw == B) && g0 >= B;  // the whole group lies below the block's triangle
         // packed factor: R above the diagonal, R_kk on it, w shifted one row down
-        if (i >= bw) {
-            store_row32<B>(a.A + (size_t)(i + 1) * lda, x[u], bw, vecA);
-        } else {
+        if (full && vecA) {
+            rows_out_f32<B>(a.A + (size_t)(g0 + 1) * lda, lda, D - g0, x[u], tiles[warp], lane);
+        } else if (i < D) {
+            if (i >= bw) {
+                store_row32<B>(a.A + (size_t)(i + 1) * lda, x[u], bw, vecA);
+            } else {
 #pragma unroll
-            for (int c = 0; c < B; ++c)
-                if (c < bw) a.A[(size_t)(i + (i >= c ? 1 : 0)) * lda + c] = x[u][c];
-            a.A[(size_t)i * lda + i] = diag[i];  // i < bw: R_ii (the loop above put w_ii one row below)
+                for (int c = 0; c < B; ++c)
+                    if (c < bw) a.A[(size_t)(i + (i >= c ? 1 : 0)) * lda + c] = x[u][c];
+                a.A[(size_t)i * lda + i] = diag[i];  // i < bw: R_ii (the loop above put w_ii one row below)
+            }
         }
         // Y: zero strictly above the diagonal and for columns without reflector
         if (i < B) {
@@ -512,8 +588,14 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
             for (int c = 0; c < B; ++c)
                 if (i < c) x[u][c] = 0.f;
         }
-        if (a.Y32.p) store_row32<B>(a.Y32.p + (size_t)i * a.Y32.ld, x[u], bw, vecY32);
-        if (a.Y16.p) store_row16<B>((char*)a.Y16.p + (size_t)i * a.Y16.ld * 2, x[u], bw, vecY16, a.bf16);
+        if (a.Y32.p) {
+            if (bw == B && vecY32) rows_out_f32<B>(a.Y32.p + (size_t)g0 * a.Y32.ld, a.Y32.ld, D - g0, x[u], tiles[warp], lane);
+            else if (i < D) store_row32<B>(a.Y32.p + (size_t)i * a.Y32.ld, x[u], bw, vecY32);
+        }
+        if (a.Y16.p) {
+            if (bw == B && vecY16) rows_out_16<B>((char*)a.Y16.p + (size_t)g0 * a.Y16.ld * 2, a.Y16.ld, D - g0, x[u], tiles[warp], lane, a.bf16);
+            else if (i < D) store_row16<B>((char*)a.Y16.p + (size_t)i * a.Y16.ld * 2, x[u], bw, vecY16, a.bf16);
+        }
     }
     if (want_w) {
         constexpr int WG = (RPT >= 2) ? 2 : 1;  // rows that share one sweep over T
@@ -541,10 +623,15 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
             }
 #pragma unroll
             for (int g2 = 0; g2 < WG; ++g2) {
-                const int i = rbase + (u0 + g2) * NT;
-                if (i >= D) continue;
-                if (a.W32.p) store_row32<B>(a.W32.p + (size_t)i * a.W32.ld, w[g2], bw, vecW32);
-                if (a.W16.p) store_row16<B>((char*)a.W16.p + (size_t)i * a.W16.ld * 2, w[g2], bw, vecW16, a.bf16);
+                const int i = rbase + (u0 + g2) * NT, g0 = wrow0 + (u0 + g2) * NT;
+                if (a.W32.p) {
+                    if (bw == B && vecW32) rows_out_f32<B>(a.W32.p + (size_t)g0 * a.W32.ld, a.W32.ld, D - g0, w[g2], tiles[warp], lane);
+                    else if (i < D) store_row32<B>(a.W32.p + (size_t)i * a.W32.ld, w[g2], bw, vecW32);
+                }
+                if (a.W16.p) {
+                    if (bw == B && vecW16) rows_out_16<B>((char*)a.W16.p + (size_t)g0 * a.W16.ld * 2, a.W16.ld, D - g0, w[g2], tiles[warp], lane, a.bf16);
+                    else if (i < D) store_row16<B>((char*)a.W16.p + (size_t)i * a.W16.ld * 2, w[g2], bw, vecW16, a.bf16);
+                }
             }
         }
     }
@@ -600,26 +687,39 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
 // whose cross term the in-panel S kernel accumulates on the side.
 template <int RPT>
 __device__ __forceinline__ void emit_half(float (&x)[RPT][16], const BlockArgs& a, int D, int rbase, int roff, int coloff, int bwh,
-                                          const float* diag, bool vecA, bool vecY32, bool vecY16) {
+                                          const float* diag, bool vecA, bool vecY32, bool vecY16, uint4* tile, int lane) {
     constexpr int B = 16;
     const long lda = a.lda;
+    const int wrow0 = rbase - lane;
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
-        const int i = rbase + u * NT;
-        if (i >= D) continue;
-        if (i >= roff + B) {
-            store_row32<B>(a.A + (size_t)(i + 1) * lda + coloff, x[u], bwh, vecA);
-        } else {
+        const int i = rbase + u * NT, g0 = wrow0 + u * NT;
+        const bool full = (bwh == B) && g0 >= roff + B;
+        if (full && vecA) {
+            rows_out_f32<B>(a.A + (size_t)(g0 + 1) * lda + coloff, lda, D - g0, x[u], tile, lane);
+        } else if (i < D) {
+            if (i >= roff + B) {
+                store_row32<B>(a.A + (size_t)(i + 1) * lda + coloff, x[u], bwh, vecA);
+            } else {
 #pragma unroll
-            for (int c = 0; c < B; ++c)
-                if (c < bwh) a.A[(size_t)(i + (i >= c + roff ? 1 : 0)) * lda + coloff + c] = x[u][c];
-            if (i >= roff && i - roff < bwh) a.A[(size_t)i * lda + coloff + (i - roff)] = diag[i - roff];
+                for (int c = 0; c < B; ++c)
+                    if (c < bwh) a.A[(size_t)(i + (i >= c + roff ? 1 : 0)) * lda + coloff + c] = x[u][c];
+                if (i >= roff && i - roff < bwh) a.A[(size_t)i * lda + coloff + (i - roff)] = diag[i - roff];
+            }
+        }
+        if (i < roff + B) {
 #pragma unroll
             for (int c = 0; c < B; ++c)
                 if (i < c + roff) x[u][c] = 0.f;  // Y: zero above the diagonal
         }
-        if (a.Y32.p) store_row32<B>(a.Y32.p + (size_t)i * a.Y32.ld + coloff, x[u], bwh, vecY32);
-        if (a.Y16.p) store_row16<B>((char*)a.Y16.p + ((size_t)i * a.Y16.ld + coloff) * 2, x[u], bwh, vecY16, a.bf16);
+        if (a.Y32.p) {
+            if (bwh == B && vecY32) rows_out_f32<B>(a.Y32.p + (size_t)g0 * a.Y32.ld + coloff, a.Y32.ld, D - g0, x[u], tile, lane);
+            else if (i < D) store_row32<B>(a.Y32.p + (size_t)i * a.Y32.ld + coloff, x[u], bwh, vecY32);
+        }
+        if (a.Y16.p) {
+            if (bwh == B && vecY16) rows_out_16<B>((char*)a.Y16.p + ((size_t)g0 * a.Y16.ld + coloff) * 2, a.Y16.ld, D - g0, x[u], tile, lane, a.bf16);
+            else if (i < D) store_row16<B>((char*)a.Y16.p + ((size_t)i * a.Y16.ld + coloff) * 2, x[u], bwh, vecY16, a.bf16);
+        }
     }
 }
 
@@ -641,6 +741,7 @@ __global__ void __launch_bounds__(NT, 1) panel_dblock_kernel(BlockArgs a, int CS
     __shared__ __align__(16) float Ssm[B][B];
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ __align__(8) uint64_t mbarX;
+    __shared__ __align__(16) uint4 tiles[NW][32 * 4];
     extern __shared__ __align__(16) float Bsm[];  // (NT * RPT) rows x 16 floats; 16-byte chunk q of row r at q ^ ((r >> 1) & 3)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -672,7 +773,11 @@ __global__ void __launch_bounds__(NT, 1) panel_dblock_kernel(BlockArgs a, int CS
     for (int u = 0; u < RPT; ++u) {
         const int i = rbase + u * NT, lr = u * NT + tid;
         float b[B];
-        if (i < D) {
+        if (vecA && bw2 == B) {
+            const int g0 = rbase - lane + u * NT;
+            rows_in_f32<B>(a.A + (size_t)g0 * lda, lda, D - g0, x[u], tiles[warp], lane);
+            rows_in_f32<B>(a.A + (size_t)g0 * lda + B, lda, D - g0, b, tiles[warp], lane);
+        } else if (i < D) {
             load_row<B>(a.A + (size_t)i * lda, x[u], B, vecA);
             load_row<B>(a.A + (size_t)i * lda + B, b, bw2, vecA);
         } else {
@@ -699,7 +804,7 @@ __global__ void __launch_bounds__(NT, 1) panel_dblock_kernel(BlockArgs a, int CS
     __syncthreads();
     tinv_smem<B, B + 4>(gt, &red[0][0][0], tid);
     for (int idx = tid; idx < B * (B + 4); idx += NT) (&TA[0][0])[idx] = (&gt[0][0])[idx];
-    emit_half<RPT>(x, a, D, rbase, 0, 0, B, diag, vecA, vecY32, vecY16);  // x becomes Y_A (zero above the diagonal)
+    emit_half<RPT>(x, a, D, rbase, 0, 0, B, diag, vecA, vecY32, vecY16, tiles[warp], lane);  // x becomes Y_A (zero above the diagonal)
     __syncthreads();
 
     // ---- S' = Y_A^T B, four 16 x 4 column chunks
@@ -808,7 +913,7 @@ __global__ void __launch_bounds__(NT, 1) panel_dblock_kernel(BlockArgs a, int CS
     }
     __syncthreads();
     tinv_smem<B, B + 4>(gt, &red[0][0][0], tid);
-    emit_half<RPT>(x, a, D, rbase, B, B, bw2, diag, vecA, vecY32, vecY16);
+    emit_half<RPT>(x, a, D, rbase, B, B, bw2, diag, vecA, vecY32, vecY16, tiles[warp], lane);
     // rows above the block are structurally zero in the compact outputs
     {
         const int gtid = (int)crank * NT + tid, nthr = CS * NT, bw = a.bw;
