@@ -160,6 +160,24 @@ int mpqr_mg_global_col(const mpqr_handle* h, int local_col);
 int mpqr_mg_factor_device(mpqr_handle* h, float* dA_local, long lda_local, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Least-squares solve on top of a factorisation: the reference's dev_QR_Solver
+ * (Cuda/QR/Solver/solver.cu:39-87) is an unimplemented stub of GVL 5.3.2, x = R^-1 Q^T b;
+ * python/linear_least_sqare.py:5-22 is its NumPy demo.  dA_packed: the factor produced by
+ * mpqr_factor_device on THIS handle (m >= n).  dB: m x nrhs row-major (ldb >= nrhs, 1 <= nrhs <= 8);
+ * on return rows 0..n-1 hold the solution x, rows n..m-1 the remaining components of Q^T b
+ * (their norm is the residual).  FP32 arithmetic.
+ * ------------------------------------------------------------------------------------- */
+int mpqr_solve_device(mpqr_handle* h, const float* dA_packed, long lda, float* dB, long ldb, int nrhs, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * EuRoC Jacobian text file -> packed (rows+1) x cols host buffer (replaces read_euroc_jacobian,
+ * Cuda/qr.cu:696-776: "<rows> <cols>" then 0-based "<row> <col> <value>" triples, zero fill).
+ * Host only.  Free the buffer with mpqr_free_host.
+ * ------------------------------------------------------------------------------------- */
+int mpqr_read_euroc_jacobian(const char* path, int* rows, int* cols, float** packed_out);
+void mpqr_free_host(void* p);
+
+/* ---------------------------------------------------------------------------------------
  * Tall-skinny QR (replaces python/ca_qr.py:25-43 ts_qr): A is m x n (m >> n), row-major FP32
  * on the device.  Row blocks are factored independently, the n x n R factors are reduced by
  * a tree; R (n x n, ldr) is returned and, if dQ != NULL, the thin Q (m x n, ldq).

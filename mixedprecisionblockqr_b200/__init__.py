@@ -31,7 +31,7 @@ ABI_SYMBOLS = (
     "mpqr_gemm_tn_device", "mpqr_gemm_nn_device", "mpqr_fill_uniform_device", "mpqr_mg_layout_local_cols",
     "mpqr_mg_layout_global_col", "mpqr_mg_get_unique_id",
     "mpqr_mg_create", "mpqr_mg_local_cols", "mpqr_mg_global_col", "mpqr_mg_factor_device",
-    "mpqr_tsqr_device",
+    "mpqr_tsqr_device", "mpqr_solve_device", "mpqr_read_euroc_jacobian", "mpqr_free_host",
 )
 
 
@@ -77,6 +77,10 @@ def lib():
         L.mpqr_mg_global_col.argtypes = [vp, c_int]
         L.mpqr_mg_factor_device.argtypes = [vp, vp, c_long, vp]
         L.mpqr_tsqr_device.argtypes = [vp, c_long, c_long, c_int, vp, c_long, vp, c_long, vp]
+        L.mpqr_solve_device.argtypes = [vp, vp, c_long, vp, c_long, c_int, vp]
+        L.mpqr_read_euroc_jacobian.argtypes = [ctypes.c_char_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(ctypes.POINTER(ctypes.c_float))]
+        L.mpqr_free_host.argtypes = [vp]
+        L.mpqr_free_host.restype = None
         _lib = L
     return _lib
 
@@ -138,6 +142,10 @@ class BlockQR:
     def form_q(self, dQ_ptr, ldq, stream=0):
         check(lib().mpqr_form_q_device(self._h, dQ_ptr, ldq, stream), "mpqr_form_q_device")
 
+    def solve(self, dA_ptr, lda, dB_ptr, ldb, nrhs, stream=0):
+        """Least squares x = R^-1 Q^T b on the factor this plan produced (mpqr_solve_device)."""
+        check(lib().mpqr_solve_device(self._h, dA_ptr, lda, dB_ptr, ldb, nrhs, stream), "mpqr_solve_device")
+
     def panel_T(self, panel, dT_ptr, ldt, stream=0):
         check(lib().mpqr_get_panel_T(self._h, panel, dT_ptr, ldt, stream), "mpqr_get_panel_T")
 
@@ -174,6 +182,18 @@ class BlockQR:
 
 def fill_uniform(dA_ptr, lda, n_total, row0, rows, col0, cols, seed, stream=0):
     check(lib().mpqr_fill_uniform_device(dA_ptr, lda, n_total, row0, rows, col0, cols, seed, stream), "mpqr_fill_uniform_device")
+
+
+def read_euroc_jacobian(path):
+    """EuRoC Jacobian text file (reference Cuda/qr.cu:696-776) -> packed (rows+1) x cols float32 numpy array."""
+    m, n = ctypes.c_int(), ctypes.c_int()
+    buf = ctypes.POINTER(ctypes.c_float)()
+    check(lib().mpqr_read_euroc_jacobian(os.fsencode(path), ctypes.byref(m), ctypes.byref(n), ctypes.byref(buf)),
+          "mpqr_read_euroc_jacobian")
+    try:
+        return np.ctypeslib.as_array(buf, shape=(m.value + 1, n.value)).copy()
+    finally:
+        lib().mpqr_free_host(buf)
 
 
 def tsqr(dA_ptr, lda, m, n, dQ_ptr, ldq, dR_ptr, ldr, stream=0):
