@@ -1215,6 +1215,41 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
         }
         __syncthreads();
     }
+    if (!(B == 32 && Cacc)) {
+        // T^T is linear: every CTA applies it to its OWN partial S' and adds the result into one of two replicas of the
+        // final S (no ticket, no last-CTA fold: four dependent global round trips fewer on the panel chain)
+        float* Ts2 = ysm;  // B x (B + 4); the tree above is done with this memory
+        if (warp == 0) {
+#pragma unroll
+            for (int t = 0; t < B; ++t) *reinterpret_cast<float4*>(&red[t * 128 + 4 * lane]) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+        }
+        for (int idx = tid; idx < B * B; idx += NTHR) Ts2[(idx / B) * (B + 4) + (idx % B)] = Tj[idx];
+        __syncthreads();
+        constexpr int NG = NTHR / 128, TQ = B / NG;  // thread: column cc, TQ consecutive rows t of S
+        const int cc = tid & 127, tg = tid >> 7;
+        float v[TQ];
+#pragma unroll
+        for (int q = 0; q < TQ; ++q) v[q] = 0.f;
+#pragma unroll 4
+        for (int u2 = 0; u2 < B; ++u2) {  // T is zero below its diagonal
+            const float sp = red[u2 * 128 + cc];
+#pragma unroll
+            for (int q = 0; q < TQ; q += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(&Ts2[u2 * (B + 4) + tg * TQ + q]);
+                v[q] = fmaf(t4.x, sp, v[q]);
+                v[q + 1] = fmaf(t4.y, sp, v[q + 1]);
+                v[q + 2] = fmaf(t4.z, sp, v[q + 2]);
+                v[q + 3] = fmaf(t4.w, sp, v[q + 3]);
+            }
+        }
+        if (c0 + cc < ncols) {
+            float* S = Srep + (size_t)(blockIdx.x & 1) * RMAX * SLD + c0 + cc;
+#pragma unroll
+            for (int q = 0; q < TQ; ++q) atomicAdd(&S[(size_t)(tg * TQ + q) * SLD], v[q]);
+        }
+        return;
+    }
+    // pair mode (after a double block): T_32 needs the complete cross Gram first -> replicas + last-CTA fold
     if (warp == 0 && on) {
         float* S = Srep + (size_t)(blockIdx.x % NREP) * RMAX * SLD + col;
 #pragma unroll
@@ -1288,7 +1323,8 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
 
 template <int B>
 __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* __restrict__ Y, long ldy, float* __restrict__ A, long lda,
-                                                                  int D, int ncols, const float* __restrict__ Sfin, int rows_per_cta) {
+                                                                  int D, int ncols, const float* __restrict__ Sfin, int nrep, int rows_per_cta) {
+    // Sfin: nrep replicas (stride RMAX * SLD) of S = T^T (Y^T A_rest), summed here
     constexpr int NTHR = Su4<B>::NTHR, NWARP = NTHR / 32, RB = Su4<B>::RB;
     extern __shared__ __align__(16) float sm[];
     float* ysm = sm;
@@ -1310,7 +1346,11 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* _
     float sv[B][4];
 #pragma unroll
     for (int t = 0; t < B; ++t) {
-        const float4 s4 = on ? __ldcg(reinterpret_cast<const float4*>(Sfin + (size_t)t * SLD + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 s4 = on ? __ldcg(reinterpret_cast<const float4*>(Sfin + (size_t)t * SLD + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on && nrep > 1) {
+            const float4 s5 = __ldcg(reinterpret_cast<const float4*>(Sfin + (size_t)RMAX * SLD + (size_t)t * SLD + col));
+            s4.x += s5.x; s4.y += s5.y; s4.z += s5.z; s4.w += s5.w;
+        }
         sv[t][0] = s4.x; sv[t][1] = s4.y; sv[t][2] = s4.z; sv[t][3] = s4.w;
     }
     for (int idx = tid; idx < nrows * B; idx += NTHR) {
@@ -1685,7 +1725,7 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
                                      ysm_floats, Cacc));
         if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st, 2.0 * D * ncols * B, 4.0 * D * (2 * ncols + B)); }
         cfg.dynamicSmemBytes = (size_t)rows * B * sizeof(float);
-        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_u4_kernel<B>, Yj, ldy, Arest, lda, D, ncols, (const float*)Sfin, rows));
+        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_u4_kernel<B>, Yj, ldy, Arest, lda, D, ncols, pair ? (const float*)Sfin : (const float*)Srep, pair ? 1 : 2, rows));
     } else {
         cfg.blockDim = dim3(512);
         cfg.dynamicSmemBytes = (size_t)((rows * B > 3 * B * 128) ? rows * B : 3 * B * 128) * sizeof(float);
