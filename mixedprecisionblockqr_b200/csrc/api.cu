@@ -217,20 +217,25 @@ void overlap_init(mpqr_handle* h, const int* sizes, int nsizes) {
         CUgreenCtx gP = nullptr, gU = nullptr;
         if (g->GreenCtxCreate(&gP, dP, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) continue;
         if (g->GreenCtxCreate(&gU, dU, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { g->GreenCtxDestroy(gP); continue; }
-        CUstream sP = nullptr, sU = nullptr;
+        CUstream sP = nullptr, sP2 = nullptr, sU = nullptr;
         if (g->GreenCtxStreamCreate(&sP, gP, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS ||
+            g->GreenCtxStreamCreate(&sP2, gP, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
             g->GreenCtxStreamCreate(&sU, gU, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
             if (sP) cudaStreamDestroy((cudaStream_t)sP);
+            if (sP2) cudaStreamDestroy((cudaStream_t)sP2);
             g->GreenCtxDestroy(gP); g->GreenCtxDestroy(gU);
             continue;
         }
         mpqr_handle::Overlap::Pair pr;
-        pr.gP = gP; pr.gU = gU; pr.sP = (cudaStream_t)sP; pr.sU = (cudaStream_t)sU;
+        pr.gP = gP; pr.gU = gU; pr.sP = (cudaStream_t)sP; pr.sP2 = (cudaStream_t)sP2; pr.sU = (cudaStream_t)sU;
         pr.nsmP = (int)grp[0].sm.smCount; pr.nsmU = (int)rem.sm.smCount;
         o.pairs.push_back(pr);
     }
     if (o.pairs.empty()) return;
     if (cudaStreamCreateWithFlags(&o.sF, cudaStreamNonBlocking) != cudaSuccess) { o.sF = nullptr; }
+    if (cudaStreamCreateWithFlags(&o.sF2, cudaStreamNonBlocking) != cudaSuccess) { o.sF2 = nullptr; }
+    o.ev_rest.resize(2 * (ceil_div(h->nb, h->r) + 1));
+    for (auto& e : o.ev_rest) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     const int nblk = ceil_div(h->kmax, h->nb);
     o.ev_bp.resize(nblk); o.ev_fn.resize(nblk); o.ev_fr.resize(nblk);
     for (int i = 0; i < nblk; ++i) {
@@ -249,7 +254,7 @@ void overlap_init(mpqr_handle* h, const int* sizes, int nsizes) {
         o.tr.resize(nblk);
         for (auto& t : o.tr) { cudaEventCreate(&t.b0); cudaEventCreate(&t.b1); cudaEventCreate(&t.f0); cudaEventCreate(&t.f1); cudaEventCreate(&t.f2); t.psm = 0; }
     }
-    o.on = o.sF != nullptr;
+    o.on = o.sF != nullptr && o.sF2 != nullptr;
 }
 
 void overlap_destroy(mpqr_handle* h) {
@@ -262,9 +267,12 @@ void overlap_destroy(mpqr_handle* h) {
     if (o.ev_accdone) cudaEventDestroy(o.ev_accdone);
     for (auto e : o.ev_acc) cudaEventDestroy(e);
     if (o.sF) cudaStreamDestroy(o.sF);
+    if (o.sF2) cudaStreamDestroy(o.sF2);
+    for (auto e : o.ev_rest) cudaEventDestroy(e);
     const GreenApi* g = green_api();
     for (auto& pr : o.pairs) {
         if (pr.sP) cudaStreamDestroy(pr.sP);
+        if (pr.sP2) cudaStreamDestroy(pr.sP2);
         if (pr.sU) cudaStreamDestroy(pr.sU);
         if (g->ok) { g->GreenCtxDestroy((CUgreenCtx)pr.gP); g->GreenCtxDestroy((CUgreenCtx)pr.gU); }
     }
@@ -377,19 +385,29 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     const char* fix = getenv("MPQR_PANEL_SMS");
     const int fixed_sms = fix ? atoi(fix) : 0;
     // interval b-1 decided where block_phase(b) runs; block 0 runs on the whole device
-    cudaStream_t s_bp = o.sF, s_uprev = nullptr;
+    cudaStream_t s_bp = o.sF, s_bp2 = o.sF2, s_uprev = nullptr;
     int nsm_bp = o.nsm_full, nsm_uprev = 0;
+    const bool inblock_la = !getenv("MPQR_NO_INBLOCK_LA") && (h->r % 8) == 0;
     MPQR_CUDA(cudaStreamWaitEvent(s_bp, o.ev_start, 0));
     for (int c0 = 0, b = 0; c0 < h->kmax; c0 += nb, ++b) {
         const int c1 = (c0 + nb < h->kmax) ? c0 + nb : h->kmax;
         BlockCtx c = ctx_of(b, c0);
-        // WY accumulation of this block: on the update partition of the previous interval (it idles once its
-        // far update is done), unless that interval ran serially on the whole device
-        const bool defer_acc = s_uprev && s_uprev != s_bp && !getenv("MPQR_NO_DEFER_ACC");
-        if (defer_acc) {
-            c.acc_stream = s_uprev; c.acc_sms = nsm_uprev == o.nsm_full ? 0 : nsm_uprev;
-            c.acc_S32 = h->S32u; c.acc_S16 = h->S16u; c.acc_ev = o.ev_acc.data();
+        // In-block look-ahead: the part of every in-block update that is not the next panel's columns runs on a
+        // second stream of the same partition, next to the next panel's register-block kernels.
+        if (inblock_la) {
+            c.rest_stream = s_bp2; c.rest_S32 = h->S32r; c.rest_S16 = h->S16r; c.rest_ev = o.ev_rest.data();
+            // (the previous block's last rest event completed before fn(b-1), which this block waits for)
         }
+        // WY accumulation of this block (only the far update needs it): on the update partition of the previous
+        // interval (it idles once its far update is done); else behind the in-block rest updates on their stream
+        const bool defer_u = s_uprev && s_uprev != s_bp && !getenv("MPQR_NO_DEFER_ACC");
+        cudaStream_t s_acc = defer_u ? s_uprev : (inblock_la ? s_bp2 : nullptr);
+        if (s_acc) {
+            c.acc_stream = s_acc;
+            c.acc_sms = defer_u ? (nsm_uprev == o.nsm_full ? 0 : nsm_uprev) : (nsm_bp == o.nsm_full ? 0 : nsm_bp);
+            c.acc_S32 = defer_u ? h->S32u : h->S32r; c.acc_S16 = defer_u ? h->S16u : h->S16r; c.acc_ev = o.ev_acc.data();
+        }
+        const bool defer_acc = s_acc != nullptr;
         if (b > 0) MPQR_CUDA(cudaStreamWaitEvent(s_bp, o.ev_fn[b - 1], 0));
         if (o.trace) { cudaEventRecord(o.tr[b].b0, s_bp); o.tr[b].psm = nsm_bp; }
         {
@@ -398,7 +416,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         }
         if (o.trace) cudaEventRecord(o.tr[b].b1, s_bp);
         MPQR_CUDA(cudaEventRecord(o.ev_bp[b], s_bp));
-        if (defer_acc) MPQR_CUDA(cudaEventRecord(o.ev_accdone, s_uprev));
+        if (defer_acc) MPQR_CUDA(cudaEventRecord(o.ev_accdone, s_acc));
         MPQR_TRY(emit(b, c0, c1, s_bp));
         const int nfar = n - c1;
         // ---- choose the partition of interval b
@@ -441,6 +459,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         }
         // where the next block_phase runs
         s_bp = best >= 0 ? o.pairs[best].sP : o.sF;
+        s_bp2 = best >= 0 ? o.pairs[best].sP2 : o.sF2;
         nsm_bp = best >= 0 ? o.pairs[best].nsmP : o.nsm_full;
         s_uprev = best >= 0 ? s_u : nullptr;
         nsm_uprev = nsm_u;
@@ -476,6 +495,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
     const int Dblk = m - c0;
     float* S32 = c.S32 ? c.S32 : h->S32;
     void* S16 = c.S16 ? c.S16 : h->S16;
+    int last_rest = -1;
     for (int lam = c0; lam < c1; lam += r) {
         const int p = lam / r;
         const int pw = (lam + r < c1) ? r : c1 - lam;
@@ -492,18 +512,35 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         const int nin = c1 - tau;  // in-block trailing columns
         const int acol_tau = c.acol0 + jc + pw;
-        if (nin > 0) {
-            // S = W_p^T A[lam:, tau:c1]   (operands: 16-bit W_p rows lam.., shadow of A)
-            const void* Wp = (char*)c.W16 + ((size_t)jc * c.ldw + jc) * 2;
-            const void* Yp = (char*)c.Y16 + ((size_t)jc * c.ldy + jc) * 2;
-            PROF(1, 2.0 * pw * nin * D, tn_bytes(pw, nin, D),
-                 tc_gemm_tn(Wp, c.ldw, at16(c.Ah, c.ldh, lam, acol_tau), c.ldh, S32, h->lds32, pw, nin, D, bf, 1, st, &h->launches));
-            PROF(3, 0, 6.0 * pw * nin, convert_f32_to_16(S32, h->lds32, S16, h->lds16, pw, nin, bf, st));
+        // in-block update of the columns [tau + ofs, tau + ofs + nc):  S = W_p^T A ; A -= Y_p S (+ shadow)
+        const void* Wpp = (char*)c.W16 + ((size_t)jc * c.ldw + jc) * 2;   // the panel's own W / Y, rows lam..
+        const void* Ypp = (char*)c.Y16 + ((size_t)jc * c.ldy + jc) * 2;
+        auto inblock = [&](int ofs, int nc, float* xS32, void* xS16, int pad_ok, cudaStream_t st) -> int {
+            PROF(1, 2.0 * pw * nc * D, tn_bytes(pw, nc, D),
+                 tc_gemm_tn(Wpp, c.ldw, at16(c.Ah, c.ldh, lam, acol_tau + ofs), c.ldh, xS32, h->lds32, pw, nc, D, bf, 1, st, &h->launches));
+            PROF(3, 0, 6.0 * pw * nc, convert_f32_to_16(xS32, h->lds32, xS16, h->lds16, pw, nc, bf, st));
             h->launches += 1;
-            // A[lam:, tau:c1] -= Y_p S   (+ shadow)
-            PROF(2, 2.0 * D * nin * pw, nn_bytes(D, nin, pw),
-                 tc_gemm_nn(Yp, c.ldy, S16, h->lds16, c.A + (size_t)lam * c.lda + acol_tau, c.lda,
-                            at16(c.Ah, c.ldh, lam, acol_tau), c.ldh, D, nin, pw, bf, end_is_matrix_end, st, &h->launches));
+            PROF(2, 2.0 * D * nc * pw, nn_bytes(D, nc, pw),
+                 tc_gemm_nn(Ypp, c.ldy, xS16, h->lds16, c.A + (size_t)lam * c.lda + acol_tau + ofs, c.lda,
+                            at16(c.Ah, c.ldh, lam, acol_tau + ofs), c.ldh, D, nc, pw, bf, pad_ok, st, &h->launches));
+            return MPQR_OK;
+        };
+        const int pidx = jc / r;
+        const bool split = c.rest_stream && nin > r && (r % 8) == 0;
+        if (c.rest_stream && nin > 0) last_rest = 2 * pidx + 1;
+        if (nin > 0 && !split) {
+            if (c.rest_stream && pidx > 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (pidx - 1) + 1], 0));
+            MPQR_TRY(inblock(0, nin, S32, S16, end_is_matrix_end, st));
+            if (c.rest_stream) MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], st));
+        } else if (nin > 0) {
+            // the rest of the block on the second stream (it only needs this panel's Y, W and the previous rest)
+            MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx], st));
+            MPQR_CUDA(cudaStreamWaitEvent(c.rest_stream, c.rest_ev[2 * pidx], 0));
+            // the next panel's columns were last written by the previous panel's rest update
+            if (pidx > 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (pidx - 1) + 1], 0));
+            MPQR_TRY(inblock(0, r, S32, S16, 0, st));
+            MPQR_TRY(inblock(r, nin - r, c.rest_S32, c.rest_S16, end_is_matrix_end, c.rest_stream));
+            MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], c.rest_stream));
         }
         if (jc > 0) {
             // WY accumulation: X = Y_prev^T W_p ; W_p -= W_prev X   (rows c0..m)
@@ -516,6 +553,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
                 cudaEvent_t ev = c.acc_ev[jc / r];
                 MPQR_CUDA(cudaEventRecord(ev, st_panel));
                 MPQR_CUDA(cudaStreamWaitEvent(c.acc_stream, ev, 0));
+                if (c.rest_stream && nin > 0) MPQR_CUDA(cudaStreamWaitEvent(c.acc_stream, c.rest_ev[2 * pidx + 1], 0));
                 aS32 = c.acc_S32; aS16 = c.acc_S16;
             }
             {
@@ -530,6 +568,8 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             }
         }
     }
+    // everything of this block is complete when the panel stream is (events of one stream complete in order)
+    if (c.rest_stream && last_rest >= 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[last_rest], 0));
     return MPQR_OK;
 }
 
@@ -631,6 +671,8 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
                 overlap_init(h, sizes, 5);
                 if (h->ov.on) {
                     if ((rc = dev_alloc(h, (void**)&h->S32u, (size_t)h->sk * h->lds32 * sizeof(float)))) break;
+                    if ((rc = dev_alloc(h, (void**)&h->S32r, (size_t)h->sk * h->lds32 * sizeof(float)))) break;
+                    if ((rc = dev_alloc(h, &h->S16r, (size_t)h->sk * h->lds16 * 2))) break;
                     if ((rc = dev_alloc(h, &h->S16u, (size_t)h->sk * h->lds16 * 2))) break;
                     if (!h->keep_wy && (rc = dev_alloc(h, &h->W16b, (size_t)m * h->ldw16 * 2))) break;
                 }

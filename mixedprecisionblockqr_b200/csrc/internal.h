@@ -50,11 +50,12 @@ struct mpqr_handle {
         struct Pair {
             void* gP = nullptr;  // CUgreenCtx: panel partition
             void* gU = nullptr;  // CUgreenCtx: update partition
-            cudaStream_t sP = nullptr, sU = nullptr;
+            cudaStream_t sP = nullptr, sP2 = nullptr, sU = nullptr;  // sP2: second stream of the panel partition
             int nsmP = 0, nsmU = 0;
         };
         std::vector<Pair> pairs;
-        cudaStream_t sF = nullptr;  // whole-device stream (intervals that are not worth splitting)
+        cudaStream_t sF = nullptr, sF2 = nullptr;  // whole-device streams (intervals that are not worth splitting)
+        std::vector<cudaEvent_t> ev_rest;  // BlockCtx::rest_ev
         int nsm_full = 0;
         std::vector<cudaEvent_t> ev_bp, ev_fn, ev_fr;
         cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_accdone = nullptr;
@@ -64,6 +65,8 @@ struct mpqr_handle {
         struct Tr { cudaEvent_t b0, b1, f0, f1, f2; int psm; };
         std::vector<Tr> tr;
     } ov;
+    float* S32r = nullptr;  // scratch of the in-block look-ahead stream (r x lds32)
+    void* S16r = nullptr;
     float* S32u = nullptr;  // scratch of the update stream (same shape as S32 / S16)
     void* S16u = nullptr;
     void* W16b = nullptr;   // second W buffer (blocks alternate) when the look-ahead driver is on
@@ -174,6 +177,13 @@ struct BlockCtx {
     float* acc_S32;            // its GEMM scratch
     void* acc_S16;
     cudaEvent_t* acc_ev;       // >= (c1 - c0) / r events
+    // Optional: in-block look-ahead.  The in-block update of panel p is split: the NEXT panel's columns on the
+    // panel stream, the other in-block columns on `rest_stream` (a second stream of the same SM partition), so
+    // that the next panel's register-block kernels (16 SMs) run while the rest of the block is updated.
+    cudaStream_t rest_stream;  // null: one in-block update on the panel stream
+    float* rest_S32;           // its GEMM scratch (r x lds32)
+    void* rest_S16;
+    cudaEvent_t* rest_ev;      // 2 events per panel: [2p] panel factored, [2p+1] rest of panel p's in-block update done
 };
 // panels + in-block updates + WY accumulation of block [c0, c1); `ncols_in` = columns of A
 // (starting at acol0) that belong to the block's own panel region (= c1 - c0)

@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict_
     }
     __syncthreads();
     if (rg == 0 && on) {
-        float* S = Srep + (size_t)(blockIdx.x % NREP) * RMAX * SLD;
+        float* S = Srep + (size_t)(blockIdx.x & 1) * RMAX * SLD;
 #pragma unroll
         for (int t = 0; t < B; ++t) {
             float v = acc[t] + sm[(0 * B + t) * 128 + c] + sm[(1 * B + t) * 128 + c] + sm[(2 * B + t) * 128 + c];
@@ -1046,7 +1046,7 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
         float v = 0.f;
         if (c0 + cc < ncols) {
 #pragma unroll
-            for (int rep = 0; rep < NREP; ++rep) v += __ldcg(&Srep[(size_t)rep * RMAX * SLD + t * SLD + c0 + cc]);
+            for (int rep = 0; rep < 2; ++rep) v += __ldcg(&Srep[(size_t)rep * RMAX * SLD + t * SLD + c0 + cc]);
         }
         Sp[t][cc] = v;
     }
@@ -1822,7 +1822,9 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         if (nrest > 0) { b.T = w.Wj; b.ldt = B; }  // block T for the in-panel update ([T_A | T_B] after a double block)
         if (Y16l) b.Y16 = {Y16l + ((size_t)j0 * a.ldy16 + j0) * 2, a.ldy16, j0 + zr};
         b.bf16 = a.bf16; b.dbg = a.dbg;
-        if (nrest > 0) { b.zero_buf = w.Srep; b.zero_n = NREP * RMAX * SLD + 4 + 256; }
+        // the following S kernel accumulates into two replicas; only the double-block (pair) flow uses all NREP
+        // replicas, the ticket counter and the cross-Gram accumulator behind them
+        if (nrest > 0) { b.zero_buf = w.Srep; b.zero_n = dbl ? NREP * RMAX * SLD + 4 + 256 : 2 * RMAX * SLD; }
         if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 4.0 * Dj * bw * bw, 14.0 * Dj * bw);
         if (dbl) MPQR_TRY(launch_dblock(b, rpt, cs, stream));
         else MPQR_TRY(launch_block(B, b, rpt, cs, stream));
