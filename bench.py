@@ -262,13 +262,14 @@ def main_native(args):
         src = host.clone().pin_memory()
         flags = {"fp16": pkg.MPQR_FP16, "bf16": pkg.MPQR_BF16, "fp32": pkg.MPQR_FP32}[args.precision]
         torch.cuda.synchronize()
+        dt = 0.0
         for w in range(1 + esteps):   # one warm-up
-            host.copy_(src)
-            if w == 1:
-                t0 = time.perf_counter()
+            host.copy_(src)           # restore the caller's input (host memcpy): not part of the call, not timed
+            t0 = time.perf_counter()
             pkg.check(pkg.lib().mpqr_block_qr_host(host.data_ptr(), None, m, n, r, flags), "mpqr_block_qr_host")
-        dt = (time.perf_counter() - t0) / esteps
-        # note: host.copy_(src) (host memcpy restoring the input) is inside dt as well
+            if w >= 1:
+                dt += time.perf_counter() - t0   # the call returns with the factor in `host` (device-synchronous)
+        dt /= esteps
         nbytes = (m + 1) * n * 4
         e2e = {"value": F / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "ms_per_step": dt * 1e3, "path": "mpqr_block_qr_host(A_host_pinned, Q=NULL): alloc + H2D + factor + D2H"}
@@ -279,17 +280,18 @@ def main_native(args):
         hostA[m].zero_()
         hostSrc = hostA.clone().pin_memory()
         barrier()
+        dt = 0.0
         for w in range(1 + esteps):
-            if w == 1:
-                barrier()
-                t0 = time.perf_counter()
-            hostA.copy_(hostSrc)                      # restore the host input (host memcpy)
+            hostA.copy_(hostSrc)                      # restore the host input (host memcpy): not timed
+            barrier()
+            t0 = time.perf_counter()
             A.copy_(hostA, non_blocking=True)         # H2D of this rank's shard
             plan.factor(A.data_ptr(), lda, st)
             hostA.copy_(A, non_blocking=True)         # D2H of the packed factor shard
-            torch.cuda.synchronize()
-        barrier()
-        dt = (time.perf_counter() - t0) / esteps
+            barrier()
+            if w >= 1:
+                dt += time.perf_counter() - t0
+        dt /= esteps
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())

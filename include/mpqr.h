@@ -178,6 +178,40 @@ int mpqr_read_euroc_jacobian(const char* path, int* rows, int* cols, float** pac
 void mpqr_free_host(void* p);
 
 /* ---------------------------------------------------------------------------------------
+ * Device-side parity metrics: the reference's harness metrics are O(m^3) FP32 host
+ * loops (Cuda/qr.cu:85-196); these compute the same quantities on the GPU with FP64 accumulation,
+ * never materialising Q R or Q^T Q.  All matrix pointers are DEVICE pointers (row-major FP32),
+ * results are written to HOST doubles and the calls synchronise `stream`.  Deterministic.
+ *   mpqr_strip_r_device               h_strip_R_from_A         (Cuda/qr.cu:85-100)
+ *   mpqr_backward_error_device        h_backward_error         (Cuda/qr.cu:115-135): ||A0 - Q R||_F / ||A0||_F;
+ *                                     dR is read through the mask row <= col, so the packed factor may be
+ *                                     passed directly; a_norm (may be NULL) receives ||A0||_F
+ *   mpqr_q_error_device               h_q_error                (Cuda/qr.cu:137-171): max_signed is the
+ *                                     reference's quantity (max entry of Q^T Q - I, no abs), max_abs and
+ *                                     fro = ||Q^T Q - I||_F are north_star's orthogonality figures (any may be NULL)
+ *   mpqr_lower_trapezoid_error_device h_lower_trapezoid_error  (Cuda/qr.cu:173-196): ||strict lower part||_F
+ *   mpqr_frobenius_norm_device        h_matrix_norm
+ *   mpqr_r_agreement_device           north_star's "elementwise |R| agreement": max | |R| - |Rref| | over
+ *                                     row <= col, max |Rref|, and the Frobenius norm of the difference
+ * ------------------------------------------------------------------------------------- */
+int mpqr_strip_r_device(const float* dA_packed, long lda, float* dR, long ldr, int m, int n, void* stream);
+int mpqr_backward_error_device(const float* dA0, long lda0, const float* dR, long ldr, const float* dQ, long ldq,
+                               int m, int n, double* err, double* a_norm, void* stream);
+int mpqr_q_error_device(const float* dQ, long ldq, int m, double* max_signed, double* max_abs, double* fro, void* stream);
+int mpqr_lower_trapezoid_error_device(const float* dR, long ldr, int m, int n, double* err, void* stream);
+int mpqr_frobenius_norm_device(const float* dX, long ldx, long rows, long cols, double* nrm, void* stream);
+int mpqr_r_agreement_device(const float* dR, long ldr, const float* dRref, long ldref, int m, int n,
+                            double* max_abs_diff, double* max_abs_ref, double* fro_diff, void* stream);
+/* Host: the reference's own operation count 4m^2n - mn^2 + n^3/3 per second (h_qr_flops_per_second,
+ * Cuda/qr.cu:102-113) and its result log (h_write_results_to_log, Cuda/qr.cu:58-83): appends
+ * "rows,cols,runtime,flops,error" lines to <log_dir>/<file_name>.txt, the format
+ * Cuda/performance/util.py:19-31 reads.  log_dir NULL = "log", file_name NULL = "logFile" (the
+ * reference's defaults). */
+float mpqr_qr_flops_per_second(float time_ms, int m, int n);
+int mpqr_write_results_to_log(const char* log_dir, const char* file_name, int height, int width, float time_ms,
+                              float flops_per_second, float backward_error);
+
+/* ---------------------------------------------------------------------------------------
  * Tall-skinny QR (replaces python/ca_qr.py:25-43 ts_qr): A is m x n (m >> n), row-major FP32
  * on the device.  Row blocks are factored independently, the n x n R factors are reduced by
  * a tree; R (n x n, ldr) is returned and, if dQ != NULL, the thin Q (m x n, ldq).

@@ -32,6 +32,8 @@ ABI_SYMBOLS = (
     "mpqr_mg_layout_global_col", "mpqr_mg_get_unique_id",
     "mpqr_mg_create", "mpqr_mg_local_cols", "mpqr_mg_global_col", "mpqr_mg_factor_device",
     "mpqr_tsqr_device", "mpqr_solve_device", "mpqr_read_euroc_jacobian", "mpqr_free_host",
+    "mpqr_strip_r_device", "mpqr_backward_error_device", "mpqr_q_error_device", "mpqr_lower_trapezoid_error_device",
+    "mpqr_frobenius_norm_device", "mpqr_r_agreement_device", "mpqr_qr_flops_per_second", "mpqr_write_results_to_log",
 )
 
 
@@ -80,6 +82,17 @@ def lib():
         L.mpqr_solve_device.argtypes = [vp, vp, c_long, vp, c_long, c_int, vp]
         L.mpqr_read_euroc_jacobian.argtypes = [ctypes.c_char_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(ctypes.POINTER(ctypes.c_float))]
         L.mpqr_free_host.argtypes = [vp]
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.mpqr_strip_r_device.argtypes = [vp, c_long, vp, c_long, c_int, c_int, vp]
+        L.mpqr_backward_error_device.argtypes = [vp, c_long, vp, c_long, vp, c_long, c_int, c_int, dp, dp, vp]
+        L.mpqr_q_error_device.argtypes = [vp, c_long, c_int, dp, dp, dp, vp]
+        L.mpqr_lower_trapezoid_error_device.argtypes = [vp, c_long, c_int, c_int, dp, vp]
+        L.mpqr_frobenius_norm_device.argtypes = [vp, c_long, c_long, c_long, dp, vp]
+        L.mpqr_r_agreement_device.argtypes = [vp, c_long, vp, c_long, c_int, c_int, dp, dp, dp, vp]
+        L.mpqr_qr_flops_per_second.argtypes = [ctypes.c_float, c_int, c_int]
+        L.mpqr_qr_flops_per_second.restype = ctypes.c_float
+        L.mpqr_write_results_to_log.argtypes = [ctypes.c_char_p, ctypes.c_char_p, c_int, c_int, ctypes.c_float,
+                                                ctypes.c_float, ctypes.c_float]
         L.mpqr_free_host.restype = None
         _lib = L
     return _lib
@@ -194,6 +207,61 @@ def read_euroc_jacobian(path):
         return np.ctypeslib.as_array(buf, shape=(m.value + 1, n.value)).copy()
     finally:
         lib().mpqr_free_host(buf)
+
+
+# ------------------------------------------------------------------ device metrics (reference Cuda/qr.cu:58-196)
+def strip_R(dA_ptr, lda, dR_ptr, ldr, m, n, stream=0):
+    """h_strip_R_from_A (Cuda/qr.cu:85-100) on the device."""
+    check(lib().mpqr_strip_r_device(dA_ptr, lda, dR_ptr, ldr, m, n, stream), "mpqr_strip_r_device")
+
+
+def backward_error(dA0_ptr, lda0, dR_ptr, ldr, dQ_ptr, ldq, m, n, stream=0):
+    """h_backward_error (Cuda/qr.cu:115-135): (||A0 - QR||_F / ||A0||_F, ||A0||_F), FP64 accumulation."""
+    err, an = ctypes.c_double(), ctypes.c_double()
+    check(lib().mpqr_backward_error_device(dA0_ptr, lda0, dR_ptr, ldr, dQ_ptr, ldq, m, n, ctypes.byref(err),
+                                           ctypes.byref(an), stream), "mpqr_backward_error_device")
+    return err.value, an.value
+
+
+def q_error(dQ_ptr, ldq, m, stream=0):
+    """h_q_error (Cuda/qr.cu:137-171): dict(max_signed=<the reference's quantity>, max_abs, fro) of Q^T Q - I."""
+    a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    check(lib().mpqr_q_error_device(dQ_ptr, ldq, m, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), stream),
+          "mpqr_q_error_device")
+    return {"max_signed": a.value, "max_abs": b.value, "fro": c.value}
+
+
+def lower_trapezoid_error(dR_ptr, ldr, m, n, stream=0):
+    """h_lower_trapezoid_error (Cuda/qr.cu:173-196)."""
+    e = ctypes.c_double()
+    check(lib().mpqr_lower_trapezoid_error_device(dR_ptr, ldr, m, n, ctypes.byref(e), stream),
+          "mpqr_lower_trapezoid_error_device")
+    return e.value
+
+
+def frobenius_norm(dX_ptr, ldx, rows, cols, stream=0):
+    e = ctypes.c_double()
+    check(lib().mpqr_frobenius_norm_device(dX_ptr, ldx, rows, cols, ctypes.byref(e), stream), "mpqr_frobenius_norm_device")
+    return e.value
+
+
+def r_agreement(dR_ptr, ldr, dRref_ptr, ldref, m, n, stream=0):
+    """max | |R| - |Rref| | over row <= col, max |Rref|, ||.||_F of the difference (north_star's |R| criterion)."""
+    a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    check(lib().mpqr_r_agreement_device(dR_ptr, ldr, dRref_ptr, ldref, m, n, ctypes.byref(a), ctypes.byref(b),
+                                        ctypes.byref(c), stream), "mpqr_r_agreement_device")
+    return {"max_abs_diff": a.value, "max_abs_ref": b.value, "fro_diff": c.value}
+
+
+def qr_flops_per_second(time_ms, m, n):
+    """h_qr_flops_per_second (Cuda/qr.cu:102-113): the reference's own count 4m^2n - mn^2 + n^3/3."""
+    return float(lib().mpqr_qr_flops_per_second(time_ms, m, n))
+
+
+def write_results_to_log(height, width, time_ms, flops_per_second, backward_error, file_name="logFile", log_dir="log"):
+    """h_write_results_to_log (Cuda/qr.cu:58-83); readable by the reference's Cuda/performance/util.py."""
+    check(lib().mpqr_write_results_to_log(os.fsencode(log_dir), os.fsencode(file_name), height, width, time_ms,
+                                          flops_per_second, backward_error), "mpqr_write_results_to_log")
 
 
 def tsqr(dA_ptr, lda, m, n, dQ_ptr, ldq, dR_ptr, ldr, stream=0):

@@ -11,7 +11,7 @@ CSRC = os.path.join(_HERE, "csrc")
 OBJ = os.path.join(_HERE, "build")
 LIB = os.path.join(_HERE, "libmpqr.so")
 SHIM = os.path.join(_HERE, "libmpqr_refshim.so")
-SOURCES = ["api.cu", "panel.cu", "panel_legacy.cu", "gemm_simt.cu", "gemm_tc.cu", "mg.cu", "tsqr.cu", "solve.cu", "loader.cu"]
+SOURCES = ["api.cu", "panel.cu", "panel_legacy.cu", "gemm_simt.cu", "gemm_tc.cu", "mg.cu", "tsqr.cu", "solve.cu", "loader.cu", "metrics.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "internal.h"), os.path.join(_HERE, "..", "include", "mpqr.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -69,3 +69,26 @@ def test_reference_symbol_shim_exports():
     L = ctypes.CDLL(shim)
     for sym in REF_SYMBOLS.values():
         assert hasattr(L, sym), sym
+
+
+def test_reference_log_format_and_flop_model(tmp_path):
+    """mpqr_write_results_to_log / mpqr_qr_flops_per_second (host only): same file format and the same
+    operation count as h_write_results_to_log / h_qr_flops_per_second (reference Cuda/qr.cu:58-83, :102-113);
+    the file parses the way the reference's Cuda/performance/util.py:19-31 reads it."""
+    import csv
+    import mixedprecisionblockqr_b200 as pkg
+    d = str(tmp_path / "log")
+    pkg.write_results_to_log(2048, 1024, 12.5, 3.0e9, 1.25e-4, file_name="dev_mixed", log_dir=d)
+    pkg.write_results_to_log(4096, 4096, 100.0, 5.0e10, 2.0e-4, file_name="dev_mixed", log_dir=d)
+    rows = list(csv.reader(open(tmp_path / "log" / "dev_mixed.txt", newline="")))
+    assert rows[0] == ["rows", "cols", "runtime", "flops", "error"]
+    assert len(rows) == 3 and all(len(r) == 5 for r in rows)
+    assert rows[1] == ["2048.000000", "1024.000000", "12.500000", "3000000000.000000", "0.000125"]  # std::to_string(double)
+    assert int(float(rows[2][0])) == 4096 and abs(float(rows[2][4]) - 2.0e-4) < 1e-6
+    for (t, m, n) in [(10.0, 2048, 2048), (3.5, 97, 90), (1000.0, 1024, 512)]:
+        got = pkg.qr_flops_per_second(t, m, n)
+        want = (4.0 * m * m * n - m * n * n + n ** 3 / 3.0) / (t / 1000.0)
+        assert abs(got - want) <= 1e-5 * want
+    import oracle
+    if oracle.ref_available():
+        assert pkg.qr_flops_per_second(7.0, 640, 480) == oracle.ref().ref_h_qr_flops_per_second(7.0, 640, 480)
