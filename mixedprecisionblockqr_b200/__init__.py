@@ -34,6 +34,7 @@ ABI_SYMBOLS = (
     "mpqr_tsqr_device", "mpqr_solve_device", "mpqr_read_euroc_jacobian", "mpqr_free_host",
     "mpqr_strip_r_device", "mpqr_backward_error_device", "mpqr_q_error_device", "mpqr_lower_trapezoid_error_device",
     "mpqr_frobenius_norm_device", "mpqr_r_agreement_device", "mpqr_qr_flops_per_second", "mpqr_write_results_to_log",
+    "mpqr_mg_tsqr_create", "mpqr_mg_tsqr_device",
 )
 
 
@@ -94,6 +95,8 @@ def lib():
         L.mpqr_write_results_to_log.argtypes = [ctypes.c_char_p, ctypes.c_char_p, c_int, c_int, ctypes.c_float,
                                                 ctypes.c_float, ctypes.c_float]
         L.mpqr_free_host.restype = None
+        L.mpqr_mg_tsqr_create.argtypes = [ctypes.POINTER(vp), c_int, c_int, vp]
+        L.mpqr_mg_tsqr_device.argtypes = [vp, vp, c_long, c_long, c_int, vp, c_long, vp, c_long, vp]
         _lib = L
     return _lib
 
@@ -320,3 +323,20 @@ class MultiGpuBlockQR:
             self.close()
         except Exception:
             pass
+
+
+class MultiGpuTSQR:
+    """Row-block TSQR over the GPUs of one box (mpqr_mg_tsqr_*; replaces python/ca_qr.py:25-43 at scale):
+    rank p passes its m_local x n rows; R is returned on every rank, the thin Q rows stay local."""
+
+    def __init__(self, rank, nranks, uid):
+        self._h = ctypes.c_void_p()
+        check(lib().mpqr_mg_tsqr_create(ctypes.byref(self._h), rank, nranks, uid), "mpqr_mg_tsqr_create")
+        self.rank, self.nranks = rank, nranks
+
+    def factor(self, dA_local_ptr, lda, m_local, n, dQ_local_ptr, ldq, dR_ptr, ldr, stream=0):
+        check(lib().mpqr_mg_tsqr_device(self._h, dA_local_ptr, lda, m_local, n, dQ_local_ptr, ldq, dR_ptr, ldr, stream),
+              "mpqr_mg_tsqr_device")
+
+    close = MultiGpuBlockQR.close
+    __del__ = MultiGpuBlockQR.__del__

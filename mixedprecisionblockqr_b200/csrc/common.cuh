@@ -128,6 +128,10 @@ int sgemm_tn(const float* X, long ldx, const float* Z, long ldz, float* S, long 
 int sgemm_nn_sub(const float* X, long ldx, const float* S, long lds, float* C, long ldc, int M,
                  int N, int K, cudaStream_t stream, long* launches);
 
+// C[M x N] = X S (store; the TSQR thin-Q products)
+int sgemm_nn_store(const float* X, long ldx, const float* S, long lds, float* C, long ldc, int M, int N, int K,
+                   cudaStream_t stream);
+
 // 16-bit-operand CUDA-core fallbacks (sub-blocks that are not 16-byte aligned, see gemm_tc.cu)
 int simt16_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long lds, int M, int N, int K,
                    int bf16, cudaStream_t stream);

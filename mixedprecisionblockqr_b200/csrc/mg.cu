@@ -28,6 +28,7 @@ typedef int (*fn_GetUniqueId)(NcclUid*);
 typedef int (*fn_CommInitRank)(ncclComm_t*, int, NcclUid, int);
 typedef int (*fn_CommDestroy)(ncclComm_t);
 typedef int (*fn_Broadcast)(const void*, void*, size_t, int /*dtype*/, int /*root*/, ncclComm_t, cudaStream_t);
+typedef int (*fn_AllGather)(const void*, void*, size_t /*sendcount*/, int /*dtype*/, ncclComm_t, cudaStream_t);
 typedef const char* (*fn_GetErrorString)(int);
 constexpr int kNcclChar = 0;
 
@@ -37,6 +38,7 @@ struct NcclApi {
     fn_CommInitRank CommInitRank = nullptr;
     fn_CommDestroy CommDestroy = nullptr;
     fn_Broadcast Broadcast = nullptr;
+    fn_AllGather AllGather = nullptr;
     fn_GetErrorString GetErrorString = nullptr;
 };
 
@@ -56,8 +58,9 @@ int load_nccl(NcclApi** out) {
         api.CommInitRank = (fn_CommInitRank)dlsym(api.lib, "ncclCommInitRank");
         api.CommDestroy = (fn_CommDestroy)dlsym(api.lib, "ncclCommDestroy");
         api.Broadcast = (fn_Broadcast)dlsym(api.lib, "ncclBroadcast");
+        api.AllGather = (fn_AllGather)dlsym(api.lib, "ncclAllGather");
         api.GetErrorString = (fn_GetErrorString)dlsym(api.lib, "ncclGetErrorString");
-        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Broadcast) {
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Broadcast || !api.AllGather) {
             set_error("libnccl lacks a required symbol");
             api.lib = nullptr;
             return MPQR_ENCCL;
@@ -219,6 +222,79 @@ int mpqr_mg_factor_device(mpqr_handle* h, float* dA, long lda, void* stream) {
     h->factored = true;
     (void)n;
     return MPQR_OK;
+}
+
+// ---------------------------------------------------------------------------------------- multi-GPU TSQR
+// 1-D ROW-block layout, rank p owns m_local rows.  Local TSQR -> R_p (n x n) and thin
+// Q_p; ncclAllGather of the R_p (n*n*4 bytes per rank, the ONLY exchange); every rank factors the same
+// stacked (P*n) x n matrix (bitwise identical inputs and code => identical R everywhere) and multiplies its
+// Q_p by its own n x n slice of the stack's Q.  ts_qr's tree (python/ca_qr.py:36-41) with P leaves.
+int mpqr_mg_tsqr_create(mpqr_handle** out, int rank, int nranks, const void* uid) {
+    if (!out || !uid || nranks < 1 || rank < 0 || rank >= nranks) {
+        set_error("mpqr_mg_tsqr_create: bad arguments");
+        return MPQR_EINVAL;
+    }
+    DeviceInfo di;
+    MPQR_TRY(get_device_info(&di));  // no CPU fallback: fails without an sm_100 device
+    mpqr_handle* h = new mpqr_handle();
+    MgState* g = new MgState();
+    h->mg = g;
+    g->rank = rank;
+    g->nranks = nranks;
+    int rc = load_nccl(&g->api);
+    if (rc == MPQR_OK) {
+        NcclUid id;
+        memcpy(&id, uid, sizeof(id));
+        int nr = g->api->CommInitRank(&g->comm, nranks, id, rank);
+        if (nr != 0) {
+            set_error("ncclCommInitRank failed: %d", nr);
+            rc = MPQR_ENCCL;
+        }
+    }
+    if (rc != MPQR_OK) {
+        mpqr_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return MPQR_OK;
+}
+
+int mpqr_mg_tsqr_device(mpqr_handle* h, const float* dA_local, long lda, long m_local, int n, float* dQ_local, long ldq,
+                        float* dR, long ldr, void* stream) {
+    if (!h || !h->mg || !dA_local || !dR || n < 1 || m_local < n || lda < n || ldr < n || (dQ_local && ldq < n)) {
+        set_error("mpqr_mg_tsqr_device: bad arguments (every rank needs m_local >= n)");
+        return MPQR_EINVAL;
+    }
+    MgState* g = (MgState*)h->mg;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = g->nranks;
+    if (P == 1) return mpqr_tsqr_device(dA_local, lda, m_local, n, dQ_local, ldq, dR, ldr, stream);
+    float *rloc = nullptr, *rstack = nullptr, *qstack = nullptr, *qtmp = nullptr;
+    const size_t nn = (size_t)n * n;
+    int rc = MPQR_OK;
+    do {
+        if (cudaMalloc(&rloc, nn * sizeof(float)) != cudaSuccess || cudaMalloc(&rstack, nn * P * sizeof(float)) != cudaSuccess ||
+            (dQ_local && cudaMalloc(&qstack, nn * P * sizeof(float)) != cudaSuccess) ||
+            (dQ_local && cudaMalloc(&qtmp, (size_t)m_local * n * sizeof(float)) != cudaSuccess)) {
+            set_error("mpqr_mg_tsqr_device: device allocation failed");
+            cudaGetLastError();
+            rc = MPQR_ENOMEM;
+            break;
+        }
+        // local leaf: R_p and (optionally) the thin Q_p, kept aside until the tree is known
+        if ((rc = mpqr_tsqr_device(dA_local, lda, m_local, n, dQ_local ? qtmp : nullptr, n, rloc, n, st))) break;
+        int nr = g->api->AllGather(rloc, rstack, nn * sizeof(float), kNcclChar, g->comm, st);
+        if (nr != 0) { set_error("ncclAllGather failed: %d", nr); rc = MPQR_ENCCL; break; }
+        // every rank factors the same (P n) x n stack
+        if ((rc = mpqr_tsqr_device(rstack, n, (long)P * n, n, dQ_local ? qstack : nullptr, n, dR, ldr, st))) break;
+        if (dQ_local) {
+            rc = sgemm_nn_store(qtmp, n, qstack + (size_t)g->rank * nn, n, dQ_local, ldq, (int)m_local, n, n, st);
+        }
+    } while (0);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == MPQR_OK && e != cudaSuccess) { set_error("mpqr_mg_tsqr_device: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; }
+    cudaFree(rloc); cudaFree(rstack); cudaFree(qstack); cudaFree(qtmp);
+    return rc;
 }
 
 }  // extern "C"

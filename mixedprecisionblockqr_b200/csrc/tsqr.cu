@@ -7,9 +7,11 @@
 // it is itself tall).  Block factorisations use the FP32 driver (panel kernel + SIMT GEMMs):
 // TSQR is bandwidth-bound (64 flop/B at n = 256), not tensor-bound.
 //
-// Round-1 status: functional and parity-tested; blocks are processed one after the other, so
-// the GPU is latency-bound on the panel kernel.  A batched CTA-per-block kernel is the planned
-// replacement ("next").
+// The row blocks are independent: they are spread over up to 8 LANES (stream + handle + buffers
+// each, SM budget = device / lanes), so several blocks' register-block clusters (16 SMs each) run
+// at the same time instead of one latency-bound panel chain.  Every block is factored ONCE: its
+// thin Q_b is formed right away into the output rows and multiplied by its n x n slice of the
+// stack's Q after the tree is known.
 #include "internal.h"
 
 using namespace mpqr;
@@ -62,11 +64,22 @@ int form_thin_q(mpqr_handle* h, float* Q, long ldq, cudaStream_t st) {
     return MPQR_OK;
 }
 
-struct Level {
-    long rows;
-    int nblk;
-    long h;  // rows per block (last block may be shorter)
+struct Lane {
+    cudaStream_t s = nullptr;
+    cudaEvent_t done = nullptr;
+    float* work = nullptr;   // (hrows + 1) x ldp packed factor of the current block
+    float* qblk = nullptr;   // hrows x ldp thin Q of the current block (pass 2 source)
+    mpqr_handle* hb = nullptr;
+    mpqr_handle* hl = nullptr;  // handle of the (shorter) last block, on the lane that owns it
 };
+
+int tsqr_lanes(long nblk) {
+    const char* e = getenv("MPQR_TSQR_LANES");
+    long want = e ? atol(e) : 8;
+    if (want < 1) want = 1;
+    if (want > 16) want = 16;
+    return (int)(want < nblk ? want : nblk);
+}
 
 }  // namespace
 
@@ -76,6 +89,8 @@ extern "C" int mpqr_tsqr_device(const float* dA, long lda, long m, int n, float*
         set_error("mpqr_tsqr_device: bad arguments (needs m >= n)");
         return MPQR_EINVAL;
     }
+    DeviceInfo di;
+    MPQR_TRY(get_device_info(&di));
     cudaStream_t st = (cudaStream_t)stream;
     const long HMAX = 32768;
     const int r = n < 128 ? n : 128;
@@ -87,51 +102,87 @@ extern "C" int mpqr_tsqr_device(const float* dA, long lda, long m, int n, float*
     while (nblk > 1 && m - (nblk - 1) * hrows < n) { --nblk; hrows = (m + nblk - 1) / nblk; }
 
     const long ldp = round_up(n, 4);
-    float *work = nullptr, *rstack = nullptr, *qblk = nullptr, *qstack = nullptr;
-    mpqr_handle *hb = nullptr, *hl = nullptr;
-    int rc = MPQR_OK;
     const unsigned flags = MPQR_FP32 | (dQ ? MPQR_KEEP_WY : 0u);
     const long hlast = m - (nblk - 1) * hrows;
+    const int NL = tsqr_lanes(nblk);
+    const int budget = NL > 1 ? (di.num_sms / NL < 16 ? 16 : di.num_sms / NL) : 0;
+    std::vector<Lane> lanes(NL);
+    float *rstack = nullptr, *qstack = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_tree = nullptr;
+    int rc = MPQR_OK;
+    auto fail_alloc = [&]() { set_error("tsqr: device allocation failed"); cudaGetLastError(); return MPQR_ENOMEM; };
     do {
-        if (cudaMalloc(&work, (size_t)(hrows + 1) * ldp * sizeof(float)) != cudaSuccess) { set_error("tsqr: alloc failed"); rc = MPQR_ENOMEM; break; }
-        if (nblk > 1 && cudaMalloc(&rstack, (size_t)nblk * n * ldp * sizeof(float)) != cudaSuccess) { set_error("tsqr: alloc failed"); rc = MPQR_ENOMEM; break; }
-        if ((rc = mpqr_create(&hb, (int)hrows, n, r, 0, flags))) break;
-        if (hlast != hrows && (rc = mpqr_create(&hl, (int)hlast, n, r, 0, flags))) break;
-        if (dQ && nblk > 1) {
-            if (cudaMalloc(&qblk, (size_t)hrows * ldp * sizeof(float)) != cudaSuccess ||
-                cudaMalloc(&qstack, (size_t)nblk * n * ldp * sizeof(float)) != cudaSuccess) { set_error("tsqr: alloc failed"); rc = MPQR_ENOMEM; break; }
+        if (cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_tree, cudaEventDisableTiming) != cudaSuccess) { set_error("tsqr: event creation failed"); rc = MPQR_ECUDA; break; }
+        if (nblk > 1 && cudaMalloc(&rstack, (size_t)nblk * n * ldp * sizeof(float)) != cudaSuccess) { rc = fail_alloc(); break; }
+        if (nblk > 1 && dQ && cudaMalloc(&qstack, (size_t)nblk * n * ldp * sizeof(float)) != cudaSuccess) { rc = fail_alloc(); break; }
+        for (int l = 0; l < NL && rc == MPQR_OK; ++l) {
+            Lane& L = lanes[l];
+            if (NL > 1 && cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking) != cudaSuccess) { set_error("tsqr: stream creation failed"); rc = MPQR_ECUDA; break; }
+            if (NL == 1) L.s = st;
+            if (cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming) != cudaSuccess) { set_error("tsqr: event creation failed"); rc = MPQR_ECUDA; break; }
+            if (cudaMalloc(&L.work, (size_t)(hrows + 1) * ldp * sizeof(float)) != cudaSuccess) { rc = fail_alloc(); break; }
+            if (dQ && nblk > 1 && cudaMalloc(&L.qblk, (size_t)hrows * ldp * sizeof(float)) != cudaSuccess) { rc = fail_alloc(); break; }
+            if ((rc = mpqr_create(&L.hb, (int)hrows, n, r, 0, flags))) break;
+            if (hlast != hrows && (int)((nblk - 1) % NL) == l && (rc = mpqr_create(&L.hl, (int)hlast, n, r, 0, flags))) break;
         }
-        // Pass 1: R factor of every block (Q needs a second pass after the tree is known).
+        if (rc != MPQR_OK) break;
+        if (NL > 1) {
+            if (cudaEventRecord(ev_start, st) != cudaSuccess) { set_error("tsqr: event record failed"); rc = MPQR_ECUDA; break; }
+            for (auto& L : lanes) cudaStreamWaitEvent(L.s, ev_start, 0);
+        }
+        // Pass 1: every block is factored once; R_b goes to the stack.  A lane's buffers are reused block after
+        // block, so the block's thin Q_b (rows x n) is parked in the OUTPUT rows until the tree is known.
         for (long b = 0; b < nblk && rc == MPQR_OK; ++b) {
+            Lane& L = lanes[b % NL];
+            SmBudget sb(budget);
             const long rows = (b == nblk - 1) ? hlast : hrows;
-            mpqr_handle* h = (rows == hrows) ? hb : hl;
-            copy_block_kernel<<<grid_of(rows * n), 256, 0, st>>>(dA + (size_t)b * hrows * lda, lda, work, ldp, rows, n);
-            if ((rc = mpqr_factor_device(h, work, ldp, st))) break;
+            mpqr_handle* h = (rows == hrows) ? L.hb : L.hl;
+            copy_block_kernel<<<grid_of(rows * n), 256, 0, L.s>>>(dA + (size_t)b * hrows * lda, lda, L.work, ldp, rows, n);
+            if ((rc = mpqr_factor_device(h, L.work, ldp, L.s))) break;
             if (nblk == 1) {
-                extract_r_kernel<<<grid_of((long)n * n), 256, 0, st>>>(work, ldp, dR, ldr, n);
-                if (dQ) rc = form_thin_q(h, dQ, ldq, st);
+                extract_r_kernel<<<grid_of((long)n * n), 256, 0, L.s>>>(L.work, ldp, dR, ldr, n);
+                if (dQ) rc = form_thin_q(h, dQ, ldq, L.s);
             } else {
-                extract_r_kernel<<<grid_of((long)n * n), 256, 0, st>>>(work, ldp, rstack + (size_t)b * n * ldp, ldp, n);
+                extract_r_kernel<<<grid_of((long)n * n), 256, 0, L.s>>>(L.work, ldp, rstack + (size_t)b * n * ldp, ldp, n);
+                if (dQ) rc = form_thin_q(h, dQ + (size_t)b * hrows * ldq, ldq, L.s);
             }
         }
         if (rc != MPQR_OK || nblk == 1) break;
-        // Tree: factor the stacked R's ((nblk*n) x n) — recursion handles a tall stack.
+        // join the lanes, factor the stacked R's ((nblk*n) x n) on the caller's stream — recursion handles a tall stack
+        if (NL > 1)
+            for (auto& L : lanes) { cudaEventRecord(L.done, L.s); cudaStreamWaitEvent(st, L.done, 0); }
         if ((rc = mpqr_tsqr_device(rstack, ldp, nblk * (long)n, n, dQ ? qstack : nullptr, ldp, dR, ldr, st))) break;
         if (!dQ) break;
-        // Pass 2: thin Q rows of block b = Q_b[:, :n] * Qstack[b*n:(b+1)*n, :]
-        for (long b = 0; b < nblk && rc == MPQR_OK; ++b) {
-            const long rows = (b == nblk - 1) ? hlast : hrows;
-            mpqr_handle* h = (rows == hrows) ? hb : hl;
-            copy_block_kernel<<<grid_of(rows * n), 256, 0, st>>>(dA + (size_t)b * hrows * lda, lda, work, ldp, rows, n);
-            if ((rc = mpqr_factor_device(h, work, ldp, st))) break;
-            if ((rc = form_thin_q(h, qblk, ldp, st))) break;
-            rc = sgemm_nn_store(qblk, ldp, qstack + (size_t)b * n * ldp, ldp, dQ + (size_t)b * hrows * ldq, ldq, (int)rows, n, n, st);
+        // Pass 2: thin Q rows of block b = Q_b[:, :n] * Qstack[b*n:(b+1)*n, :]   (Q_b parked in the output rows)
+        if (NL > 1) {
+            cudaEventRecord(ev_tree, st);
+            for (auto& L : lanes) cudaStreamWaitEvent(L.s, ev_tree, 0);
         }
+        for (long b = 0; b < nblk && rc == MPQR_OK; ++b) {
+            Lane& L = lanes[b % NL];
+            SmBudget sb(budget);
+            const long rows = (b == nblk - 1) ? hlast : hrows;
+            float* Qb = dQ + (size_t)b * hrows * ldq;
+            copy_block_kernel<<<grid_of(rows * n), 256, 0, L.s>>>(Qb, ldq, L.qblk, ldp, rows, n);
+            rc = sgemm_nn_store(L.qblk, ldp, qstack + (size_t)b * n * ldp, ldp, Qb, ldq, (int)rows, n, n, L.s);
+        }
+        if (NL > 1)
+            for (auto& L : lanes) { cudaEventRecord(L.done, L.s); cudaStreamWaitEvent(st, L.done, 0); }
     } while (0);
     cudaError_t e = cudaStreamSynchronize(st);
+    for (auto& L : lanes)
+        if (NL > 1 && L.s) { cudaError_t e2 = cudaStreamSynchronize(L.s); if (e == cudaSuccess) e = e2; }
     if (rc == MPQR_OK && e != cudaSuccess) { set_error("tsqr: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; }
-    if (hb) mpqr_destroy(hb);
-    if (hl) mpqr_destroy(hl);
-    cudaFree(work); cudaFree(rstack); cudaFree(qblk); cudaFree(qstack);
+    for (auto& L : lanes) {
+        if (L.hb) mpqr_destroy(L.hb);
+        if (L.hl) mpqr_destroy(L.hl);
+        cudaFree(L.work); cudaFree(L.qblk);
+        if (L.done) cudaEventDestroy(L.done);
+        if (NL > 1 && L.s) cudaStreamDestroy(L.s);
+    }
+    if (ev_start) cudaEventDestroy(ev_start);
+    if (ev_tree) cudaEventDestroy(ev_tree);
+    cudaFree(rstack); cudaFree(qstack);
     return rc;
 }

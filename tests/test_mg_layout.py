@@ -74,3 +74,50 @@ def test_two_rank_gloo_plumbing():
         assert p.exitcode == 0
     for rank, uid_ok, rebuilt_ok, tmax in res:
         assert uid_ok and rebuilt_ok and tmax == 11.0
+
+
+def _tsqr_worker(rank, world, port, m, n, q):
+    """The exchange structure of mpqr_mg_tsqr_device over gloo, with the oracle's ts_qr restatement as the leaf
+    factoriser: row-block leaves -> all_gather of the n x n R factors -> the same stack factored on every rank
+    -> local thin-Q product.  Checks that the structure reproduces A = Q R with the same R on all ranks."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    A = oracle.uniform_matrix(m, n, 77).astype(np.float64)
+    rows = np.array_split(np.arange(m), world)[rank]        # 1-D row-block layout
+    Qp, Rp = oracle.tsqr(A[rows], 4)                        # leaf (python/ca_qr.py:25-43 restated)
+    Qp = Qp[:, :n]
+    gathered = [torch.zeros(n, n, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(np.ascontiguousarray(Rp[:n])))
+    stack = torch.cat(gathered).numpy()
+    Qs, R = np.linalg.qr(stack)                             # redundant on every rank, same input => same R
+    Qloc = Qp[: len(rows)] @ Qs[rank * n:(rank + 1) * n]
+    Rs = [torch.zeros(n, n, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(Rs, torch.from_numpy(np.ascontiguousarray(R)))
+    same_r = all(torch.equal(Rs[0], x) for x in Rs)
+    Qall = [None] * world
+    dist.all_gather_object(Qall, (rows, Qloc))
+    Q = np.zeros((m, n))
+    for rr, blk in Qall:
+        Q[rr] = blk
+    err = np.linalg.norm(A - Q @ R) / np.linalg.norm(A)
+    orth = np.linalg.norm(Q.T @ Q - np.eye(n))
+    q.put((rank, same_r, float(err), float(orth)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_tsqr_structure():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tsqr_worker, args=(r, 2, port, 640, 24, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, same_r, err, orth in res:
+        assert same_r and err < 1e-13 and orth < 1e-12
