@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/mpqr.h"
 
@@ -60,9 +61,10 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 inline cudaLaunchAttribute pdl_attr() {
+    static const int off = getenv("MPQR_NO_PDL") ? 1 : 0;  // debugging aid: plain stream order
     cudaLaunchAttribute a{};
     a.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    a.val.programmaticStreamSerializationAllowed = 1;
+    a.val.programmaticStreamSerializationAllowed = off ? 0 : 1;
     return a;
 }
 

@@ -219,12 +219,12 @@ __device__ __forceinline__ void load_row(const float* p, float (&x)[B], int bw, 
     if (vec && bw == B) {
 #pragma unroll
         for (int q = 0; q < B / 4; ++q) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(p) + q);
+            float4 v = __ldcg(reinterpret_cast<const float4*>(p) + q);
             x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
         }
     } else {
 #pragma unroll
-        for (int c = 0; c < B; ++c) x[c] = (c < bw) ? __ldg(p + c) : 0.f;
+        for (int c = 0; c < B; ++c) x[c] = (c < bw) ? __ldcg(p + c) : 0.f;
     }
 }
 template <int B>
@@ -270,7 +270,7 @@ __device__ __forceinline__ void warp_tile_in(const char* g, size_t pitch, int nv
     for (int k = 0; k < CH; ++k) {
         const int r = k * RPI + lane / CH, q = lane % CH;
         uint4 t = make_uint4(0u, 0u, 0u, 0u);
-        if (r < nvalid) t = __ldg(reinterpret_cast<const uint4*>(g + (size_t)r * pitch) + q);
+        if (r < nvalid) t = __ldcg(reinterpret_cast<const uint4*>(g + (size_t)r * pitch) + q);
         tile[r * CH + (q ^ tile_swz<CH>(r))] = t;
     }
     __syncwarp();
@@ -963,11 +963,11 @@ __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict_
 #pragma unroll
     for (int u = 0; u < SU_RB; ++u) {
         const int r2 = rg + 4 * u;
-        av[u] = (on && r2 < nrows) ? __ldg(Ac + (size_t)r2 * lda) : 0.f;
+        av[u] = (on && r2 < nrows) ? __ldcg(Ac + (size_t)r2 * lda) : 0.f;
     }
     for (int idx = tid; idx < nrows * B; idx += 512) {
         int rr = idx / B, t = idx - rr * B;
-        sm[idx] = W[(size_t)(r0 + rr) * ldw + t];
+        sm[idx] = __ldcg(&W[(size_t)(r0 + rr) * ldw + t]);
     }
     __syncthreads();
     float acc[B];
@@ -978,7 +978,7 @@ __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict_
 #pragma unroll
         for (int u = 0; u < SU_RB; ++u) {  // next batch in flight while this one is consumed
             const int r2 = rr + 4 * SU_RB + 4 * u;
-            nx[u] = (on && r2 < nrows) ? __ldg(Ac + (size_t)r2 * lda) : 0.f;
+            nx[u] = (on && r2 < nrows) ? __ldcg(Ac + (size_t)r2 * lda) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < SU_RB; ++u) {
@@ -1038,7 +1038,7 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
 #pragma unroll
     for (int u = 0; u < SU_RB; ++u) {  // first batch of A in flight during the prologue
         const int r2 = rg + 4 * u;
-        av[u] = (on && r2 < nrows) ? Ac[(size_t)r2 * lda] : 0.f;
+        av[u] = (on && r2 < nrows) ? __ldcg(&Ac[(size_t)r2 * lda]) : 0.f;
     }
     // S' = sum of the replicas (B x 128 chunk), once per CTA
     for (int idx = tid; idx < B * 128; idx += 512) {
@@ -1050,10 +1050,10 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
         }
         Sp[t][cc] = v;
     }
-    for (int idx = tid; idx < B * B; idx += 512) Ts[idx / B][idx % B] = Tj[idx];
+    for (int idx = tid; idx < B * B; idx += 512) Ts[idx / B][idx % B] = __ldcg(&Tj[idx]);
     for (int idx = tid; idx < nrows * B; idx += 512) {
         int rr = idx / B, t = idx - rr * B;
-        sm[idx] = Y[(size_t)(r0 + rr) * ldy + t];
+        sm[idx] = __ldcg(&Y[(size_t)(r0 + rr) * ldy + t]);
     }
     __syncthreads();
     // S = T^T S': row group rg computes B/4 consecutive rows t of its column; T is zero below its
@@ -1088,7 +1088,7 @@ __global__ void __launch_bounds__(512) inpanel_u_kernel(const float* __restrict_
 #pragma unroll
         for (int u = 0; u < SU_RB; ++u) {
             const int r2 = rr + 4 * SU_RB + 4 * u;
-            nx[u] = (r2 < nrows) ? Ac[(size_t)r2 * lda] : 0.f;
+            nx[u] = (r2 < nrows) ? __ldcg(&Ac[(size_t)r2 * lda]) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < SU_RB; ++u) {
@@ -1148,11 +1148,11 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
 #pragma unroll
     for (int u = 0; u < RB; ++u) {  // first batch in flight while Y is staged
         const int r2 = warp + u * NWARP;
-        a4[u] = (on && r2 < nrows) ? __ldg(reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a4[u] = (on && r2 < nrows) ? __ldcg(reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int idx = tid; idx < nrows * B; idx += NTHR) {
         const int rr = idx / B, t = idx - rr * B;
-        ysm[idx] = Y[(size_t)(r0 + rr) * ldy + t];
+        ysm[idx] = __ldcg(&Y[(size_t)(r0 + rr) * ldy + t]);
     }
     __syncthreads();
     if (B == 32 && Cacc && blockIdx.y == 0) {  // NTHR == 256: thread <-> entry (ta, tb) of C
@@ -1192,7 +1192,7 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
             const int r2 = rb + NWARP * RB + u * NWARP;
-            a4[u] = (on && r2 < nrows) ? __ldg(reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a4[u] = (on && r2 < nrows) ? __ldcg(reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     // cross-warp tree through shared memory (conflict-free 16-byte slots), then warp 0 adds the
@@ -1223,7 +1223,7 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
 #pragma unroll
             for (int t = 0; t < B; ++t) *reinterpret_cast<float4*>(&red[t * 128 + 4 * lane]) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
         }
-        for (int idx = tid; idx < B * B; idx += NTHR) Ts2[(idx / B) * (B + 4) + (idx % B)] = Tj[idx];
+        for (int idx = tid; idx < B * B; idx += NTHR) Ts2[(idx / B) * (B + 4) + (idx % B)] = __ldcg(&Tj[idx]);
         __syncthreads();
         constexpr int NG = NTHR / 128, TQ = B / NG;  // thread: column cc, TQ consecutive rows t of S
         const int cc = tid & 127, tg = tid >> 7;
@@ -1282,8 +1282,8 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
         Cs[tid] = __ldcg(&Cacc[tid]);
         for (int idx = tid; idx < B * (B + 4); idx += NTHR) Ts[idx] = 0.f;
         __syncthreads();
-        Ts[i2 * (B + 4) + j2] = Tj[tid];                    // T_A
-        Ts[(16 + i2) * (B + 4) + 16 + j2] = Tj[256 + tid];  // T_B
+        Ts[i2 * (B + 4) + j2] = __ldcg(&Tj[tid]);                    // T_A
+        Ts[(16 + i2) * (B + 4) + 16 + j2] = __ldcg(&Tj[256 + tid]);  // T_B
         __syncthreads();
         float xv = 0.f;
 #pragma unroll
@@ -1295,7 +1295,7 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
         for (int k = 0; k < 16; ++k) tv = fmaf(Ts[i2 * (B + 4) + k], Xs[k * 16 + j2], tv);
         Ts[i2 * (B + 4) + 16 + j2] = -tv;
     } else {
-        for (int idx = tid; idx < B * B; idx += NTHR) Ts[(idx / B) * (B + 4) + (idx % B)] = Tj[idx];
+        for (int idx = tid; idx < B * B; idx += NTHR) Ts[(idx / B) * (B + 4) + (idx % B)] = __ldcg(&Tj[idx]);
     }
     __syncthreads();
     {
@@ -1341,7 +1341,7 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* _
 #pragma unroll
     for (int u = 0; u < RB; ++u) {
         const int r2 = warp + u * NWARP;
-        a4[u] = (on && r2 < nrows) ? *reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a4[u] = (on && r2 < nrows) ? __ldcg(reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float sv[B][4];
 #pragma unroll
@@ -1355,7 +1355,7 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* _
     }
     for (int idx = tid; idx < nrows * B; idx += NTHR) {
         const int rr = idx / B, t = idx - rr * B;
-        ysm[idx] = Y[(size_t)(r0 + rr) * ldy + t];
+        ysm[idx] = __ldcg(&Y[(size_t)(r0 + rr) * ldy + t]);
     }
     __syncthreads();
     if (!on) return;
@@ -1384,7 +1384,7 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* _
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
             const int r2 = rb + NWARP * RB + u * NWARP;
-            a4[u] = (r2 < nrows) ? *reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a4[u] = (r2 < nrows) ? __ldcg(reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 }
@@ -1406,7 +1406,7 @@ __global__ void __launch_bounds__(1024) tinv_kernel(const float* __restrict__ G,
     while (R < pw) R *= 2;
     for (int idx = tid; idx < R * R; idx += 1024) {
         int t = idx / R, c = idx - t * R;
-        Ts[t * TLD + c] = (t < c && c < pw) ? G[(size_t)t * ldg + c] : 0.f;
+        Ts[t * TLD + c] = (t < c && c < pw) ? __ldcg(&G[(size_t)t * ldg + c]) : 0.f;
     }
     __syncthreads();
     // diagonal blocks: thread (block b, column c) runs the larft recurrence restricted to the block

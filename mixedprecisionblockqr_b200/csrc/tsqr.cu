@@ -7,7 +7,7 @@
 // it is itself tall).  Block factorisations use the FP32 driver (panel kernel + SIMT GEMMs):
 // TSQR is bandwidth-bound (64 flop/B at n = 256), not tensor-bound.
 //
-// The row blocks are independent: they are spread over up to 8 LANES (stream + handle + buffers
+// The row blocks are independent: they are spread over up to 4 LANES (MPQR_TSQR_LANES) (stream + handle + buffers
 // each, SM budget = device / lanes), so several blocks' register-block clusters (16 SMs each) run
 // at the same time instead of one latency-bound panel chain.  Every block is factored ONCE: its
 // thin Q_b is formed right away into the output rows and multiplied by its n x n slice of the
@@ -75,7 +75,7 @@ struct Lane {
 
 int tsqr_lanes(long nblk) {
     const char* e = getenv("MPQR_TSQR_LANES");
-    long want = e ? atol(e) : 8;
+    long want = e ? atol(e) : 4;  // B200, 1048576 x 256: 68 ms with 1 lane, 59 ms with 4, 75 ms with 8 (clusters queue for SMs)
     if (want < 1) want = 1;
     if (want > 16) want = 16;
     return (int)(want < nblk ? want : nblk);

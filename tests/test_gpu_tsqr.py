@@ -53,3 +53,17 @@ def test_tsqr_r_only():
     _, R = _tsqr(A, want_q=False)
     _, Rl = np.linalg.qr(A.astype(np.float64))
     assert np.abs(np.abs(R) - np.abs(Rl)).max() <= 2e-5 * np.abs(Rl).max()
+
+
+def test_tsqr_lanes_repeatable(monkeypatch):
+    """Regression: with several lanes in flight the PDL-chained panel kernels become resident early and at staggered
+    times; reads of data produced earlier in the chain through the non-coherent path (__ldg / const __restrict__)
+    then returned stale L1 lines now and then (|R| off by 1e-3, sporadically).  All such reads are ld.global.cg now."""
+    monkeypatch.setenv("MPQR_TSQR_LANES", "8")
+    A = oracle.uniform_matrix(65836, 128, 65836 + 128)
+    _, Rl = np.linalg.qr(A.astype(np.float64))
+    for _ in range(6):
+        Q, R = _tsqr(A)
+        assert np.abs(np.abs(R) - np.abs(Rl)).max() <= 2e-5 * np.abs(Rl).max()
+        Ad = A.astype(np.float64)
+        assert np.linalg.norm(Ad - Q.astype(np.float64) @ R) / np.linalg.norm(Ad) <= 5e-6
