@@ -31,6 +31,7 @@ WORKLOADS = {
     "c2": (2048, 2048, 32),
     "c16k": (16384, 16384, 128),
     "c8k": (8192, 8192, 128),
+    "c5": (1048576, 256, 128),   # tall-skinny: TSQR path (mpqr_tsqr_device / mpqr_mg_tsqr_device), row blocks over the GPUs
 }
 REF_SAMPLE = (640, 640, 32)  # bounded sample of the same workload family for the CPU reference arm
 
@@ -358,6 +359,118 @@ def main_native(args):
         dist.destroy_process_group()
 
 
+def main_tsqr(args):
+    """BASELINE config 5 (1048576 x 256, python/ca_qr.py TSQR path): R and the thin Q of the SAME matrix at every N,
+    rows split evenly over the ranks (strong scaling), one ncclAllGather of the 256 x 256 R factors."""
+    import torch
+    import mixedprecisionblockqr_b200 as pkg
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+    m, n, _ = WORKLOADS[args.workload]
+    F = householder_flops(m, n)
+    st = torch.cuda.current_stream().cuda_stream
+    peaks = load_peaks()
+    r0, r1 = m * rank // world, m * (rank + 1) // world
+    mloc = r1 - r0
+    A = torch.zeros(mloc, n, device="cuda")
+    pkg.fill_uniform(A.data_ptr(), n, n, r0, mloc, 0, n, args.seed, st)
+    Q = torch.zeros(mloc, n, device="cuda")
+    R = torch.zeros(n, n, device="cuda")
+    plan = None
+    if world > 1:
+        uid = [pkg.mg_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        plan = pkg.MultiGpuTSQR(rank, world, uid[0])
+
+    def step():   # device-synchronous calls (they allocate their lanes and free them again)
+        if plan is None:
+            pkg.tsqr(A.data_ptr(), n, mloc, n, Q.data_ptr(), n, R.data_ptr(), n, st)
+        else:
+            plan.factor(A.data_ptr(), n, mloc, n, Q.data_ptr(), n, R.data_ptr(), n, st)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    # accuracy (FP64 on the device): local residual and Gram pieces, reduced over the ranks
+    Ad, Qd, Rd = A.double(), Q.double(), R.double()
+    parts = torch.stack([((Ad - Qd @ Rd) ** 2).sum(), (Ad ** 2).sum()])
+    G = Qd.T @ Qd
+    # end to end: pinned host rows -> H2D -> TSQR -> D2H of the thin Q rows and R
+    hostA = torch.empty((mloc, n), dtype=torch.float32, pin_memory=True)
+    hostA.copy_(A)
+    hostQ = torch.empty((mloc, n), dtype=torch.float32, pin_memory=True)
+    hostR = torch.empty((n, n), dtype=torch.float32, pin_memory=True)
+    esteps = max(1, min(args.steps, args.e2e_steps))
+    dt = 0.0
+    for w in range(1 + esteps):
+        barrier()
+        t0 = time.perf_counter()
+        A.copy_(hostA, non_blocking=True)
+        step()
+        hostQ.copy_(Q, non_blocking=True)
+        hostR.copy_(R, non_blocking=True)
+        barrier()
+        if w >= 1:
+            dt += time.perf_counter() - t0
+    dt /= esteps
+    if dist is not None:
+        t = torch.tensor([ms, dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, dt = float(t[0].item()), float(t[1].item())
+        dist.all_reduce(parts)
+        dist.all_reduce(G)
+    if rank == 0:
+        ms_per_step = ms / args.steps
+        value = F / (ms_per_step * 1e-3) / 1e12
+        alg_bytes = 8.0 * m * n + 4.0 * n * n       # read A once, write the thin Q once (+ R): SURVEY 8d
+        ach = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": "block-QR TFLOP/s (2mn^2-2n^3/3)", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"{m}x{n} tall-skinny TSQR ({args.workload}), R + thin Q",
+                       "parallelism": "single GPU" if world == 1 else f"1-D row blocks x{world}, one ncclAllGather of the R factors",
+                       "seed": args.seed, "l2": "input (1.07 GB) is larger than L2", "flop_model": "2mn^2-2n^3/3"},
+            "backward_error": float((parts[0] / parts[1]).sqrt().item()),
+            "orthogonality_fro": float((G - torch.eye(n, device="cuda", dtype=torch.float64)).norm().item()),
+            "e2e": {"value": F / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 4 * m * n, "d2h_bytes_per_step": 4 * m * n + 4 * n * n,
+                    "ms_per_step": dt * 1e3, "path": "per rank: pinned host rows -> H2D -> mpqr_(mg_)tsqr_device -> D2H of Q rows and R"},
+            "gpu_launches": None, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"] * world, "unit": "GB/s", "frac": ach / (peaks["hbm_gbs"] * world),
+                         "traffic": None, "kernel": "whole TSQR call (per-call lane set-up included)", "peak_source": peaks["source"] + ", copy bandwidth x n_gpus"},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    if plan is not None:
+        plan.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -376,5 +489,7 @@ if __name__ == "__main__":
         a.warmup = 3   # timing rule: at least 3 warm-up steps
     if a.impl == "reference":
         main_reference(a)
+    elif a.workload == "c5":
+        main_tsqr(a)
     else:
         main_native(a)

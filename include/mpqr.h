@@ -218,6 +218,9 @@ int mpqr_write_results_to_log(const char* log_dir, const char* file_name, int he
  * ------------------------------------------------------------------------------------- */
 int mpqr_tsqr_device(const float* dA, long lda, long m, int n, float* dQ, long ldq, float* dR,
                      long ldr, void* stream);
+/* mpqr_tsqr_device keeps its plans (streams, workspaces; ~0.7 GB for 1048576 x 256) for the next call with
+ * the same shape; this frees them. */
+int mpqr_tsqr_release_cache(void);
 
 /* Multi-GPU TSQR (BASELINE config 5): 1-D ROW-block layout, one process per GPU, rank p holds
  * m_local rows of A (row-major, device).  Local TSQR, ONE ncclAllGather of the n x n R factors, the

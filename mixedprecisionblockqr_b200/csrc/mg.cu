@@ -79,6 +79,24 @@ struct MgState {
     long ldw = 0;
     void* Ah = nullptr;  // local shadow, m x ldh
     long ldh = 0;
+    // TSQR scratch (grow-only, freed with the handle): R_p | R stack | Q of the stack | thin Q_p
+    float* tq[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t tq_bytes[4] = {0, 0, 0, 0};
+    int tq_get(int i, size_t bytes, float** out) {
+        if (tq_bytes[i] < bytes) {
+            cudaFree(tq[i]);
+            tq[i] = nullptr;
+            tq_bytes[i] = 0;
+            if (cudaMalloc(&tq[i], bytes) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("mpqr_mg_tsqr_device: device allocation of %zu bytes failed", bytes);
+                return MPQR_ENOMEM;
+            }
+            tq_bytes[i] = bytes;
+        }
+        *out = tq[i];
+        return MPQR_OK;
+    }
 };
 
 #define MPQR_NCCL(api, expr)                                                                     \
@@ -273,14 +291,9 @@ int mpqr_mg_tsqr_device(mpqr_handle* h, const float* dA_local, long lda, long m_
     const size_t nn = (size_t)n * n;
     int rc = MPQR_OK;
     do {
-        if (cudaMalloc(&rloc, nn * sizeof(float)) != cudaSuccess || cudaMalloc(&rstack, nn * P * sizeof(float)) != cudaSuccess ||
-            (dQ_local && cudaMalloc(&qstack, nn * P * sizeof(float)) != cudaSuccess) ||
-            (dQ_local && cudaMalloc(&qtmp, (size_t)m_local * n * sizeof(float)) != cudaSuccess)) {
-            set_error("mpqr_mg_tsqr_device: device allocation failed");
-            cudaGetLastError();
-            rc = MPQR_ENOMEM;
-            break;
-        }
+        if ((rc = g->tq_get(0, nn * sizeof(float), &rloc)) || (rc = g->tq_get(1, nn * P * sizeof(float), &rstack))) break;
+        if (dQ_local && ((rc = g->tq_get(2, nn * P * sizeof(float), &qstack)) ||
+                         (rc = g->tq_get(3, (size_t)m_local * n * sizeof(float), &qtmp)))) break;
         // local leaf: R_p and (optionally) the thin Q_p, kept aside until the tree is known
         if ((rc = mpqr_tsqr_device(dA_local, lda, m_local, n, dQ_local ? qtmp : nullptr, n, rloc, n, st))) break;
         int nr = g->api->AllGather(rloc, rstack, nn * sizeof(float), kNcclChar, g->comm, st);
@@ -293,7 +306,6 @@ int mpqr_mg_tsqr_device(mpqr_handle* h, const float* dA_local, long lda, long m_
     } while (0);
     cudaError_t e = cudaStreamSynchronize(st);
     if (rc == MPQR_OK && e != cudaSuccess) { set_error("mpqr_mg_tsqr_device: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; }
-    cudaFree(rloc); cudaFree(rstack); cudaFree(qstack); cudaFree(qtmp);
     return rc;
 }
 
@@ -304,6 +316,7 @@ void mg_destroy(void* state) {
     MgState* g = (MgState*)state;
     if (!g) return;
     if (g->comm && g->api) g->api->CommDestroy(g->comm);
+    for (float* p : g->tq) cudaFree(p);
     delete g;
 }
 }  // namespace mpqr

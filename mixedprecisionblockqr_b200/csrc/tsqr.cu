@@ -12,6 +12,8 @@
 // at the same time instead of one latency-bound panel chain.  Every block is factored ONCE: its
 // thin Q_b is formed right away into the output rows and multiplied by its n x n slice of the
 // stack's Q after the tree is known.
+#include <mutex>
+
 #include "internal.h"
 
 using namespace mpqr;
@@ -65,7 +67,7 @@ int form_thin_q(mpqr_handle* h, float* Q, long ldq, cudaStream_t st) {
 }
 
 struct Lane {
-    cudaStream_t s = nullptr;
+    cudaStream_t s = nullptr;   // own stream (always: a plan outlives the caller's stream)
     cudaEvent_t done = nullptr;
     float* work = nullptr;   // (hrows + 1) x ldp packed factor of the current block
     float* qblk = nullptr;   // hrows x ldp thin Q of the current block (pass 2 source)
@@ -81,6 +83,151 @@ int tsqr_lanes(long nblk) {
     return (int)(want < nblk ? want : nblk);
 }
 
+// Everything a call needs besides its arguments: lanes (stream, handles, buffers), the R stack and the
+// stack's Q.  Plans are cached per (device, m, n, with-Q, lanes): creating one costs ~10 cudaMalloc and a
+// memset per lane, more than the factorisation of a small matrix.  mpqr_tsqr_release_cache() frees them.
+struct Plan {
+    int dev = -1;
+    long m = 0;
+    int n = 0, NL = 0;
+    bool with_q = false;
+    long nblk = 1, hrows = 0, hlast = 0, ldp = 0;
+    int budget = 0;
+    std::vector<Lane> lanes;
+    float *rstack = nullptr, *qstack = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_tree = nullptr;
+    bool busy = false;  // a recursive call never shares its caller's plan (different m), but be explicit
+    ~Plan() {
+        for (auto& L : lanes) {
+            if (L.hb) mpqr_destroy(L.hb);
+            if (L.hl) mpqr_destroy(L.hl);
+            cudaFree(L.work); cudaFree(L.qblk);
+            if (L.done) cudaEventDestroy(L.done);
+            if (L.s) cudaStreamDestroy(L.s);
+        }
+        if (ev_start) cudaEventDestroy(ev_start);
+        if (ev_tree) cudaEventDestroy(ev_tree);
+        cudaFree(rstack); cudaFree(qstack);
+    }
+};
+std::mutex g_plans_mu;
+std::vector<Plan*> g_plans;
+constexpr size_t kMaxPlans = 8;
+
+int build_plan(Plan* P, const DeviceInfo& di) {
+    const long HMAX = 32768;
+    const long m = P->m;
+    const int n = P->n;
+    const int r = n < 128 ? n : 128;
+    long nblk = (m + HMAX - 1) / HMAX;  // block height <= HMAX: panels stay in the register-resident kernel
+    if (nblk < 1 || m < 2L * n) nblk = 1;  // single block: plain blocked QR
+    long hrows = (m + nblk - 1) / nblk;
+    if (hrows < n) { nblk = 1; hrows = m; }
+    while (nblk > 1 && m - (nblk - 1) * hrows < n) { --nblk; hrows = (m + nblk - 1) / nblk; }
+    P->nblk = nblk; P->hrows = hrows; P->hlast = m - (nblk - 1) * hrows; P->ldp = round_up(n, 4);
+    P->NL = tsqr_lanes(nblk);
+    P->budget = P->NL > 1 ? (di.num_sms / P->NL < 16 ? 16 : di.num_sms / P->NL) : 0;
+    P->lanes.resize(P->NL);
+    const unsigned flags = MPQR_FP32 | (P->with_q ? MPQR_KEEP_WY : 0u);
+    const long ldp = P->ldp;
+    auto fail_alloc = [&]() { set_error("tsqr: device allocation failed"); cudaGetLastError(); return MPQR_ENOMEM; };
+    if (cudaEventCreateWithFlags(&P->ev_start, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&P->ev_tree, cudaEventDisableTiming) != cudaSuccess) { set_error("tsqr: event creation failed"); return MPQR_ECUDA; }
+    if (nblk > 1 && cudaMalloc(&P->rstack, (size_t)nblk * n * ldp * sizeof(float)) != cudaSuccess) return fail_alloc();
+    if (nblk > 1 && P->with_q && cudaMalloc(&P->qstack, (size_t)nblk * n * ldp * sizeof(float)) != cudaSuccess) return fail_alloc();
+    for (int l = 0; l < P->NL; ++l) {
+        Lane& L = P->lanes[l];
+        if (cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking) != cudaSuccess) { set_error("tsqr: stream creation failed"); return MPQR_ECUDA; }
+        if (cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming) != cudaSuccess) { set_error("tsqr: event creation failed"); return MPQR_ECUDA; }
+        if (cudaMalloc(&L.work, (size_t)(hrows + 1) * ldp * sizeof(float)) != cudaSuccess) return fail_alloc();
+        if (P->with_q && nblk > 1 && cudaMalloc(&L.qblk, (size_t)hrows * ldp * sizeof(float)) != cudaSuccess) return fail_alloc();
+        MPQR_TRY(mpqr_create(&L.hb, (int)hrows, n, r, 0, flags));
+        if (P->hlast != hrows && (int)((nblk - 1) % P->NL) == l) MPQR_TRY(mpqr_create(&L.hl, (int)P->hlast, n, r, 0, flags));
+    }
+    // mpqr_create clears its workspaces on the legacy default stream; the lanes are non-blocking streams
+    MPQR_CUDA(cudaDeviceSynchronize());
+    return MPQR_OK;
+}
+
+int acquire_plan(long m, int n, bool with_q, Plan** out) {
+    DeviceInfo di;
+    MPQR_TRY(get_device_info(&di));
+    int dev = 0;
+    MPQR_CUDA(cudaGetDevice(&dev));
+    const int NLwant = tsqr_lanes(1L << 30);
+    std::lock_guard<std::mutex> lk(g_plans_mu);
+    for (size_t i = 0; i < g_plans.size(); ++i) {
+        Plan* P = g_plans[i];
+        if (!P->busy && P->dev == dev && P->m == m && P->n == n && P->with_q == with_q && P->NL == (NLwant < P->nblk ? NLwant : (int)P->nblk)) {
+            g_plans.erase(g_plans.begin() + i);  // most recently used at the back
+            g_plans.push_back(P);
+            P->busy = true;
+            *out = P;
+            return MPQR_OK;
+        }
+    }
+    for (size_t i = 0; g_plans.size() >= kMaxPlans && i < g_plans.size(); ++i)
+        if (!g_plans[i]->busy) { delete g_plans[i]; g_plans.erase(g_plans.begin() + i); break; }
+    Plan* P = new Plan();
+    P->dev = dev; P->m = m; P->n = n; P->with_q = with_q;
+    int rc = build_plan(P, di);
+    if (rc != MPQR_OK) { delete P; return rc; }
+    P->busy = true;
+    g_plans.push_back(P);
+    *out = P;
+    return MPQR_OK;
+}
+
+void release_plan(Plan* P) {
+    std::lock_guard<std::mutex> lk(g_plans_mu);
+    P->busy = false;
+}
+
+int run_plan(Plan* P, const float* dA, long lda, float* dQ, long ldq, float* dR, long ldr, cudaStream_t st) {
+    const long nblk = P->nblk, hrows = P->hrows, hlast = P->hlast, ldp = P->ldp;
+    const int n = P->n, NL = P->NL, budget = P->budget;
+    auto& lanes = P->lanes;
+    int rc = MPQR_OK;
+    MPQR_CUDA(cudaEventRecord(P->ev_start, st));
+    for (auto& L : lanes) MPQR_CUDA(cudaStreamWaitEvent(L.s, P->ev_start, 0));
+    // Pass 1: every block is factored once; R_b goes to the stack.  A lane's buffers are reused block after
+    // block, so the block's thin Q_b (rows x n) is parked in the OUTPUT rows until the tree is known.
+    for (long b = 0; b < nblk && rc == MPQR_OK; ++b) {
+        Lane& L = lanes[b % NL];
+        SmBudget sb(budget);
+        const long rows = (b == nblk - 1) ? hlast : hrows;
+        mpqr_handle* h = (rows == hrows) ? L.hb : L.hl;
+        copy_block_kernel<<<grid_of(rows * n), 256, 0, L.s>>>(dA + (size_t)b * hrows * lda, lda, L.work, ldp, rows, n);
+        if ((rc = mpqr_factor_device(h, L.work, ldp, L.s))) break;
+        if (nblk == 1) {
+            extract_r_kernel<<<grid_of((long)n * n), 256, 0, L.s>>>(L.work, ldp, dR, ldr, n);
+            if (dQ) rc = form_thin_q(h, dQ, ldq, L.s);
+        } else {
+            extract_r_kernel<<<grid_of((long)n * n), 256, 0, L.s>>>(L.work, ldp, P->rstack + (size_t)b * n * ldp, ldp, n);
+            if (dQ) rc = form_thin_q(h, dQ + (size_t)b * hrows * ldq, ldq, L.s);
+        }
+    }
+    // join the lanes on the caller's stream
+    for (auto& L : lanes) { cudaEventRecord(L.done, L.s); cudaStreamWaitEvent(st, L.done, 0); }
+    if (rc != MPQR_OK || nblk == 1) return rc;
+    // factor the stacked R's ((nblk*n) x n) — recursion handles a tall stack
+    MPQR_TRY(mpqr_tsqr_device(P->rstack, ldp, nblk * (long)n, n, dQ ? P->qstack : nullptr, ldp, dR, ldr, st));
+    if (!dQ) return MPQR_OK;
+    // Pass 2: thin Q rows of block b = Q_b[:, :n] * Qstack[b*n:(b+1)*n, :]   (Q_b parked in the output rows)
+    MPQR_CUDA(cudaEventRecord(P->ev_tree, st));
+    for (auto& L : lanes) MPQR_CUDA(cudaStreamWaitEvent(L.s, P->ev_tree, 0));
+    for (long b = 0; b < nblk && rc == MPQR_OK; ++b) {
+        Lane& L = lanes[b % NL];
+        SmBudget sb(budget);
+        const long rows = (b == nblk - 1) ? hlast : hrows;
+        float* Qb = dQ + (size_t)b * hrows * ldq;
+        copy_block_kernel<<<grid_of(rows * n), 256, 0, L.s>>>(Qb, ldq, L.qblk, ldp, rows, n);
+        rc = sgemm_nn_store(L.qblk, ldp, P->qstack + (size_t)b * n * ldp, ldp, Qb, ldq, (int)rows, n, n, L.s);
+    }
+    for (auto& L : lanes) { cudaEventRecord(L.done, L.s); cudaStreamWaitEvent(st, L.done, 0); }
+    return rc;
+}
+
 }  // namespace
 
 extern "C" int mpqr_tsqr_device(const float* dA, long lda, long m, int n, float* dQ, long ldq, float* dR, long ldr,
@@ -89,100 +236,23 @@ extern "C" int mpqr_tsqr_device(const float* dA, long lda, long m, int n, float*
         set_error("mpqr_tsqr_device: bad arguments (needs m >= n)");
         return MPQR_EINVAL;
     }
-    DeviceInfo di;
-    MPQR_TRY(get_device_info(&di));
     cudaStream_t st = (cudaStream_t)stream;
-    const long HMAX = 32768;
-    const int r = n < 128 ? n : 128;
-    // single block: plain blocked QR
-    long nblk = (m + HMAX - 1) / HMAX;  // block height <= HMAX: panels stay in the register-resident kernel
-    if (nblk < 1 || m < 2L * n) nblk = 1;
-    long hrows = (m + nblk - 1) / nblk;
-    if (hrows < n) { nblk = 1; hrows = m; }
-    while (nblk > 1 && m - (nblk - 1) * hrows < n) { --nblk; hrows = (m + nblk - 1) / nblk; }
-
-    const long ldp = round_up(n, 4);
-    const unsigned flags = MPQR_FP32 | (dQ ? MPQR_KEEP_WY : 0u);
-    const long hlast = m - (nblk - 1) * hrows;
-    const int NL = tsqr_lanes(nblk);
-    const int budget = NL > 1 ? (di.num_sms / NL < 16 ? 16 : di.num_sms / NL) : 0;
-    std::vector<Lane> lanes(NL);
-    float *rstack = nullptr, *qstack = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_tree = nullptr;
-    int rc = MPQR_OK;
-    auto fail_alloc = [&]() { set_error("tsqr: device allocation failed"); cudaGetLastError(); return MPQR_ENOMEM; };
-    do {
-        if (cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ev_tree, cudaEventDisableTiming) != cudaSuccess) { set_error("tsqr: event creation failed"); rc = MPQR_ECUDA; break; }
-        if (nblk > 1 && cudaMalloc(&rstack, (size_t)nblk * n * ldp * sizeof(float)) != cudaSuccess) { rc = fail_alloc(); break; }
-        if (nblk > 1 && dQ && cudaMalloc(&qstack, (size_t)nblk * n * ldp * sizeof(float)) != cudaSuccess) { rc = fail_alloc(); break; }
-        for (int l = 0; l < NL && rc == MPQR_OK; ++l) {
-            Lane& L = lanes[l];
-            if (NL > 1 && cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking) != cudaSuccess) { set_error("tsqr: stream creation failed"); rc = MPQR_ECUDA; break; }
-            if (NL == 1) L.s = st;
-            if (cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming) != cudaSuccess) { set_error("tsqr: event creation failed"); rc = MPQR_ECUDA; break; }
-            if (cudaMalloc(&L.work, (size_t)(hrows + 1) * ldp * sizeof(float)) != cudaSuccess) { rc = fail_alloc(); break; }
-            if (dQ && nblk > 1 && cudaMalloc(&L.qblk, (size_t)hrows * ldp * sizeof(float)) != cudaSuccess) { rc = fail_alloc(); break; }
-            if ((rc = mpqr_create(&L.hb, (int)hrows, n, r, 0, flags))) break;
-            if (hlast != hrows && (int)((nblk - 1) % NL) == l && (rc = mpqr_create(&L.hl, (int)hlast, n, r, 0, flags))) break;
-        }
-        if (rc != MPQR_OK) break;
-        if (NL > 1) {
-            if (cudaEventRecord(ev_start, st) != cudaSuccess) { set_error("tsqr: event record failed"); rc = MPQR_ECUDA; break; }
-            for (auto& L : lanes) cudaStreamWaitEvent(L.s, ev_start, 0);
-        }
-        // Pass 1: every block is factored once; R_b goes to the stack.  A lane's buffers are reused block after
-        // block, so the block's thin Q_b (rows x n) is parked in the OUTPUT rows until the tree is known.
-        for (long b = 0; b < nblk && rc == MPQR_OK; ++b) {
-            Lane& L = lanes[b % NL];
-            SmBudget sb(budget);
-            const long rows = (b == nblk - 1) ? hlast : hrows;
-            mpqr_handle* h = (rows == hrows) ? L.hb : L.hl;
-            copy_block_kernel<<<grid_of(rows * n), 256, 0, L.s>>>(dA + (size_t)b * hrows * lda, lda, L.work, ldp, rows, n);
-            if ((rc = mpqr_factor_device(h, L.work, ldp, L.s))) break;
-            if (nblk == 1) {
-                extract_r_kernel<<<grid_of((long)n * n), 256, 0, L.s>>>(L.work, ldp, dR, ldr, n);
-                if (dQ) rc = form_thin_q(h, dQ, ldq, L.s);
-            } else {
-                extract_r_kernel<<<grid_of((long)n * n), 256, 0, L.s>>>(L.work, ldp, rstack + (size_t)b * n * ldp, ldp, n);
-                if (dQ) rc = form_thin_q(h, dQ + (size_t)b * hrows * ldq, ldq, L.s);
-            }
-        }
-        if (rc != MPQR_OK || nblk == 1) break;
-        // join the lanes, factor the stacked R's ((nblk*n) x n) on the caller's stream — recursion handles a tall stack
-        if (NL > 1)
-            for (auto& L : lanes) { cudaEventRecord(L.done, L.s); cudaStreamWaitEvent(st, L.done, 0); }
-        if ((rc = mpqr_tsqr_device(rstack, ldp, nblk * (long)n, n, dQ ? qstack : nullptr, ldp, dR, ldr, st))) break;
-        if (!dQ) break;
-        // Pass 2: thin Q rows of block b = Q_b[:, :n] * Qstack[b*n:(b+1)*n, :]   (Q_b parked in the output rows)
-        if (NL > 1) {
-            cudaEventRecord(ev_tree, st);
-            for (auto& L : lanes) cudaStreamWaitEvent(L.s, ev_tree, 0);
-        }
-        for (long b = 0; b < nblk && rc == MPQR_OK; ++b) {
-            Lane& L = lanes[b % NL];
-            SmBudget sb(budget);
-            const long rows = (b == nblk - 1) ? hlast : hrows;
-            float* Qb = dQ + (size_t)b * hrows * ldq;
-            copy_block_kernel<<<grid_of(rows * n), 256, 0, L.s>>>(Qb, ldq, L.qblk, ldp, rows, n);
-            rc = sgemm_nn_store(L.qblk, ldp, qstack + (size_t)b * n * ldp, ldp, Qb, ldq, (int)rows, n, n, L.s);
-        }
-        if (NL > 1)
-            for (auto& L : lanes) { cudaEventRecord(L.done, L.s); cudaStreamWaitEvent(st, L.done, 0); }
-    } while (0);
+    Plan* P = nullptr;
+    MPQR_TRY(acquire_plan(m, n, dQ != nullptr, &P));
+    int rc = run_plan(P, dA, lda, dQ, ldq, dR, ldr, st);
+    // the plan's buffers are reused by the next call: the call is synchronous with respect to the host
     cudaError_t e = cudaStreamSynchronize(st);
-    for (auto& L : lanes)
-        if (NL > 1 && L.s) { cudaError_t e2 = cudaStreamSynchronize(L.s); if (e == cudaSuccess) e = e2; }
+    for (auto& L : P->lanes) { cudaError_t e2 = cudaStreamSynchronize(L.s); if (e == cudaSuccess) e = e2; }
+    release_plan(P);
     if (rc == MPQR_OK && e != cudaSuccess) { set_error("tsqr: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; }
-    for (auto& L : lanes) {
-        if (L.hb) mpqr_destroy(L.hb);
-        if (L.hl) mpqr_destroy(L.hl);
-        cudaFree(L.work); cudaFree(L.qblk);
-        if (L.done) cudaEventDestroy(L.done);
-        if (NL > 1 && L.s) cudaStreamDestroy(L.s);
-    }
-    if (ev_start) cudaEventDestroy(ev_start);
-    if (ev_tree) cudaEventDestroy(ev_tree);
-    cudaFree(rstack); cudaFree(qstack);
     return rc;
+}
+
+extern "C" int mpqr_tsqr_release_cache(void) {
+    std::lock_guard<std::mutex> lk(g_plans_mu);
+    for (size_t i = 0; i < g_plans.size();) {
+        if (!g_plans[i]->busy) { delete g_plans[i]; g_plans.erase(g_plans.begin() + i); }
+        else ++i;
+    }
+    return MPQR_OK;
 }
