@@ -225,7 +225,7 @@ int mpqr_tsqr_release_cache(void);
 /* Multi-GPU TSQR (BASELINE config 5): 1-D ROW-block layout, one process per GPU, rank p holds
  * m_local rows of A (row-major, device).  Local TSQR, ONE ncclAllGather of the n x n R factors, the
  * (nranks*n) x n stack factored redundantly on every rank (ts_qr's tree, python/ca_qr.py:36-41, with nranks
- * leaves).  dR (n x n) is identical on all ranks; dQ_local (m_local x n, may be NULL) receives this rank's
+ * leaves); rank 0's R is then broadcast, so dR (n x n) is identical on all ranks.  dQ_local (m_local x n, may be NULL) receives this rank's
  * rows of the thin Q.  The handle only owns the NCCL communicator (destroy with mpqr_destroy). */
 int mpqr_mg_tsqr_create(mpqr_handle** out, int rank, int nranks, const void* uid);
 int mpqr_mg_tsqr_device(mpqr_handle* h, const float* dA_local, long lda, long m_local, int n, float* dQ_local,

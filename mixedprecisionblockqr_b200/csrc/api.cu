@@ -217,23 +217,31 @@ void overlap_init(mpqr_handle* h, const int* sizes, int nsizes) {
         CUgreenCtx gP = nullptr, gU = nullptr;
         if (g->GreenCtxCreate(&gP, dP, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) continue;
         if (g->GreenCtxCreate(&gU, dU, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { g->GreenCtxDestroy(gP); continue; }
-        CUstream sP = nullptr, sP2 = nullptr, sU = nullptr;
+        CUstream sP = nullptr, sP2 = nullptr, sP3 = nullptr, sP4 = nullptr, sU = nullptr;
         if (g->GreenCtxStreamCreate(&sP, gP, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS ||
             g->GreenCtxStreamCreate(&sP2, gP, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
+            g->GreenCtxStreamCreate(&sP3, gP, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS ||
+            g->GreenCtxStreamCreate(&sP4, gP, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
             g->GreenCtxStreamCreate(&sU, gU, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
             if (sP) cudaStreamDestroy((cudaStream_t)sP);
             if (sP2) cudaStreamDestroy((cudaStream_t)sP2);
+            if (sP3) cudaStreamDestroy((cudaStream_t)sP3);
+            if (sP4) cudaStreamDestroy((cudaStream_t)sP4);
             g->GreenCtxDestroy(gP); g->GreenCtxDestroy(gU);
             continue;
         }
         mpqr_handle::Overlap::Pair pr;
-        pr.gP = gP; pr.gU = gU; pr.sP = (cudaStream_t)sP; pr.sP2 = (cudaStream_t)sP2; pr.sU = (cudaStream_t)sU;
+        pr.gP = gP; pr.gU = gU; pr.sP = (cudaStream_t)sP; pr.sP2 = (cudaStream_t)sP2; pr.sP3 = (cudaStream_t)sP3; pr.sP4 = (cudaStream_t)sP4; pr.sU = (cudaStream_t)sU;
         pr.nsmP = (int)grp[0].sm.smCount; pr.nsmU = (int)rem.sm.smCount;
         o.pairs.push_back(pr);
     }
     if (o.pairs.empty()) return;
     if (cudaStreamCreateWithFlags(&o.sF, cudaStreamNonBlocking) != cudaSuccess) { o.sF = nullptr; }
     if (cudaStreamCreateWithFlags(&o.sF2, cudaStreamNonBlocking) != cudaSuccess) { o.sF2 = nullptr; }
+    if (cudaStreamCreateWithFlags(&o.sF3, cudaStreamNonBlocking) != cudaSuccess) { o.sF3 = nullptr; }
+    if (cudaStreamCreateWithFlags(&o.sF4, cudaStreamNonBlocking) != cudaSuccess) { o.sF4 = nullptr; }
+    o.ev_la.resize(kPanelLaEvents);
+    for (auto& e : o.ev_la) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     o.ev_rest.resize(2 * (ceil_div(h->nb, h->r) + 1));
     for (auto& e : o.ev_rest) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     const int nblk = ceil_div(h->kmax, h->nb);
@@ -268,11 +276,16 @@ void overlap_destroy(mpqr_handle* h) {
     for (auto e : o.ev_acc) cudaEventDestroy(e);
     if (o.sF) cudaStreamDestroy(o.sF);
     if (o.sF2) cudaStreamDestroy(o.sF2);
+    if (o.sF3) cudaStreamDestroy(o.sF3);
+    if (o.sF4) cudaStreamDestroy(o.sF4);
     for (auto e : o.ev_rest) cudaEventDestroy(e);
+    for (auto e : o.ev_la) cudaEventDestroy(e);
     const GreenApi* g = green_api();
     for (auto& pr : o.pairs) {
         if (pr.sP) cudaStreamDestroy(pr.sP);
         if (pr.sP2) cudaStreamDestroy(pr.sP2);
+        if (pr.sP3) cudaStreamDestroy(pr.sP3);
+        if (pr.sP4) cudaStreamDestroy(pr.sP4);
         if (pr.sU) cudaStreamDestroy(pr.sU);
         if (g->ok) { g->GreenCtxDestroy((CUgreenCtx)pr.gP); g->GreenCtxDestroy((CUgreenCtx)pr.gU); }
     }
@@ -385,9 +398,11 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     const char* fix = getenv("MPQR_PANEL_SMS");
     const int fixed_sms = fix ? atoi(fix) : 0;
     // interval b-1 decided where block_phase(b) runs; block 0 runs on the whole device
-    cudaStream_t s_bp = o.sF, s_bp2 = o.sF2, s_uprev = nullptr;
+    cudaStream_t s_bp = o.sF, s_bp2 = o.sF2, s_bp3 = o.sF3, s_bp4 = o.sF4, s_uprev = nullptr;
     int nsm_bp = o.nsm_full, nsm_uprev = 0;
     const bool inblock_la = !getenv("MPQR_NO_INBLOCK_LA") && (h->r % 8) == 0;
+    // register-block look-ahead inside the panels (needs whole 32-column groups and the register-block kernels)
+    const bool rb_la = inblock_la && !getenv("MPQR_NO_RBLA") && (h->r % 32) == 0 && h->r >= 64 && o.sF3 != nullptr && o.sF4 != nullptr;
     MPQR_CUDA(cudaStreamWaitEvent(s_bp, o.ev_start, 0));
     for (int c0 = 0, b = 0; c0 < h->kmax; c0 += nb, ++b) {
         const int c1 = (c0 + nb < h->kmax) ? c0 + nb : h->kmax;
@@ -396,6 +411,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         // second stream of the same partition, next to the next panel's register-block kernels.
         if (inblock_la) {
             c.rest_stream = s_bp2; c.rest_S32 = h->S32r; c.rest_S16 = h->S16r; c.rest_ev = o.ev_rest.data();
+            if (rb_la && s_bp3 && s_bp4) { c.side_stream = s_bp3; c.side2_stream = s_bp4; c.la_ev = o.ev_la.data(); }
             // (the previous block's last rest event completed before fn(b-1), which this block waits for)
         }
         // WY accumulation of this block (only the far update needs it): on the update partition of the previous
@@ -460,6 +476,8 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         // where the next block_phase runs
         s_bp = best >= 0 ? o.pairs[best].sP : o.sF;
         s_bp2 = best >= 0 ? o.pairs[best].sP2 : o.sF2;
+        s_bp3 = best >= 0 ? o.pairs[best].sP3 : o.sF3;
+        s_bp4 = best >= 0 ? o.pairs[best].sP4 : o.sF4;
         nsm_bp = best >= 0 ? o.pairs[best].nsmP : o.nsm_full;
         s_uprev = best >= 0 ? s_u : nullptr;
         nsm_uprev = nsm_u;
@@ -496,6 +514,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
     float* S32 = c.S32 ? c.S32 : h->S32;
     void* S16 = c.S16 ? c.S16 : h->S16;
     int last_rest = -1;
+    bool la_prev = false;
     for (int lam = c0; lam < c1; lam += r) {
         const int p = lam / r;
         const int pw = (lam + r < c1) ? r : c1 - lam;
@@ -509,8 +528,25 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         a.T = h->T + (size_t)p * r * r; a.ldt = r;
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
-        PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         const int nin = c1 - tau;  // in-block trailing columns
+        // register-block look-ahead: the panel also updates the next panel's first 32 columns (FP32, block by block),
+        // Gram/T/W and the tensor-core in-block updates leave the panel stream
+        bool la = false;
+        if (c.side_stream && c.side2_stream && c.rest_stream && c.la_ev) {
+            a.side = c.side_stream; a.side2 = c.side2_stream; a.gtw_stream = c.rest_stream; a.la_ev = c.la_ev;
+            a.next_cols = nin >= r ? r : 0;   // the whole next panel, when there is a full one in this outer block
+            a.ev_next_ready = (la_prev && jc >= r) ? c.rest_ev[2 * (jc / r - 1) + 1] : nullptr;  // N(p-1): next panel's columns
+            la = panel_lookahead_ok(a) && (nin == 0 || nin >= r);
+            if (!la) { a.side = a.side2 = a.gtw_stream = nullptr; a.la_ev = nullptr; a.next_cols = 0; a.ev_next_ready = nullptr; }
+        }
+        if (la != la_prev && lam > c0) {
+            // switching flows inside a block: everything issued so far must be complete for the other flow's assumptions
+            if (last_rest >= 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[last_rest], 0));
+            if (la_prev) { MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[16], 0)); }
+        }
+        // this panel's columns received the earlier panels' updates through N(q), q <= p-2 (panel p-1 reached them in FP32)
+        if (la && la_prev && jc >= 2 * r) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (jc / r - 2) + 1], 0));
+        PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         const int acol_tau = c.acol0 + jc + pw;
         // in-block update of the columns [tau + ofs, tau + ofs + nc):  S = W_p^T A ; A -= Y_p S (+ shadow)
         const void* Wpp = (char*)c.W16 + ((size_t)jc * c.ldw + jc) * 2;   // the panel's own W / Y, rows lam..
@@ -526,7 +562,18 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             return MPQR_OK;
         };
         const int pidx = jc / r;
-        const bool split = c.rest_stream && nin > r && (r % 8) == 0;
+        if (la) {
+            cudaStream_t sg = c.rest_stream;  // (Gram/T/W of this panel were issued on sg by launch_panel)
+            const int nc0 = a.next_cols;      // the next panel: updated in FP32 by this panel's blocks themselves
+            if (nin - nc0 > 0) MPQR_TRY(inblock(nc0, nin - nc0, c.rest_S32, c.rest_S16, end_is_matrix_end, sg));
+            MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx], sg));
+            MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], sg));
+            last_rest = 2 * pidx + 1;
+        }
+        la_prev = la;
+        const bool split = !la && c.rest_stream && nin > r && (r % 8) == 0;
+        if (la) { /* in-block updates done above */ } else
+        {
         if (c.rest_stream && nin > 0) last_rest = 2 * pidx + 1;
         if (nin > 0 && !split) {
             if (c.rest_stream && pidx > 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (pidx - 1) + 1], 0));
@@ -542,6 +589,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             MPQR_TRY(inblock(r, nin - r, c.rest_S32, c.rest_S16, end_is_matrix_end, c.rest_stream));
             MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], c.rest_stream));
         }
+        }
         if (jc > 0) {
             // WY accumulation: X = Y_prev^T W_p ; W_p -= W_prev X   (rows c0..m)
             const void* Wp = (char*)c.W16 + (size_t)jc * 2;
@@ -553,7 +601,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
                 cudaEvent_t ev = c.acc_ev[jc / r];
                 MPQR_CUDA(cudaEventRecord(ev, st_panel));
                 MPQR_CUDA(cudaStreamWaitEvent(c.acc_stream, ev, 0));
-                if (c.rest_stream && nin > 0) MPQR_CUDA(cudaStreamWaitEvent(c.acc_stream, c.rest_ev[2 * pidx + 1], 0));
+                if (c.rest_stream && (nin > 0 || la)) MPQR_CUDA(cudaStreamWaitEvent(c.acc_stream, c.rest_ev[2 * pidx + 1], 0));
                 aS32 = c.acc_S32; aS16 = c.acc_S16;
             }
             {
@@ -570,6 +618,12 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
     }
     // everything of this block is complete when the panel stream is (events of one stream complete in order)
     if (c.rest_stream && last_rest >= 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[last_rest], 0));
+    if (c.side_stream && c.la_ev) {  // (every side update was already consumed by a waiting panel-stream kernel; belt and braces)
+        MPQR_CUDA(cudaEventRecord(c.la_ev[kPanelLaEvents - 1], c.side_stream));
+        MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[kPanelLaEvents - 1], 0));
+        MPQR_CUDA(cudaEventRecord(c.la_ev[kPanelLaEvents - 1], c.side2_stream));
+        MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[kPanelLaEvents - 1], 0));
+    }
     return MPQR_OK;
 }
 
@@ -660,12 +714,13 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
             if ((rc = dev_alloc(h, (void**)&h->Wblk32, (size_t)m * h->ldwb * sizeof(float)))) break;
             h->lds16 = h->lds32;
             if ((rc = dev_alloc(h, &h->S16, (size_t)h->sk * h->lds16 * 2))) break;
-            // Look-ahead on two green-context SM partitions: on by default for problems with >= 12 outer
+            // Look-ahead on two green-context SM partitions: on by default for problems with >= 4 outer
             // blocks (measured on B200, 32768^2: 181 ms serial, 159 ms with an 80-SM panel partition; a
             // small partition starves the panel chain's device-wide kernels: 280 ms at 16 SMs).
             const char* env = getenv("MPQR_OVERLAP");
             const int nblk_outer = ceil_div(h->kmax, h->nb);
-            const bool want_overlap = env ? (env[0] == '1' && nblk_outer >= 3) : (nblk_outer >= 12);
+            // (round 1, with the register-block look-ahead: 8192^2 19.3 -> 18.2 ms, 4096 x 16384 10.7 -> 9.4 ms, so from 4 blocks on)
+            const bool want_overlap = env ? (env[0] == '1' && nblk_outer >= 3) : (nblk_outer >= 4);
             if (want_overlap) {
                 const int sizes[5] = {32, 48, 64, 80, 112};
                 overlap_init(h, sizes, 5);

@@ -245,7 +245,7 @@ int mpqr_mg_factor_device(mpqr_handle* h, float* dA, long lda, void* stream) {
 // ---------------------------------------------------------------------------------------- multi-GPU TSQR
 // 1-D ROW-block layout, rank p owns m_local rows.  Local TSQR -> R_p (n x n) and thin
 // Q_p; ncclAllGather of the R_p (n*n*4 bytes per rank, the ONLY exchange); every rank factors the same
-// stacked (P*n) x n matrix (bitwise identical inputs and code => identical R everywhere) and multiplies its
+// stacked (P*n) x n matrix, rank 0's R is broadcast (the copies agree only to rounding: atomics), and each rank multiplies its
 // Q_p by its own n x n slice of the stack's Q.  ts_qr's tree (python/ca_qr.py:36-41) with P leaves.
 int mpqr_mg_tsqr_create(mpqr_handle** out, int rank, int nranks, const void* uid) {
     if (!out || !uid || nranks < 1 || rank < 0 || rank >= nranks) {
@@ -300,6 +300,18 @@ int mpqr_mg_tsqr_device(mpqr_handle* h, const float* dA_local, long lda, long m_
         if (nr != 0) { set_error("ncclAllGather failed: %d", nr); rc = MPQR_ENCCL; break; }
         // every rank factors the same (P n) x n stack
         if ((rc = mpqr_tsqr_device(rstack, n, (long)P * n, n, dQ_local ? qstack : nullptr, n, dR, ldr, st))) break;
+        // The stack is factored redundantly, but the in-panel reductions use atomics, so the copies agree only to
+        // rounding: rank 0's R is made THE R on every rank (256 KB); each rank's Q rows stay consistent with its
+        // own copy to the same rounding level.
+        const size_t rowb = (size_t)n * sizeof(float);
+        if (cudaMemcpy2DAsync(rloc, rowb, dR, (size_t)ldr * sizeof(float), rowb, n, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            set_error("mpqr_mg_tsqr_device: copy failed"); rc = MPQR_ECUDA; break;
+        }
+        nr = g->api->Broadcast(rloc, rloc, nn * sizeof(float), kNcclChar, 0, g->comm, st);
+        if (nr != 0) { set_error("ncclBroadcast failed: %d", nr); rc = MPQR_ENCCL; break; }
+        if (cudaMemcpy2DAsync(dR, (size_t)ldr * sizeof(float), rloc, rowb, rowb, n, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            set_error("mpqr_mg_tsqr_device: copy failed"); rc = MPQR_ECUDA; break;
+        }
         if (dQ_local) {
             rc = sgemm_nn_store(qtmp, n, qstack + (size_t)g->rank * nn, n, dQ_local, ldq, (int)m_local, n, n, st);
         }

@@ -1689,7 +1689,7 @@ int launch_tinv(const float* G, long ldg, int pw, float* T32, int ldt, void* T16
 
 template <int B>
 int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, float* Sfin,
-              int num_sms, cudaStream_t st, long* launches, const ProfHook* prof, bool pair = false) {
+              int num_sms, cudaStream_t st, long* launches, const ProfHook* prof, bool pair = false, bool pdl_first = true) {
     static bool attr = false;
     // one wave of CTAs over the SMs this stream may use (up to 512 rows = 32 KB of staged Y per CTA);
     // taller blocks take k balanced waves
@@ -1721,8 +1721,12 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
         cfg.dynamicSmemBytes = s4_floats * sizeof(float);
         unsigned* counter = reinterpret_cast<unsigned*>(Srep + (size_t)NREP * RMAX * SLD);
         float* Cacc = pair ? Srep + (size_t)NREP * RMAX * SLD + 4 : nullptr;
+        // pdl_first = false: the S kernel must not become resident (and hold its SMs idle) while the register-block
+        // kernel before it is still running: those SMs belong to the side stream's updates during that time
+        if (!pdl_first) cfg.numAttrs = 0;
         MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_s4_kernel<B>, Yj, ldy, (const float*)Arest, lda, D, ncols, Srep, counter, Tj, Sfin, rows,
                                      ysm_floats, Cacc));
+        cfg.numAttrs = 1;
         if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st, 2.0 * D * ncols * B, 4.0 * D * (2 * ncols + B)); }
         cfg.dynamicSmemBytes = (size_t)rows * B * sizeof(float);
         MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_u4_kernel<B>, Yj, ldy, Arest, lda, D, ncols, pair ? (const float*)Sfin : (const float*)Srep, pair ? 1 : 2, rows));
@@ -1744,6 +1748,22 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
 size_t panel_ws_bytes(long max_rows) {
     return ((size_t)max_rows * (RMAX + 32) + (size_t)(NREP + 1) * RMAX * SLD + 4 + 256 + 2 * (size_t)RMAX * RMAX) * sizeof(float) +
            (size_t)RMAX * RMAX * 2 + 256;
+}
+
+bool panel_lookahead_ok(const PanelArgs& a) {
+    if (!a.side || !a.side2 || !a.la_ev || !a.ws) return false;
+    const int D = a.m - a.lam, pw = a.pw;
+    if (pw <= 32 || (pw & 31) || a.next_cols < 0 || a.next_cols > 128 || (a.next_cols & 31)) return false;
+    // Measured on B200 (32768^2 and 16384^2, r = 128): with 32-column register blocks (D <= 16384, 4 blocks per panel)
+    // the look-ahead shortens the chain by ~9 %; with 16-column blocks (taller panels, 8 blocks per panel) the FP32
+    // block-by-block update of the next panel is 3x the in-panel update work and the side streams cannot keep up
+    // (162 ms against 146 ms), so tall panels keep the classic flow.  MPQR_RBLA_TALL=1 overrides (experiments).
+    static const bool tall = getenv("MPQR_RBLA_TALL") != nullptr;
+    if ((long)D > (tall ? block_capacity(16) : block_capacity(32)) || D < 2 * pw || a.ws_rows < 256) return false;
+    if ((a.lda & 3) || (reinterpret_cast<uintptr_t>(a.A + (size_t)a.lam * a.lda + a.acol) & 15)) return false;  // vectorised S/U only
+    if (a.force_b || a.force_cs || a.force_rpt || a.prof) return false;
+    const char* dbl_env = getenv("MPQR_DBLOCK");
+    return !(dbl_env && dbl_env[0] == '1');
 }
 
 // PanelArgs output pointers address (row blk_row0, first panel column); zr = lam - blk_row0 rows
@@ -1808,7 +1828,73 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     // (its in-panel update needs the vectorised kernels: 16-byte aligned rows and widths that are multiples of 4)
     const bool use_dblock = (B == 16) && dbl_env && dbl_env[0] == '1' && ((a.lda & 3) == 0) && ((pw & 3) == 0) &&
                             ((reinterpret_cast<uintptr_t>(Ablk) & 15) == 0);
-    for (int j0 = 0; j0 < pw;) {
+    const bool la = panel_lookahead_ok(a);
+    static const bool la_pdl = getenv("MPQR_RBLA_PDL") != nullptr;  // experiment: keep PDL on the near S kernel
+    cudaStream_t gtw_st = (la && a.gtw_stream) ? a.gtw_stream : stream;
+    int la_last = -1;  // index of the last register block (its "factored" event orders Gram/T/W)
+    if (la) {
+        // Register-block look-ahead.  Block jb: K (register-block kernel) on `stream`, then on `stream` only the update of
+        // the next B columns ("near": the next block; after the last block the next panel's first block).  Block jb's
+        // update of the other columns runs next to the following K's: rest of this panel on `side` (far A), the next
+        // panel's columns on `side2` (far B).  near(jb) needs far A(jb-1) (event [2(jb-1)+1]); the near update after the
+        // last block and everything of the next panel that touches its columns need far B: event [16] (side2 is one
+        // stream, so its last record covers all earlier far B's).  T of block jb lives in its own slot: the side streams
+        // still read T_jb while K(jb+1) writes T_jb+1.  S replicas: near 0-1 (cleared by K), far A 2-3, far B 4-5.
+        float* SrepA = w.Srep + (size_t)2 * RMAX * SLD;
+        float* SrepB = w.Srep + (size_t)4 * RMAX * SLD;
+        const size_t srep_bytes = (size_t)2 * RMAX * SLD * sizeof(float);
+        const int nblocks = pw / B;
+        bool prev_farA = false, b_started = false;
+        auto su = [&](int Bw, const float* Tj, const float* Yj, float* Ar, int Dj, int nc, float* Srep, cudaStream_t s2, bool pdl_first) -> int {
+            if (Bw == 32) return launch_su<32>(Tj, Yj, ldyp, Ar, a.lda, Dj, nc, Srep, w.Sfin, sm_count(di), s2, launches, nullptr, false, pdl_first);
+            return launch_su<16>(Tj, Yj, ldyp, Ar, a.lda, Dj, nc, Srep, w.Sfin, sm_count(di), s2, launches, nullptr, false, pdl_first);
+        };
+        for (int jb = 0; jb < nblocks; ++jb) {
+            const int j0 = jb * B, Dj = D - j0, bw = B;
+            if (!pick_shape(B, Dj, 0, 0, &rpt, &cs)) { set_error("panel: sizing error D=%d", Dj); return MPQR_EINVAL; }
+            const bool last = jb == nblocks - 1;
+            const int nrest = pw - (j0 + bw);                 // columns of this panel right of the block
+            const int nnear = last ? (a.next_cols > 0 ? B : 0) : B;
+            const int nfarA = last ? 0 : nrest - B;           // rest of the panel beyond the next block
+            const int nfarB = last ? a.next_cols - nnear : a.next_cols;
+            float* Tslot = w.Wj + (size_t)jb * 32 * 32;
+            BlockArgs b{};
+            b.A = Ablk + (size_t)j0 * a.lda + j0; b.lda = a.lda; b.D = Dj; b.bw = bw;
+            b.Y32 = {Yp + (size_t)j0 * ldyp + j0, ldyp, j0 + (Y32l ? zr : 0)};
+            if (nnear + nfarA + nfarB > 0) { b.T = Tslot; b.ldt = B; b.zero_buf = w.Srep; b.zero_n = 2 * RMAX * SLD; }
+            if (Y16l) b.Y16 = {Y16l + ((size_t)j0 * a.ldy16 + j0) * 2, a.ldy16, j0 + zr};
+            b.bf16 = a.bf16; b.dbg = a.dbg;
+            MPQR_TRY(launch_block(B, b, rpt, cs, stream));
+            if (launches) *launches += 1;
+            MPQR_CUDA(cudaEventRecord(a.la_ev[2 * jb], stream));
+            la_last = jb;
+            float* Arest = b.A + bw;  // first column right of the block
+            if (nnear > 0) {
+                if (prev_farA) MPQR_CUDA(cudaStreamWaitEvent(stream, a.la_ev[2 * (jb - 1) + 1], 0));
+                // the previous panel's far B's wrote this panel's columns; the last block's near columns belong to far B
+                if (jb == 0 || last) MPQR_CUDA(cudaStreamWaitEvent(stream, a.la_ev[16], 0));
+                MPQR_TRY(su(B, Tslot, b.Y32.p, Arest, Dj, nnear, w.Srep, stream, la_pdl));
+            }
+            if (nfarA > 0) {
+                MPQR_CUDA(cudaStreamWaitEvent(a.side, a.la_ev[2 * jb], 0));
+                if (jb == 0) MPQR_CUDA(cudaStreamWaitEvent(a.side, a.la_ev[16], 0));
+                MPQR_CUDA(cudaMemsetAsync(SrepA, 0, srep_bytes, a.side));
+                MPQR_TRY(su(B, Tslot, b.Y32.p, Arest + B, Dj, nfarA, SrepA, a.side, true));
+                MPQR_CUDA(cudaEventRecord(a.la_ev[2 * jb + 1], a.side));
+            }
+            prev_farA = nfarA > 0;
+            if (nfarB > 0) {
+                MPQR_CUDA(cudaStreamWaitEvent(a.side2, a.la_ev[2 * jb], 0));
+                if (!b_started && a.ev_next_ready) MPQR_CUDA(cudaStreamWaitEvent(a.side2, a.ev_next_ready, 0));
+                b_started = true;
+                MPQR_CUDA(cudaMemsetAsync(SrepB, 0, srep_bytes, a.side2));
+                MPQR_TRY(su(B, Tslot, b.Y32.p, Arest + nrest + (last ? nnear : 0), Dj, nfarB, SrepB, a.side2, true));
+                MPQR_CUDA(cudaEventRecord(a.la_ev[16], a.side2));
+            }
+        }
+        if (gtw_st != stream && la_last >= 0) MPQR_CUDA(cudaStreamWaitEvent(gtw_st, a.la_ev[2 * la_last], 0));
+    }
+    for (int j0 = 0; !la && j0 < pw;) {
         const int Dj = D - j0;
         if (Dj <= 0) break;
         const bool dbl = use_dblock && (pw - j0 > B) && (Dj > 2 * B);
@@ -1853,10 +1939,10 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     if (a.prof) a.prof->begin(a.prof->ctx, 6, stream, 4.0 * D * pw * pw, 10.0 * D * pw);
     if (mixed) {
         // Gram and W on tensor cores, from the 16-bit Y the trailing update uses
-        MPQR_TRY(tc_gemm_tn(Y16l, a.ldy16, Y16l, a.ldy16, w.G, RMAX, pw, pw, D, a.bf16, 1, stream, launches));
-        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, w.T16, RMAX, a.bf16, tsmem, stream));
+        MPQR_TRY(tc_gemm_tn(Y16l, a.ldy16, Y16l, a.ldy16, w.G, RMAX, pw, pw, D, a.bf16, 1, gtw_st, launches));
+        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, w.T16, RMAX, a.bf16, tsmem, gtw_st));
         if (launches) *launches += 1;
-        MPQR_TRY(tc_gemm_nn_store(a.Y16, a.ldy16, w.T16, RMAX, a.W32, a.ld32, a.W16, a.ldw16, Dz, pw, pw, a.bf16, stream, launches));
+        MPQR_TRY(tc_gemm_nn_store(a.Y16, a.ldy16, w.T16, RMAX, a.W32, a.ld32, a.W16, a.ldw16, Dz, pw, pw, a.bf16, gtw_st, launches));
     } else {
         MPQR_TRY(sgemm_tn(Yp, ldyp, Yp, ldyp, w.G, RMAX, pw, pw, D, stream, launches));
         MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, nullptr, 0, 0, tsmem, stream));

@@ -38,7 +38,9 @@ def main():
         Af = np.concatenate([p[0] for p in parts]).astype(np.float64)
         Qf = np.concatenate([p[1] for p in parts]).astype(np.float64)
         Rr = parts[0][2].astype(np.float64)
-        same = all(np.array_equal(parts[0][2], p[2]) and np.array_equal(parts[0][2], p[3]) for p in parts)
+        # rank 0's R is broadcast: identical everywhere; a second call agrees to rounding (atomics in the reductions)
+        same = all(np.array_equal(parts[0][2], p[2]) for p in parts) and all(
+            np.abs(p[3] - parts[0][2]).max() <= 2e-6 * np.abs(parts[0][2]).max() for p in parts)
         _, Rl = np.linalg.qr(Af)
         d = np.abs(np.abs(Rr) - np.abs(Rl)).max() / np.abs(Rl).max()
         be = np.linalg.norm(Af - Qf @ Rr) / np.linalg.norm(Af)

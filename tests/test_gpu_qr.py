@@ -112,3 +112,35 @@ def test_reference_symbol_shim_matches_oracle():
         assert oracle.backward_error(A, R, Q) <= m * 2.0 ** -bits
         assert oracle.q_error_max(Q) <= m * 2.0 ** -bits
         assert np.abs(np.abs(R) - np.abs(oracle.strip_R(Pref))).max() <= tol * np.abs(Pref).max()
+
+
+@pytest.mark.parametrize("m,n,r,nb", [(1536, 1536, 64, 256), (2048, 2048, 128, 512), (2200, 1600, 64, 256), (1024, 3072, 128, 256),
+                                      (1800, 1536, 96, 384)])
+@pytest.mark.parametrize("rbla", [True, False])
+def test_lookahead_driver_vs_oracle(m, n, r, nb, rbla, monkeypatch):
+    """The look-ahead driver (green-context partitions, in-block and register-block look-ahead; normally only on from
+    12 outer blocks) forced on for small shapes: same criteria as the serial driver, against the oracle."""
+    import torch
+    monkeypatch.setenv("MPQR_OVERLAP", "1")
+    if not rbla:
+        monkeypatch.setenv("MPQR_NO_RBLA", "1")
+    A = oracle.uniform_matrix(m, n, 31 * m + n)
+    lda = (n + 7) // 8 * 8
+    dA = torch.zeros(m + 1, lda, device="cuda")
+    dA[:m, :n] = torch.from_numpy(A).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    plan = pkg.BlockQR(m, n, r, nb=nb, precision="fp16")
+    assert plan.nb == nb and plan.r == r
+    for _ in range(2):          # twice: event / stream reuse across calls
+        dA[:m, :n] = torch.from_numpy(A).cuda()
+        dA[m].zero_()
+        plan.factor(dA.data_ptr(), lda, st)
+        torch.cuda.synchronize()
+        P = np.ascontiguousarray(dA.cpu().numpy()[:, :n])
+        be = oracle.backward_error_packed(A, P)
+        assert be <= 12 * 2.0 ** -11, be
+        Pref, _ = oracle.block_qr(A, r, want_q=False)
+        Rref = oracle.strip_R(Pref)
+        dr = np.abs(np.abs(oracle.strip_R(P)) - np.abs(Rref)).max() / np.abs(Rref).max()
+        assert dr <= 60 * 2.0 ** -11, dr
+    plan.close()
