@@ -65,6 +65,11 @@ const char* mpqr_version(void);
  * (the packed result does not depend on the grouping beyond rounding).
  * ------------------------------------------------------------------------------------- */
 int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned flags);
+/* One difference from the reference's "leaves nothing resident" (Cuda/qr.cu:1221-1226 frees everything): the plan of
+ * the LAST host call (workspaces + device copies of A and Q, ~12 GB at 32768^2) is kept for the next call with the
+ * same shape, because allocating and freeing it costs more than the factorisation.  mpqr_release_cache() frees it
+ * (and the TSQR plans); the environment variable MPQR_NO_HOST_CACHE=1 restores allocate-and-free per call. */
+int mpqr_release_cache(void);
 
 /* ---------------------------------------------------------------------------------------
  * Device-resident API (what bench.py times as `value`): plan once, factor many times.

@@ -34,7 +34,7 @@ ABI_SYMBOLS = (
     "mpqr_tsqr_device", "mpqr_solve_device", "mpqr_read_euroc_jacobian", "mpqr_free_host",
     "mpqr_strip_r_device", "mpqr_backward_error_device", "mpqr_q_error_device", "mpqr_lower_trapezoid_error_device",
     "mpqr_frobenius_norm_device", "mpqr_r_agreement_device", "mpqr_qr_flops_per_second", "mpqr_write_results_to_log",
-    "mpqr_mg_tsqr_create", "mpqr_mg_tsqr_device", "mpqr_tsqr_release_cache",
+    "mpqr_mg_tsqr_create", "mpqr_mg_tsqr_device", "mpqr_tsqr_release_cache", "mpqr_release_cache",
 )
 
 

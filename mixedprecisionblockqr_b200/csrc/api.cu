@@ -22,6 +22,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
+#include <mutex>
+
 #include "internal.h"
 
 namespace mpqr {
@@ -871,22 +874,78 @@ int mpqr_get_profile(mpqr_handle* h, int cls, double* ms_total, long* launches, 
     return MPQR_OK;
 }
 
+// The host drop-in keeps its plan (handle + device copies of A and Q) for the next call with the same shape on the
+// same device: creating and above all FREEING ~12 GB of workspaces per call costs 30-330 ms at 32768^2 (measured on
+// B200: cudaFree + green-context teardown), more than the factorisation.  mpqr_release_cache() returns the memory.
+namespace {
+struct HostPlan {
+    int dev = -1, m = 0, n = 0, r = 0;
+    unsigned f = 0;
+    bool with_q = false;
+    mpqr_handle* h = nullptr;
+    float *dA = nullptr, *dQ = nullptr;
+    bool busy = false;
+};
+std::mutex g_host_mu;
+HostPlan g_host_plan;
+void host_plan_free(HostPlan& p) {
+    if (p.h) mpqr_destroy(p.h);  // (dA, dQ were allocated through the handle)
+    p = HostPlan();
+}
+}  // namespace
+
+int mpqr_release_cache(void) {
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        if (!g_host_plan.busy) host_plan_free(g_host_plan);
+    }
+    return mpqr_tsqr_release_cache();
+}
+
 int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned flags) {
     if (!A_packed || m < 1 || n < 1 || r < 1) {
         set_error("mpqr_block_qr_host: bad arguments m=%d n=%d r=%d", m, n, r);
         return MPQR_EINVAL;
     }
-    mpqr_handle* h = nullptr;
-    unsigned f = (flags & MPQR_PRECISION_MASK) | (Q ? MPQR_KEEP_WY : 0u);
-    MPQR_TRY(mpqr_create(&h, m, n, r, 0, f));
+    const unsigned f = (flags & MPQR_PRECISION_MASK) | (Q ? MPQR_KEEP_WY : 0u);
+    const bool htrace = getenv("MPQR_HOST_TRACE") != nullptr;  // phase times of this call on stderr
+    const bool no_cache = getenv("MPQR_NO_HOST_CACHE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_created = 0, t_h2d = 0, t_issued = 0;
+    int dev = 0;
+    MPQR_CUDA(cudaGetDevice(&dev));
     const long lda = round_up(n, 8), ldq = round_up(m, 8);
-    float *dA = nullptr, *dQ = nullptr;
+    HostPlan P;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        HostPlan& c = g_host_plan;
+        if (!no_cache && !c.busy && c.h && c.dev == dev && c.m == m && c.n == n && c.r == r && c.f == f && c.with_q == (Q != nullptr)) {
+            c.busy = true;
+            P = c;
+        } else if (!c.busy && c.h) {
+            host_plan_free(c);  // another shape: one plan at a time
+        }
+    }
+    const bool reused = P.h != nullptr;
     int rc = MPQR_OK;
+    if (!reused) {
+        P.dev = dev; P.m = m; P.n = n; P.r = r; P.f = f; P.with_q = Q != nullptr;
+        rc = mpqr_create(&P.h, m, n, r, 0, f);
+        if (rc == MPQR_OK) rc = dev_alloc(P.h, (void**)&P.dA, (size_t)(m + 1) * lda * sizeof(float));
+        if (rc == MPQR_OK && Q) rc = dev_alloc(P.h, (void**)&P.dQ, (size_t)m * ldq * sizeof(float));
+        if (rc != MPQR_OK) {
+            if (P.h) mpqr_destroy(P.h);
+            return rc;
+        }
+    }
+    mpqr_handle* h = P.h;
+    float *dA = P.dA, *dQ = P.dQ;
+    t_created = now();
     do {
-        if ((rc = dev_alloc(h, (void**)&dA, (size_t)(m + 1) * lda * sizeof(float)))) break;
-        if (Q && (rc = dev_alloc(h, (void**)&dQ, (size_t)m * ldq * sizeof(float)))) break;
         cudaError_t e = cudaMemcpy2D(dA, lda * sizeof(float), A_packed, (size_t)n * sizeof(float), (size_t)n * sizeof(float),
                                      m + 1, cudaMemcpyHostToDevice);
+        t_h2d = now();
         if (e != cudaSuccess) { set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; break; }
         // mixed path: finished column blocks go back to the host while later blocks are still being factored
         // (only for page-locked host buffers: an "async" copy to pageable memory blocks the issuing thread)
@@ -894,13 +953,15 @@ int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned 
         const bool pinned = cudaPointerGetAttributes(&pa, A_packed) == cudaSuccess && pa.type == cudaMemoryTypeHost;
         if (!pinned) cudaGetLastError();
         const bool pipelined = pinned && (f & MPQR_PRECISION_MASK) != 0;
+        h->sink_host = nullptr;
         if (pipelined) {
-            if (cudaStreamCreateWithFlags(&h->sink_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
+            if (!h->sink_stream && cudaStreamCreateWithFlags(&h->sink_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
             h->sink_host = A_packed;
             h->sink_pitch = (size_t)n * sizeof(float);
         }
         if ((rc = mpqr_factor_device(h, dA, lda, nullptr))) break;
         if (Q && (rc = mpqr_form_q_device(h, dQ, ldq, nullptr))) break;
+        t_issued = now();
         if (pipelined) {
             e = cudaStreamSynchronize(h->sink_stream);
             if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -913,7 +974,25 @@ int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned 
                              cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { set_error("D2H copy / kernel execution failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; break; }
     } while (0);
-    mpqr_destroy(h);
+    h->sink_host = nullptr;
+    const double t_done = now();
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        HostPlan& c = g_host_plan;
+        if (reused) {
+            c.busy = false;
+            if (rc != MPQR_OK) host_plan_free(c);  // do not keep a plan whose last run failed
+        } else if (rc == MPQR_OK && !no_cache && !c.h) {
+            c = P;
+            c.busy = false;
+        } else {
+            mpqr_destroy(P.h);
+        }
+    }
+    if (htrace)
+        fprintf(stderr, "mpqr_block_qr_host %dx%d: plan %.1f ms (%s), H2D %.1f, issue %.1f, wait+D2H %.1f, release %.1f, total %.1f\n",
+                m, n, t_created - t_begin, reused ? "cached" : "created", t_h2d - t_created, t_issued - t_h2d, t_done - t_issued,
+                now() - t_done, now() - t_begin);
     return rc;
 }
 

@@ -1762,6 +1762,10 @@ bool panel_lookahead_ok(const PanelArgs& a) {
     if ((long)D > (tall ? block_capacity(16) : block_capacity(32)) || D < 2 * pw || a.ws_rows < 256) return false;
     if ((a.lda & 3) || (reinterpret_cast<uintptr_t>(a.A + (size_t)a.lam * a.lda + a.acol) & 15)) return false;  // vectorised S/U only
     if (a.force_b || a.force_cs || a.force_rpt || a.prof) return false;
+    // the side streams share the panel partition with the chain: on a small partition they slow the chain down more than
+    // they take off it (B200, D = 16384: 4.3 ms per outer block on 80 SMs against 3.8 ms classic; faster from ~100 SMs)
+    static const int min_sms = getenv("MPQR_RBLA_MIN_SMS") ? atoi(getenv("MPQR_RBLA_MIN_SMS")) : 100;
+    if (g_sm_budget > 0 && g_sm_budget < min_sms) return false;
     const char* dbl_env = getenv("MPQR_DBLOCK");
     return !(dbl_env && dbl_env[0] == '1');
 }
