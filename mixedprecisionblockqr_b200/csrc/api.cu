@@ -670,6 +670,13 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
     h->keep_wy = (flags & MPQR_KEEP_WY) != 0;
     h->kmax = m < n ? m : n;
     h->r = r > kPanelMaxWidth ? kPanelMaxWidth : r;
+    {
+        // The packed result does not depend on the panel grouping beyond rounding, so a narrow caller r (the reference's
+        // r = 16 / 32 / 64) is widened to a multiple of it near 128: fewer, better filled panels.
+        const char* e = getenv("MPQR_MIN_R");
+        const int min_r = e ? atoi(e) : 0;
+        if (min_r > h->r && min_r <= kPanelMaxWidth) h->r = (min_r / h->r) * h->r;
+    }
     if (h->r > h->kmax) h->r = h->kmax;
     if (prec == 0) {
         h->nb = h->r;
