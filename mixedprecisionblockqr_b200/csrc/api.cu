@@ -532,8 +532,8 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
         const int nin = c1 - tau;  // in-block trailing columns
-        // register-block look-ahead: the panel also updates the next panel's first 32 columns (FP32, block by block),
-        // Gram/T/W and the tensor-core in-block updates leave the panel stream
+        // register-block look-ahead: the panel's blocks also update the whole NEXT panel (FP32, block by block, on a side
+        // stream), Gram/T/W and the tensor-core in-block update of the columns right of it leave the panel stream
         bool la = false;
         if (c.side_stream && c.side2_stream && c.rest_stream && c.la_ev) {
             a.side = c.side_stream; a.side2 = c.side2_stream; a.gtw_stream = c.rest_stream; a.la_ev = c.la_ev;

@@ -92,3 +92,23 @@ def test_reference_log_format_and_flop_model(tmp_path):
     import oracle
     if oracle.ref_available():
         assert pkg.qr_flops_per_second(7.0, 640, 480) == oracle.ref().ref_h_qr_flops_per_second(7.0, 640, 480)
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`bench.py --impl reference` (the reference's own CPU block QR from oracle/_ref, or the oracle port) must print
+    ONE JSON line with the contract's keys; it needs no GPU.  (~15 s: four 640 x 640 factorisations on one core.)"""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("block-QR TFLOP/s") and d["unit"] == "TFLOP/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["backward_error"] < 640 * 2.0 ** -23          # the reference's own FP32 pass bound (Cuda/qr.cu:120-129)
