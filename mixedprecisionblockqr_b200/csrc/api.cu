@@ -545,7 +545,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         if (la != la_prev && lam > c0) {
             // switching flows inside a block: everything issued so far must be complete for the other flow's assumptions
             if (last_rest >= 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[last_rest], 0));
-            if (la_prev) { MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[16], 0)); }
+            if (la_prev) { MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[16], 0)); MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[18], 0)); }
         }
         // this panel's columns received the earlier panels' updates through N(q), q <= p-2 (panel p-1 reached them in FP32)
         if (la && la_prev && jc >= 2 * r) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (jc / r - 2) + 1], 0));
@@ -622,10 +622,10 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
     // everything of this block is complete when the panel stream is (events of one stream complete in order)
     if (c.rest_stream && last_rest >= 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[last_rest], 0));
     if (c.side_stream && c.la_ev) {  // (every side update was already consumed by a waiting panel-stream kernel; belt and braces)
-        MPQR_CUDA(cudaEventRecord(c.la_ev[kPanelLaEvents - 1], c.side_stream));
-        MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[kPanelLaEvents - 1], 0));
-        MPQR_CUDA(cudaEventRecord(c.la_ev[kPanelLaEvents - 1], c.side2_stream));
-        MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[kPanelLaEvents - 1], 0));
+        MPQR_CUDA(cudaEventRecord(c.la_ev[17], c.side_stream));
+        MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[17], 0));
+        MPQR_CUDA(cudaEventRecord(c.la_ev[17], c.side2_stream));
+        MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[17], 0));
     }
     return MPQR_OK;
 }

@@ -128,9 +128,10 @@ struct PanelArgs {
     cudaStream_t gtw_stream;  // Gram / T / W of the whole panel run here (after the last block kernel); null: `stream`
     int next_cols;            // 0, or a multiple of 32 (<= 128)
     cudaEvent_t ev_next_ready;  // may be null
-    cudaEvent_t* la_ev;       // kPanelLaEvents events: [2j] K(j) done, [2j+1] side update of block j done, [16] side2 position
+    cudaEvent_t* la_ev;       // kPanelLaEvents events: [2j] K(j) done, [2j+1] side update of block j done, [16] side2 position,
+                              // [17] caller's join, [18] deferred outputs of the panel written (panel_finalize_kernel)
 };
-constexpr int kPanelLaEvents = 2 * 8 + 2;
+constexpr int kPanelLaEvents = 2 * 8 + 4;
 // true if launch_panel will honour the look-ahead fields for this panel (else it ignores them and the caller
 // must not rely on next_cols having been updated)
 bool panel_lookahead_ok(const PanelArgs& a);

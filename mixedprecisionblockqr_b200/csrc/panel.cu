@@ -212,6 +212,8 @@ struct BlockArgs {
     float* zero_buf;  // optional buffer to clear (S replicas of the following in-panel update)
     int zero_n;
     long long* dbg;   // optional phase timers (tools/panel_probe.py)
+    int defer_out;    // 1: the packed factor below the first 32 rows and the 16-bit Y are written later, per panel, by
+                      // panel_finalize_kernel from the FP32 Y (the kernel then only stores Y32 and its top 32 rows of A)
 };
 
 template <int B>
@@ -571,7 +573,7 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
         const bool full = (bw == B) && g0 >= B;  // the whole group lies below the block's triangle
         // packed factor: R above the diagonal, R_kk on it, w shifted one row down
         if (full && vecA) {
-            rows_out_f32<B>(a.A + (size_t)(g0 + 1) * lda, lda, D - g0, x[u], tiles[warp], lane);
+            if (!a.defer_out) rows_out_f32<B>(a.A + (size_t)(g0 + 1) * lda, lda, D - g0, x[u], tiles[warp], lane);
         } else if (i < D) {
             if (i >= bw) {
                 store_row32<B>(a.A + (size_t)(i + 1) * lda, x[u], bw, vecA);
@@ -592,7 +594,7 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
             if (bw == B && vecY32) rows_out_f32<B>(a.Y32.p + (size_t)g0 * a.Y32.ld, a.Y32.ld, D - g0, x[u], tiles[warp], lane);
             else if (i < D) store_row32<B>(a.Y32.p + (size_t)i * a.Y32.ld, x[u], bw, vecY32);
         }
-        if (a.Y16.p) {
+        if (a.Y16.p && !a.defer_out) {
             if (bw == B && vecY16) rows_out_16<B>((char*)a.Y16.p + (size_t)g0 * a.Y16.ld * 2, a.Y16.ld, D - g0, x[u], tiles[warp], lane, a.bf16);
             else if (i < D) store_row16<B>((char*)a.Y16.p + (size_t)i * a.Y16.ld * 2, x[u], bw, vecY16, a.bf16);
         }
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
                 long rr = idx / bw; int c = (int)(idx - rr * bw);
                 a.W32.p[(rr - a.W32.zrows) * a.W32.ld + c] = 0.f;
             }
-        if (a.Y16.p)
+        if (a.Y16.p && !a.defer_out)
             for (long idx = gtid; idx < (long)a.Y16.zrows * bw; idx += nthr) {
                 long rr = idx / bw; int c = (int)(idx - rr * bw);
                 store16(a.Y16.p, (rr - a.Y16.zrows) * a.Y16.ld + c, 0.f, a.bf16);
@@ -673,6 +675,37 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
     }
     // shared memory must stay alive until no peer can signal into it any more
     if (CS > 1) cluster_sync_all();
+}
+
+// ------------------------------------------------------------------ deferred outputs of a multi-block panel
+// The register-block kernels touch their outputs as 64-byte (A, stride lda) and 32-byte (16-bit Y, stride ldh) row
+// pieces through 16 SMs: ~8 of their 40 us at D = 32768.  With defer_out they only store the FP32 Y (compact, 512-byte
+// rows, needed by the in-panel updates at once) and the top 32 rows of the block; this kernel then writes, once per
+// panel and device-wide, the packed factor (w shifted one row down: A[i + 1][c] = Y[i][c] for rows below the top 32 of
+// c's block) and the 16-bit Y (all rows, zeros above the panel included) from the FP32 Y.
+//   Yp: D x ncols (ldyp) FP32 Y of the panel, zeros above each block's diagonal.   A: element (panel row 0, panel col 0).
+//   Y16: element (row blk_row0 = panel row -zr, panel col 0) or null.   One thread per 4 columns of a row.
+__global__ void __launch_bounds__(256) panel_finalize_kernel(const float* Yp, long ldyp, float* A, long lda, void* Y16, long ldy16,
+                                                             int D, int ncols, int B, int zr, int bf16) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int cq = ncols >> 2;  // float4 chunks per row
+    const long total = (long)(D + zr) * cq;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long rr = idx / cq;          // 0 .. D + zr - 1: row of the 16-bit output, starting at blk_row0
+        const int c = (int)(idx - rr * cq) * 4;
+        const long i = rr - zr;            // panel row
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i >= 0) y = __ldcg(reinterpret_cast<const float4*>(Yp + (size_t)i * ldyp + c));
+        if (Y16) {
+            uint2 h = make_uint2(pack16(y.x, y.y, bf16), pack16(y.z, y.w, bf16));
+            *reinterpret_cast<uint2*>((char*)Y16 + ((size_t)rr * ldy16 + c) * 2) = h;
+        }
+        if (i >= 0) {
+            const int j0 = (c / B) * B;    // first row / column of c's register block
+            if (i >= j0 + 32) *reinterpret_cast<float4*>(A + (size_t)(i + 1) * lda + c) = y;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ double block (tall panels)
@@ -1832,6 +1865,20 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     // (its in-panel update needs the vectorised kernels: 16-byte aligned rows and widths that are multiples of 4)
     const bool use_dblock = (B == 16) && dbl_env && dbl_env[0] == '1' && ((a.lda & 3) == 0) && ((pw & 3) == 0) &&
                             ((reinterpret_cast<uintptr_t>(Ablk) & 15) == 0);
+    // deferred outputs (panel_finalize_kernel): full register blocks only, vector-aligned A and 16-bit Y
+    static const bool no_defer = getenv("MPQR_NO_DEFER_OUT") != nullptr;
+    const bool defer = !no_defer && !use_dblock && !a.dbg && (pw % B) == 0 && D >= pw + 32 && ((a.lda & 3) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(Ablk) & 15) == 0) && ((ldyp & 3) == 0) && ((reinterpret_cast<uintptr_t>(Yp) & 15) == 0) &&
+                       (!Y16l || (((a.ldy16 & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y16) & 7) == 0)));
+    auto finalize = [&](cudaStream_t fs) -> int {
+        const int grid = sm_count(di) * 4;
+        cudaLaunchAttribute pat[1] = {pdl_attr()};
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.stream = fs; cfg.attrs = pat; cfg.numAttrs = 1;
+        MPQR_CUDA(cudaLaunchKernelEx(&cfg, panel_finalize_kernel, (const float*)Yp, ldyp, Ablk, a.lda, (void*)a.Y16, a.ldy16, D, pw, B, zr, a.bf16));
+        if (launches) *launches += 1;
+        return MPQR_OK;
+    };
     const bool la = panel_lookahead_ok(a);
     static const bool la_pdl = getenv("MPQR_RBLA_PDL") != nullptr;  // experiment: keep PDL on the near S kernel
     cudaStream_t gtw_st = (la && a.gtw_stream) ? a.gtw_stream : stream;
@@ -1867,7 +1914,8 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
             b.Y32 = {Yp + (size_t)j0 * ldyp + j0, ldyp, j0 + (Y32l ? zr : 0)};
             if (nnear + nfarA + nfarB > 0) { b.T = Tslot; b.ldt = B; b.zero_buf = w.Srep; b.zero_n = 2 * RMAX * SLD; }
             if (Y16l) b.Y16 = {Y16l + ((size_t)j0 * a.ldy16 + j0) * 2, a.ldy16, j0 + zr};
-            b.bf16 = a.bf16; b.dbg = a.dbg;
+            b.bf16 = a.bf16; b.dbg = a.dbg; b.defer_out = defer ? 1 : 0;
+            if (jb == 0) MPQR_CUDA(cudaStreamWaitEvent(stream, a.la_ev[18], 0));  // the previous panel's finalize still reads the FP32 Y
             MPQR_TRY(launch_block(B, b, rpt, cs, stream));
             if (launches) *launches += 1;
             MPQR_CUDA(cudaEventRecord(a.la_ev[2 * jb], stream));
@@ -1896,6 +1944,13 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
                 MPQR_CUDA(cudaEventRecord(a.la_ev[16], a.side2));
             }
         }
+        if (defer) {
+            // on the first side stream (idle by now: the last two blocks have no far A update)
+            MPQR_CUDA(cudaStreamWaitEvent(a.side, a.la_ev[2 * la_last], 0));
+            MPQR_TRY(finalize(a.side));
+            MPQR_CUDA(cudaEventRecord(a.la_ev[18], a.side));
+            if (gtw_st != a.side) MPQR_CUDA(cudaStreamWaitEvent(gtw_st, a.la_ev[18], 0));
+        }
         if (gtw_st != stream && la_last >= 0) MPQR_CUDA(cudaStreamWaitEvent(gtw_st, a.la_ev[2 * la_last], 0));
     }
     for (int j0 = 0; !la && j0 < pw;) {
@@ -1911,7 +1966,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         b.Y32 = {Yp + (size_t)j0 * ldyp + j0, ldyp, j0 + (Y32l ? zr : 0)};
         if (nrest > 0) { b.T = w.Wj; b.ldt = B; }  // block T for the in-panel update ([T_A | T_B] after a double block)
         if (Y16l) b.Y16 = {Y16l + ((size_t)j0 * a.ldy16 + j0) * 2, a.ldy16, j0 + zr};
-        b.bf16 = a.bf16; b.dbg = a.dbg;
+        b.bf16 = a.bf16; b.dbg = a.dbg; b.defer_out = (defer && !dbl) ? 1 : 0;
         // the following S kernel accumulates into two replicas; only the double-block (pair) flow uses all NREP
         // replicas, the ticket counter and the cross-Gram accumulator behind them
         if (nrest > 0) { b.zero_buf = w.Srep; b.zero_n = dbl ? NREP * RMAX * SLD + 4 + 256 : 2 * RMAX * SLD; }
@@ -1928,6 +1983,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         }
         j0 += bw;
     }
+    if (defer && !la) MPQR_TRY(finalize(stream));
     if (a.dbg_caps) { a.dbg_caps[0] = max_cluster(); a.dbg_caps[1] = cs; a.dbg_caps[2] = rpt; }
     if (!need_t) return MPQR_OK;
 
