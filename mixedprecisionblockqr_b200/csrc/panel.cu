@@ -1983,7 +1983,11 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         }
         j0 += bw;
     }
-    if (defer && !la) MPQR_TRY(finalize(stream));
+    if (defer && !la) {
+        if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 0.0, 10.0 * D * pw);  // reads the FP32 Y, writes A and the 16-bit Y
+        MPQR_TRY(finalize(stream));
+        if (a.prof) a.prof->end(a.prof->ctx, stream);
+    }
     if (a.dbg_caps) { a.dbg_caps[0] = max_cluster(); a.dbg_caps[1] = cs; a.dbg_caps[2] = rpt; }
     if (!need_t) return MPQR_OK;
 
