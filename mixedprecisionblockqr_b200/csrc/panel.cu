@@ -434,12 +434,21 @@ __device__ __forceinline__ void factor_steps(float (&x)[RPT][B], const StepMem<B
             PROF_MARK(3);
             mbar_wait_cluster(&mbar[par], (uint32_t)((s >> 1) & 1));
             PROF_MARK(4);
-            float g0 = 0.f, g1 = 0.f;
-            for (int c = 0; c < CS; c += 2) {
-                g0 += slot[par][c][lane & (B - 1)];
-                g1 += slot[par][c + 1][lane & (B - 1)];
+            // (fully unrolled over the largest cluster with a uniform predicate: the 16 LDS issue back to back instead
+            // of one latency-exposed pair per trip of a rolled loop; CS is even)
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CSMAX; c += 4) {
+                if (c < CS) {
+                    g0 += slot[par][c][lane & (B - 1)];
+                    g1 += slot[par][c + 1][lane & (B - 1)];
+                }
+                if (c + 2 < CS) {
+                    g2 += slot[par][c + 2][lane & (B - 1)];
+                    g3 += slot[par][c + 3][lane & (B - 1)];
+                }
             }
-            g = g0 + g1;
+            g = (g0 + g1) + (g2 + g3);
             pv = pslot[par][lane & (B - 1)];
         } else {
             float csum = 0.f;
