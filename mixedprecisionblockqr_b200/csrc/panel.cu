@@ -280,6 +280,32 @@ __device__ __forceinline__ void warp_tile_in(const char* g, size_t pitch, int nv
     for (int q = 0; q < CH; ++q) v[q] = tile[lane * CH + (q ^ tile_swz<CH>(lane))];
     __syncwarp();
 }
+// The same in two halves, so that a caller can put ALL its rows' global loads in flight before the first
+// transposition (the __syncwarp()s of one fused call would serialise one L2 round trip per 32-row group).
+template <int CH>
+__device__ __forceinline__ void warp_tile_fetch(const char* g, size_t pitch, int nvalid, uint4 (&t)[CH], int lane) {
+    constexpr int RPI = 32 / CH;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        const int r = k * RPI + lane / CH, q = lane % CH;
+        t[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (r < nvalid) t[k] = __ldcg(reinterpret_cast<const uint4*>(g + (size_t)r * pitch) + q);
+    }
+}
+template <int CH>
+__device__ __forceinline__ void warp_tile_transpose(const uint4 (&t)[CH], uint4 (&v)[CH], uint4* tile, int lane) {
+    constexpr int RPI = 32 / CH;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        const int r = k * RPI + lane / CH, q = lane % CH;
+        tile[r * CH + (q ^ tile_swz<CH>(r))] = t[k];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < CH; ++q) v[q] = tile[lane * CH + (q ^ tile_swz<CH>(lane))];
+    __syncwarp();
+}
+
 template <int CH>
 __device__ __forceinline__ void warp_tile_out(char* g, size_t pitch, int nvalid, const uint4 (&v)[CH], uint4* tile, int lane) {
     constexpr int RPI = 32 / CH;
@@ -539,17 +565,34 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
 
     float x[RPT][B];
     const int wrow0 = rbase - lane;  // first row of this warp's 32-row group for u = 0
+    if (vecA && bw == B) {
+        // all RPT groups' loads in flight first (RPT * B / 4 independent 16-byte loads per lane), then the transpositions
+        uint4 t[RPT][B / 4];
 #pragma unroll
-    for (int u = 0; u < RPT; ++u) {
-        const int i = rbase + u * NT;
-        if (vecA && bw == B) {
+        for (int u = 0; u < RPT; ++u) {
             const int g0 = wrow0 + u * NT;
-            rows_in_f32<B>(a.A + (size_t)g0 * lda, lda, D - g0, x[u], tiles[warp], lane);  // rows >= D read as zero
-        } else if (i < D) {
-            load_row<B>(a.A + (size_t)i * lda, x[u], bw, vecA);
-        } else {
+            warp_tile_fetch<B / 4>(reinterpret_cast<const char*>(a.A + (size_t)g0 * lda), (size_t)lda * 4, D - g0, t[u], lane);  // rows >= D read as zero
+        }
 #pragma unroll
-            for (int c = 0; c < B; ++c) x[u][c] = 0.f;
+        for (int u = 0; u < RPT; ++u) {
+            uint4 v[B / 4];
+            warp_tile_transpose<B / 4>(t[u], v, tiles[warp], lane);
+#pragma unroll
+            for (int q = 0; q < B / 4; ++q) {
+                x[u][4 * q] = __uint_as_float(v[q].x); x[u][4 * q + 1] = __uint_as_float(v[q].y);
+                x[u][4 * q + 2] = __uint_as_float(v[q].z); x[u][4 * q + 3] = __uint_as_float(v[q].w);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const int i = rbase + u * NT;
+            if (i < D) {
+                load_row<B>(a.A + (size_t)i * lda, x[u], bw, vecA);
+            } else {
+#pragma unroll
+                for (int c = 0; c < B; ++c) x[u][c] = 0.f;
+            }
         }
     }
     if (a.zero_buf) {
