@@ -219,7 +219,8 @@ int mpqr_write_results_to_log(const char* log_dir, const char* file_name, int he
 /* ---------------------------------------------------------------------------------------
  * Tall-skinny QR (replaces python/ca_qr.py:25-43 ts_qr): A is m x n (m >> n), row-major FP32
  * on the device.  Row blocks are factored independently, the n x n R factors are reduced by
- * a tree; R (n x n, ldr) is returned and, if dQ != NULL, the thin Q (m x n, ldq).
+ * a tree; R (n x n, ldr) is returned and, if dQ != NULL, the thin Q (m x n, ldq).  The call is SYNCHRONOUS with
+ * respect to the host (it returns after `stream` and its internal lanes have finished).
  * ------------------------------------------------------------------------------------- */
 int mpqr_tsqr_device(const float* dA, long lda, long m, int n, float* dQ, long ldq, float* dR,
                      long ldr, void* stream);
