@@ -10,6 +10,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    # The built libraries are git-ignored: in a fresh checkout build them once (nvcc cross-compiles without a GPU).
+    lib = os.path.join(ROOT, "mixedprecisionblockqr_b200", "libmpqr.so")
+    orc = os.path.join(ROOT, "oracle", "libmpqr_oracle.so")
+    if not (os.path.exists(lib) and os.path.exists(orc)):
+        import shutil
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            import __graft_entry__
+            __graft_entry__.build()
 
 
 def _has_gpu():
