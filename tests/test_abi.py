@@ -112,3 +112,11 @@ def test_bench_reference_arm_prints_contract_line():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["backward_error"] < 640 * 2.0 ** -23          # the reference's own FP32 pass bound (Cuda/qr.cu:120-129)
+
+
+def test_release_cache_without_plans_is_a_noop():
+    """mpqr_release_cache / mpqr_tsqr_release_cache free the plans kept between calls; with nothing cached (and no GPU)
+    they must simply succeed."""
+    import mixedprecisionblockqr_b200 as pkg
+    assert pkg.lib().mpqr_release_cache() == 0
+    assert pkg.lib().mpqr_tsqr_release_cache() == 0
