@@ -144,3 +144,32 @@ def test_lookahead_driver_vs_oracle(m, n, r, nb, rbla, monkeypatch):
         dr = np.abs(np.abs(oracle.strip_R(P)) - np.abs(Rref)).max() / np.abs(Rref).max()
         assert dr <= 60 * 2.0 ** -11, dr
     plan.close()
+
+
+def test_host_driver_plan_cache(monkeypatch):
+    """mpqr_block_qr_host keeps its plan between calls of the same shape: repeated calls, a shape change in between,
+    the explicit release and MPQR_NO_HOST_CACHE=1 must all give the same factor (to FP16-level run-to-run noise)."""
+    m, n, r = 700, 512, 64
+    A = oracle.uniform_matrix(m, n, 4711)
+    Pref, _ = oracle.block_qr(A, r, want_q=False)
+    Rref = np.abs(oracle.strip_R(Pref))
+
+    def run(mm=m, nn=n, AA=A):
+        P = oracle.pack(AA)
+        pkg.dev_mixed_precision_block_qr(P, None, mm, nn, r)
+        return P
+
+    def check(P):
+        assert oracle.backward_error_packed(A, P) <= 12 * 2.0 ** -11
+        assert np.abs(np.abs(oracle.strip_R(P)) - Rref).max() <= 60 * 2.0 ** -11 * Rref.max()
+
+    check(run())
+    check(run())                                   # cached plan
+    B = oracle.uniform_matrix(300, 200, 5)
+    run(300, 200, B)                               # another shape replaces the plan
+    check(run())
+    assert pkg.lib().mpqr_release_cache() == 0
+    check(run())
+    monkeypatch.setenv("MPQR_NO_HOST_CACHE", "1")
+    check(run())
+    check(run())
