@@ -306,7 +306,8 @@ double model_bp_ms(const mpqr_handle* h, int c0, int c1) {
         const double D = h->m - lam;
         t += (D <= 16384) ? 0.15 + 0.0116 * D / 1024.0 : 0.52 + 0.0122 * (D - 16384) / 1024.0;
     }
-    return t * (h->r / 128.0 < 0.25 ? 0.25 : h->r / 128.0);
+    static const double scale = getenv("MPQR_BP_SCALE") ? atof(getenv("MPQR_BP_SCALE")) : 1.0;  // tuning knob of the cost model
+    return scale * t * (h->r / 128.0 < 0.25 ? 0.25 : h->r / 128.0);
 }
 double model_far_ms(const mpqr_handle* h, int c0, int c1, int ncols, int sms) {
     const double flops = 4.0 * (double)(h->m - c0) * (double)ncols * (double)(c1 - c0);
@@ -518,6 +519,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
     void* S16 = c.S16 ? c.S16 : h->S16;
     int last_rest = -1;
     bool la_prev = false;
+    int prev_nc = 0;  // next_cols of the previous look-ahead panel
     for (int lam = c0; lam < c1; lam += r) {
         const int p = lam / r;
         const int pw = (lam + r < c1) ? r : c1 - lam;
@@ -540,6 +542,10 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             a.next_cols = nin >= r ? r : 0;   // the whole next panel, when there is a full one in this outer block
             a.ev_next_ready = (la_prev && jc >= r) ? c.rest_ev[2 * (jc / r - 1) + 1] : nullptr;  // N(p-1): next panel's columns
             la = panel_lookahead_ok(a) && (nin == 0 || nin >= r);
+            if (!la && getenv("MPQR_FUSED")) {  // experimental: tall panels, near update fused into the register-block kernels
+                a.next_cols = 0; a.ev_next_ready = nullptr;
+                la = panel_lookahead_ok(a);
+            }
             if (!la) { a.side = a.side2 = a.gtw_stream = nullptr; a.la_ev = nullptr; a.next_cols = 0; a.ev_next_ready = nullptr; }
         }
         if (la != la_prev && lam > c0) {
@@ -547,8 +553,10 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             if (last_rest >= 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[last_rest], 0));
             if (la_prev) { MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[16], 0)); MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[18], 0)); }
         }
-        // this panel's columns received the earlier panels' updates through N(q), q <= p-2 (panel p-1 reached them in FP32)
-        if (la && la_prev && jc >= 2 * r) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (jc / r - 2) + 1], 0));
+        // this panel's columns received the earlier panels' updates through N(q), q <= p-2 (panel p-1 reached them in FP32),
+        // or through N(p-1) as well if panel p-1 did not cover its successor (next_cols == 0)
+        if (la && la_prev && prev_nc > 0 && jc >= 2 * r) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (jc / r - 2) + 1], 0));
+        if (la && la_prev && prev_nc == 0 && jc >= r) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (jc / r - 1) + 1], 0));
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         const int acol_tau = c.acol0 + jc + pw;
         // in-block update of the columns [tau + ofs, tau + ofs + nc):  S = W_p^T A ; A -= Y_p S (+ shadow)
@@ -574,6 +582,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             last_rest = 2 * pidx + 1;
         }
         la_prev = la;
+        prev_nc = la ? a.next_cols : 0;
         const bool split = !la && c.rest_stream && nin > r && (r % 8) == 0;
         if (la) { /* in-block updates done above */ } else
         {

@@ -214,6 +214,11 @@ struct BlockArgs {
     long long* dbg;   // optional phase timers (tools/panel_probe.py)
     int defer_out;    // 1: the packed factor below the first 32 rows and the 16-bit Y are written later, per panel, by
                       // panel_finalize_kernel from the FP32 Y (the kernel then only stores Y32 and its top 32 rows of A)
+    // Fused near update (16-column blocks, MPQR_FUSED=1): before factoring, the block applies the PREVIOUS register
+    // block's reflectors to its own columns, X -= Y_prev T_prev^T (Y_prev^T X), incl. the B rows above its slab.
+    const float* prevY;  // FP32 Y of the previous block: element (its row 0, its column 0); null = no prologue
+    long prev_ldy;
+    const float* prevT;  // its block T (B x B, ld B)
 };
 
 template <int B>
@@ -527,6 +532,121 @@ __device__ __forceinline__ void factor_steps(float (&x)[RPT][B], const StepMem<B
     }
     }
 
+// Prologue of the fused flow (B = 16): X -= Y_p S, S = T_p^T (Y_p^T X), for the previous register block p.
+//   P = Y_p^T X (16 x 16) is accumulated in four passes over 4-row chunks of P (64 accumulators next to the 128
+//   registers of X), reduced over the warp (transpose-reduce), the CTA (shared memory) and the cluster (ONE DSMEM
+//   all-gather of 256 floats per CTA, own mbarrier); the B rows above the slab (the previous block's diagonal rows,
+//   final R entries afterwards) are taken by CTA 0.  All reads of in-chain data are ld.global.cg.
+//   pred: NW x 256 floats, pslotP: CSMAX x 256, ptot / ssm / topx / topy: 256 each.
+template <int RPT>
+__device__ __forceinline__ void fused_prev_update(float (&x)[RPT][16], const BlockArgs& a, int D, int rbase, int tid, int lane, int warp,
+                                                  int CS, unsigned crank, float* pred, float (*pslotP)[256], float* ptot, float* ssm,
+                                                  float* topx, float* topy, uint64_t* mbarP) {
+    constexpr int B = 16;
+    const long ldy = a.prev_ldy;
+    const float* Ys = a.prevY + (size_t)B * ldy;  // Y_p row of the slab's row 0
+    if (crank == 0) {
+        const int r = tid >> 4, c = tid & 15;
+        topx[tid] = __ldcg(a.A + ((long)r - B) * a.lda + c);
+        topy[tid] = __ldcg(a.prevY + (size_t)r * ldy + c);
+    }
+    if (CS > 1 && tid == 0) mbar_arrive_expect_tx(mbarP, (uint32_t)CS * 1024u);
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        float acc[4][B];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int b = 0; b < B; ++b) acc[k][b] = 0.f;
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const int i = rbase + u * NT;
+            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < D) y = __ldcg(reinterpret_cast<const float4*>(Ys + (size_t)i * ldy + 4 * g));
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                acc[0][b] = fmaf(y.x, x[u][b], acc[0][b]);
+                acc[1][b] = fmaf(y.y, x[u][b], acc[1][b]);
+                acc[2][b] = fmaf(y.z, x[u][b], acc[2][b]);
+                acc[3][b] = fmaf(y.w, x[u][b], acc[3][b]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            warp_transpose_reduce<B>(acc[k], lane);  // lane l: column l >> 1
+            if ((lane & 1) == 0) pred[warp * 256 + (4 * g + k) * B + (lane >> 1)] = acc[k][0];
+        }
+    }
+    __syncthreads();
+    {
+        float cs = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) cs += pred[w * 256 + tid];
+        if (crank == 0) {
+            const int a2 = tid >> 4, b2 = tid & 15;
+#pragma unroll
+            for (int r = 0; r < B; ++r) cs = fmaf(topy[r * B + a2], topx[r * B + b2], cs);
+        }
+        ptot[tid] = cs;  // this CTA's part of P, element (tid >> 4, tid & 15)
+    }
+    __syncthreads();
+    if (CS > 1) {
+        const uint32_t bar_local = smem_addr(mbarP);
+        for (int o = tid; o < CS * 64; o += NT) {
+            const unsigned peer = (unsigned)(o >> 6);
+            const int ch = o & 63;
+            const float4 v = *reinterpret_cast<const float4*>(&ptot[4 * ch]);
+            st_async_v4(map_to_cta(smem_addr(&pslotP[crank][4 * ch]), peer), v, map_to_cta(bar_local, peer));
+        }
+        mbar_wait_cluster(mbarP, 0u);
+        float t = 0.f;
+        for (int c = 0; c < CS; ++c) t += pslotP[c][tid];
+        __syncthreads();  // every sender has read its chunk of ptot
+        ptot[tid] = t;
+    }
+    __syncthreads();
+    {
+        const int a2 = tid >> 4, b2 = tid & 15;
+        float sv = 0.f;
+#pragma unroll
+        for (int c = 0; c < B; ++c) sv = fmaf(__ldcg(&a.prevT[c * B + a2]), ptot[c * B + b2], sv);  // S = T^T P
+        ssm[tid] = sv;
+    }
+    __syncthreads();
+    if (crank == 0) {
+        const int r = tid >> 4, c = tid & 15;
+        float d = 0.f;
+#pragma unroll
+        for (int a2 = 0; a2 < B; ++a2) d = fmaf(topy[r * B + a2], ssm[a2 * B + c], d);
+        a.A[((long)r - B) * a.lda + c] = topx[tid] - d;
+    }
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        float sreg[4][B];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int q = 0; q < B / 4; ++q) {
+                const float4 s4 = *reinterpret_cast<const float4*>(&ssm[(4 * g + k) * B + 4 * q]);
+                sreg[k][4 * q] = s4.x; sreg[k][4 * q + 1] = s4.y; sreg[k][4 * q + 2] = s4.z; sreg[k][4 * q + 3] = s4.w;
+            }
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const int i = rbase + u * NT;
+            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < D) y = __ldcg(reinterpret_cast<const float4*>(Ys + (size_t)i * ldy + 4 * g));
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                float d = y.x * sreg[0][b];
+                d = fmaf(y.y, sreg[1][b], d);
+                d = fmaf(y.z, sreg[2][b], d);
+                d = fmaf(y.w, sreg[3][b], d);
+                x[u][b] -= d;
+            }
+        }
+    }
+}
+
 template <int B, int RPT>
 __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS) {
     __shared__ __align__(16) float red[2][NW][B];
@@ -538,6 +658,10 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
     __shared__ float diag[B];
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ __align__(16) uint4 tiles[NW][32 * (B / 4)];  // warp-private transposition tiles (coalesced I/O)
+    // fused near update (B == 16 only): all-gather slots of P, P / S / top tiles, own mbarrier
+    __shared__ __align__(16) float pslotP[B == 16 ? CSMAX : 1][256];
+    __shared__ __align__(16) float fusedsm[B == 16 ? 4 * 256 : 4];
+    __shared__ __align__(8) uint64_t mbarP;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned crank = (CS > 1) ? cluster_ctarank() : 0u;
@@ -557,6 +681,7 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
         if (tid == 0) {
             mbar_init(&mbar[0], 1);
             mbar_init(&mbar[1], 1);
+            mbar_init(&mbarP, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         cluster_sync_all();  // peers must not signal a barrier that is not initialised yet
@@ -600,6 +725,13 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
         for (int idx = (int)crank * NT + tid; idx < a.zero_n; idx += nthr) a.zero_buf[idx] = 0.f;
     }
     __syncthreads();
+    if (B == 16 && a.prevY) {
+        // (the transposition tiles are idle between the load and the stores: they hold the per-warp partial P)
+        if constexpr (B == 16)
+            fused_prev_update<RPT>(x, a, D, rbase, tid, lane, warp, CS, crank, reinterpret_cast<float*>(&tiles[0][0]), pslotP, fusedsm,
+                                   fusedsm + 256, fusedsm + 512, fusedsm + 768, &mbarP);
+        __syncthreads();
+    }
     PROF_MARK(6);
 
     {
@@ -1844,13 +1976,17 @@ bool panel_lookahead_ok(const PanelArgs& a) {
     // block-by-block update of the next panel is 3x the in-panel update work and the side streams cannot keep up
     // (162 ms against 146 ms), so tall panels keep the classic flow.  MPQR_RBLA_TALL=1 overrides (experiments).
     static const bool tall = getenv("MPQR_RBLA_TALL") != nullptr;
-    if ((long)D > (tall ? block_capacity(16) : block_capacity(32)) || D < 2 * pw || a.ws_rows < 256) return false;
+    // MPQR_FUSED=1 (experimental): tall panels take the look-ahead flow with the near update fused into the register-block
+    // kernel (fused_prev_update) and WITHOUT the FP32 update of the next panel (next_cols == 0)
+    static const bool fused_env = getenv("MPQR_FUSED") != nullptr;
+    const bool fused_tall = fused_env && a.next_cols == 0 && (long)D > block_capacity(32);
+    if ((long)D > ((tall || fused_tall) ? block_capacity(16) : block_capacity(32)) || D < 2 * pw || a.ws_rows < 256) return false;
     if ((a.lda & 3) || (reinterpret_cast<uintptr_t>(a.A + (size_t)a.lam * a.lda + a.acol) & 15)) return false;  // vectorised S/U only
     if (a.force_b || a.force_cs || a.force_rpt || a.prof) return false;
     // the side streams share the panel partition with the chain: on a small partition they slow the chain down more than
     // they take off it (B200, D = 16384: 4.3 ms per outer block on 80 SMs against 3.8 ms classic; faster from ~100 SMs)
     static const int min_sms = getenv("MPQR_RBLA_MIN_SMS") ? atoi(getenv("MPQR_RBLA_MIN_SMS")) : 100;
-    if (g_sm_budget > 0 && g_sm_budget < min_sms) return false;
+    if (g_sm_budget > 0 && g_sm_budget < min_sms && !fused_tall) return false;
     const char* dbl_env = getenv("MPQR_DBLOCK");
     return !(dbl_env && dbl_env[0] == '1');
 }
@@ -1948,6 +2084,9 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         const size_t srep_bytes = (size_t)2 * RMAX * SLD * sizeof(float);
         const int nblocks = pw / B;
         bool prev_farA = false, b_started = false;
+        static const bool fused_env2 = getenv("MPQR_FUSED") != nullptr;
+        const bool fused = fused_env2 && B == 16 && a.next_cols == 0;  // near update inside the next register-block kernel
+        bool farA_issued[16] = {false};
         auto su = [&](int Bw, const float* Tj, const float* Yj, float* Ar, int Dj, int nc, float* Srep, cudaStream_t s2, bool pdl_first) -> int {
             if (Bw == 32) return launch_su<32>(Tj, Yj, ldyp, Ar, a.lda, Dj, nc, Srep, w.Sfin, sm_count(di), s2, launches, nullptr, false, pdl_first);
             return launch_su<16>(Tj, Yj, ldyp, Ar, a.lda, Dj, nc, Srep, w.Sfin, sm_count(di), s2, launches, nullptr, false, pdl_first);
@@ -1965,6 +2104,16 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
             b.A = Ablk + (size_t)j0 * a.lda + j0; b.lda = a.lda; b.D = Dj; b.bw = bw;
             b.Y32 = {Yp + (size_t)j0 * ldyp + j0, ldyp, j0 + (Y32l ? zr : 0)};
             if (nnear + nfarA + nfarB > 0) { b.T = Tslot; b.ldt = B; b.zero_buf = w.Srep; b.zero_n = 2 * RMAX * SLD; }
+            if (fused) {
+                b.zero_buf = nullptr; b.zero_n = 0;  // no near S kernel follows
+                if (jb > 0) {
+                    b.prevY = Yp + (size_t)(j0 - B) * ldyp + (j0 - B);
+                    b.prev_ldy = ldyp;
+                    b.prevT = w.Wj + (size_t)(jb - 1) * 32 * 32;
+                    // this block's columns got blocks <= jb-2 through the side stream's far updates
+                    if (jb >= 2 && farA_issued[jb - 2]) MPQR_CUDA(cudaStreamWaitEvent(stream, a.la_ev[2 * (jb - 2) + 1], 0));
+                }
+            }
             if (Y16l) b.Y16 = {Y16l + ((size_t)j0 * a.ldy16 + j0) * 2, a.ldy16, j0 + zr};
             b.bf16 = a.bf16; b.dbg = a.dbg; b.defer_out = defer ? 1 : 0;
             if (jb == 0) MPQR_CUDA(cudaStreamWaitEvent(stream, a.la_ev[18], 0));  // the previous panel's finalize still reads the FP32 Y
@@ -1973,7 +2122,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
             MPQR_CUDA(cudaEventRecord(a.la_ev[2 * jb], stream));
             la_last = jb;
             float* Arest = b.A + bw;  // first column right of the block
-            if (nnear > 0) {
+            if (nnear > 0 && !fused) {
                 if (prev_farA) MPQR_CUDA(cudaStreamWaitEvent(stream, a.la_ev[2 * (jb - 1) + 1], 0));
                 // the previous panel's far B's wrote this panel's columns; the last block's near columns belong to far B
                 if (jb == 0 || last) MPQR_CUDA(cudaStreamWaitEvent(stream, a.la_ev[16], 0));
@@ -1985,6 +2134,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
                 MPQR_CUDA(cudaMemsetAsync(SrepA, 0, srep_bytes, a.side));
                 MPQR_TRY(su(B, Tslot, b.Y32.p, Arest + B, Dj, nfarA, SrepA, a.side, true));
                 MPQR_CUDA(cudaEventRecord(a.la_ev[2 * jb + 1], a.side));
+                farA_issued[jb] = true;
             }
             prev_farA = nfarA > 0;
             if (nfarB > 0) {
