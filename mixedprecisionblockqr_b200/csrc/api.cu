@@ -60,6 +60,20 @@ int get_device_info(DeviceInfo* out) {
     return MPQR_OK;
 }
 
+int func_attr_once(const void* func, cudaFuncAttribute attr, int value) {
+    struct Key { const void* f; int a, dev; };
+    static std::mutex mu;
+    static std::vector<Key> done;
+    int dev = 0;
+    MPQR_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    for (const Key& k : done)
+        if (k.f == func && k.a == (int)attr && k.dev == dev) return MPQR_OK;
+    MPQR_CUDA(cudaFuncSetAttribute(func, attr, value));
+    done.push_back({func, (int)attr, dev});
+    return MPQR_OK;
+}
+
 // ------------------------------------------------------------------------ utility kernels
 namespace {
 
@@ -336,6 +350,7 @@ int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         a.T = h->T + (size_t)p * r * r; a.ldt = r;
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
+        a.chain_side = h->chain_side; a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         if (nt > 0) {
             float* A22 = A + (size_t)lam * lda + tau;
@@ -413,6 +428,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         BlockCtx c = ctx_of(b, c0);
         // In-block look-ahead: the part of every in-block update that is not the next panel's columns runs on a
         // second stream of the same partition, next to the next panel's register-block kernels.
+        c.chain_side = s_bp3;
         if (inblock_la) {
             c.rest_stream = s_bp2; c.rest_S32 = h->S32r; c.rest_S16 = h->S16r; c.rest_ev = o.ev_rest.data();
             if (rb_la && s_bp3 && s_bp4) { c.side_stream = s_bp3; c.side2_stream = s_bp4; c.la_ev = o.ev_la.data(); }
@@ -533,11 +549,13 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         a.T = h->T + (size_t)p * r * r; a.ldt = r;
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
+        a.chain_side = c.chain_side ? c.chain_side : h->chain_side; a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
+        const bool chain = panel_chain_ok(a);  // persistent cluster kernel: no register-block look-ahead streams needed
         const int nin = c1 - tau;  // in-block trailing columns
         // register-block look-ahead: the panel's blocks also update the whole NEXT panel (FP32, block by block, on a side
         // stream), Gram/T/W and the tensor-core in-block update of the columns right of it leave the panel stream
         bool la = false;
-        if (c.side_stream && c.side2_stream && c.rest_stream && c.la_ev) {
+        if (!chain && c.side_stream && c.side2_stream && c.rest_stream && c.la_ev) {
             a.side = c.side_stream; a.side2 = c.side2_stream; a.gtw_stream = c.rest_stream; a.la_ev = c.la_ev;
             a.next_cols = nin >= r ? r : 0;   // the whole next panel, when there is a full one in this outer block
             a.ev_next_ready = (la_prev && jc >= r) ? c.rest_ev[2 * (jc / r - 1) + 1] : nullptr;  // N(p-1): next panel's columns
@@ -624,7 +642,10 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
                 PROF(3, 0, 6.0 * jc * pw, convert_f32_to_16(aS32, h->lds32, aS16, h->lds16, jc, pw, bf, st));
                 h->launches += 1;
                 PROF(2, 2.0 * Dblk * pw * jc, nn_bytes(Dblk, pw, jc),
-                     tc_gemm_nn(c.W16, c.ldw, aS16, h->lds16, h->Wblk32 + jc, h->ldwb, (void*)Wp, c.ldw, Dblk, pw, jc, bf, 1, st, &h->launches));
+                     tc_gemm_nn(c.W16, c.ldw, aS16, h->lds16, h->Wblk32 + jc, h->ldwb, (void*)Wp, c.ldw, Dblk, pw, jc, bf,
+                                // a deferred accumulation may run after the NEXT panel produced its W: the zero spill of a
+                                // clipped TMA store (16-byte granules) must not reach those columns
+                                (c.acc_stream && (pw & 7)) ? 0 : 1, st, &h->launches));
             }
         }
     }
@@ -708,6 +729,9 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
             if ((rc = dev_alloc(h, (void**)&h->scratch, panel_scratch_bytes(m)))) break;
         }
         if ((rc = dev_alloc(h, (void**)&h->T, (size_t)h->npanels * h->r * h->r * sizeof(float)))) break;
+        if ((rc = dev_alloc(h, (void**)&h->chain_flags, 64))) break;
+        if (cudaMemset(h->chain_flags, 0, 64) != cudaSuccess) { set_error("memset failed"); rc = MPQR_ECUDA; break; }
+        if (cudaStreamCreateWithFlags(&h->chain_side, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
         h->panel_ws_rows = m;
         if ((rc = dev_alloc(h, (void**)&h->panel_ws, panel_ws_bytes(m)))) break;
         const int wide = m > n ? m : n;
@@ -765,6 +789,7 @@ int mpqr_destroy(mpqr_handle* h) {
     if (!h) return MPQR_OK;
     mg_destroy(h->mg);
     overlap_destroy(h);
+    if (h->chain_side) cudaStreamDestroy(h->chain_side);
     for (auto e : h->sink_ev) cudaEventDestroy(e);
     if (h->sink_stream) cudaStreamDestroy(h->sink_stream);
     for (void* p : h->allocs) cudaFree(p);
@@ -1045,8 +1070,19 @@ int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
     a.T = dT; a.ldt = pw;
     a.sync_ws = ws; a.host_ctr = &host_ctr; a.scratch = scratch; a.scratch_rows = scratch_rows;
     a.ws = pws; a.ws_rows = m - lam;
+    unsigned* cflags = nullptr;
+    unsigned cctr = 0;
+    cudaStream_t cside = nullptr;
+    if (cudaMalloc(&cflags, 64) == cudaSuccess && cudaMemset(cflags, 0, 64) == cudaSuccess &&
+        cudaStreamCreateWithFlags(&cside, cudaStreamNonBlocking) == cudaSuccess) {
+        a.chain_side = cside; a.chain_flags = cflags; a.chain_ctr = &cctr;
+    } else {
+        cudaGetLastError();
+    }
     int rc = launch_panel(a, (cudaStream_t)stream, nullptr);
     cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (cside) { cudaStreamSynchronize(cside); cudaStreamDestroy(cside); }
+    cudaFree(cflags);
     cudaFree(ws);
     cudaFree(scratch);
     cudaFree(pws);

@@ -52,6 +52,10 @@ struct SmBudget {
 };
 inline int sm_count(const DeviceInfo& di) { return g_sm_budget > 0 ? g_sm_budget : di.num_sms; }
 
+// cudaFuncSetAttribute(func, attr, value) once per (function, attribute, device): function attributes are per device,
+// and the library is used on several devices from one process (host plan cache, TSQR lanes, multi-GPU tests).
+int func_attr_once(const void* func, cudaFuncAttribute attr, int value);
+
 // Programmatic dependent launch (PDL): every kernel of the factorisation chain lets its successor
 // become resident at once (launch_dependents) and waits for its predecessor's completion and
 // memory flush (wait) only after its own set-up, so launch latency and prologues overlap the
@@ -130,11 +134,18 @@ struct PanelArgs {
     cudaEvent_t ev_next_ready;  // may be null
     cudaEvent_t* la_ev;       // kPanelLaEvents events: [2j] K(j) done, [2j+1] side update of block j done, [16] side2 position,
                               // [17] caller's join, [18] deferred outputs of the panel written (panel_finalize_kernel)
+    // Persistent panel chain (panel_chain_kernel): one cluster launch per panel on `stream`; the updates of the rest of
+    // the panel run on `chain_side`, ordered against the running kernel through two device flags.
+    cudaStream_t chain_side;  // null: the chain flow is not used
+    unsigned* chain_flags;    // device: [0] block done (kernel -> side stream), [1] far update done (side stream -> kernel)
+    unsigned* chain_ctr;      // host mirror: the flags only grow
 };
 constexpr int kPanelLaEvents = 2 * 8 + 4;
 // true if launch_panel will honour the look-ahead fields for this panel (else it ignores them and the caller
 // must not rely on next_cols having been updated)
 bool panel_lookahead_ok(const PanelArgs& a);
+// true if launch_panel will take the persistent chain flow for this panel
+bool panel_chain_ok(const PanelArgs& a);
 size_t panel_ws_bytes(long max_rows);
 int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches);
 

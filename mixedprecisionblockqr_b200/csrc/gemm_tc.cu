@@ -461,12 +461,7 @@ template <int BN, bool kAMN, int kEpi>
 int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tH,
            const GemmParams& p, int fmt16, int grid, cudaStream_t stream) {
     using C_ = Cfg<BN>;
-    static bool attr = false;
-    if (!attr) {
-        MPQR_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, kAMN, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       C_::SMEM_BYTES));
-        attr = true;
-    }
+    MPQR_TRY(func_attr_once((const void*)tc_gemm_kernel<BN, kAMN, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
     cudaLaunchAttribute pat[1] = {pdl_attr()};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.stream = stream; cfg.attrs = pat; cfg.numAttrs = 1;

@@ -21,6 +21,10 @@ struct mpqr_handle {
     long scratch_rows = 0;
     float* panel_ws = nullptr;  // panel.cu workspace (in-panel blocks, Gram, T)
     long panel_ws_rows = 0;
+    // persistent panel chain (panel.cu): device flags [done, far], their host mirror, the default side stream
+    unsigned* chain_flags = nullptr;
+    unsigned chain_ctr = 0;
+    cudaStream_t chain_side = nullptr;
     float* T = nullptr;    // npanels * r * r
     float* S32 = nullptr;  // sk x lds32
     long lds32 = 0;
@@ -191,6 +195,7 @@ struct BlockCtx {
     // columns right of panel p+1 run on rest_stream (event rest_ev[2p+1]) with a whole panel's time of slack.
     cudaStream_t side_stream, side2_stream;
     cudaEvent_t* la_ev;        // kPanelLaEvents events
+    cudaStream_t chain_side;   // side stream of the persistent panel chain (null: the handle's own)
 };
 // panels + in-block updates + WY accumulation of block [c0, c1); `ncols_in` = columns of A
 // (starting at acol0) that belong to the block's own panel region (= c1 - c0)

@@ -861,6 +861,270 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
     if (CS > 1) cluster_sync_all();
 }
 
+// ------------------------------------------------------------------ persistent panel chain
+// ONE cluster launch factors every 16-column register block of an r-wide panel (panel_chain_kernel).  The rows keep
+// their threads for the whole panel (slab row i = crank*NT*RPT + u*NT + tid; block jb's diagonal sits at slab row
+// 16*jb, rows above it are inactive), so per block the chain pays neither a launch nor a drain:
+//   wait far(jb-2)   the side stream's update of block jb's columns by blocks <= jb-2 (device flag, see below)
+//   load X_jb        D x 16 from A (L2 hits: written by the update kernels just before), coalesced through warp tiles
+//   near update      X -= Y_{jb-1} T_{jb-1}^T (Y_{jb-1}^T X): Y_{jb-1} comes back from THIS thread's shared-memory spill
+//                    (thread-private rows, conflict-free layout), P through one DSMEM all-gather
+//   16 reflector steps (factor_steps), T_jb (tinv_smem)
+//   outputs          FP32 Y (compact, coalesced), the block's first 32 packed rows of A, T_jb; Y_jb -> shared memory
+//   signal           flag_done = base + jb + 1 once every CTA's stores are fenced
+// The update of the rest of the panel (blocks jb+2 ..) stays on the device-wide S/U kernels, issued by the host on a
+// side stream BEHIND a stream wait on flag_done (cuStreamWaitValue32, or a one-thread gate kernel) and followed by a
+// stream write of flag_far, which the cluster polls before it loads block jb+2.  Flags only grow (host mirror `base`).
+struct ChainArgs {
+    float* A;        // element (panel row 0, panel column 0) of the packed FP32 master
+    long lda;
+    int D, pw;       // rows below the panel top, panel width (multiple of 16, D >= pw + 32)
+    float* Yp;       // FP32 Y of the panel, element (panel row 0, panel column 0)
+    long ldyp;
+    float* Tslots;   // block jb's T at Tslots + jb * tstride (16 x 16, ld 16)
+    int tstride;
+    unsigned* flag_done;
+    const unsigned* flag_far;
+    unsigned base;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Near update from shared memory.  ysl: this thread's Y_{jb-1} rows, float4 index (g * RPT + u) * NT + tid holds columns
+// 4g..4g+3 of row u.  gtT: T_{jb-1} (upper triangular, zeros below).  pred: NW x 256 floats, pslotP: CSMAX x 256.
+template <int RPT>
+__device__ __forceinline__ void chain_near_update(float (&x)[RPT][16], const float4* ysl, const float (*gtT)[20], int tid, int lane,
+                                                  int warp, int CS, unsigned crank, float* pred, float (*pslotP)[256], float* ptot,
+                                                  float* ssm, uint64_t* mbarP, uint32_t parity) {
+    constexpr int B = 16;
+    if (CS > 1 && tid == 0) mbar_arrive_expect_tx(mbarP, (uint32_t)CS * 1024u);
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        float acc[4][B];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int b = 0; b < B; ++b) acc[k][b] = 0.f;
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const float4 y = ysl[(g * RPT + u) * NT + tid];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                acc[0][b] = fmaf(y.x, x[u][b], acc[0][b]);
+                acc[1][b] = fmaf(y.y, x[u][b], acc[1][b]);
+                acc[2][b] = fmaf(y.z, x[u][b], acc[2][b]);
+                acc[3][b] = fmaf(y.w, x[u][b], acc[3][b]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            warp_transpose_reduce<B>(acc[k], lane);  // lane l: column l >> 1
+            if ((lane & 1) == 0) pred[warp * 256 + (4 * g + k) * B + (lane >> 1)] = acc[k][0];
+        }
+    }
+    __syncthreads();
+    {
+        float cs = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) cs += pred[w * 256 + tid];
+        ptot[tid] = cs;  // this CTA's part of P, element (tid >> 4, tid & 15)
+    }
+    __syncthreads();
+    if (CS > 1) {
+        const uint32_t bar_local = smem_addr(mbarP);
+        for (int o = tid; o < CS * 64; o += NT) {
+            const unsigned peer = (unsigned)(o >> 6);
+            const int ch = o & 63;
+            const float4 v = *reinterpret_cast<const float4*>(&ptot[4 * ch]);
+            st_async_v4(map_to_cta(smem_addr(&pslotP[crank][4 * ch]), peer), v, map_to_cta(bar_local, peer));
+        }
+        mbar_wait_cluster(mbarP, parity);
+        float t = 0.f;
+        for (int c = 0; c < CS; ++c) t += pslotP[c][tid];  // fixed order: every CTA gets the same bits
+        __syncthreads();  // every sender has read its chunk of ptot
+        ptot[tid] = t;
+    }
+    __syncthreads();
+    {
+        const int a2 = tid >> 4, b2 = tid & 15;
+        float sv = 0.f;
+#pragma unroll
+        for (int c = 0; c < B; ++c) sv = fmaf(gtT[c][a2], ptot[c * B + b2], sv);  // S = T^T P
+        ssm[tid] = sv;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        float sreg[4][B];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int q = 0; q < B / 4; ++q) {
+                const float4 s4 = *reinterpret_cast<const float4*>(&ssm[(4 * g + k) * B + 4 * q]);
+                sreg[k][4 * q] = s4.x; sreg[k][4 * q + 1] = s4.y; sreg[k][4 * q + 2] = s4.z; sreg[k][4 * q + 3] = s4.w;
+            }
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const float4 y = ysl[(g * RPT + u) * NT + tid];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                float d = y.x * sreg[0][b];
+                d = fmaf(y.y, sreg[1][b], d);
+                d = fmaf(y.z, sreg[2][b], d);
+                d = fmaf(y.w, sreg[3][b], d);
+                x[u][b] -= d;
+            }
+        }
+    }
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS) {
+    constexpr int B = 16;
+    __shared__ __align__(16) float red[2][NW][B];
+    __shared__ __align__(16) float prow[2][B];
+    __shared__ __align__(16) float slot[2][CSMAX][B];
+    __shared__ __align__(16) float pslot[2][B];
+    __shared__ __align__(16) float tauS[NW][B];
+    __shared__ __align__(16) float gt[B][B + 4];
+    __shared__ float diag[B];
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ __align__(16) uint4 tiles[NW][32 * (B / 4)];  // warp transposition tiles; the near update's per-warp partial P
+    __shared__ __align__(16) float pslotP[CSMAX][256];
+    __shared__ __align__(16) float fusedsm[2 * 256];
+    __shared__ __align__(8) uint64_t mbarP;
+    extern __shared__ __align__(16) float4 ysl[];  // 4 * RPT * NT float4: this thread's rows of the previous block's Y
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned crank = (CS > 1) ? cluster_ctarank() : 0u;
+    const int D = a.D;
+    const int nblk = a.pw / B;
+    const int rbase = (int)crank * (NT * RPT) + tid;
+    const int wrow0 = rbase - lane;
+    const long lda = a.lda, ldyp = a.ldyp;
+
+    for (int idx = tid; idx < B * (B + 4); idx += NT) (&gt[0][0])[idx] = 0.f;
+    if (CS > 1) {
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            mbar_init(&mbarP, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster_sync_all();
+    }
+    pdl_wait();
+
+    long long dummy_acc[1];
+    long long dummy_prev = 0;
+#pragma unroll 1
+    for (int jb = 0; jb < nblk; ++jb) {
+        const int roff = jb * B;
+        float* Ab = a.A + roff;  // the block's first column
+        if (jb >= 2 && a.flag_far) {
+            if (tid == 0) {
+                const unsigned want = a.base + (unsigned)(jb - 1);  // far(jb-2) posted base + jb - 1
+                while ((int)(ld_acquire_u32(a.flag_far) - want) < 0) __nanosleep(64);
+            }
+            __syncthreads();
+        }
+        float x[RPT][B];
+        {
+            uint4 t[RPT][B / 4];
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) {
+                const int g0 = wrow0 + u * NT;
+                warp_tile_fetch<B / 4>(reinterpret_cast<const char*>(Ab + (size_t)g0 * lda), (size_t)lda * 4, D - g0, t[u], lane);
+            }
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) {
+                uint4 v[B / 4];
+                warp_tile_transpose<B / 4>(t[u], v, tiles[warp], lane);
+#pragma unroll
+                for (int q = 0; q < B / 4; ++q) {
+                    x[u][4 * q] = __uint_as_float(v[q].x); x[u][4 * q + 1] = __uint_as_float(v[q].y);
+                    x[u][4 * q + 2] = __uint_as_float(v[q].z); x[u][4 * q + 3] = __uint_as_float(v[q].w);
+                }
+            }
+        }
+        __syncthreads();
+        if (jb > 0) {
+            chain_near_update<RPT>(x, ysl, gt, tid, lane, warp, CS, crank, reinterpret_cast<float*>(&tiles[0][0]), pslotP, fusedsm,
+                                   fusedsm + 256, &mbarP, (uint32_t)((jb - 1) & 1));
+            // rows [roff-16, roff) of these columns are final R entries now
+            if (crank == 0 && tid >= roff - B && tid < roff) {
+#pragma unroll
+                for (int q = 0; q < B / 4; ++q)
+                    *reinterpret_cast<float4*>(Ab + (size_t)tid * lda + 4 * q) = make_float4(x[0][4 * q], x[0][4 * q + 1], x[0][4 * q + 2], x[0][4 * q + 3]);
+            }
+            __syncthreads();
+        }
+        {
+            StepMem<B> M{red, prow, slot, pslot, tauS, gt, diag, mbar};
+            StepCtx sc{tid, lane, warp, CS, rbase, B, B, roff, crank, false, dummy_acc, &dummy_prev};
+            factor_steps<B, RPT>(x, M, sc);
+        }
+        __syncthreads();
+        tinv_smem<B, B + 4>(gt, &red[0][0][0], tid);
+        if (jb == nblk - 1) pdl_launch_dependents();
+
+        // the block's first 32 rows of the packed factor (CTA 0, u = 0); the rest is written per panel by panel_finalize_kernel
+        if (crank == 0 && tid >= roff && tid < roff + 32) {
+            const int i = tid, i2 = i - roff;
+            if (i2 >= B) {
+#pragma unroll
+                for (int q = 0; q < B / 4; ++q)
+                    *reinterpret_cast<float4*>(Ab + (size_t)(i + 1) * lda + 4 * q) = make_float4(x[0][4 * q], x[0][4 * q + 1], x[0][4 * q + 2], x[0][4 * q + 3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < B; ++c) Ab[(size_t)(i + (i2 >= c ? 1 : 0)) * lda + c] = x[0][c];
+                Ab[(size_t)i * lda + i2] = diag[i2];
+            }
+        }
+        // Y: zero above the block's diagonal (incl. all rows above the block)
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const int i = rbase + u * NT;
+            if (i < roff + B) {
+#pragma unroll
+                for (int c = 0; c < B; ++c)
+                    if (i < roff + c) x[u][c] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const int g0 = wrow0 + u * NT;
+            rows_out_f32<B>(a.Yp + (size_t)g0 * ldyp + roff, ldyp, D - g0, x[u], tiles[warp], lane);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) ysl[(g * RPT + u) * NT + tid] = make_float4(x[u][4 * g], x[u][4 * g + 1], x[u][4 * g + 2], x[u][4 * g + 3]);
+        }
+        if (crank == 0) {
+            float* Tj = a.Tslots + (size_t)jb * a.tstride;
+            const int t = tid >> 4, c = tid & 15;
+            Tj[tid] = (t <= c) ? gt[t][c] : 0.f;
+        }
+        __threadfence();
+        if (CS > 1) cluster_sync_all(); else __syncthreads();
+        if (crank == 0 && tid == 0) {
+            atomicExch(a.flag_done, a.base + (unsigned)(jb + 1));
+            __threadfence_system();
+        }
+    }
+    // shared memory must stay alive until no peer can signal into it any more (the last cluster barrier above covers it)
+}
+
+__global__ void chain_gate_kernel(const unsigned* flag, unsigned want) {
+    while ((int)(ld_acquire_u32(flag) - want) < 0) __nanosleep(200);
+}
+__global__ void chain_post_kernel(unsigned* flag, unsigned v) {
+    atomicExch(flag, v);
+    __threadfence_system();
+}
+
 // ------------------------------------------------------------------ deferred outputs of a multi-block panel
 // The register-block kernels touch their outputs as 64-byte (A, stride lda) and 32-byte (16-bit Y, stride ldh) row
 // pieces through 16 SMs: ~8 of their 40 us at D = 32768.  With defer_out they only store the FP32 Y (compact, 512-byte
@@ -1907,7 +2171,6 @@ int launch_tinv(const float* G, long ldg, int pw, float* T32, int ldt, void* T16
 template <int B>
 int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, float* Sfin,
               int num_sms, cudaStream_t st, long* launches, const ProfHook* prof, bool pair = false, bool pdl_first = true) {
-    static bool attr = false;
     // one wave of CTAs over the SMs this stream may use (up to 512 rows = 32 KB of staged Y per CTA);
     // taller blocks take k balanced waves
     const int max_rows = 512;
@@ -1915,13 +2178,10 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
     int rows = ceil_div(D, waves * num_sms);
     rows = round_up(rows < 16 ? 16 : rows, 16);
     if (rows > max_rows) rows = max_rows;
-    if (!attr) {
-        MPQR_CUDA(cudaFuncSetAttribute(inpanel_s_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        MPQR_CUDA(cudaFuncSetAttribute(inpanel_u_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        MPQR_CUDA(cudaFuncSetAttribute(inpanel_s4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        MPQR_CUDA(cudaFuncSetAttribute(inpanel_u4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr = true;
-    }
+    MPQR_TRY(func_attr_once((const void*)inpanel_s_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    MPQR_TRY(func_attr_once((const void*)inpanel_u_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MPQR_TRY(func_attr_once((const void*)inpanel_s4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MPQR_TRY(func_attr_once((const void*)inpanel_u4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     dim3 grid(ceil_div(D, rows), ceil_div(ncols, 128));
     cudaLaunchAttribute pat[1] = {pdl_attr()};
     cudaLaunchConfig_t cfg{};
@@ -1960,7 +2220,96 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
     return MPQR_OK;
 }
 
+// ---- persistent panel chain: host side
+// Stream memory operations (driver API, resolved at run time like the green-context calls in api.cu): the side stream
+// waits on the kernel's progress flag and posts its own without any kernel of ours occupying an SM.  MPQR_GATE_KERNEL=1
+// (or a driver without the entry points) uses a one-thread gate / post kernel instead.
+struct MemopApi {
+    CUresult (*Wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    CUresult (*Write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    bool ok;
+};
+const MemopApi* memop_api() {
+    static MemopApi api{};
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        auto get = [](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+        };
+        api.ok = !getenv("MPQR_GATE_KERNEL") && get("cuStreamWaitValue32", (void**)&api.Wait32) && get("cuStreamWriteValue32", (void**)&api.Write32);
+        if (!api.ok) cudaGetLastError();
+    }
+    return &api;
+}
+int stream_wait_geq(cudaStream_t st, unsigned* flag, unsigned want) {
+    const MemopApi* m = memop_api();
+    if (m->ok) {
+        if (m->Wait32((CUstream)st, (CUdeviceptr)(uintptr_t)flag, want, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS) return MPQR_OK;
+        set_error("cuStreamWaitValue32 failed");
+        return MPQR_ECUDA;
+    }
+    chain_gate_kernel<<<1, 1, 0, st>>>(flag, want);
+    MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+int stream_post(cudaStream_t st, unsigned* flag, unsigned v) {
+    const MemopApi* m = memop_api();
+    if (m->ok) {
+        if (m->Write32((CUstream)st, (CUdeviceptr)(uintptr_t)flag, v, CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS) return MPQR_OK;
+        set_error("cuStreamWriteValue32 failed");
+        return MPQR_ECUDA;
+    }
+    chain_post_kernel<<<1, 1, 0, st>>>(flag, v);
+    MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+
+template <int RPT>
+int launch_chain_t(const ChainArgs& a, int CS, cudaStream_t stream) {
+    const size_t smem = (size_t)RPT * NT * 64;
+    MPQR_TRY(func_attr_once((const void*)panel_chain_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CS > 8) MPQR_TRY(func_attr_once((const void*)panel_chain_kernel<RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CS);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (CS > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = CS;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    at[na++] = pdl_attr();
+    cfg.attrs = at;
+    cfg.numAttrs = na;
+    MPQR_CUDA(cudaLaunchKernelEx(&cfg, panel_chain_kernel<RPT>, a, CS));
+    return MPQR_OK;
+}
+int launch_chain(const ChainArgs& a, int RPT, int CS, cudaStream_t st) {
+    if (RPT == 1) return launch_chain_t<1>(a, CS, st);
+    if (RPT == 2) return launch_chain_t<2>(a, CS, st);
+    if (RPT == 4) return launch_chain_t<4>(a, CS, st);
+    return launch_chain_t<8>(a, CS, st);
+}
+
 }  // namespace
+
+bool panel_chain_ok(const PanelArgs& a) {
+    if (getenv("MPQR_NO_CHAIN") || !a.chain_side || !a.chain_flags || !a.chain_ctr || !a.ws) return false;
+    const int D = a.m - a.lam, pw = a.pw;
+    if (pw < 32 || (pw & 15) || D < pw + 32 || (long)D > block_capacity(16) || a.ws_rows < D) return false;
+    if ((a.lda & 3) || (reinterpret_cast<uintptr_t>(a.A + (size_t)a.lam * a.lda + a.acol) & 15)) return false;
+    if (a.Y32 && ((a.ld32 & 3) || (reinterpret_cast<uintptr_t>(a.Y32) & 15) || a.lam != a.blk_row0)) return false;
+    if (a.Y16 && ((a.ldy16 & 3) || (reinterpret_cast<uintptr_t>(a.Y16) & 7))) return false;
+    if (a.force_b || a.dbg) return false;
+    return true;
+}
 
 size_t panel_ws_bytes(long max_rows) {
     return ((size_t)max_rows * (RMAX + 32) + (size_t)(NREP + 1) * RMAX * SLD + 4 + 256 + 2 * (size_t)RMAX * RMAX) * sizeof(float) +
@@ -2003,6 +2352,8 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     const int D = a.m - a.lam, pw = a.pw;
     // register-block width: 32 columns when two rows per thread are enough, else 16
     int B = (a.force_b == 16 || a.force_b == 32) ? a.force_b : ((pw > 16 && (long)D <= block_capacity(32)) ? 32 : 16);
+    const bool chain = panel_chain_ok(a);  // persistent cluster kernel: 16-column register blocks for every D
+    if (chain) B = 16;
     if ((long)D > block_capacity(B)) {
         if ((long)D <= block_capacity(16)) B = 16;
         else return launch_panel_legacy(a, stream, launches);
@@ -2067,7 +2418,39 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         if (launches) *launches += 1;
         return MPQR_OK;
     };
-    const bool la = panel_lookahead_ok(a);
+    if (chain) {
+        if (!pick_shape(16, D, a.force_cs, a.force_rpt, &rpt, &cs)) { set_error("panel: sizing error D=%d", D); return MPQR_EINVAL; }
+        const int nblocks = pw / 16;
+        ChainArgs ca{};
+        ca.A = Ablk; ca.lda = a.lda; ca.D = D; ca.pw = pw;
+        ca.Yp = Yp; ca.ldyp = ldyp;
+        ca.Tslots = w.Wj; ca.tstride = 32 * 32;
+        ca.base = *a.chain_ctr;
+        *a.chain_ctr += (unsigned)nblocks;
+        ca.flag_done = a.chain_flags;
+        ca.flag_far = nblocks >= 3 ? a.chain_flags + 1 : nullptr;
+        if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 4.0 * D * pw * 16 + 4.0 * D * 16 * 16 * (nblocks - 1), 8.0 * D * pw);
+        MPQR_TRY(launch_chain(ca, rpt, cs, stream));  // issued BEFORE the side stream's waits (a wait never queues ahead of its producer)
+        if (a.prof) a.prof->end(a.prof->ctx, stream);
+        if (launches) *launches += 1;
+        float* SrepA = w.Srep + (size_t)2 * RMAX * SLD;
+        const size_t srep_bytes = (size_t)2 * RMAX * SLD * sizeof(float);
+        int side_sms = sm_count(di) - cs;  // the cluster keeps its SMs for the whole panel
+        if (side_sms < 8) side_sms = 8;
+        for (int jb = 0; jb + 2 < nblocks; ++jb) {
+            const int j0 = jb * 16, Dj = D - j0, nfar = pw - (j0 + 32);
+            MPQR_CUDA(cudaMemsetAsync(SrepA, 0, srep_bytes, a.chain_side));
+            MPQR_TRY(stream_wait_geq(a.chain_side, a.chain_flags, ca.base + (unsigned)(jb + 1)));
+            MPQR_TRY(launch_su<16>(w.Wj + (size_t)jb * 32 * 32, Yp + (size_t)j0 * ldyp + j0, ldyp, Ablk + (size_t)j0 * a.lda + j0 + 32, a.lda, Dj,
+                                   nfar, SrepA, w.Sfin, side_sms, a.chain_side, launches, a.prof, false, false));
+            MPQR_TRY(stream_post(a.chain_side, a.chain_flags + 1, ca.base + (unsigned)(jb + 1)));
+        }
+        // every side update was consumed by the kernel before it finished: stream order is enough from here on
+        if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 0.0, 10.0 * D * pw);
+        MPQR_TRY(finalize(stream));
+        if (a.prof) a.prof->end(a.prof->ctx, stream);
+    }
+    const bool la = !chain && panel_lookahead_ok(a);
     static const bool la_pdl = getenv("MPQR_RBLA_PDL") != nullptr;  // experiment: keep PDL on the near S kernel
     cudaStream_t gtw_st = (la && a.gtw_stream) ? a.gtw_stream : stream;
     int la_last = -1;  // index of the last register block (its "factored" event orders Gram/T/W)
@@ -2155,7 +2538,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         }
         if (gtw_st != stream && la_last >= 0) MPQR_CUDA(cudaStreamWaitEvent(gtw_st, a.la_ev[2 * la_last], 0));
     }
-    for (int j0 = 0; !la && j0 < pw;) {
+    for (int j0 = 0; !la && !chain && j0 < pw;) {
         const int Dj = D - j0;
         if (Dj <= 0) break;
         const bool dbl = use_dblock && (pw - j0 > B) && (Dj > 2 * B);
@@ -2185,7 +2568,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         }
         j0 += bw;
     }
-    if (defer && !la) {
+    if (defer && !la && !chain) {
         if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 0.0, 10.0 * D * pw);  // reads the FP32 Y, writes A and the 16-bit Y
         MPQR_TRY(finalize(stream));
         if (a.prof) a.prof->end(a.prof->ctx, stream);
@@ -2193,12 +2576,8 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     if (a.dbg_caps) { a.dbg_caps[0] = max_cluster(); a.dbg_caps[1] = cs; a.dbg_caps[2] = rpt; }
     if (!need_t) return MPQR_OK;
 
-    static bool tattr = false;
     const size_t tsmem = ((size_t)RMAX * TLD + 64 * 65) * sizeof(float);
-    if (!tattr) {
-        MPQR_CUDA(cudaFuncSetAttribute(tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-        tattr = true;
-    }
+    MPQR_TRY(func_attr_once((const void*)tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     const int Dz = D + zr;  // W is produced from the enclosing block's first row on (zero rows of Y give zero rows of W)
     float* Tdst = a.T ? a.T : w.T32;
     const int ldt = a.T ? a.ldt : RMAX;

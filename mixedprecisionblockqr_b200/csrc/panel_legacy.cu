@@ -675,7 +675,7 @@ int launch_t(const PanelArgs& a, cudaStream_t stream, const DeviceInfo& di) {
             // (the pass is issue-bound, ~10 cycles per row per step, so rows per CTA must be small)
             CS = 1;
             NC = ceil_div(D, a.rows_hint > 0 ? a.rows_hint : 64);
-            if (NC > di.num_sms) NC = di.num_sms;
+            if (NC > sm_count(di)) NC = sm_count(di);  // cooperative grid: co-resident inside the issuing stream's SM partition
             if (NC > MAXNC) NC = MAXNC;
             if (NC < need) {
                 use_smem = 0;

@@ -187,12 +187,8 @@ extern "C" int mpqr_solve_device(mpqr_handle* h, const float* dA_packed, long ld
         h->launches += 2;
     }
     // ---- back substitution R x = (Q^T b)[0:n]
-    static bool attr = false;
     const size_t smem = ((size_t)TB * (TB + 1) + (size_t)TB * MAXRHS) * sizeof(float);
-    if (!attr) {
-        MPQR_CUDA(cudaFuncSetAttribute(trsv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    MPQR_TRY(func_attr_once((const void*)trsv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int j1 = n; j1 > 0;) {
         const int j0 = (j1 - 1) / TB * TB;
         const int nbk = j1 - j0;
