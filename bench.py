@@ -121,6 +121,40 @@ def run_reference_sample(steps, warmup):
             "backward_error": be, "seconds_per_step": dt}
 
 
+def extra_cpu_baselines():
+    """SURVEY 8(d) CPU lines beside the reference's own h_block_qr: (a) Eigen::HouseholderQR, the library call of the
+    reference's CPU toy C++/main.cpp:54, prebuilt into oracle/_ref/eigen_qr against the vendored Eigen 3.4.0 (1 thread);
+    (b) LAPACK sgeqrf through scipy on all host cores.  Bounded samples, reported as baselines only."""
+    out = {"host_cores": os.cpu_count()}
+    exe = os.path.join(ROOT, "oracle", "_ref", "eigen_qr")
+    if os.path.exists(exe):
+        try:
+            m = n = 4096
+            r = json.loads(subprocess.run([exe, str(m), str(n), "4096064", "1"], capture_output=True, text=True, timeout=300).stdout)
+            out["eigen_householder_qr"] = {"value": householder_flops(m, n) / r["seconds"] / 1e12, "unit": "TFLOP/s", "cores": 1,
+                                           "kind": "reference (Eigen::HouseholderQR<float>, C++/main.cpp:54, Eigen " + r["eigen"] + ")",
+                                           "sample": f"{m}x{n} uniform[0,1) FP32, {r['seconds']:.2f} s"}
+        except Exception as ex:   # noqa: BLE001
+            out["eigen_householder_qr"] = {"unavailable": str(ex)[:200]}
+    else:
+        out["eigen_householder_qr"] = {"unavailable": "oracle/_ref/eigen_qr not built"}
+    try:
+        import numpy as np
+        from scipy.linalg import lapack
+        m = n = 8192
+        rng = np.random.default_rng(8192)
+        A = np.asfortranarray(rng.random((m, n), dtype=np.float32))
+        lapack.sgeqrf(np.asfortranarray(A[:256, :256].copy()))          # warm the BLAS threads
+        t0 = time.perf_counter()
+        _, _, _, info = lapack.sgeqrf(A, overwrite_a=1)
+        dt = time.perf_counter() - t0
+        out["lapack_sgeqrf"] = {"value": householder_flops(m, n) / dt / 1e12, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "LAPACK sgeqrf (scipy/OpenBLAS, all host cores)",
+                                "sample": f"{m}x{n} uniform[0,1) FP32, {dt:.2f} s, info={info}"}
+    except Exception as ex:   # noqa: BLE001
+        out["lapack_sgeqrf"] = {"unavailable": str(ex)[:200]}
+    return out
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -130,7 +164,10 @@ def main_reference(args):
     line = {"impl": "reference", "metric": "block-QR TFLOP/s (2mn^2-2n^3/3)", "value": cb["value"], "unit": "TFLOP/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": f"{m}x{n} r={r} block QR", "timed_sample": cb["sample"]},
+            "config": {"workload": f"bounded sample {REF_SAMPLE[0]}x{REF_SAMPLE[1]} r={REF_SAMPLE[2]} of the {args.workload} family "
+                                   f"(the reference's h_block_qr is O(m^2 n^2 / r): {m}x{n} r={r} itself is infeasible on a CPU)",
+                       "timed_sample": cb["sample"], "same_config": False, "requested_workload": f"{m}x{n} r={r} block QR",
+                       "host_cores": os.cpu_count()},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "backward_error": cb["backward_error"]}
@@ -159,6 +196,49 @@ def sampled_backward_error(torch, A0, P, r, k=16):
         Tinv = torch.triu(Y.T @ Y, 1) + 0.5 * torch.eye(pw, device="cuda", dtype=torch.float64)
         Z[lam:] -= Y @ torch.linalg.solve_triangular(Tinv, Y.T @ Z[lam:], upper=True)
     return float(torch.linalg.norm(AX - Z)) / (anorm2 ** 0.5 * k ** 0.5)
+
+
+def sampled_backward_error_mg(torch, dist, A0loc, Ploc, plan, m, n, r, rank, world, k=16):
+    """The same estimate for the 1-D column-block-cyclic layout: every rank holds its columns of A and of the packed
+    factor; A X and R X are summed over the ranks, the panels are applied by their owners (last to first) and the
+    running m x k product is handed on by a broadcast per outer block.  Outside the timed region."""
+    nb = plan.nb
+    g = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.randn(n, k, device="cuda", dtype=torch.float64, generator=g)
+    dist.broadcast(X, src=0)
+    nloc = plan.local_cols
+    gcols = torch.tensor([(j // nb * world + rank) * nb + j % nb for j in range(nloc)], device="cuda", dtype=torch.long)
+    Xl = X[gcols] if nloc else torch.zeros(0, k, device="cuda", dtype=torch.float64)
+    AX = torch.zeros(m, k, device="cuda", dtype=torch.float64)
+    Z = torch.zeros(m, k, device="cuda", dtype=torch.float64)
+    an2 = torch.zeros(1, device="cuda", dtype=torch.float64)
+    step = 4096
+    for i in range(0, m, step):
+        if nloc == 0:
+            break
+        blk = A0loc[i:i + step, :nloc].double()
+        AX[i:i + step] = blk @ Xl
+        an2 += (blk * blk).sum()
+        rows = torch.arange(i, min(i + step, m), device="cuda").unsqueeze(1)
+        Z[i:i + step] = (Ploc[i:min(i + step, m), :nloc].double() * (rows <= gcols.unsqueeze(0))) @ Xl
+    dist.all_reduce(AX)
+    dist.all_reduce(Z)
+    dist.all_reduce(an2)
+    kmax = min(m, n)
+    nblk = (kmax + nb - 1) // nb
+    for b in range(nblk - 1, -1, -1):
+        owner = b % world
+        if rank == owner:
+            c0, c1 = b * nb, min((b + 1) * nb, kmax)
+            l0 = (b // world) * nb
+            for lam in range(c0 + ((c1 - c0 - 1) // r) * r, c0 - 1, -r):
+                pw = min(r, c1 - lam)
+                lc = l0 + lam - c0
+                Y = torch.tril(Ploc[lam + 1:m + 1, lc:lc + pw].double())
+                Tinv = torch.triu(Y.T @ Y, 1) + 0.5 * torch.eye(pw, device="cuda", dtype=torch.float64)
+                Z[lam:] -= Y @ torch.linalg.solve_triangular(Tinv, Y.T @ Z[lam:], upper=True)
+        dist.broadcast(Z, src=owner)
+    return float(torch.linalg.norm(AX - Z)) / (float(an2.item()) ** 0.5 * k ** 0.5)
 
 
 def main_native(args):
@@ -252,6 +332,8 @@ def main_native(args):
     be = None
     if world == 1 and not args.no_check:
         be = sampled_backward_error(torch, A0[:, :n], A[:, :n], plan.r)
+    elif not args.no_check:
+        be = sampled_backward_error_mg(torch, dist, A0, A, plan, m, n, plan.r, rank, world)
 
     # ---- end to end through the host-pointer C-ABI (pinned host buffers, H2D + D2H inside)
     e2e = None
@@ -309,8 +391,16 @@ def main_native(args):
     # classes panel_* are the parts of "panel"; shares are taken over the leaf classes only
     leaves = [k for k in prof if k != "panel"] if any(prof[k]["launches"] for k in prof if k.startswith("panel_")) else list(prof)
     by_kernel, total_kernel_ms = {}, sum(prof[k]["ms"] for k in leaves) or 1.0
+    # `traffic`: DRAM bytes per launch from an ncu --set full capture of THIS workload (profiles/ncu_traffic.json:
+    # {workload: {class: {"dram_bytes_per_launch": ..., "algorithmic_bytes_that_launch": ..., "shape": ...}}}); null when
+    # no capture of the benchmarked workload exists (never a figure taken at another shape)
     traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
+    traffic = {}
+    if os.path.exists(traffic_file):
+        try:
+            traffic = json.load(open(traffic_file)).get(args.workload, {})
+        except Exception:   # noqa: BLE001
+            traffic = {}
     for name in leaves:
         v = prof[name]
         if v["launches"] == 0:
@@ -337,10 +427,13 @@ def main_native(args):
     whole = {"t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / ms_per_step,
              "frac_of_tensor_peak": value / peaks["tc_sustained"]}
 
-    cpu_baseline = None
+    cpu_baseline, cpu_extra = None, None
     if world == 1 and not args.no_cpu_baseline:
         cb = run_reference_sample(1, 0)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu_baseline["host_cores"] = os.cpu_count()
+        cpu_baseline["same_config"] = False
+        cpu_extra = extra_cpu_baselines()
 
     line = {
         "metric": "block-QR TFLOP/s (2mn^2-2n^3/3)", "value": value, "unit": "TFLOP/s", "n_gpus": world,
@@ -352,7 +445,7 @@ def main_native(args):
                    "flop_model": "2mn^2-2n^3/3 (m>=n) / 2m^2n-2m^3/3 (m<n)"},
         "backward_error_sampled": be, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "roofline": roofline, "roofline_by_kernel": by_kernel, "whole_qr_roofline": whole, "cpu_baseline": cpu_baseline,
-        "profiled_step_ms": prof_ms,
+        "profiled_step_ms": prof_ms, "cpu_baselines_extra": cpu_extra,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

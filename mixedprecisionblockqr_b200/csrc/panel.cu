@@ -28,6 +28,9 @@
 // one row below the diagonal (:283-285); R_kk = -sign*||u||.
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace mpqr {
@@ -886,6 +889,8 @@ struct ChainArgs {
     unsigned* flag_done;
     const unsigned* flag_far;
     unsigned base;
+    float* srep[2];  // S replicas of the far updates (blocks alternate); the cluster clears srep[jb & 1] before it posts block jb
+    int srep_n;      // floats per buffer
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -1106,6 +1111,11 @@ __global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS)
             float* Tj = a.Tslots + (size_t)jb * a.tstride;
             const int t = tid >> 4, c = tid & 15;
             Tj[tid] = (t <= c) ? gt[t][c] : 0.f;
+        }
+        if (jb + 2 < nblk) {  // far(jb) accumulates into srep[jb & 1]; its previous user far(jb-2) was awaited above
+            float4* z = reinterpret_cast<float4*>(a.srep[jb & 1]);
+            const int n4 = a.srep_n >> 2;
+            for (int idx = (int)crank * NT + tid; idx < n4; idx += CS * NT) z[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __threadfence();
         if (CS > 1) cluster_sync_all(); else __syncthreads();
@@ -2169,6 +2179,15 @@ int launch_tinv(const float* G, long ldg, int pw, float* T32, int ldt, void* T16
 }
 
 template <int B>
+int su_attrs() {
+    MPQR_TRY(func_attr_once((const void*)inpanel_s_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    MPQR_TRY(func_attr_once((const void*)inpanel_u_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MPQR_TRY(func_attr_once((const void*)inpanel_s4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MPQR_TRY(func_attr_once((const void*)inpanel_u4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    return MPQR_OK;
+}
+
+template <int B>
 int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, float* Sfin,
               int num_sms, cudaStream_t st, long* launches, const ProfHook* prof, bool pair = false, bool pdl_first = true) {
     // one wave of CTAs over the SMs this stream may use (up to 512 rows = 32 KB of staged Y per CTA);
@@ -2178,10 +2197,7 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
     int rows = ceil_div(D, waves * num_sms);
     rows = round_up(rows < 16 ? 16 : rows, 16);
     if (rows > max_rows) rows = max_rows;
-    MPQR_TRY(func_attr_once((const void*)inpanel_s_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    MPQR_TRY(func_attr_once((const void*)inpanel_u_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    MPQR_TRY(func_attr_once((const void*)inpanel_s4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    MPQR_TRY(func_attr_once((const void*)inpanel_u4_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MPQR_TRY(su_attrs<B>());
     dim3 grid(ceil_div(D, rows), ceil_div(ncols, 128));
     cudaLaunchAttribute pat[1] = {pdl_attr()};
     cudaLaunchConfig_t cfg{};
@@ -2263,6 +2279,31 @@ int stream_post(cudaStream_t st, unsigned* flag, unsigned v) {
     }
     chain_post_kernel<<<1, 1, 0, st>>>(flag, v);
     MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+
+// CUDA loads kernels lazily, and loading one may need a context synchronisation: a first-time load of a side-stream
+// kernel WHILE the cluster spins on that side stream's flag would never return (CUDA programming guide, lazy loading,
+// "concurrent execution").  Everything that is issued between a chain launch and the end of its side-stream items is
+// therefore loaded (and given its attributes) before the first chain launch on a device.
+int chain_preload() {
+    static std::mutex mu;
+    static std::vector<int> done;
+    int dev = 0;
+    MPQR_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    for (int d : done)
+        if (d == dev) return MPQR_OK;
+    MPQR_TRY(su_attrs<16>());
+    const void* fns[] = {(const void*)inpanel_s_kernel<16>, (const void*)inpanel_u_kernel<16>, (const void*)inpanel_s4_kernel<16>,
+                         (const void*)inpanel_u4_kernel<16>, (const void*)chain_gate_kernel, (const void*)chain_post_kernel,
+                         (const void*)panel_finalize_kernel};
+    for (const void* f : fns) {
+        cudaFuncAttributes fa;
+        MPQR_CUDA(cudaFuncGetAttributes(&fa, f));
+    }
+    memop_api();
+    done.push_back(dev);
     return MPQR_OK;
 }
 
@@ -2429,20 +2470,21 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         *a.chain_ctr += (unsigned)nblocks;
         ca.flag_done = a.chain_flags;
         ca.flag_far = nblocks >= 3 ? a.chain_flags + 1 : nullptr;
+        float* SrepA = w.Srep + (size_t)2 * RMAX * SLD;
+        ca.srep[0] = SrepA; ca.srep[1] = SrepA + (size_t)2 * RMAX * SLD;
+        ca.srep_n = 2 * RMAX * SLD;
+        MPQR_TRY(chain_preload());
         if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 4.0 * D * pw * 16 + 4.0 * D * 16 * 16 * (nblocks - 1), 8.0 * D * pw);
         MPQR_TRY(launch_chain(ca, rpt, cs, stream));  // issued BEFORE the side stream's waits (a wait never queues ahead of its producer)
         if (a.prof) a.prof->end(a.prof->ctx, stream);
         if (launches) *launches += 1;
-        float* SrepA = w.Srep + (size_t)2 * RMAX * SLD;
-        const size_t srep_bytes = (size_t)2 * RMAX * SLD * sizeof(float);
         int side_sms = sm_count(di) - cs;  // the cluster keeps its SMs for the whole panel
         if (side_sms < 8) side_sms = 8;
         for (int jb = 0; jb + 2 < nblocks; ++jb) {
             const int j0 = jb * 16, Dj = D - j0, nfar = pw - (j0 + 32);
-            MPQR_CUDA(cudaMemsetAsync(SrepA, 0, srep_bytes, a.chain_side));
             MPQR_TRY(stream_wait_geq(a.chain_side, a.chain_flags, ca.base + (unsigned)(jb + 1)));
             MPQR_TRY(launch_su<16>(w.Wj + (size_t)jb * 32 * 32, Yp + (size_t)j0 * ldyp + j0, ldyp, Ablk + (size_t)j0 * a.lda + j0 + 32, a.lda, Dj,
-                                   nfar, SrepA, w.Sfin, side_sms, a.chain_side, launches, a.prof, false, false));
+                                   nfar, ca.srep[jb & 1], w.Sfin, side_sms, a.chain_side, launches, a.prof, false, false));
             MPQR_TRY(stream_post(a.chain_side, a.chain_flags + 1, ca.base + (unsigned)(jb + 1)));
         }
         // every side update was consumed by the kernel before it finished: stream order is enough from here on

@@ -27,3 +27,9 @@ wait
     "$OUT/qr.o" "$OUT/mmult.o" "$OUT/ref_wrap.o" -o "$OUT/libref_qr.so" -lcudart
 rm -f "$OUT"/*.o
 echo "built $OUT/libref_qr.so"
+# Eigen::HouseholderQR timing driver (the library call of C++/main.cpp:54) against the vendored Eigen 3.4.0 headers
+if [ -d "$REF/Cuda/QR/Solver/Eigen" ]; then
+    g++ -O3 -march=x86-64-v3 -DNDEBUG -std=c++17 -I"$REF/Cuda/QR/Solver" "$HERE/eigen_qr_bench.cpp" -o "$OUT/eigen_qr" \
+        || g++ -O3 -DNDEBUG -std=c++17 -I"$REF/Cuda/QR/Solver" "$HERE/eigen_qr_bench.cpp" -o "$OUT/eigen_qr"
+    echo "built $OUT/eigen_qr"
+fi

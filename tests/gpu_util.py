@@ -69,3 +69,66 @@ def gemm_nn(X, S, C, bf16=False, shadow=True, coff=0):
     pkg.check(rc, "mpqr_gemm_nn_device")
     torch.cuda.synchronize()
     return dC.cpu().numpy(), dH.float().cpu().numpy()
+
+
+# ------------------------------------------------------------------ whole-factorisation helpers (GPU side, FP64)
+def sampled_backward_error(A0, P, r, k=16):
+    """||(A - QR) X||_F / (||A||_F sqrt(k)) with Gaussian X, FP64 on the device, straight from the packed factor
+    (torch tensors: A0 m x n, P (m+1) x n).  Q is applied panel by panel from the stored unit vectors, so this is the
+    reference's ||A - QR||_F / ||A||_F (Cuda/qr.cu:115-135) sampled on k random directions."""
+    m, n = A0.shape
+    g = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.randn(n, k, device="cuda", dtype=torch.float64, generator=g)
+    AX = torch.zeros(m, k, device="cuda", dtype=torch.float64)
+    Z = torch.zeros(m, k, device="cuda", dtype=torch.float64)
+    an2 = 0.0
+    step = 4096
+    for i in range(0, m, step):
+        blk = A0[i:i + step].double()
+        AX[i:i + step] = blk @ X
+        an2 += float((blk * blk).sum())
+        Z[i:i + step] = torch.triu(P[i:min(i + step, m)].double(), diagonal=i) @ X
+    kmax = min(m, n)
+    for lam in range(((kmax - 1) // r) * r, -1, -r):
+        pw = min(r, kmax - lam)
+        Y = torch.tril(P[lam + 1:m + 1, lam:lam + pw].double())
+        Tinv = torch.triu(Y.T @ Y, 1) + 0.5 * torch.eye(pw, device="cuda", dtype=torch.float64)
+        Z[lam:] -= Y @ torch.linalg.solve_triangular(Tinv, Y.T @ Z[lam:], upper=True)
+    return float(torch.linalg.norm(AX - Z)) / (an2 ** 0.5 * k ** 0.5)
+
+
+def factor_device(A, r, precision="fp16", nb=0, reps=1):
+    """Factors the numpy matrix A through the plan API with device-resident buffers; returns (A0 device m x n view,
+    packed factor as a device tensor (m+1) x n view, plan.r, plan.nb)."""
+    m, n = A.shape
+    lda = (n + 7) // 8 * 8
+    A0 = torch.zeros(m, lda, device="cuda")
+    A0[:, :n] = torch.from_numpy(np.ascontiguousarray(A, np.float32)).cuda()
+    dA = torch.zeros(m + 1, lda, device="cuda")
+    plan = pkg.BlockQR(m, n, r, nb=nb, precision=precision)
+    for _ in range(reps):
+        dA[:m].copy_(A0)
+        dA[m].zero_()
+        plan.factor(dA.data_ptr(), lda, stream())
+        torch.cuda.synchronize()
+    rr, nbb = plan.r, plan.nb
+    plan.close()
+    return A0[:, :n], dA[:, :n], rr, nbb
+
+
+def r_rel_diff(P, Rref):
+    """max | |R| - |R_ref| | / max |R_ref| with R taken from the packed factor (device tensor or numpy)."""
+    Pn = P.cpu().numpy() if hasattr(P, "cpu") else P
+    m, n = Rref.shape[0], Rref.shape[1]
+    R = np.triu(Pn[:m, :n])[:Rref.shape[0]]
+    return float(np.abs(np.abs(R) - np.abs(Rref)).max() / np.abs(Rref).max())
+
+
+def observe(name, **vals):
+    """Appends the observed figures of a test to gpurun_out/observed.jsonl (tolerances are kept at <= 3x of these)."""
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "observed.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: float(v) for k, v in vals.items()}}) + "\n")

@@ -1,0 +1,220 @@
+"""Parity in the regimes the headline configurations actually take: tall panels (16-column
+register blocks with 8 rows per thread, the persistent panel chain), >= 3 outer blocks on the look-ahead driver,
+BASELINE configs C3 and C5 at full size, the secondary accuracy sets of SURVEY 8(d) (N(0,1), signed, conditioned
+U diag(s) V^T as python/utils.py:13-24), the FP16 range limit, run-to-run spread, and the reference's own GPU drivers
+(Cuda/qr.cu:958, :1049) on the same box.  References: the oracle where it finishes in seconds, else LAPACK in FP64
+(|R| is unique up to row signs for full-rank input).  Tolerances are <= 3x the figures observed on B200
+(gpurun_out/observed.jsonl -> profiles/r2_observed_tolerances.txt)."""
+import numpy as np
+import pytest
+import torch
+
+import mixedprecisionblockqr_b200 as pkg
+import oracle
+from gpu_util import factor_device, observe, r_rel_diff, sampled_backward_error
+
+pytestmark = pytest.mark.gpu
+EPS16, EPSB = 2.0 ** -11, 2.0 ** -8
+
+
+def _lapack_r(A):
+    return np.linalg.qr(A.astype(np.float64), mode="r")
+
+
+@pytest.mark.parametrize("chain", [True, False])
+def test_tall_panel_regime_vs_oracle(chain, monkeypatch):
+    # 32768 x 512, r = 128: D > 16384 -> 16-column register blocks, 8 rows per thread, cluster of 16, 4 panels of one
+    # outer block (in-block tensor-core updates + WY accumulation); elementwise against the oracle's packed factor
+    if not chain:
+        monkeypatch.setenv("MPQR_NO_CHAIN", "1")
+    m, n, r = 32768, 512, 128
+    A = oracle.uniform_matrix(m, n, 32768512)
+    Pref, _ = oracle.block_qr(A, r, want_q=False)
+    for prec, tol_r, tol_y, tol_be in (("fp32", 2e-5, 2e-5, 3e-6), ("fp16", 6 * EPS16, 6 * EPS16, 5.5 * EPS16)):
+        A0, P, rr, _ = factor_device(A, r, prec)
+        assert rr == r
+        Pn = P.cpu().numpy()
+        dr = r_rel_diff(Pn, np.triu(Pref[:m])[:n])
+        # Householder vectors: entries below the diagonal of the packed factor (unit vectors, |w| <= 1)
+        low = np.tril(np.ones((m + 1, n), bool), -1)
+        dy = float(np.abs(Pn[low] - Pref[low]).max())
+        be = sampled_backward_error(A0, P, r)
+        observe(f"tall_panel_{prec}_chain{int(chain)}", dr=dr, dy=dy, be=be)
+        assert dr <= tol_r and dy <= tol_y and be <= tol_be, (prec, dr, dy, be)
+
+
+@pytest.mark.parametrize("m,n,r,nb,prec", [(20000, 1536, 128, 512, "fp16"), (32768, 1536, 128, 512, "fp16"), (20000, 1536, 128, 512, "bf16"),
+                                           (17000, 1280, 100, 400, "fp16")])
+def test_lookahead_tall_vs_lapack(m, n, r, nb, prec, monkeypatch):
+    # three outer blocks on the look-ahead driver (green-context partitions, deferred WY accumulation) with tall panels;
+    # r = 100 exercises panel widths that are not a multiple of 8 (clipped TMA stores + deferred accumulation)
+    monkeypatch.setenv("MPQR_OVERLAP", "1")
+    A = oracle.uniform_matrix(m, n, m + 3 * n)
+    Rref = _lapack_r(A)
+    eps = EPSB if prec == "bf16" else EPS16
+    for rep in range(2):
+        A0, P, rr, nbb = factor_device(A, r, prec, nb=nb)
+        assert nbb == nb
+        dr = r_rel_diff(P, Rref)
+        be = sampled_backward_error(A0, P, rr)
+        observe(f"lookahead_tall_{m}x{n}_r{r}_{prec}", dr=dr, be=be)
+        assert be <= 5.5 * eps and dr <= 10 * eps, (dr, be)
+
+
+def test_c3_full_size_vs_lapack():
+    # BASELINE config 3: wide 4096 x 16384, r = 64 (m < n: R is 4096 x 16384, reflectors stop at column 4095)
+    m, n, r = 4096, 16384, 64
+    A = oracle.uniform_matrix(m, n, 4096064)
+    Rref = _lapack_r(A)
+    A0, P, rr, _ = factor_device(A, r, "fp16")
+    dr = r_rel_diff(P, Rref)
+    be = sampled_backward_error(A0, P, rr)
+    observe("c3_full_fp16", dr=dr, be=be)
+    assert be <= 5.5 * EPS16 and dr <= 10 * EPS16, (dr, be)
+
+
+def test_c5_full_size_vs_lapack():
+    # BASELINE config 5: 1048576 x 256 through the TSQR entry (python/ca_qr.py:25-43): |R| against FP64 LAPACK, thin Q
+    m, n = 1048576, 256
+    st = torch.cuda.current_stream().cuda_stream
+    A = torch.zeros(m, n, device="cuda")
+    pkg.fill_uniform(A.data_ptr(), n, n, 0, m, 0, n, 1048576256, st)
+    Q = torch.zeros(m, n, device="cuda")
+    R = torch.zeros(n, n, device="cuda")
+    pkg.tsqr(A.data_ptr(), n, m, n, Q.data_ptr(), n, R.data_ptr(), n, st)
+    torch.cuda.synchronize()
+    Rref = torch.linalg.qr(A.double(), mode="r").R.cpu().numpy()
+    Rn = R.cpu().numpy()
+    dr = float(np.abs(np.abs(Rn) - np.abs(Rref)).max() / np.abs(Rref).max())
+    Ad, Qd, Rd = A.double(), Q.double(), R.double()
+    be = float(torch.linalg.norm(Ad - Qd @ Rd) / torch.linalg.norm(Ad))
+    orth = float(torch.linalg.norm(Qd.T @ Qd - torch.eye(n, device="cuda", dtype=torch.float64)))
+    observe("c5_full_tsqr", dr=dr, be=be, orth=orth)
+    assert dr <= 2e-5 and be <= 3e-6 and orth <= 5e-5, (dr, be, orth)
+
+
+def _conditioned(m, n, cond, seed):
+    """U diag(s) V^T with log-spaced singular values, as the reference's generator python/utils.py:13-24."""
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    s = np.logspace(0, -np.log10(cond), n)
+    return (U * s) @ V.T
+
+
+@pytest.mark.parametrize("kind", ["normal", "signed", "cond1e3", "cond1e5", "cond1e7"])
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
+def test_secondary_accuracy_sets(kind, prec):
+    # N(0,1), signed uniform, conditioned matrices at n = 1024 (2 outer blocks at nb = 512).  Householder QR is
+    # backward stable whatever the condition number: the backward error stays at the operand precision.  |R| is compared
+    # against FP64 LAPACK relative to max|R| (the small trailing R_kk of an ill-conditioned matrix carry no relative accuracy).
+    m, n, r = 1536, 1024, 64
+    rng = np.random.default_rng(11)
+    if kind == "normal":
+        A = rng.standard_normal((m, n))
+    elif kind == "signed":
+        A = rng.random((m, n)) * 2 - 1
+    else:
+        A = _conditioned(m, n, float(kind[4:]), 5)
+    A = A.astype(np.float32)
+    Rref = _lapack_r(A)
+    A0, P, rr, _ = factor_device(A, r, prec, nb=512)
+    assert torch.isfinite(P).all()
+    be = sampled_backward_error(A0, P, rr)
+    dr = r_rel_diff(P, Rref)
+    observe(f"secondary_{kind}_{prec}", dr=dr, be=be)
+    eps = {"fp32": None, "fp16": EPS16, "bf16": EPSB}[prec]
+    if prec == "fp32":
+        assert be <= 3e-6 and dr <= 3e-5, (dr, be)
+    else:
+        assert be <= 5.5 * eps and dr <= 10 * eps, (dr, be)
+
+
+def test_fp16_range_limit():
+    # The FP16 path keeps a 16-bit operand shadow of A: entries of the trailing matrix grow to ~ the column norms, so the
+    # input must satisfy max|a| sqrt(m) < 65504.  Inside the range the result is as accurate as for O(1) data (the backward
+    # error is scale invariant); outside it the FP16 path returns non-finite entries while BF16 (FP32 exponent range) still works.
+    m, n, r = 1024, 512, 64
+    A = oracle.uniform_matrix(m, n, 99)
+    for scale, prec, ok in ((1e3, "fp16", True), (1e-3, "fp16", True), (1e6, "bf16", True), (1e6, "fp16", False)):
+        As = (A * np.float32(scale)).astype(np.float32)
+        A0, P, rr, _ = factor_device(As, r, prec)
+        finite = bool(torch.isfinite(P).all())
+        assert finite == ok, (scale, prec)
+        if ok:
+            be = sampled_backward_error(A0, P, rr)
+            observe(f"range_{prec}_{scale:g}", be=be)
+            assert be <= 5.5 * (EPSB if prec == "bf16" else EPS16)
+
+
+def test_run_to_run_spread_is_bounded():
+    # The in-panel S reductions (atomics into two replicas) and the split-K TMA reduce-add are not order-deterministic:
+    # two runs on the same input agree to rounding, not bit for bit.  Bound the spread (observed on B200: see the log).
+    m, n, r = 6000, 4096, 128
+    A = oracle.uniform_matrix(m, n, 6000)
+    for prec, tol in (("fp32", 2e-5), ("fp16", 6 * EPS16)):
+        _, P1, _, _ = factor_device(A, r, prec)
+        P1 = P1.clone()
+        _, P2, _, _ = factor_device(A, r, prec)
+        R1, R2 = torch.triu(P1[:m]), torch.triu(P2[:m])
+        spread = float((R1.abs() - R2.abs()).abs().max() / R1.abs().max())
+        observe(f"spread_{prec}", spread=spread)
+        assert spread <= tol, spread
+
+
+@pytest.mark.parametrize("m,n,r", [(60, 40, 8), (129, 80, 16), (240, 160, 16), (256, 256, 32)])
+def test_reference_gpu_drivers_on_this_box(m, n, r):
+    """The UNMODIFIED reference GPU drivers dev_block_qr_wy / dev_mixed_precision_block_qr (Cuda/qr.cu:958, :1049; compiled
+    into oracle/_ref by oracle/build_ref.sh) run on the same B200 on the same input: their packed factors and ours must
+    agree (FP32 driver: rounding level; mixed driver: the reference keeps A in FP32 and uses FP16 only in the Q product,
+    ours uses FP16 operands in the trailing update, so R agrees at FP16-GEMM level).  Sizes stay small: the reference's K2
+    prints from every device thread (Cuda/qr.cu:500)."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref_qr.so not built")
+    A = oracle.uniform_matrix(m, n, 1000 * m + n + r)
+    for mixed in (False, True):
+        Pref, Qref = oracle.ref_dev_block_qr(A, r, mixed=mixed)
+        P = oracle.pack(A)
+        Q = np.full((m, m), np.nan, np.float32)
+        (pkg.dev_mixed_precision_block_qr if mixed else pkg.dev_block_qr_wy)(P, Q, m, n, r)
+        scale = np.abs(Pref).max()
+        dp = float(np.abs(np.abs(np.triu(P[:m])) - np.abs(np.triu(Pref[:m]))).max() / scale)
+        be_ref = oracle.backward_error(A, oracle.strip_R(Pref), Qref)
+        be = oracle.backward_error(A, oracle.strip_R(P), Q)
+        observe(f"refgpu_{m}x{n}_r{r}_mixed{int(mixed)}", dp=dp, be=be, be_ref=be_ref)
+        assert dp <= (6 * EPS16 if mixed else 2e-5), dp
+        assert be <= (5.5 * EPS16 if mixed else 3e-6)
+        assert be_ref <= m * 2.0 ** (-11 if mixed else -23)      # the reference passes its own criterion on this box
+
+
+def test_c1_substitute_through_the_euroc_loader(tmp_path):
+    """BASELINE config 1 substitute (the EuRoC blob is absent): a block-sparse "Jacobian-like" 2000 x 2000
+    matrix (6-row residual blocks touching two 9-column state blocks and a prior diagonal, ~1 % fill) written in the
+    EuRoC text format, read back by mpqr_read_euroc_jacobian and factored at r = 16 exactly as the reference's test_qr
+    does with its Jacobians (Cuda/qr.cu:1795-1804: read_euroc_jacobian, f(m, n, 16, A_in)); the reference has no
+    sparse path of its own (it runs the dense driver on the zero-filled matrix) and neither has this one."""
+    rng = np.random.default_rng(2000)
+    m = n = 2000
+    A = np.zeros((m, n), np.float32)
+    for rb in range(0, m - 5, 6):
+        for _ in range(2):
+            cb = 9 * int(rng.integers(0, n // 9))
+            A[rb:rb + 6, cb:cb + 9] = rng.standard_normal((6, min(9, n - cb))).astype(np.float32)
+    A[np.arange(m), np.arange(n)] += 4.0          # priors: full column rank
+    p = tmp_path / "A_000000100.txt"
+    with open(p, "w") as f:
+        f.write(f"{m} {n}\n")
+        ii, jj = np.nonzero(A)
+        for i, j in zip(ii, jj):
+            f.write(f"{i} {j} {A[i, j]:.9g}\n")
+    P0 = pkg.read_euroc_jacobian(str(p))
+    assert P0.shape == (m + 1, n) and np.array_equal(P0[:m], A)
+    Rref = _lapack_r(A)
+    for name, fn, tol_r, tol_be in (("fp32", pkg.dev_block_qr_wy, 3e-5, 3e-6), ("fp16", pkg.dev_mixed_precision_block_qr, 10 * EPS16, 5.5 * EPS16)):
+        P = P0.copy()
+        fn(P, None, m, n, 16)
+        dr = r_rel_diff(P, Rref)
+        be = sampled_backward_error(torch.from_numpy(A).cuda(), torch.from_numpy(P).cuda(), 64)   # (any grouping of the reflectors works)
+        observe(f"c1_substitute_{name}", dr=dr, be=be, fill=float((A != 0).mean()))
+        assert dr <= tol_r and be <= tol_be, (name, dr, be)
+
