@@ -309,16 +309,16 @@ void overlap_destroy(mpqr_handle* h) {
     o = mpqr_handle::Overlap();
 }
 
-// Cost model of the look-ahead driver (B200 measurements of round 1).  Times in ms.
-//   panel chain of one r-wide panel on the whole device: 0.15 + 0.0116 * D/1024   (D <= 16384, 32-column register blocks)
-//                                                        0.33 + 0.0122 * (D - 16384)/1024 + 0.19  (taller: 16-column blocks)
-//   the chain is latency-bound, but its device-wide kernels slow down on a small partition:  x (1 + 22 / SMs)
-//   far update: 4 D N' kb flops at ~6.6 TFLOP/s per SM (measured: 4.1e12 flop in 6.2 ms on 100 SMs)
+// Cost model of the look-ahead driver (B200 measurements of round 2 with the persistent panel chain).
+// Times in ms.  One r = 128 panel of the chain (cluster kernel + finalize + Gram/T/W + the next panel's in-block update):
+//   D > 16384 (8 rows per thread):  0.30 + 0.0078 * D/1024        D <= 16384:  0.19 + 0.0088 * D/1024
+// measured on 64-80 SM partitions; the cluster itself needs 16 SMs, the side updates and the in-block GEMMs share the rest:
+//   x (1 + 12 / SMs).   Far update: 4 D N' kb flops at ~6.6 TFLOP/s per SM (measured: 4.1e12 flop in 6.2 ms on 100 SMs).
 double model_bp_ms(const mpqr_handle* h, int c0, int c1) {
     double t = 0;
     for (int lam = c0; lam < c1; lam += h->r) {
         const double D = h->m - lam;
-        t += (D <= 16384) ? 0.15 + 0.0116 * D / 1024.0 : 0.52 + 0.0122 * (D - 16384) / 1024.0;
+        t += (D <= 16384) ? 0.19 + 0.0088 * D / 1024.0 : 0.30 + 0.0078 * D / 1024.0;
     }
     static const double scale = getenv("MPQR_BP_SCALE") ? atof(getenv("MPQR_BP_SCALE")) : 1.0;  // tuning knob of the cost model
     return scale * t * (h->r / 128.0 < 0.25 ? 0.25 : h->r / 128.0);
@@ -465,7 +465,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
             double best_t = bp_full + model_far_ms(h, c0, c1, nfar - nnext, o.nsm_full);
             for (size_t k = 0; k < o.pairs.size(); ++k) {
                 if (fixed_sms > 0 && o.pairs[k].nsmP != fixed_sms) continue;
-                const double tb = bp_full * (1.0 + 22.0 / o.pairs[k].nsmP);
+                const double tb = bp_full * (1.0 + 12.0 / o.pairs[k].nsmP);
                 const double tf = model_far_ms(h, c0, c1, nfar - nnext, o.pairs[k].nsmU);
                 const double t = tb > tf ? tb : tf;
                 if (t < best_t || (fixed_sms > 0 && best < 0)) { best_t = t; best = (int)k; }
@@ -581,10 +581,13 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         const void* Wpp = (char*)c.W16 + ((size_t)jc * c.ldw + jc) * 2;   // the panel's own W / Y, rows lam..
         const void* Ypp = (char*)c.Y16 + ((size_t)jc * c.ldy + jc) * 2;
         auto inblock = [&](int ofs, int nc, float* xS32, void* xS16, int pad_ok, cudaStream_t st) -> int {
+            int w16 = 0;
             PROF(1, 2.0 * pw * nc * D, tn_bytes(pw, nc, D),
-                 tc_gemm_tn(Wpp, c.ldw, at16(c.Ah, c.ldh, lam, acol_tau + ofs), c.ldh, xS32, h->lds32, pw, nc, D, bf, 1, st, &h->launches));
-            PROF(3, 0, 6.0 * pw * nc, convert_f32_to_16(xS32, h->lds32, xS16, h->lds16, pw, nc, bf, st));
-            h->launches += 1;
+                 tc_gemm_tn16(Wpp, c.ldw, at16(c.Ah, c.ldh, lam, acol_tau + ofs), c.ldh, xS32, h->lds32, xS16, h->lds16, &w16, pw, nc, D, bf, 1, st, &h->launches));
+            if (!w16) {
+                PROF(3, 0, 6.0 * pw * nc, convert_f32_to_16(xS32, h->lds32, xS16, h->lds16, pw, nc, bf, st));
+                h->launches += 1;
+            }
             PROF(2, 2.0 * D * nc * pw, nn_bytes(D, nc, pw),
                  tc_gemm_nn(Ypp, c.ldy, xS16, h->lds16, c.A + (size_t)lam * c.lda + acol_tau + ofs, c.lda,
                             at16(c.Ah, c.ldh, lam, acol_tau + ofs), c.ldh, D, nc, pw, bf, pad_ok, st, &h->launches));
@@ -637,10 +640,13 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             {
                 cudaStream_t st = c.acc_stream ? c.acc_stream : st_panel;  // (PROF records on `st`)
                 SmBudget budget(c.acc_stream ? c.acc_sms : g_sm_budget);
+                int w16 = 0;
                 PROF(1, 2.0 * jc * pw * Dblk, tn_bytes(jc, pw, Dblk),
-                     tc_gemm_tn(c.Y16, c.ldy, Wp, c.ldw, aS32, h->lds32, jc, pw, Dblk, bf, 1, st, &h->launches));
-                PROF(3, 0, 6.0 * jc * pw, convert_f32_to_16(aS32, h->lds32, aS16, h->lds16, jc, pw, bf, st));
-                h->launches += 1;
+                     tc_gemm_tn16(c.Y16, c.ldy, Wp, c.ldw, aS32, h->lds32, aS16, h->lds16, &w16, jc, pw, Dblk, bf, 1, st, &h->launches));
+                if (!w16) {
+                    PROF(3, 0, 6.0 * jc * pw, convert_f32_to_16(aS32, h->lds32, aS16, h->lds16, jc, pw, bf, st));
+                    h->launches += 1;
+                }
                 PROF(2, 2.0 * Dblk * pw * jc, nn_bytes(Dblk, pw, jc),
                      tc_gemm_nn(c.W16, c.ldw, aS16, h->lds16, h->Wblk32 + jc, h->ldwb, (void*)Wp, c.ldw, Dblk, pw, jc, bf,
                                 // a deferred accumulation may run after the NEXT panel produced its W: the zero spill of a
@@ -666,10 +672,13 @@ int far_update(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int afar, int 
     const int Dblk = h->m - c0, kb = c1 - c0;
     float* S32 = c.S32 ? c.S32 : h->S32;
     void* S16 = c.S16 ? c.S16 : h->S16;
+    int w16 = 0;
     PROF(1, 2.0 * kb * nfar * Dblk, tn_bytes(kb, nfar, Dblk),
-         tc_gemm_tn(c.W16, c.ldw, at16(c.Ah, c.ldh, c0, afar), c.ldh, S32, h->lds32, kb, nfar, Dblk, bf, 1, st, &h->launches));
-    PROF(3, 0, 6.0 * kb * nfar, convert_f32_to_16(S32, h->lds32, S16, h->lds16, kb, nfar, bf, st));
-    h->launches += 1;
+         tc_gemm_tn16(c.W16, c.ldw, at16(c.Ah, c.ldh, c0, afar), c.ldh, S32, h->lds32, S16, h->lds16, &w16, kb, nfar, Dblk, bf, 1, st, &h->launches));
+    if (!w16) {
+        PROF(3, 0, 6.0 * kb * nfar, convert_f32_to_16(S32, h->lds32, S16, h->lds16, kb, nfar, bf, st));
+        h->launches += 1;
+    }
     PROF(2, 2.0 * Dblk * nfar * kb, nn_bytes(Dblk, nfar, kb),
          tc_gemm_nn(c.Y16, c.ldy, S16, h->lds16, c.A + (size_t)c0 * c.lda + afar, c.lda, at16(c.Ah, c.ldh, c0, afar), c.ldh,
                     Dblk, nfar, kb, bf, 1, st, &h->launches));
@@ -1131,12 +1140,30 @@ int mpqr_debug_panel_probe(float* dA, long lda, int m, int n, int lam, int pw, i
     a.A = dA; a.lda = lda; a.m = m; a.n = n; a.lam = lam; a.acol = lam; a.pw = pw; a.blk_row0 = lam;
     a.Y32 = Y; a.W32 = W; a.ld32 = pw; a.T = T; a.ldt = pw;
     a.ws = pws; a.ws_rows = m - lam;
-    a.dbg = dDbg; a.force_b = force_b; a.force_cs = force_cs; a.force_rpt = force_rpt;
+    a.force_b = force_b; a.force_cs = force_cs; a.force_rpt = force_rpt;
     int caps[3] = {0, 0, 0};
     a.dbg_caps = caps;
+    // force_b == -1: probe the persistent chain (dDbg receives 8 globaltimer stamps per register block) instead of the
+    // phase counters of the single-block kernels
+    unsigned* cflags = nullptr;
+    unsigned cctr = 0;
+    cudaStream_t cside = nullptr;
+    if (force_b == -1) {
+        a.force_b = 0;
+        a.chain_dbg = dDbg;
+        MPQR_CUDA(cudaMalloc(&cflags, 64));
+        MPQR_CUDA(cudaMemset(cflags, 0, 64));
+        MPQR_CUDA(cudaStreamCreateWithFlags(&cside, cudaStreamNonBlocking));
+        a.chain_side = cside; a.chain_flags = cflags; a.chain_ctr = &cctr;
+    } else {
+        a.dbg = dDbg;
+    }
     int rc = launch_panel(a, (cudaStream_t)stream, nullptr);
     cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (cside) { cudaStreamSynchronize(cside); cudaStreamDestroy(cside); }
+    cudaFree(cflags);
     cudaFree(Y); cudaFree(W); cudaFree(T); cudaFree(pws);
+    if (force_b == -1) return (rc == MPQR_OK && e != cudaSuccess) ? MPQR_ECUDA : rc;
     if (rc == MPQR_OK && e != cudaSuccess) { set_error("panel probe failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; }
     if (rc == MPQR_OK && dDbg) {
         long long c[3] = {caps[0], caps[1], caps[2]};

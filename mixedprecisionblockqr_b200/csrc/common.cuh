@@ -139,6 +139,7 @@ struct PanelArgs {
     cudaStream_t chain_side;  // null: the chain flow is not used
     unsigned* chain_flags;    // device: [0] block done (kernel -> side stream), [1] far update done (side stream -> kernel)
     unsigned* chain_ctr;      // host mirror: the flags only grow
+    long long* chain_dbg;     // optional device buffer, 8 x int64 per register block: globaltimer stamps of the cluster
 };
 constexpr int kPanelLaEvents = 2 * 8 + 4;
 // true if launch_panel will honour the look-ahead fields for this panel (else it ignores them and the caller
@@ -172,6 +173,10 @@ int simt16_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* 
 // the tile count cannot fill the GPU (S is zeroed internally in that case).
 int tc_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long lds, int M, int N,
                int K, int bf16, int pad_ok, cudaStream_t stream, long* launches);
+// The same with a 16-bit copy of S for the following NN GEMM: without split-K the epilogue writes S16 directly
+// (*wrote16 = 1, S untouched), else S is produced and the caller converts.
+int tc_gemm_tn16(const void* X, long ldx, const void* Z, long ldz, float* S, long lds, void* S16, long lds16, int* wrote16,
+                 int M, int N, int K, int bf16, int pad_ok, cudaStream_t stream, long* launches);
 // C[M x N] (fp32) -= X S16, X [M x K] 16-bit (K-major), S16 [K x N] 16-bit; optionally mirrors
 // the updated C into C16 (16-bit shadow).
 int tc_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* C, long ldc, void* C16,

@@ -168,6 +168,7 @@ struct GemmParams {
     int splits;    // split-K factor (TN only)
     int kblocks_per_split;
     int has_shadow;
+    int no_c;      // TN only: the FP32 result is not wanted, only its 16-bit copy (operand of the following NN GEMM)
 };
 
 // kAMN : A operand is MN-major (TN GEMM) else K-major (NN GEMM)
@@ -203,7 +204,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         prefetch_tmap(&tmC);
-        if (kEpi >= 1 && p.has_shadow) prefetch_tmap(&tmH);
+        if (p.has_shadow) prefetch_tmap(&tmH);
     }
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < STAGES; ++i) {
@@ -363,10 +364,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else {
                         r4 = a4;
                     }
-                    *pc = r4;
+                    if (kEpi != 0 || !p.no_c) *pc = r4;
                     o[4 * i] = r4.x; o[4 * i + 1] = r4.y; o[4 * i + 2] = r4.z; o[4 * i + 3] = r4.w;
                 }
-                if (kEpi >= 1 && p.has_shadow) {
+                if (p.has_shadow) {
                     uint8_t* hrow = hb + row * 64;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -395,8 +396,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (leader) {
                     const int cx = p.cx0 + nb * BN + j * CCH, cy = p.cy0 + mb * BM;
                     if (kEpi == 0 && p.splits > 1) tma_reduce_add_2d(&tmC, cb, cx, cy);
-                    else tma_store_2d(&tmC, cb, cx, cy);
-                    if (kEpi >= 1 && p.has_shadow) tma_store_2d(&tmH, hb, p.hx0 + nb * BN + j * CCH, p.hy0 + mb * BM);
+                    else if (kEpi != 0 || !p.no_c) tma_store_2d(&tmC, cb, cx, cy);
+                    if (p.has_shadow) tma_store_2d(&tmH, hb, p.hx0 + nb * BN + j * CCH, p.hy0 + mb * BM);
                     tma_commit();
                 }
                 ++g;
@@ -491,6 +492,14 @@ int pick_bn(int N) { return N > 128 ? 256 : 128; }
 
 int tc_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long lds, int M, int N, int K,
                int bf16, int pad_ok, cudaStream_t stream, long* launches) {
+    return tc_gemm_tn16(X, ldx, Z, ldz, S, lds, nullptr, 0, nullptr, M, N, K, bf16, pad_ok, stream, launches);
+}
+
+// S16 != null: when the launch needs no split-K the epilogue rounds the result to 16 bit itself and writes ONLY S16
+// (*wrote16 = 1; S stays untouched); otherwise S (FP32) is produced as usual and the caller converts (*wrote16 = 0).
+int tc_gemm_tn16(const void* X, long ldx, const void* Z, long ldz, float* S, long lds, void* S16, long lds16, int* wrote16,
+                 int M, int N, int K, int bf16, int pad_ok, cudaStream_t stream, long* launches) {
+    if (wrote16) *wrote16 = 0;
     if (M <= 0 || N <= 0) return MPQR_OK;
     DeviceInfo di;
     MPQR_TRY(get_device_info(&di));
@@ -520,12 +529,19 @@ int tc_gemm_tn(const void* X, long ldx, const void* Z, long ldz, float* S, long 
     }
     p.kblocks_per_split = ceil_div(kblocks, splits);
     p.splits = ceil_div(kblocks, p.kblocks_per_split);
+    CUtensorMap tH = tC;
+    if (S16 && p.splits == 1 && !align_blk(S16, 2).x0 && !(lds16 & 7) && (pad_ok || !(N & 7))) {
+        MPQR_TRY(make_map(&tH, S16, 2, bf16, N, M, lds16, CCH, BM, CU_TENSOR_MAP_SWIZZLE_64B));
+        p.has_shadow = 1;
+        p.no_c = 1;
+        if (wrote16) *wrote16 = 1;
+    }
     if (p.splits > 1)
         MPQR_CUDA(cudaMemset2DAsync(S, lds * sizeof(float), 0, (size_t)N * sizeof(float), M, stream));
     int total = tiles * p.splits;
     int grid = total < sm_count(di) ? total : sm_count(di);
-    int rc = (BN == 256) ? launch<256, true, 0>(tA, tB, tC, tC, p, bf16 ? 1 : 0, grid, stream)
-                         : launch<128, true, 0>(tA, tB, tC, tC, p, bf16 ? 1 : 0, grid, stream);
+    int rc = (BN == 256) ? launch<256, true, 0>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream)
+                         : launch<128, true, 0>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream);
     if (rc == MPQR_OK && launches) *launches += 1;
     return rc;
 }

@@ -75,8 +75,14 @@ struct MgState {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     int nloc = 0;        // local columns
-    void* YW16 = nullptr;  // staging: Y block then W block, each m x ldw 16-bit
+    void* YW16[2] = {nullptr, nullptr};  // staging (blocks alternate): Y block then W block, each m x ldw 16-bit
     long ldw = 0;
+    // look-ahead schedule: panel chain / far updates / NCCL on their own streams (green-context partitions when the
+    // handle has them), ordered by events
+    cudaStream_t s_comm = nullptr, s_panel = nullptr, s_upd = nullptr;
+    bool own_streams = false;
+    std::vector<cudaEvent_t> ev_bp, ev_bc, ev_far, ev_next;
+    cudaEvent_t ev_start = nullptr;
     void* Ah = nullptr;  // local shadow, m x ldh
     long ldh = 0;
     // TSQR scratch (grow-only, freed with the handle): R_p | R stack | Q of the stack | thin Q_p
@@ -150,8 +156,9 @@ int mpqr_mg_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flag
         return MPQR_EINVAL;
     }
     mpqr_handle* h = nullptr;
-    // The base handle provides T, sync workspace, S32/S16, Wblk32; its own shadow/W16 buffers are
-    // sized for the full matrix, so create it for a 1-column-block-wide dummy and add ours below.
+    // The base handle provides T, the panel workspaces, S32/S16, Wblk32 and (for >= 4 outer blocks) the green-context
+    // partitions; its full-matrix shadow / W16 buffers stay unused on this path (memory is not the constraint here:
+    // 180 GB per GPU), the local shadow and the Y|W staging buffers are added below.
     int nb_eff = nb > 0 ? nb : 1024;
     MPQR_TRY(mpqr_create(&h, m, n, r, nb_eff, flags));
     MgState* g = new MgState();
@@ -171,9 +178,30 @@ int mpqr_mg_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flag
             break;
         }
         g->ldw = round_up(h->nb, 8);
-        if ((rc = dev_alloc(h, &g->YW16, (size_t)2 * m * g->ldw * 2))) break;
+        if ((rc = dev_alloc(h, &g->YW16[0], (size_t)2 * m * g->ldw * 2))) break;
+        if ((rc = dev_alloc(h, &g->YW16[1], (size_t)2 * m * g->ldw * 2))) break;
         g->ldh = round_up(g->nloc > 0 ? g->nloc : 8, 8);
         if ((rc = dev_alloc(h, &g->Ah, (size_t)m * g->ldh * 2))) break;
+        // GEMM scratch of the update / in-block-rest streams (the base handle only has them when its own look-ahead is on)
+        if (!h->S32u && (rc = dev_alloc(h, (void**)&h->S32u, (size_t)h->sk * h->lds32 * sizeof(float)))) break;
+        if (!h->S16u && (rc = dev_alloc(h, &h->S16u, (size_t)h->sk * h->lds16 * 2))) break;
+        if (!h->S32r && (rc = dev_alloc(h, (void**)&h->S32r, (size_t)h->sk * h->lds32 * sizeof(float)))) break;
+        if (!h->S16r && (rc = dev_alloc(h, &h->S16r, (size_t)h->sk * h->lds16 * 2))) break;
+        if (cudaStreamCreateWithFlags(&g->s_comm, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
+        if (!h->ov.on || h->ov.pairs.empty()) {
+            if (cudaStreamCreateWithFlags(&g->s_panel, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&g->s_upd, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
+            g->own_streams = true;
+        }
+        const int nblk = ceil_div(h->kmax, h->nb);
+        g->ev_bp.resize(nblk); g->ev_bc.resize(nblk); g->ev_far.resize(nblk); g->ev_next.resize(nblk);
+        for (int i = 0; i < nblk; ++i) {
+            cudaEventCreateWithFlags(&g->ev_bp[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&g->ev_bc[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&g->ev_far[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&g->ev_next[i], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&g->ev_start, cudaEventDisableTiming);
     } while (0);
     if (rc != MPQR_OK) {
         mpqr_destroy(h);
@@ -212,30 +240,107 @@ int mpqr_mg_factor_device(mpqr_handle* h, float* dA, long lda, void* stream) {
         PROF(3, 0, 6.0 * m * g->nloc, convert_f32_to_16(dA, lda, g->Ah, g->ldh, m, g->nloc, bf, st));
         h->launches += 1;
     }
-    void* Y16 = g->YW16;
-    void* W16 = (char*)g->YW16 + (size_t)m * g->ldw * 2;
+    // Look-ahead schedule: block b+1's owner updates that block's columns first (far_next on the panel
+    // stream), factors it and broadcasts it on the comm stream WHILE every rank still applies block b to the rest of
+    // its columns (far_rest on the update stream).  Y|W staging is double buffered.  Dependencies:
+    //   bp(b)    : far_next(b-1) [same stream]; staging[b&1] free = far_rest(b-2), far_next(b-2) done
+    //   bcast(b) : bp(b) on the owner; staging[b&1] free on the receivers
+    //   far_*(b) : bcast(b); far_next(b) additionally far_rest(b-1) (same columns, other stream)
+    const int nblk = ceil_div(h->kmax, nb);
+    // streams: a (panel, update) green-context pair of the base handle when it has one, else plain streams
+    cudaStream_t s_panel = g->s_panel, s_upd = g->s_upd, s_rest = nullptr, s_side = nullptr;
+    int nsm_p = 0, nsm_u = 0;
+    if (!g->own_streams) {
+        size_t pick = 0;  // the pair whose panel partition is closest to 64 SMs
+        for (size_t k = 0; k < h->ov.pairs.size(); ++k)
+            if (abs(h->ov.pairs[k].nsmP - 64) < abs(h->ov.pairs[pick].nsmP - 64)) pick = k;
+        const auto& pr = h->ov.pairs[pick];
+        s_panel = pr.sP; s_rest = pr.sP2; s_side = pr.sP3; s_upd = pr.sU;
+        nsm_p = pr.nsmP; nsm_u = pr.nsmU;
+    }
+    cudaStream_t s_comm = g->s_comm;
+    MPQR_CUDA(cudaEventRecord(g->ev_start, st));
+    MPQR_CUDA(cudaStreamWaitEvent(s_panel, g->ev_start, 0));
+    MPQR_CUDA(cudaStreamWaitEvent(s_upd, g->ev_start, 0));
+    MPQR_CUDA(cudaStreamWaitEvent(s_comm, g->ev_start, 0));
+    std::vector<char> did_next(nblk, 0);
     for (int c0 = 0, b = 0; c0 < h->kmax; c0 += nb, ++b) {
         const int c1 = (c0 + nb < h->kmax) ? c0 + nb : h->kmax;
         const int owner = b % P, Dblk = m - c0;
+        void* Y16 = g->YW16[b & 1];
+        void* W16 = (char*)g->YW16[b & 1] + (size_t)m * g->ldw * 2;
         BlockCtx c{};
         c.A = dA; c.lda = lda; c.Ah = g->Ah; c.ldh = g->ldh;
         c.Y16 = Y16; c.ldy = g->ldw; c.W16 = W16; c.ldw = g->ldw;
+        const int acol0 = (b / P) * nb;                    // local column of global column c0 on the owner
+        const int bw_full = (c0 + nb <= n) ? nb : n - c0;  // all columns of global block b (reflectors may stop earlier: m < n)
         if (owner == g->rank) {
-            c.acol0 = (b / P) * nb;
-            // the block's own trailing columns end where the next local block (a later global block)
-            // begins, so a spill past the last in-block column would hit live data unless it is the
-            // physical end of the local matrix
-            const int end_ok = (c.acol0 + (c1 - c0) == g->nloc);
-            MPQR_TRY(block_phase(h, c, c0, c1, end_ok, st));
+            c.acol0 = acol0;
+            if (b >= 2) {
+                MPQR_CUDA(cudaStreamWaitEvent(s_panel, g->ev_far[b - 2], 0));
+                if (did_next[b - 2]) MPQR_CUDA(cudaStreamWaitEvent(s_panel, g->ev_next[b - 2], 0));
+            }
+            // the block's own trailing columns end where the next local block (a later global block) begins, so a
+            // spill past the last in-block column would hit live data unless it is the physical end of the local matrix
+            const int end_ok = (acol0 + (c1 - c0) == g->nloc);
+            BlockCtx cp = c;
+            cp.chain_side = s_side;
+            if (s_rest && !h->ov.ev_rest.empty()) { cp.rest_stream = s_rest; cp.rest_S32 = h->S32r; cp.rest_S16 = h->S16r; cp.rest_ev = h->ov.ev_rest.data(); }
+            {
+                SmBudget budget(nsm_p);
+                MPQR_TRY(block_phase(h, cp, c0, c1, end_ok, s_panel));
+            }
+            MPQR_CUDA(cudaEventRecord(g->ev_bp[b], s_panel));
+            MPQR_CUDA(cudaStreamWaitEvent(s_comm, g->ev_bp[b], 0));
+        }
+        if (b >= 2) {  // the receivers overwrite staging[b & 1]: its readers of block b-2 must be done
+            MPQR_CUDA(cudaStreamWaitEvent(s_comm, g->ev_far[b - 2], 0));
+            if (did_next[b - 2]) MPQR_CUDA(cudaStreamWaitEvent(s_comm, g->ev_next[b - 2], 0));
         }
         // Y and W of block b to everyone (rows c0..m of each staging half are contiguous)
         const size_t bytes = (size_t)Dblk * g->ldw * 2;
-        MPQR_NCCL(g->api, g->api->Broadcast(Y16, Y16, bytes, kNcclChar, owner, g->comm, st));
-        MPQR_NCCL(g->api, g->api->Broadcast(W16, W16, bytes, kNcclChar, owner, g->comm, st));
-        // local columns that belong to global blocks > b
+        MPQR_NCCL(g->api, g->api->Broadcast(Y16, Y16, bytes, kNcclChar, owner, g->comm, s_comm));
+        MPQR_NCCL(g->api, g->api->Broadcast(W16, W16, bytes, kNcclChar, owner, g->comm, s_comm));
+        MPQR_CUDA(cudaEventRecord(g->ev_bc[b], s_comm));
+        // ---- updates with block b
+        // first local column that belongs to a global block > b; on the owner of a block whose reflectors stop before
+        // its last column (the last block of a wide matrix whose m is not a multiple of nb), the rest of that block first
         const int li0 = (b >= g->rank) ? (b - g->rank) / P + 1 : 0;
-        const int afar = li0 * nb;
-        if (afar < g->nloc) MPQR_TRY(far_update(h, c, c0, c1, afar, g->nloc - afar, st));
+        int afar = li0 * nb;
+        if (owner == g->rank && (c1 - c0) < bw_full) afar = acol0 + (c1 - c0);
+        BlockCtx cu = c;
+        cu.S32 = h->S32u; cu.S16 = h->S16u;
+        const bool has_next = (b + 1 < nblk);
+        if (has_next && (b + 1) % P == g->rank && afar < g->nloc) {
+            // this rank factors block b+1 next: its columns first, on the panel stream (with that stream's GEMM scratch)
+            const int lnext0 = ((b + 1) / P) * nb;
+            const int wnext = ((b + 2) * nb <= n) ? nb : n - (b + 1) * nb;
+            MPQR_CUDA(cudaStreamWaitEvent(s_panel, g->ev_bc[b], 0));
+            if (b >= 1) MPQR_CUDA(cudaStreamWaitEvent(s_panel, g->ev_far[b - 1], 0));
+            {
+                SmBudget budget(nsm_p);
+                MPQR_TRY(far_update(h, c, c0, c1, lnext0, wnext, s_panel));
+            }
+            MPQR_CUDA(cudaEventRecord(g->ev_next[b], s_panel));
+            did_next[b] = 1;
+            afar = lnext0 + wnext;
+        }
+        MPQR_CUDA(cudaStreamWaitEvent(s_upd, g->ev_bc[b], 0));
+        if (afar < g->nloc) {
+            // (these columns were last written by far_rest(b-1) on this stream, or by far_next(b-1) / bp(b) on the panel stream)
+            if (b >= 1 && did_next[b - 1]) MPQR_CUDA(cudaStreamWaitEvent(s_upd, g->ev_next[b - 1], 0));
+            if (owner == g->rank) MPQR_CUDA(cudaStreamWaitEvent(s_upd, g->ev_bp[b], 0));
+            SmBudget budget(nsm_u);
+            MPQR_TRY(far_update(h, cu, c0, c1, afar, g->nloc - afar, s_upd));
+        }
+        MPQR_CUDA(cudaEventRecord(g->ev_far[b], s_upd));
+    }
+    // join
+    MPQR_CUDA(cudaStreamWaitEvent(st, g->ev_far[nblk - 1], 0));
+    MPQR_CUDA(cudaStreamWaitEvent(st, g->ev_bc[nblk - 1], 0));
+    for (int b = 0; b < nblk; ++b) {
+        if (did_next[b]) MPQR_CUDA(cudaStreamWaitEvent(st, g->ev_next[b], 0));
+        if (b % P == g->rank) MPQR_CUDA(cudaStreamWaitEvent(st, g->ev_bp[b], 0));
     }
     h->factored = true;
     (void)n;
@@ -328,6 +433,13 @@ void mg_destroy(void* state) {
     MgState* g = (MgState*)state;
     if (!g) return;
     if (g->comm && g->api) g->api->CommDestroy(g->comm);
+    for (auto e : g->ev_bp) cudaEventDestroy(e);
+    for (auto e : g->ev_bc) cudaEventDestroy(e);
+    for (auto e : g->ev_far) cudaEventDestroy(e);
+    for (auto e : g->ev_next) cudaEventDestroy(e);
+    if (g->ev_start) cudaEventDestroy(g->ev_start);
+    if (g->s_comm) cudaStreamDestroy(g->s_comm);
+    if (g->own_streams) { if (g->s_panel) cudaStreamDestroy(g->s_panel); if (g->s_upd) cudaStreamDestroy(g->s_upd); }
     for (float* p : g->tq) cudaFree(p);
     delete g;
 }

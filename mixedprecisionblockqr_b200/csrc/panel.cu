@@ -217,11 +217,6 @@ struct BlockArgs {
     long long* dbg;   // optional phase timers (tools/panel_probe.py)
     int defer_out;    // 1: the packed factor below the first 32 rows and the 16-bit Y are written later, per panel, by
                       // panel_finalize_kernel from the FP32 Y (the kernel then only stores Y32 and its top 32 rows of A)
-    // Fused near update (16-column blocks, MPQR_FUSED=1): before factoring, the block applies the PREVIOUS register
-    // block's reflectors to its own columns, X -= Y_prev T_prev^T (Y_prev^T X), incl. the B rows above its slab.
-    const float* prevY;  // FP32 Y of the previous block: element (its row 0, its column 0); null = no prologue
-    long prev_ldy;
-    const float* prevT;  // its block T (B x B, ld B)
 };
 
 template <int B>
@@ -535,121 +530,6 @@ __device__ __forceinline__ void factor_steps(float (&x)[RPT][B], const StepMem<B
     }
     }
 
-// Prologue of the fused flow (B = 16): X -= Y_p S, S = T_p^T (Y_p^T X), for the previous register block p.
-//   P = Y_p^T X (16 x 16) is accumulated in four passes over 4-row chunks of P (64 accumulators next to the 128
-//   registers of X), reduced over the warp (transpose-reduce), the CTA (shared memory) and the cluster (ONE DSMEM
-//   all-gather of 256 floats per CTA, own mbarrier); the B rows above the slab (the previous block's diagonal rows,
-//   final R entries afterwards) are taken by CTA 0.  All reads of in-chain data are ld.global.cg.
-//   pred: NW x 256 floats, pslotP: CSMAX x 256, ptot / ssm / topx / topy: 256 each.
-template <int RPT>
-__device__ __forceinline__ void fused_prev_update(float (&x)[RPT][16], const BlockArgs& a, int D, int rbase, int tid, int lane, int warp,
-                                                  int CS, unsigned crank, float* pred, float (*pslotP)[256], float* ptot, float* ssm,
-                                                  float* topx, float* topy, uint64_t* mbarP) {
-    constexpr int B = 16;
-    const long ldy = a.prev_ldy;
-    const float* Ys = a.prevY + (size_t)B * ldy;  // Y_p row of the slab's row 0
-    if (crank == 0) {
-        const int r = tid >> 4, c = tid & 15;
-        topx[tid] = __ldcg(a.A + ((long)r - B) * a.lda + c);
-        topy[tid] = __ldcg(a.prevY + (size_t)r * ldy + c);
-    }
-    if (CS > 1 && tid == 0) mbar_arrive_expect_tx(mbarP, (uint32_t)CS * 1024u);
-#pragma unroll 1
-    for (int g = 0; g < 4; ++g) {
-        float acc[4][B];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int b = 0; b < B; ++b) acc[k][b] = 0.f;
-#pragma unroll
-        for (int u = 0; u < RPT; ++u) {
-            const int i = rbase + u * NT;
-            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < D) y = __ldcg(reinterpret_cast<const float4*>(Ys + (size_t)i * ldy + 4 * g));
-#pragma unroll
-            for (int b = 0; b < B; ++b) {
-                acc[0][b] = fmaf(y.x, x[u][b], acc[0][b]);
-                acc[1][b] = fmaf(y.y, x[u][b], acc[1][b]);
-                acc[2][b] = fmaf(y.z, x[u][b], acc[2][b]);
-                acc[3][b] = fmaf(y.w, x[u][b], acc[3][b]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            warp_transpose_reduce<B>(acc[k], lane);  // lane l: column l >> 1
-            if ((lane & 1) == 0) pred[warp * 256 + (4 * g + k) * B + (lane >> 1)] = acc[k][0];
-        }
-    }
-    __syncthreads();
-    {
-        float cs = 0.f;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) cs += pred[w * 256 + tid];
-        if (crank == 0) {
-            const int a2 = tid >> 4, b2 = tid & 15;
-#pragma unroll
-            for (int r = 0; r < B; ++r) cs = fmaf(topy[r * B + a2], topx[r * B + b2], cs);
-        }
-        ptot[tid] = cs;  // this CTA's part of P, element (tid >> 4, tid & 15)
-    }
-    __syncthreads();
-    if (CS > 1) {
-        const uint32_t bar_local = smem_addr(mbarP);
-        for (int o = tid; o < CS * 64; o += NT) {
-            const unsigned peer = (unsigned)(o >> 6);
-            const int ch = o & 63;
-            const float4 v = *reinterpret_cast<const float4*>(&ptot[4 * ch]);
-            st_async_v4(map_to_cta(smem_addr(&pslotP[crank][4 * ch]), peer), v, map_to_cta(bar_local, peer));
-        }
-        mbar_wait_cluster(mbarP, 0u);
-        float t = 0.f;
-        for (int c = 0; c < CS; ++c) t += pslotP[c][tid];
-        __syncthreads();  // every sender has read its chunk of ptot
-        ptot[tid] = t;
-    }
-    __syncthreads();
-    {
-        const int a2 = tid >> 4, b2 = tid & 15;
-        float sv = 0.f;
-#pragma unroll
-        for (int c = 0; c < B; ++c) sv = fmaf(__ldcg(&a.prevT[c * B + a2]), ptot[c * B + b2], sv);  // S = T^T P
-        ssm[tid] = sv;
-    }
-    __syncthreads();
-    if (crank == 0) {
-        const int r = tid >> 4, c = tid & 15;
-        float d = 0.f;
-#pragma unroll
-        for (int a2 = 0; a2 < B; ++a2) d = fmaf(topy[r * B + a2], ssm[a2 * B + c], d);
-        a.A[((long)r - B) * a.lda + c] = topx[tid] - d;
-    }
-#pragma unroll 1
-    for (int g = 0; g < 4; ++g) {
-        float sreg[4][B];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int q = 0; q < B / 4; ++q) {
-                const float4 s4 = *reinterpret_cast<const float4*>(&ssm[(4 * g + k) * B + 4 * q]);
-                sreg[k][4 * q] = s4.x; sreg[k][4 * q + 1] = s4.y; sreg[k][4 * q + 2] = s4.z; sreg[k][4 * q + 3] = s4.w;
-            }
-#pragma unroll
-        for (int u = 0; u < RPT; ++u) {
-            const int i = rbase + u * NT;
-            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < D) y = __ldcg(reinterpret_cast<const float4*>(Ys + (size_t)i * ldy + 4 * g));
-#pragma unroll
-            for (int b = 0; b < B; ++b) {
-                float d = y.x * sreg[0][b];
-                d = fmaf(y.y, sreg[1][b], d);
-                d = fmaf(y.z, sreg[2][b], d);
-                d = fmaf(y.w, sreg[3][b], d);
-                x[u][b] -= d;
-            }
-        }
-    }
-}
-
 template <int B, int RPT>
 __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS) {
     __shared__ __align__(16) float red[2][NW][B];
@@ -661,10 +541,6 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
     __shared__ float diag[B];
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ __align__(16) uint4 tiles[NW][32 * (B / 4)];  // warp-private transposition tiles (coalesced I/O)
-    // fused near update (B == 16 only): all-gather slots of P, P / S / top tiles, own mbarrier
-    __shared__ __align__(16) float pslotP[B == 16 ? CSMAX : 1][256];
-    __shared__ __align__(16) float fusedsm[B == 16 ? 4 * 256 : 4];
-    __shared__ __align__(8) uint64_t mbarP;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned crank = (CS > 1) ? cluster_ctarank() : 0u;
@@ -684,7 +560,6 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
         if (tid == 0) {
             mbar_init(&mbar[0], 1);
             mbar_init(&mbar[1], 1);
-            mbar_init(&mbarP, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         cluster_sync_all();  // peers must not signal a barrier that is not initialised yet
@@ -728,13 +603,6 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
         for (int idx = (int)crank * NT + tid; idx < a.zero_n; idx += nthr) a.zero_buf[idx] = 0.f;
     }
     __syncthreads();
-    if (B == 16 && a.prevY) {
-        // (the transposition tiles are idle between the load and the stores: they hold the per-warp partial P)
-        if constexpr (B == 16)
-            fused_prev_update<RPT>(x, a, D, rbase, tid, lane, warp, CS, crank, reinterpret_cast<float*>(&tiles[0][0]), pslotP, fusedsm,
-                                   fusedsm + 256, fusedsm + 512, fusedsm + 768, &mbarP);
-        __syncthreads();
-    }
     PROF_MARK(6);
 
     {
@@ -891,7 +759,16 @@ struct ChainArgs {
     unsigned base;
     float* srep[2];  // S replicas of the far updates (blocks alternate); the cluster clears srep[jb & 1] before it posts block jb
     int srep_n;      // floats per buffer
+    long long* dbg;  // optional: 8 globaltimer stamps per block (CTA 0, thread 0), tools/chain_probe.py
 };
+
+__device__ __forceinline__ long long gtime_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define CHAIN_STAMP(k)                                                       \
+    if (a.dbg && crank == 0 && tid == 0) a.dbg[jb * 8 + (k)] = gtime_ns();
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -1030,6 +907,7 @@ __global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS)
     for (int jb = 0; jb < nblk; ++jb) {
         const int roff = jb * B;
         float* Ab = a.A + roff;  // the block's first column
+        CHAIN_STAMP(0);
         if (jb >= 2 && a.flag_far) {
             if (tid == 0) {
                 const unsigned want = a.base + (unsigned)(jb - 1);  // far(jb-2) posted base + jb - 1
@@ -1037,6 +915,7 @@ __global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS)
             }
             __syncthreads();
         }
+        CHAIN_STAMP(1);
         float x[RPT][B];
         {
             uint4 t[RPT][B / 4];
@@ -1057,6 +936,7 @@ __global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS)
             }
         }
         __syncthreads();
+        CHAIN_STAMP(2);
         if (jb > 0) {
             chain_near_update<RPT>(x, ysl, gt, tid, lane, warp, CS, crank, reinterpret_cast<float*>(&tiles[0][0]), pslotP, fusedsm,
                                    fusedsm + 256, &mbarP, (uint32_t)((jb - 1) & 1));
@@ -1068,14 +948,17 @@ __global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS)
             }
             __syncthreads();
         }
+        CHAIN_STAMP(3);
         {
             StepMem<B> M{red, prow, slot, pslot, tauS, gt, diag, mbar};
             StepCtx sc{tid, lane, warp, CS, rbase, B, B, roff, crank, false, dummy_acc, &dummy_prev};
             factor_steps<B, RPT>(x, M, sc);
         }
         __syncthreads();
+        CHAIN_STAMP(4);
         tinv_smem<B, B + 4>(gt, &red[0][0][0], tid);
         if (jb == nblk - 1) pdl_launch_dependents();
+        CHAIN_STAMP(5);
 
         // the block's first 32 rows of the packed factor (CTA 0, u = 0); the rest is written per panel by panel_finalize_kernel
         if (crank == 0 && tid >= roff && tid < roff + 32) {
@@ -1117,12 +1000,14 @@ __global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS)
             const int n4 = a.srep_n >> 2;
             for (int idx = (int)crank * NT + tid; idx < n4; idx += CS * NT) z[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        CHAIN_STAMP(6);
         __threadfence();
         if (CS > 1) cluster_sync_all(); else __syncthreads();
         if (crank == 0 && tid == 0) {
             atomicExch(a.flag_done, a.base + (unsigned)(jb + 1));
             __threadfence_system();
         }
+        CHAIN_STAMP(7);
     }
     // shared memory must stay alive until no peer can signal into it any more (the last cluster barrier above covers it)
 }
@@ -1166,273 +1051,6 @@ __global__ void __launch_bounds__(256) panel_finalize_kernel(const float* Yp, lo
     }
 }
 
-// ------------------------------------------------------------------ double block (tall panels)
-// For D > 16384 a 32-column block does not fit the cluster's registers.  panel_dblock_kernel factors
-// 32 columns as two 16-column halves in ONE launch: half A lives in registers, half B is staged in
-// shared memory (<= 2048 rows x 64 B per CTA) and touched once, by the block update between the
-// halves  B -= Y_A T_A^T (Y_A^T B)  (partial 16 x 16 products reduced by a warp transpose-reduce, a
-// shared-memory stage and ONE DSMEM all-gather), after which B moves into the registers and is
-// factored with its diagonal at slab row 16.  Compared with two 16-column launches this saves one
-// launch's fixed cost and the device-wide in-panel update pair between the halves; the update of
-// the rest of the panel then runs once per 32 columns with T_32 = [[T_A, -T_A (Y_A^T Y_B) T_B], [0, T_B]],
-// whose cross term the in-panel S kernel accumulates on the side.
-template <int RPT>
-__device__ __forceinline__ void emit_half(float (&x)[RPT][16], const BlockArgs& a, int D, int rbase, int roff, int coloff, int bwh,
-                                          const float* diag, bool vecA, bool vecY32, bool vecY16, uint4* tile, int lane) {
-    constexpr int B = 16;
-    const long lda = a.lda;
-    const int wrow0 = rbase - lane;
-#pragma unroll
-    for (int u = 0; u < RPT; ++u) {
-        const int i = rbase + u * NT, g0 = wrow0 + u * NT;
-        const bool full = (bwh == B) && g0 >= roff + B;
-        if (full && vecA) {
-            rows_out_f32<B>(a.A + (size_t)(g0 + 1) * lda + coloff, lda, D - g0, x[u], tile, lane);
-        } else if (i < D) {
-            if (i >= roff + B) {
-                store_row32<B>(a.A + (size_t)(i + 1) * lda + coloff, x[u], bwh, vecA);
-            } else {
-#pragma unroll
-                for (int c = 0; c < B; ++c)
-                    if (c < bwh) a.A[(size_t)(i + (i >= c + roff ? 1 : 0)) * lda + coloff + c] = x[u][c];
-                if (i >= roff && i - roff < bwh) a.A[(size_t)i * lda + coloff + (i - roff)] = diag[i - roff];
-            }
-        }
-        if (i < roff + B) {
-#pragma unroll
-            for (int c = 0; c < B; ++c)
-                if (i < c + roff) x[u][c] = 0.f;  // Y: zero above the diagonal
-        }
-        if (a.Y32.p) {
-            if (bwh == B && vecY32) rows_out_f32<B>(a.Y32.p + (size_t)g0 * a.Y32.ld + coloff, a.Y32.ld, D - g0, x[u], tile, lane);
-            else if (i < D) store_row32<B>(a.Y32.p + (size_t)i * a.Y32.ld + coloff, x[u], bwh, vecY32);
-        }
-        if (a.Y16.p) {
-            if (bwh == B && vecY16) rows_out_16<B>((char*)a.Y16.p + ((size_t)g0 * a.Y16.ld + coloff) * 2, a.Y16.ld, D - g0, x[u], tile, lane, a.bf16);
-            else if (i < D) store_row16<B>((char*)a.Y16.p + ((size_t)i * a.Y16.ld + coloff) * 2, x[u], bwh, vecY16, a.bf16);
-        }
-    }
-}
-
-template <int RPT>
-__global__ void __launch_bounds__(NT, 1) panel_dblock_kernel(BlockArgs a, int CS) {
-    constexpr int B = 16;
-    __shared__ __align__(16) float red[2][NW][B];
-    __shared__ __align__(16) float prow[2][B];
-    __shared__ __align__(16) float slot[2][CSMAX][B];
-    __shared__ __align__(16) float pslot[2][B];
-    __shared__ __align__(16) float tauS[NW][B];
-    __shared__ __align__(16) float gt[B][B + 4];
-    __shared__ __align__(16) float TA[B][B + 4];
-    __shared__ float diag[B];
-    __shared__ __align__(16) float redw[NW][64];
-    __shared__ __align__(16) float csumAll[256];
-    __shared__ __align__(16) float slotX[CSMAX][256];
-    __shared__ __align__(16) float Sfull[256];
-    __shared__ __align__(16) float Ssm[B][B];
-    __shared__ __align__(8) uint64_t mbar[2];
-    __shared__ __align__(8) uint64_t mbarX;
-    __shared__ __align__(16) uint4 tiles[NW][32 * 4];
-    extern __shared__ __align__(16) float Bsm[];  // (NT * RPT) rows x 16 floats; 16-byte chunk q of row r at q ^ ((r >> 1) & 3)
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned crank = (CS > 1) ? cluster_ctarank() : 0u;
-    const int D = a.D, bw2 = a.bw - B;
-    const int rbase = (int)crank * (NT * RPT) + tid;
-    const long lda = a.lda;
-    const bool vecA = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
-    const bool vecY32 = a.Y32.p && ((a.Y32.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y32.p) & 15) == 0);
-    const bool vecY16 = a.Y16.p && ((a.Y16.ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.Y16.p) & 15) == 0);
-    long long pacc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long tprev = 0;
-
-    pdl_launch_dependents();
-    for (int idx = tid; idx < B * (B + 4); idx += NT) (&gt[0][0])[idx] = 0.f;
-    if (CS > 1) {
-        if (tid == 0) {
-            mbar_init(&mbar[0], 1);
-            mbar_init(&mbar[1], 1);
-            mbar_init(&mbarX, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        cluster_sync_all();
-    }
-    pdl_wait();
-
-    float x[RPT][B];
-#pragma unroll
-    for (int u = 0; u < RPT; ++u) {
-        const int i = rbase + u * NT, lr = u * NT + tid;
-        float b[B];
-        if (vecA && bw2 == B) {
-            const int g0 = rbase - lane + u * NT;
-            rows_in_f32<B>(a.A + (size_t)g0 * lda, lda, D - g0, x[u], tiles[warp], lane);
-            rows_in_f32<B>(a.A + (size_t)g0 * lda + B, lda, D - g0, b, tiles[warp], lane);
-        } else if (i < D) {
-            load_row<B>(a.A + (size_t)i * lda, x[u], B, vecA);
-            load_row<B>(a.A + (size_t)i * lda + B, b, bw2, vecA);
-        } else {
-#pragma unroll
-            for (int c = 0; c < B; ++c) { x[u][c] = 0.f; b[c] = 0.f; }
-        }
-        float4* dst = reinterpret_cast<float4*>(Bsm + (size_t)lr * B);
-        const int sw = (lr >> 1) & 3;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q ^ sw] = make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
-    }
-    if (a.zero_buf) {
-        const int nthr = CS * NT;
-        for (int idx = (int)crank * NT + tid; idx < a.zero_n; idx += nthr) a.zero_buf[idx] = 0.f;
-    }
-    __syncthreads();
-
-    StepMem<B> M{red, prow, slot, pslot, tauS, gt, diag, mbar};
-    // ---- half A
-    {
-        StepCtx sc{tid, lane, warp, CS, rbase, B, (B < D ? B : D), 0, crank, false, pacc, &tprev};
-        factor_steps<B, RPT>(x, M, sc);
-    }
-    __syncthreads();
-    tinv_smem<B, B + 4>(gt, &red[0][0][0], tid);
-    for (int idx = tid; idx < B * (B + 4); idx += NT) (&TA[0][0])[idx] = (&gt[0][0])[idx];
-    emit_half<RPT>(x, a, D, rbase, 0, 0, B, diag, vecA, vecY32, vecY16, tiles[warp], lane);  // x becomes Y_A (zero above the diagonal)
-    __syncthreads();
-
-    // ---- S' = Y_A^T B, four 16 x 4 column chunks
-    for (int p4 = 0; p4 < 4; ++p4) {
-        float acc[64];
-#pragma unroll
-        for (int e = 0; e < 64; ++e) acc[e] = 0.f;
-#pragma unroll
-        for (int u = 0; u < RPT; ++u) {
-            const int lr = u * NT + tid;
-            const float4 b4 = reinterpret_cast<const float4*>(Bsm + (size_t)lr * B)[p4 ^ ((lr >> 1) & 3)];
-#pragma unroll
-            for (int t = 0; t < B; ++t) {
-                acc[4 * t] = fmaf(x[u][t], b4.x, acc[4 * t]);
-                acc[4 * t + 1] = fmaf(x[u][t], b4.y, acc[4 * t + 1]);
-                acc[4 * t + 2] = fmaf(x[u][t], b4.z, acc[4 * t + 2]);
-                acc[4 * t + 3] = fmaf(x[u][t], b4.w, acc[4 * t + 3]);
-            }
-        }
-        tr_stage<64, 16>(acc, lane);
-        tr_stage<32, 8>(acc, lane);
-        tr_stage<16, 4>(acc, lane);
-        tr_stage<8, 2>(acc, lane);
-        tr_stage<4, 1>(acc, lane);  // lane l now holds the warp sums of entries 2l, 2l+1
-        redw[warp][2 * lane] = acc[0];
-        redw[warp][2 * lane + 1] = acc[1];
-        __syncthreads();
-        if (tid < 64) {
-            float v = 0.f;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) v += redw[w][tid];
-            csumAll[p4 * 64 + tid] = v;  // entry (t, k) of chunk p4 = S'[t][4 p4 + k], at t*4 + k
-        }
-        __syncthreads();
-    }
-    if (CS > 1) {
-        if (tid == 0) mbar_arrive_expect_tx(&mbarX, (uint32_t)CS * 1024u);
-        for (int o = tid; o < CS * 64; o += NT) {
-            const unsigned peer = (unsigned)(o >> 6);
-            const int ch = o & 63;
-            st_async_v4(map_to_cta(smem_addr(&slotX[crank][4 * ch]), peer), *reinterpret_cast<const float4*>(&csumAll[4 * ch]),
-                        map_to_cta(smem_addr(&mbarX), peer));
-        }
-        mbar_wait_cluster(&mbarX, 0);
-        float v = 0.f;
-        for (int cc = 0; cc < CS; ++cc) v += slotX[cc][tid];
-        Sfull[tid] = v;
-    } else {
-        Sfull[tid] = csumAll[tid];
-    }
-    __syncthreads();
-    {   // S = T_A^T S'   (thread <-> entry (t, c))
-        const int t = tid >> 4, cidx = tid & 15;
-        float v = 0.f;
-#pragma unroll
-        for (int u2 = 0; u2 < B; ++u2)
-            if (u2 <= t) v = fmaf(TA[u2][t], Sfull[(cidx >> 2) * 64 + u2 * 4 + (cidx & 3)], v);
-        Ssm[t][cidx] = v;
-    }
-    __syncthreads();
-    // ---- B -= Y_A S, two rows at a time, straight into the registers (Y_A is not needed afterwards)
-#pragma unroll
-    for (int u0 = 0; u0 < RPT; u0 += 2) {
-        constexpr int RG = (RPT >= 2) ? 2 : 1;
-        float b[RG][B], y[RG][B];
-#pragma unroll
-        for (int g2 = 0; g2 < RG; ++g2) {
-            const int lr = (u0 + g2) * NT + tid;
-            const float4* src = reinterpret_cast<const float4*>(Bsm + (size_t)lr * B);
-            const int sw = (lr >> 1) & 3;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 v4 = src[q ^ sw];
-                b[g2][4 * q] = v4.x; b[g2][4 * q + 1] = v4.y; b[g2][4 * q + 2] = v4.z; b[g2][4 * q + 3] = v4.w;
-            }
-#pragma unroll
-            for (int c = 0; c < B; ++c) y[g2][c] = x[u0 + g2][c];
-        }
-#pragma unroll
-        for (int t = 0; t < B; ++t) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 s4 = *reinterpret_cast<const float4*>(&Ssm[t][4 * q]);
-#pragma unroll
-                for (int g2 = 0; g2 < RG; ++g2) {
-                    b[g2][4 * q] = fmaf(-y[g2][t], s4.x, b[g2][4 * q]);
-                    b[g2][4 * q + 1] = fmaf(-y[g2][t], s4.y, b[g2][4 * q + 1]);
-                    b[g2][4 * q + 2] = fmaf(-y[g2][t], s4.z, b[g2][4 * q + 2]);
-                    b[g2][4 * q + 3] = fmaf(-y[g2][t], s4.w, b[g2][4 * q + 3]);
-                }
-            }
-        }
-#pragma unroll
-        for (int g2 = 0; g2 < RG; ++g2)
-#pragma unroll
-            for (int c = 0; c < B; ++c) x[u0 + g2][c] = b[g2][c];
-    }
-    for (int idx = tid; idx < B * (B + 4); idx += NT) (&gt[0][0])[idx] = 0.f;
-    __syncthreads();
-
-    // ---- half B: diagonal at slab row 16
-    const int kr2 = (D - B) < bw2 ? (D - B > 0 ? D - B : 0) : bw2;
-    {
-        StepCtx sc{tid, lane, warp, CS, rbase, bw2, kr2, B, crank, false, pacc, &tprev};
-        factor_steps<B, RPT>(x, M, sc);
-    }
-    __syncthreads();
-    tinv_smem<B, B + 4>(gt, &red[0][0][0], tid);
-    emit_half<RPT>(x, a, D, rbase, B, B, bw2, diag, vecA, vecY32, vecY16, tiles[warp], lane);
-    // rows above the block are structurally zero in the compact outputs
-    {
-        const int gtid = (int)crank * NT + tid, nthr = CS * NT, bw = a.bw;
-        if (a.Y32.p)
-            for (long idx = gtid; idx < (long)a.Y32.zrows * bw; idx += nthr) {
-                long rr = idx / bw; int c = (int)(idx - rr * bw);
-                a.Y32.p[(rr - a.Y32.zrows) * a.Y32.ld + c] = 0.f;
-            }
-        if (a.Y16.p)
-            for (long idx = gtid; idx < (long)a.Y16.zrows * bw; idx += nthr) {
-                long rr = idx / bw; int c = (int)(idx - rr * bw);
-                store16(a.Y16.p, (rr - a.Y16.zrows) * a.Y16.ld + c, 0.f, a.bf16);
-            }
-    }
-    if (a.T && crank == 0) {  // [T_A | T_B], 16 x 16 each, ld 16
-        const int t = tid >> 4, c = tid & 15;
-        a.T[tid] = (t <= c) ? TA[t][c] : 0.f;
-        a.T[256 + tid] = (t <= c && c < kr2) ? gt[t][c] : 0.f;
-    }
-    if (CS > 1) cluster_sync_all();
-}
-
-// ------------------------------------------------------------------ level 1: in-panel update
-// S'[rep][t][c] += sum_rows Y[row][t] * A[row][c]   (FP32; B x ncols, rows split over the grid)
-// 512 threads = 4 row groups x 128 columns; RB rows in flight per thread (memory-level parallelism
-// is what bounds these skinny passes: 512 x RB x 4 B in flight per SM).
-// rows in flight per thread: the loops are latency-bound (one round trip per batch), so a CTA's rows
-// should be covered in about two batches
 template <int B> struct SuRb { static constexpr int value = (B == 16) ? 32 : 16; };
 template <int B>
 __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict__ W, long ldw, const float* __restrict__ A,
@@ -2473,6 +2091,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         float* SrepA = w.Srep + (size_t)2 * RMAX * SLD;
         ca.srep[0] = SrepA; ca.srep[1] = SrepA + (size_t)2 * RMAX * SLD;
         ca.srep_n = 2 * RMAX * SLD;
+        ca.dbg = a.chain_dbg;
         MPQR_TRY(chain_preload());
         if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 4.0 * D * pw * 16 + 4.0 * D * 16 * 16 * (nblocks - 1), 8.0 * D * pw);
         MPQR_TRY(launch_chain(ca, rpt, cs, stream));  // issued BEFORE the side stream's waits (a wait never queues ahead of its producer)

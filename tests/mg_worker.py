@@ -1,5 +1,6 @@
-"""Worker for the 2-GPU parity test (launched with torchrun, one process per GPU): factors a
-seeded matrix with the column-block-cyclic driver and checks it against the single-GPU driver."""
+"""Worker for the multi-GPU parity test (launched with torchrun, one process per GPU): factors a seeded matrix with
+the column-block-cyclic look-ahead driver and checks the gathered factor against the oracle (LAPACK FP64 for the
+larger shapes) and against the single-GPU driver."""
 import os
 import sys
 
@@ -54,22 +55,32 @@ def main():
         P = np.zeros((m + 1, n), np.float32)
         for gc, blk in parts:
             P[:, gc] = blk
+        # Reference: the ORACLE's packed factor where it finishes in seconds (the restatement of h_block_qr,
+        # Cuda/qr.cu:1275), else |R| from FP64 LAPACK; plus the single-GPU driver on the same input.
+        A_host = full[:m].cpu().numpy()
+        if m * n * n <= 3e9:
+            sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            import oracle
+            Pref, _ = oracle.block_qr(A_host, r, want_q=False)
+            Rref = np.triu(Pref[:m])
+            ref_name = "oracle"
+        else:
+            Rref = np.linalg.qr(A_host.astype(np.float64), mode="r")
+            ref_name = "LAPACK fp64"
+        Rm = np.triu(P[:m])[:Rref.shape[0]]
+        d = np.abs(np.abs(Rm) - np.abs(Rref)).max() / np.abs(Rref).max()
         single = pkg.BlockQR(m, n, r, nb=plan.nb, precision="fp16")
         ref = full.clone()
         single.factor(ref.data_ptr(), n, st)
         torch.cuda.synchronize()
-        Pref = ref.cpu().numpy()
-        # Two FP16-operand factorisations that differ only in rounding (here: split-K reduce-add order,
-        # and Y/W staged in NCCL buffers instead of the shadow) agree in |R| at FP16-GEMM error level, not
-        # bit for bit, and a tiny pivot may flip its sign; so the criteria are the reference's own: backward
-        # error of the multi-GPU factor, and elementwise |R| against the single-GPU factor.
-        Rm, Rs = np.triu(np.abs(P[:m])), np.triu(np.abs(Pref[:m]))
-        d = np.abs(Rm - Rs).max() / Rs.max()
+        Rs = np.triu(np.abs(ref.cpu().numpy()[:m]))[:Rref.shape[0]]
+        ds = np.abs(np.abs(Rm) - Rs).max() / Rs.max()
         be = sampled_backward_error(full[:m], torch.from_numpy(P).cuda(), plan.r)
         bes = sampled_backward_error(full[:m], ref, plan.r)
-        print(f"mg({world}) vs single-GPU: |R| rel max diff {d:.3e}; sampled backward error mg {be:.3e} single {bes:.3e}")
+        print(f"mg({world}) {m}x{n} r={r} nb={plan.nb}: |R| rel max diff vs {ref_name} {d:.3e}, vs single GPU {ds:.3e}; "
+              f"sampled backward error mg {be:.3e} single {bes:.3e}")
         eps = 2.0 ** -11
-        ok = d <= 40 * eps and be <= 12 * eps and be <= 2.0 * bes + 1e-4
+        ok = d <= 10 * eps and ds <= 10 * eps and be <= 5.5 * eps
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()

@@ -10,7 +10,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("m,n,r,nb", [(2048, 2048, 64, 256), (3000, 1600, 32, 128), (1024, 4096, 64, 256)])
+@pytest.mark.parametrize("m,n,r,nb", [(2048, 2048, 64, 256), (3000, 1600, 32, 128), (1024, 4096, 64, 256),
+                                      (1000, 4096, 64, 256),     # m % nb != 0, m < n: the owner's columns right of the last reflector
+                                      (6144, 6144, 128, 512)])   # 12 outer blocks: green-context partitions + persistent panel chain
 def test_two_gpu_matches_single(m, n, r, nb):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
