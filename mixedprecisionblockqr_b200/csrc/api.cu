@@ -234,21 +234,19 @@ void overlap_init(mpqr_handle* h, const int* sizes, int nsizes) {
         CUgreenCtx gP = nullptr, gU = nullptr;
         if (g->GreenCtxCreate(&gP, dP, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) continue;
         if (g->GreenCtxCreate(&gU, dU, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { g->GreenCtxDestroy(gP); continue; }
-        CUstream sP = nullptr, sP2 = nullptr, sP3 = nullptr, sP4 = nullptr, sU = nullptr;
+        CUstream sP = nullptr, sP2 = nullptr, sP3 = nullptr, sU = nullptr;
         if (g->GreenCtxStreamCreate(&sP, gP, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS ||
             g->GreenCtxStreamCreate(&sP2, gP, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
             g->GreenCtxStreamCreate(&sP3, gP, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS ||
-            g->GreenCtxStreamCreate(&sP4, gP, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
             g->GreenCtxStreamCreate(&sU, gU, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
             if (sP) cudaStreamDestroy((cudaStream_t)sP);
             if (sP2) cudaStreamDestroy((cudaStream_t)sP2);
             if (sP3) cudaStreamDestroy((cudaStream_t)sP3);
-            if (sP4) cudaStreamDestroy((cudaStream_t)sP4);
             g->GreenCtxDestroy(gP); g->GreenCtxDestroy(gU);
             continue;
         }
         mpqr_handle::Overlap::Pair pr;
-        pr.gP = gP; pr.gU = gU; pr.sP = (cudaStream_t)sP; pr.sP2 = (cudaStream_t)sP2; pr.sP3 = (cudaStream_t)sP3; pr.sP4 = (cudaStream_t)sP4; pr.sU = (cudaStream_t)sU;
+        pr.gP = gP; pr.gU = gU; pr.sP = (cudaStream_t)sP; pr.sP2 = (cudaStream_t)sP2; pr.sP3 = (cudaStream_t)sP3; pr.sU = (cudaStream_t)sU;
         pr.nsmP = (int)grp[0].sm.smCount; pr.nsmU = (int)rem.sm.smCount;
         o.pairs.push_back(pr);
     }
@@ -256,9 +254,6 @@ void overlap_init(mpqr_handle* h, const int* sizes, int nsizes) {
     if (cudaStreamCreateWithFlags(&o.sF, cudaStreamNonBlocking) != cudaSuccess) { o.sF = nullptr; }
     if (cudaStreamCreateWithFlags(&o.sF2, cudaStreamNonBlocking) != cudaSuccess) { o.sF2 = nullptr; }
     if (cudaStreamCreateWithFlags(&o.sF3, cudaStreamNonBlocking) != cudaSuccess) { o.sF3 = nullptr; }
-    if (cudaStreamCreateWithFlags(&o.sF4, cudaStreamNonBlocking) != cudaSuccess) { o.sF4 = nullptr; }
-    o.ev_la.resize(kPanelLaEvents);
-    for (auto& e : o.ev_la) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     o.ev_rest.resize(2 * (ceil_div(h->nb, h->r) + 1));
     for (auto& e : o.ev_rest) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     const int nblk = ceil_div(h->kmax, h->nb);
@@ -294,15 +289,12 @@ void overlap_destroy(mpqr_handle* h) {
     if (o.sF) cudaStreamDestroy(o.sF);
     if (o.sF2) cudaStreamDestroy(o.sF2);
     if (o.sF3) cudaStreamDestroy(o.sF3);
-    if (o.sF4) cudaStreamDestroy(o.sF4);
     for (auto e : o.ev_rest) cudaEventDestroy(e);
-    for (auto e : o.ev_la) cudaEventDestroy(e);
     const GreenApi* g = green_api();
     for (auto& pr : o.pairs) {
         if (pr.sP) cudaStreamDestroy(pr.sP);
         if (pr.sP2) cudaStreamDestroy(pr.sP2);
         if (pr.sP3) cudaStreamDestroy(pr.sP3);
-        if (pr.sP4) cudaStreamDestroy(pr.sP4);
         if (pr.sU) cudaStreamDestroy(pr.sU);
         if (g->ok) { g->GreenCtxDestroy((CUgreenCtx)pr.gP); g->GreenCtxDestroy((CUgreenCtx)pr.gU); }
     }
@@ -417,11 +409,9 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     const char* fix = getenv("MPQR_PANEL_SMS");
     const int fixed_sms = fix ? atoi(fix) : 0;
     // interval b-1 decided where block_phase(b) runs; block 0 runs on the whole device
-    cudaStream_t s_bp = o.sF, s_bp2 = o.sF2, s_bp3 = o.sF3, s_bp4 = o.sF4, s_uprev = nullptr;
+    cudaStream_t s_bp = o.sF, s_bp2 = o.sF2, s_bp3 = o.sF3, s_uprev = nullptr;
     int nsm_bp = o.nsm_full, nsm_uprev = 0;
-    const bool inblock_la = !getenv("MPQR_NO_INBLOCK_LA") && (h->r % 8) == 0;
-    // register-block look-ahead inside the panels (needs whole 32-column groups and the register-block kernels)
-    const bool rb_la = inblock_la && !getenv("MPQR_NO_RBLA") && (h->r % 32) == 0 && h->r >= 64 && o.sF3 != nullptr && o.sF4 != nullptr;
+    const bool inblock_la = (h->r % 8) == 0;
     MPQR_CUDA(cudaStreamWaitEvent(s_bp, o.ev_start, 0));
     for (int c0 = 0, b = 0; c0 < h->kmax; c0 += nb, ++b) {
         const int c1 = (c0 + nb < h->kmax) ? c0 + nb : h->kmax;
@@ -431,12 +421,11 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         c.chain_side = s_bp3;
         if (inblock_la) {
             c.rest_stream = s_bp2; c.rest_S32 = h->S32r; c.rest_S16 = h->S16r; c.rest_ev = o.ev_rest.data();
-            if (rb_la && s_bp3 && s_bp4) { c.side_stream = s_bp3; c.side2_stream = s_bp4; c.la_ev = o.ev_la.data(); }
             // (the previous block's last rest event completed before fn(b-1), which this block waits for)
         }
         // WY accumulation of this block (only the far update needs it): on the update partition of the previous
         // interval (it idles once its far update is done); else behind the in-block rest updates on their stream
-        const bool defer_u = s_uprev && s_uprev != s_bp && !getenv("MPQR_NO_DEFER_ACC");
+        const bool defer_u = s_uprev && s_uprev != s_bp;
         cudaStream_t s_acc = defer_u ? s_uprev : (inblock_la ? s_bp2 : nullptr);
         if (s_acc) {
             c.acc_stream = s_acc;
@@ -497,7 +486,6 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         s_bp = best >= 0 ? o.pairs[best].sP : o.sF;
         s_bp2 = best >= 0 ? o.pairs[best].sP2 : o.sF2;
         s_bp3 = best >= 0 ? o.pairs[best].sP3 : o.sF3;
-        s_bp4 = best >= 0 ? o.pairs[best].sP4 : o.sF4;
         nsm_bp = best >= 0 ? o.pairs[best].nsmP : o.nsm_full;
         s_uprev = best >= 0 ? s_u : nullptr;
         nsm_uprev = nsm_u;
@@ -534,8 +522,6 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
     float* S32 = c.S32 ? c.S32 : h->S32;
     void* S16 = c.S16 ? c.S16 : h->S16;
     int last_rest = -1;
-    bool la_prev = false;
-    int prev_nc = 0;  // next_cols of the previous look-ahead panel
     for (int lam = c0; lam < c1; lam += r) {
         const int p = lam / r;
         const int pw = (lam + r < c1) ? r : c1 - lam;
@@ -550,31 +536,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
         a.chain_side = c.chain_side ? c.chain_side : h->chain_side; a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
-        const bool chain = panel_chain_ok(a);  // persistent cluster kernel: no register-block look-ahead streams needed
         const int nin = c1 - tau;  // in-block trailing columns
-        // register-block look-ahead: the panel's blocks also update the whole NEXT panel (FP32, block by block, on a side
-        // stream), Gram/T/W and the tensor-core in-block update of the columns right of it leave the panel stream
-        bool la = false;
-        if (!chain && c.side_stream && c.side2_stream && c.rest_stream && c.la_ev) {
-            a.side = c.side_stream; a.side2 = c.side2_stream; a.gtw_stream = c.rest_stream; a.la_ev = c.la_ev;
-            a.next_cols = nin >= r ? r : 0;   // the whole next panel, when there is a full one in this outer block
-            a.ev_next_ready = (la_prev && jc >= r) ? c.rest_ev[2 * (jc / r - 1) + 1] : nullptr;  // N(p-1): next panel's columns
-            la = panel_lookahead_ok(a) && (nin == 0 || nin >= r);
-            if (!la && getenv("MPQR_FUSED")) {  // experimental: tall panels, near update fused into the register-block kernels
-                a.next_cols = 0; a.ev_next_ready = nullptr;
-                la = panel_lookahead_ok(a);
-            }
-            if (!la) { a.side = a.side2 = a.gtw_stream = nullptr; a.la_ev = nullptr; a.next_cols = 0; a.ev_next_ready = nullptr; }
-        }
-        if (la != la_prev && lam > c0) {
-            // switching flows inside a block: everything issued so far must be complete for the other flow's assumptions
-            if (last_rest >= 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[last_rest], 0));
-            if (la_prev) { MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[16], 0)); MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[18], 0)); }
-        }
-        // this panel's columns received the earlier panels' updates through N(q), q <= p-2 (panel p-1 reached them in FP32),
-        // or through N(p-1) as well if panel p-1 did not cover its successor (next_cols == 0)
-        if (la && la_prev && prev_nc > 0 && jc >= 2 * r) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (jc / r - 2) + 1], 0));
-        if (la && la_prev && prev_nc == 0 && jc >= r) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (jc / r - 1) + 1], 0));
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         const int acol_tau = c.acol0 + jc + pw;
         // in-block update of the columns [tau + ofs, tau + ofs + nc):  S = W_p^T A ; A -= Y_p S (+ shadow)
@@ -594,19 +556,9 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             return MPQR_OK;
         };
         const int pidx = jc / r;
-        if (la) {
-            cudaStream_t sg = c.rest_stream;  // (Gram/T/W of this panel were issued on sg by launch_panel)
-            const int nc0 = a.next_cols;      // the next panel: updated in FP32 by this panel's blocks themselves
-            if (nin - nc0 > 0) MPQR_TRY(inblock(nc0, nin - nc0, c.rest_S32, c.rest_S16, end_is_matrix_end, sg));
-            MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx], sg));
-            MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], sg));
-            last_rest = 2 * pidx + 1;
-        }
-        la_prev = la;
-        prev_nc = la ? a.next_cols : 0;
-        const bool split = !la && c.rest_stream && nin > r && (r % 8) == 0;
-        if (la) { /* in-block updates done above */ } else
-        {
+        // the next panel's columns on the panel stream, the rest of the block on `rest_stream` (same SM partition) next
+        // to the next panel's chain kernel
+        const bool split = c.rest_stream && nin > r && (r % 8) == 0;
         if (c.rest_stream && nin > 0) last_rest = 2 * pidx + 1;
         if (nin > 0 && !split) {
             if (c.rest_stream && pidx > 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (pidx - 1) + 1], 0));
@@ -622,7 +574,6 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             MPQR_TRY(inblock(r, nin - r, c.rest_S32, c.rest_S16, end_is_matrix_end, c.rest_stream));
             MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], c.rest_stream));
         }
-        }
         if (jc > 0) {
             // WY accumulation: X = Y_prev^T W_p ; W_p -= W_prev X   (rows c0..m)
             const void* Wp = (char*)c.W16 + (size_t)jc * 2;
@@ -634,7 +585,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
                 cudaEvent_t ev = c.acc_ev[jc / r];
                 MPQR_CUDA(cudaEventRecord(ev, st_panel));
                 MPQR_CUDA(cudaStreamWaitEvent(c.acc_stream, ev, 0));
-                if (c.rest_stream && (nin > 0 || la)) MPQR_CUDA(cudaStreamWaitEvent(c.acc_stream, c.rest_ev[2 * pidx + 1], 0));
+                if (c.rest_stream && nin > 0) MPQR_CUDA(cudaStreamWaitEvent(c.acc_stream, c.rest_ev[2 * pidx + 1], 0));
                 aS32 = c.acc_S32; aS16 = c.acc_S16;
             }
             {
@@ -657,12 +608,6 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
     }
     // everything of this block is complete when the panel stream is (events of one stream complete in order)
     if (c.rest_stream && last_rest >= 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[last_rest], 0));
-    if (c.side_stream && c.la_ev) {  // (every side update was already consumed by a waiting panel-stream kernel; belt and braces)
-        MPQR_CUDA(cudaEventRecord(c.la_ev[17], c.side_stream));
-        MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[17], 0));
-        MPQR_CUDA(cudaEventRecord(c.la_ev[17], c.side2_stream));
-        MPQR_CUDA(cudaStreamWaitEvent(st, c.la_ev[17], 0));
-    }
     return MPQR_OK;
 }
 

@@ -122,18 +122,6 @@ struct PanelArgs {
     int force_b;        // 16 / 32: override the register-block width (tuning / tests)
     int force_rpt;      // > 0: override the rows per thread (tuning / tests)
     const ProfHook* prof;  // optional: sub-classes 4 (block kernels), 5 (in-panel S), 6 (Gram/T/W), 7 (in-panel U)
-    // Optional register-block look-ahead (multi-block panels of the mixed driver; see BlockCtx in internal.h).
-    // On `stream` stay: the register-block kernels K(j) and, after K(j), the update of the NEXT register block only
-    // (after the last block: of the next panel's first block).  `side`: block j's update of the remaining panel
-    // columns.  `side2`: block j's update of the `next_cols` columns right of the panel (the next panel of the same
-    // outer block), which must have received all EARLIER panels' updates first: `ev_next_ready`.
-    cudaStream_t side;        // null: classic flow, everything on `stream`
-    cudaStream_t side2;
-    cudaStream_t gtw_stream;  // Gram / T / W of the whole panel run here (after the last block kernel); null: `stream`
-    int next_cols;            // 0, or a multiple of 32 (<= 128)
-    cudaEvent_t ev_next_ready;  // may be null
-    cudaEvent_t* la_ev;       // kPanelLaEvents events: [2j] K(j) done, [2j+1] side update of block j done, [16] side2 position,
-                              // [17] caller's join, [18] deferred outputs of the panel written (panel_finalize_kernel)
     // Persistent panel chain (panel_chain_kernel): one cluster launch per panel on `stream`; the updates of the rest of
     // the panel run on `chain_side`, ordered against the running kernel through two device flags.
     cudaStream_t chain_side;  // null: the chain flow is not used
@@ -141,10 +129,6 @@ struct PanelArgs {
     unsigned* chain_ctr;      // host mirror: the flags only grow
     long long* chain_dbg;     // optional device buffer, 8 x int64 per register block: globaltimer stamps of the cluster
 };
-constexpr int kPanelLaEvents = 2 * 8 + 4;
-// true if launch_panel will honour the look-ahead fields for this panel (else it ignores them and the caller
-// must not rely on next_cols having been updated)
-bool panel_lookahead_ok(const PanelArgs& a);
 // true if launch_panel will take the persistent chain flow for this panel
 bool panel_chain_ok(const PanelArgs& a);
 size_t panel_ws_bytes(long max_rows);

@@ -411,6 +411,314 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2) tmem_dealloc(tmem_base, C_::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------ 2-CTA variant (cta_group::2)
+// A CTA pair (cluster of 2 = the two SMs of a TPC) computes a 256 x 256 tile: every CTA stages its own 128 rows of A and
+// HALF of the B tile (128 of the 256 columns), one thread of the leader CTA issues tcgen05.mma.cta_group::2 (M = 256),
+// which reads the B halves of both CTAs, and every CTA keeps the accumulators of its own 128 rows in its own TMEM.
+// Per k-block a CTA pulls 32 KB through its L2 port instead of 48 KB: the one-CTA kernel sits exactly at the port's
+// ~64 B/clk at full tensor rate (768 KB of operands per 128 x 256 x 1024 tile in 7.2 us), which is what capped TN at
+// ~60 % and NN (+ the FP32 master tile) at ~42 % of the tensor peak in round 1.
+//   full[]  : in the LEADER only; both CTAs' TMA loads complete their bytes there (cp.async.bulk.tensor.cta_group::2)
+//   empty[] : in both CTAs, arrived by the leader's tcgen05.commit multicast
+//   tfull[] : in both CTAs (multicast commit);  tempty[]: in the leader, 2 x 128 remote arrivals from both epilogues
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even (leader) CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & kPeerMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint64_t adesc, uint64_t bdesc, uint32_t tmem_d, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+struct Cfg2 {
+    static constexpr int BN = 256;               // pair tile: 256 x 256
+    static constexpr int BNH = 128;              // columns of B staged per CTA
+    static constexpr int B_STAGE_BYTES = BNH * BK * 2;  // 16 KB
+    static constexpr int STAGES = 4;
+    static constexpr int NCS2 = 5;               // C-chunk ring slots
+    static constexpr int CBUF_BYTES = BM * CCH * 4;
+    static constexpr int HBUF_BYTES = BM * CCH * 2;
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + STAGES * A_STAGE_BYTES;
+    static constexpr int OFF_C = OFF_B + STAGES * B_STAGE_BYTES;
+    static constexpr int OFF_H = OFF_C + NCS2 * CBUF_BYTES;
+    static constexpr int OFF_BAR = OFF_H + NHS * HBUF_BYTES;
+    static constexpr int NBARS = 2 * STAGES + 4 + 2 * NCS2;
+    static constexpr int SMEM_BYTES = OFF_BAR + NBARS * 8 + 16 + 1024;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+static_assert(Cfg2::SMEM_BYTES <= 232448, "2-CTA GEMM: shared memory budget");
+
+template <bool kAMN, int kEpi>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmH,
+                GemmParams p, int fmt16) {
+    using C_ = Cfg2;
+    constexpr int STAGES = C_::STAGES, BN = C_::BN, NCS2 = C_::NCS2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem + C_::OFF_A;
+    uint8_t* sB = smem + C_::OFF_B;
+    uint8_t* sC = smem + C_::OFF_C;
+    uint8_t* sH = smem + C_::OFF_H;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::OFF_BAR);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* cfull = tempty + 2;
+    uint64_t* cempty = cfull + NCS2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cempty + NCS2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const bool leader_cta = rank == 0;
+    const int mt = (p.M + 2 * BM - 1) / (2 * BM), nt = (p.N + BN - 1) / BN;
+    const int total = mt * nt * p.splits;
+    const int kblocks = (p.K + BK - 1) / BK;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        prefetch_tmap(&tmC);
+        if (p.has_shadow) prefetch_tmap(&tmH);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 256);
+        }
+        for (int i = 0; i < NCS2; ++i) {
+            mbar_init(&cfull[i], 1);
+            mbar_init(&cempty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc2(tmem_slot, C_::TMEM_COLS);
+    pdl_launch_dependents();
+    tc_fence_before();
+    cluster_sync_all();  // both CTAs' barriers exist before any remote signal; TMEM address visible
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    auto decode = [&](int w, int& mb, int& nb, int& kb0, int& kb1) {
+        int tile = w / p.splits, ks = w - tile * p.splits;
+        mb = tile % mt;
+        nb = tile / mt;
+        kb0 = ks * p.kblocks_per_split;
+        kb1 = kb0 + p.kblocks_per_split;
+        if (kb1 > kblocks) kb1 = kblocks;
+    };
+
+    if (warp == 0) {
+        // ================================ TMA producer (both CTAs) ====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = pair; w < total; w += npairs) {
+                int mb, nb, kb0, kb1;
+                decode(w, mb, nb, kb0, kb1);
+                const int m0 = mb * 2 * BM + (int)rank * BM;         // this CTA's rows of A (and of C)
+                const int n0 = nb * BN + (int)rank * C_::BNH;        // this CTA's half of the B tile
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (leader_cta) mbar_arrive_expect_tx(&full[stage], 2 * (A_STAGE_BYTES + C_::B_STAGE_BYTES));
+                    uint8_t* a = sA + stage * A_STAGE_BYTES;
+                    uint8_t* b = sB + stage * C_::B_STAGE_BYTES;
+                    if (kAMN) {
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i)
+                            tma_load_2d_2sm(a + i * (BK * 128), &tmA, &full[stage], p.ax0 + m0 + i * 64, p.ay0 + kb * BK);
+                    } else {
+                        tma_load_2d_2sm(a, &tmA, &full[stage], p.ax0 + kb * BK, p.ay0 + m0);
+                    }
+#pragma unroll
+                    for (int i = 0; i < C_::BNH / 64; ++i)
+                        tma_load_2d_2sm(b + i * (BK * 128), &tmB, &full[stage], p.bx0 + n0 + i * 64, p.by0 + kb * BK);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA only) ================
+        if (leader_cta) {
+            const uint32_t idesc = make_idesc(fmt16, kAMN ? 1 : 0, 1, 2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int w = pair; w < total; w += npairs, ++it) {
+                int mb, nb, kb0, kb1;
+                decode(w, mb, nb, kb0, kb1);
+                const int as = it & 1;
+                mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_base = smem_u32(sA + stage * A_STAGE_BYTES);
+                        const uint32_t b_base = smem_u32(sB + stage * C_::B_STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k) {
+                            uint64_t ad, bd;
+                            if (kAMN) ad = make_smem_desc(a_base + k * (UK * 128), BK * 128, 1024);
+                            else ad = make_smem_desc(a_base + k * (UK * 2), 0, 1024);
+                            bd = make_smem_desc(b_base + k * (UK * 128), BK * 128, 1024);
+                            umma2_f16(ad, bd, d_tmem, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
+                        umma2_commit_both(&empty[stage]);
+                        if (kb == kb1 - 1) umma2_commit_both(&tfull[as]);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ================================ C-chunk loader (NN, per CTA) ================
+        if (kEpi == 1 && elect_one()) {
+            uint32_t g = 0;
+            for (int w = pair; w < total; w += npairs) {
+                int mb, nb, kb0, kb1;
+                decode(w, mb, nb, kb0, kb1);
+                const int m0 = mb * 2 * BM + (int)rank * BM;
+                for (int j = 0; j < BN / CCH; ++j) {
+                    if (nb * BN + j * CCH >= p.N) break;
+                    const int slot = g % NCS2;
+                    mbar_wait(&cempty[slot], ((g / NCS2) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&cfull[slot], C_::CBUF_BYTES);
+                    tma_load_2d(sC + slot * C_::CBUF_BYTES, &tmC, &cfull[slot], p.cx0 + nb * BN + j * CCH, p.cy0 + m0);
+                    ++g;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue (both CTAs, own rows) ==============
+        const int q = warp - 4;
+        const int row = q * 32 + lane;
+        const bool leader = (threadIdx.x == 128);
+        uint32_t g = 0;
+        int it = 0;
+        for (int w = pair; w < total; w += npairs, ++it) {
+            int mb, nb, kb0, kb1;
+            decode(w, mb, nb, kb0, kb1);
+            const int m0 = mb * 2 * BM + (int)rank * BM;
+            const int as = it & 1;
+            mbar_wait(&tfull[as], (it >> 1) & 1);
+            tc_fence_after();
+            for (int j = 0; j < BN / CCH; ++j) {
+                if (nb * BN + j * CCH >= p.N) break;
+                const int slot = g % NCS2;
+                const int hs = g % NHS;
+                uint8_t* cb = sC + slot * C_::CBUF_BYTES;
+                uint8_t* hb = sH + hs * C_::HBUF_BYTES;
+                if (leader) {
+                    tma_wait_read<1>();
+                    if (kEpi == 1 && g >= 2) mbar_arrive(&cempty[(g - 2) % NCS2]);
+                }
+                if (kEpi == 1) mbar_wait(&cfull[slot], (g / NCS2) & 1);
+                named_bar_sync(1, 128);
+
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + j * CCH), v);
+                tmem_ld_wait();
+                uint8_t* crow = cb + row * 128;
+                float o[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4* pc = reinterpret_cast<float4*>(crow + ((i ^ (row & 7)) << 4));
+                    float4 a4 = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                    float4 r4;
+                    if (kEpi == 1) {
+                        float4 c4 = *pc;
+                        r4 = make_float4(c4.x - a4.x, c4.y - a4.y, c4.z - a4.z, c4.w - a4.w);
+                    } else {
+                        r4 = a4;
+                    }
+                    if (kEpi != 0 || !p.no_c) *pc = r4;
+                    o[4 * i] = r4.x; o[4 * i + 1] = r4.y; o[4 * i + 2] = r4.z; o[4 * i + 3] = r4.w;
+                }
+                if (p.has_shadow) {
+                    uint8_t* hrow = hb + row * 64;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float lo = o[8 * i + 2 * u], hi = o[8 * i + 2 * u + 1];
+                            if (fmt16 == 1) {
+                                __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+                                pk[u] = *reinterpret_cast<uint32_t*>(&t);
+                            } else {
+                                __half2 t = __floats2half2_rn(lo, hi);
+                                pk[u] = *reinterpret_cast<uint32_t*>(&t);
+                            }
+                        }
+                        *reinterpret_cast<uint4*>(hrow + ((i ^ ((row >> 1) & 3)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                if (j == BN / CCH - 1 || nb * BN + (j + 1) * CCH >= p.N) {
+                    // last TMEM read of this tile: hand the accumulator back to the leader's MMA warp
+                    tc_fence_before();
+                    mbar_arrive_leader(&tempty[as]);
+                }
+                fence_proxy_async();
+                named_bar_sync(2, 128);
+                if (leader) {
+                    const int cx = p.cx0 + nb * BN + j * CCH, cy = p.cy0 + m0;
+                    if (kEpi == 0 && p.splits > 1) tma_reduce_add_2d(&tmC, cb, cx, cy);
+                    else if (kEpi != 0 || !p.no_c) tma_store_2d(&tmC, cb, cx, cy);
+                    if (p.has_shadow) tma_store_2d(&tmH, hb, p.hx0 + nb * BN + j * CCH, p.hy0 + m0);
+                    tma_commit();
+                }
+                ++g;
+            }
+        }
+        if (leader) tma_wait_all();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // no remote arrival / multicast commit may still be in flight towards a CTA that exits
+    if (warp == 2) tmem_dealloc2(tmem_base, C_::TMEM_COLS);
+}
+
 // ------------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -471,6 +779,23 @@ int launch(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, 
     return MPQR_OK;
 }
 
+template <bool kAMN, int kEpi>
+int launch2(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tH,
+            const GemmParams& p, int fmt16, int pairs, cudaStream_t stream) {
+    MPQR_TRY(func_attr_once((const void*)tc_gemm2_kernel<kAMN, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1] = pdl_attr();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NTHREADS); cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 2;
+    cfg.dynamicSmemBytes = Cfg2::SMEM_BYTES;
+    MPQR_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm2_kernel<kAMN, kEpi>, tA, tB, tC, tH, p, fmt16));
+    return MPQR_OK;
+}
+// 2-CTA kernel: worth it from two 128-row tiles on (MPQR_GEMM_1CTA=1 keeps the one-CTA kernel: A/B comparisons)
+inline bool use_2cta(int M, int N) { return M > BM && N > 128 && !getenv("MPQR_GEMM_1CTA"); }
+
 // TMA needs 16-byte aligned box origins.  x0 = misalignment of a block pointer in elements;
 // blocks with x0 != 0 are routed to the CUDA-core fallback (gemm_simt.cu).  TMA stores also
 // write whole 16-byte granules (measured on B200: a store clipped at column N still zeroes the
@@ -518,11 +843,13 @@ int tc_gemm_tn16(const void* X, long ldx, const void* Z, long ldz, float* S, lon
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.ax0 = bx.x0; p.bx0 = bz.x0; p.cx0 = bs.x0;
-    const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+    const bool two = use_2cta(M, N);
+    const int units = two ? sm_count(di) / 2 : sm_count(di);   // CTAs, or CTA pairs
+    const int tiles = two ? ceil_div(M, 2 * BM) * ceil_div(N, 256) : ceil_div(M, BM) * ceil_div(N, BN);
     const int kblocks = ceil_div(K, BK);
     int splits = 1;
-    if (tiles < sm_count(di) && kblocks >= 8) {
-        splits = sm_count(di) / tiles;
+    if (tiles < units && kblocks >= 8) {
+        splits = units / tiles;
         int maxs = kblocks / 4;
         if (splits > maxs) splits = maxs;
         if (splits < 1) splits = 1;
@@ -539,9 +866,10 @@ int tc_gemm_tn16(const void* X, long ldx, const void* Z, long ldz, float* S, lon
     if (p.splits > 1)
         MPQR_CUDA(cudaMemset2DAsync(S, lds * sizeof(float), 0, (size_t)N * sizeof(float), M, stream));
     int total = tiles * p.splits;
-    int grid = total < sm_count(di) ? total : sm_count(di);
-    int rc = (BN == 256) ? launch<256, true, 0>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream)
-                         : launch<128, true, 0>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream);
+    int grid = total < units ? total : units;
+    int rc = two ? launch2<true, 0>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream)
+                 : (BN == 256) ? launch<256, true, 0>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream)
+                               : launch<128, true, 0>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream);
     if (rc == MPQR_OK && launches) *launches += 1;
     return rc;
 }
@@ -576,10 +904,14 @@ static int tc_gemm_nn_impl(const void* X, long ldx, const void* S16, long lds16,
     } else {
         tH = tC;
     }
-    const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
-    int grid = tiles < sm_count(di) ? tiles : sm_count(di);
+    const bool two = use_2cta(M, N);
+    const int units = two ? sm_count(di) / 2 : sm_count(di);
+    const int tiles = two ? ceil_div(M, 2 * BM) * ceil_div(N, 256) : ceil_div(M, BM) * ceil_div(N, BN);
+    int grid = tiles < units ? tiles : units;
     int rc;
-    if (store) rc = (BN == 256) ? launch<256, false, 2>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream)
+    if (two) rc = store ? launch2<false, 2>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream)
+                        : launch2<false, 1>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream);
+    else if (store) rc = (BN == 256) ? launch<256, false, 2>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream)
                                 : launch<128, false, 2>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream);
     else rc = (BN == 256) ? launch<256, false, 1>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream)
                           : launch<128, false, 1>(tA, tB, tC, tH, p, bf16 ? 1 : 0, grid, stream);

@@ -54,13 +54,12 @@ struct mpqr_handle {
         struct Pair {
             void* gP = nullptr;  // CUgreenCtx: panel partition
             void* gU = nullptr;  // CUgreenCtx: update partition
-            cudaStream_t sP = nullptr, sP2 = nullptr, sP3 = nullptr, sP4 = nullptr, sU = nullptr;  // sP2..sP4: more streams of the panel partition
+            cudaStream_t sP = nullptr, sP2 = nullptr, sP3 = nullptr, sU = nullptr;  // sP2 (in-block rest), sP3 (chain side): more streams of the panel partition
             int nsmP = 0, nsmU = 0;
         };
         std::vector<Pair> pairs;
-        cudaStream_t sF = nullptr, sF2 = nullptr, sF3 = nullptr, sF4 = nullptr;  // whole-device streams (intervals that are not worth splitting)
+        cudaStream_t sF = nullptr, sF2 = nullptr, sF3 = nullptr;  // whole-device streams (intervals that are not worth splitting)
         std::vector<cudaEvent_t> ev_rest;  // BlockCtx::rest_ev
-        std::vector<cudaEvent_t> ev_la;    // BlockCtx::la_ev (register-block look-ahead inside launch_panel)
         int nsm_full = 0;
         std::vector<cudaEvent_t> ev_bp, ev_fn, ev_fr;
         cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_accdone = nullptr;
@@ -189,12 +188,6 @@ struct BlockCtx {
     float* rest_S32;           // its GEMM scratch (r x lds32)
     void* rest_S16;
     cudaEvent_t* rest_ev;      // 2 events per panel: [2p] panel factored, [2p+1] rest of panel p's in-block update done
-    // Optional: register-block look-ahead (needs rest_stream too).  Inside a panel only the update of block j to the
-    // NEXT register block stays on the panel stream; the rest of the panel is updated on `side_stream`, the whole NEXT
-    // panel (FP32, block by block) on `side2_stream`; Gram/T/W and the tensor-core in-block update N(p) of the
-    // columns right of panel p+1 run on rest_stream (event rest_ev[2p+1]) with a whole panel's time of slack.
-    cudaStream_t side_stream, side2_stream;
-    cudaEvent_t* la_ev;        // kPanelLaEvents events
     cudaStream_t chain_side;   // side stream of the persistent panel chain (null: the handle's own)
 };
 // panels + in-block updates + WY accumulation of block [c0, c1); `ncols_in` = columns of A

@@ -285,10 +285,20 @@ int mpqr_mg_factor_device(mpqr_handle* h, float* dA, long lda, void* stream) {
             const int end_ok = (acol0 + (c1 - c0) == g->nloc);
             BlockCtx cp = c;
             cp.chain_side = s_side;
-            if (s_rest && !h->ov.ev_rest.empty()) { cp.rest_stream = s_rest; cp.rest_S32 = h->S32r; cp.rest_S16 = h->S16r; cp.rest_ev = h->ov.ev_rest.data(); }
+            const bool two = s_rest && !h->ov.ev_rest.empty() && !h->ov.ev_acc.empty();
+            if (two) {
+                // in-block rest updates and the WY accumulation (which rewrites W_p in place, so it must follow the rest
+                // update that reads it) on the partition's second stream
+                cp.rest_stream = s_rest; cp.rest_S32 = h->S32r; cp.rest_S16 = h->S16r; cp.rest_ev = h->ov.ev_rest.data();
+                cp.acc_stream = s_rest; cp.acc_sms = nsm_p; cp.acc_S32 = h->S32r; cp.acc_S16 = h->S16r; cp.acc_ev = h->ov.ev_acc.data();
+            }
             {
                 SmBudget budget(nsm_p);
                 MPQR_TRY(block_phase(h, cp, c0, c1, end_ok, s_panel));
+            }
+            if (two) {
+                MPQR_CUDA(cudaEventRecord(h->ov.ev_accdone, s_rest));
+                MPQR_CUDA(cudaStreamWaitEvent(s_panel, h->ov.ev_accdone, 0));
             }
             MPQR_CUDA(cudaEventRecord(g->ev_bp[b], s_panel));
             MPQR_CUDA(cudaStreamWaitEvent(s_comm, g->ev_bp[b], 0));

@@ -1051,6 +1051,12 @@ __global__ void __launch_bounds__(256) panel_finalize_kernel(const float* Yp, lo
     }
 }
 
+// ------------------------------------------------------------------ level 1: in-panel update
+// S'[rep][t][c] += sum_rows Y[row][t] * A[row][c]   (FP32; B x ncols, rows split over the grid)
+// 512 threads = 4 row groups x 128 columns; RB rows in flight per thread (memory-level parallelism
+// is what bounds these skinny passes: 512 x RB x 4 B in flight per SM).
+// rows in flight per thread: the loops are latency-bound (one round trip per batch), so a CTA's rows
+// should be covered in about two batches
 template <int B> struct SuRb { static constexpr int value = (B == 16) ? 32 : 16; };
 template <int B>
 __global__ void __launch_bounds__(512) inpanel_s_kernel(const float* __restrict__ W, long ldw, const float* __restrict__ A,
@@ -1235,15 +1241,11 @@ template <int B>
 __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* __restrict__ Y, long ldy, const float* __restrict__ A,
                                                                   long lda, int D, int ncols, float* __restrict__ Srep,
                                                                   unsigned* __restrict__ counter, const float* __restrict__ Tj,
-                                                                  float* __restrict__ Sfin, int rows_per_cta, int ysm_floats,
-                                                                  float* __restrict__ Cacc) {
-    // Cacc != null (B == 32 after a double block): Tj = [T_A | T_B] (16 x 16 each); this kernel also accumulates the
-    // cross Gram C = Y_A^T Y_B and its last CTA assembles T_32 = [[T_A, -T_A C T_B], [0, T_B]].
+                                                                  float* __restrict__ Sfin, int rows_per_cta, int ysm_floats) {
     constexpr int NTHR = Su4<B>::NTHR, NWARP = NTHR / 32, RB = Su4<B>::RB;
     extern __shared__ __align__(16) float sm[];
     float* ysm = sm;               // rows_per_cta x B  (later: T, B x (B+4))
     float* red = sm + ysm_floats;  // B x 128           (later: S')
-    __shared__ unsigned ticket;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r0 = blockIdx.x * rows_per_cta;
     int nrows = D - r0;
@@ -1264,17 +1266,6 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
         ysm[idx] = __ldcg(&Y[(size_t)(r0 + rr) * ldy + t]);
     }
     __syncthreads();
-    if (B == 32 && Cacc && blockIdx.y == 0) {  // NTHR == 256: thread <-> entry (ta, tb) of C
-        const int ta = tid >> 4, tb = tid & 15;
-        float c0 = 0.f, c1 = 0.f;
-        int r2 = 0;
-        for (; r2 + 1 < nrows; r2 += 2) {
-            c0 = fmaf(ysm[r2 * B + ta], ysm[r2 * B + 16 + tb], c0);
-            c1 = fmaf(ysm[(r2 + 1) * B + ta], ysm[(r2 + 1) * B + 16 + tb], c1);
-        }
-        if (r2 < nrows) c0 = fmaf(ysm[r2 * B + ta], ysm[r2 * B + 16 + tb], c0);
-        atomicAdd(&Cacc[tid], c0 + c1);
-    }
     float acc[B][4];
 #pragma unroll
     for (int t = 0; t < B; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
@@ -1324,109 +1315,36 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
         }
         __syncthreads();
     }
-    if (!(B == 32 && Cacc)) {
-        // T^T is linear: every CTA applies it to its OWN partial S' and adds the result into one of two replicas of the
-        // final S (no ticket, no last-CTA fold: four dependent global round trips fewer on the panel chain)
-        float* Ts2 = ysm;  // B x (B + 4); the tree above is done with this memory
-        if (warp == 0) {
+    // T^T is linear: every CTA applies it to its OWN partial S' and adds the result into one of two replicas of the
+    // final S (no ticket, no last-CTA fold: four dependent global round trips fewer on the panel chain)
+    float* Ts2 = ysm;  // B x (B + 4); the tree above is done with this memory
+    if (warp == 0) {
 #pragma unroll
-            for (int t = 0; t < B; ++t) *reinterpret_cast<float4*>(&red[t * 128 + 4 * lane]) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
-        }
-        for (int idx = tid; idx < B * B; idx += NTHR) Ts2[(idx / B) * (B + 4) + (idx % B)] = __ldcg(&Tj[idx]);
-        __syncthreads();
-        constexpr int NG = NTHR / 128, TQ = B / NG;  // thread: column cc, TQ consecutive rows t of S
-        const int cc = tid & 127, tg = tid >> 7;
-        float v[TQ];
+        for (int t = 0; t < B; ++t) *reinterpret_cast<float4*>(&red[t * 128 + 4 * lane]) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    }
+    for (int idx = tid; idx < B * B; idx += NTHR) Ts2[(idx / B) * (B + 4) + (idx % B)] = __ldcg(&Tj[idx]);
+    __syncthreads();
+    constexpr int NG = NTHR / 128, TQ = B / NG;  // thread: column cc, TQ consecutive rows t of S
+    const int cc = tid & 127, tg = tid >> 7;
+    float v[TQ];
 #pragma unroll
-        for (int q = 0; q < TQ; ++q) v[q] = 0.f;
+    for (int q = 0; q < TQ; ++q) v[q] = 0.f;
 #pragma unroll 4
-        for (int u2 = 0; u2 < B; ++u2) {  // T is zero below its diagonal
-            const float sp = red[u2 * 128 + cc];
+    for (int u2 = 0; u2 < B; ++u2) {  // T is zero below its diagonal
+        const float sp = red[u2 * 128 + cc];
 #pragma unroll
-            for (int q = 0; q < TQ; q += 4) {
-                const float4 t4 = *reinterpret_cast<const float4*>(&Ts2[u2 * (B + 4) + tg * TQ + q]);
-                v[q] = fmaf(t4.x, sp, v[q]);
-                v[q + 1] = fmaf(t4.y, sp, v[q + 1]);
-                v[q + 2] = fmaf(t4.z, sp, v[q + 2]);
-                v[q + 3] = fmaf(t4.w, sp, v[q + 3]);
-            }
+        for (int q = 0; q < TQ; q += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(&Ts2[u2 * (B + 4) + tg * TQ + q]);
+            v[q] = fmaf(t4.x, sp, v[q]);
+            v[q + 1] = fmaf(t4.y, sp, v[q + 1]);
+            v[q + 2] = fmaf(t4.z, sp, v[q + 2]);
+            v[q + 3] = fmaf(t4.w, sp, v[q + 3]);
         }
-        if (c0 + cc < ncols) {
-            float* S = Srep + (size_t)(blockIdx.x & 1) * RMAX * SLD + c0 + cc;
-#pragma unroll
-            for (int q = 0; q < TQ; ++q) atomicAdd(&S[(size_t)(tg * TQ + q) * SLD], v[q]);
-        }
-        return;
     }
-    // pair mode (after a double block): T_32 needs the complete cross Gram first -> replicas + last-CTA fold
-    if (warp == 0 && on) {
-        float* S = Srep + (size_t)(blockIdx.x % NREP) * RMAX * SLD + col;
+    if (c0 + cc < ncols) {
+        float* S = Srep + (size_t)(blockIdx.x & 1) * RMAX * SLD + c0 + cc;
 #pragma unroll
-        for (int t = 0; t < B; ++t)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) atomicAdd(&S[t * SLD + k], acc[t][k]);
-    }
-    // ---- last CTA: S = T^T (sum of the replicas)
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) ticket = atomicAdd(counter, 1u);
-    __syncthreads();
-    if (ticket != gridDim.x * gridDim.y - 1) return;
-    __threadfence();
-    float* Ts = ysm;  // B x (B + 4)
-    for (int idx = tid; idx < B * 128; idx += NTHR) {
-        const int t = idx >> 7, cc = idx & 127;
-        float v = 0.f;
-        if (cc < ncols) {
-#pragma unroll
-            for (int rep = 0; rep < NREP; ++rep) v += __ldcg(&Srep[(size_t)rep * RMAX * SLD + t * SLD + cc]);
-        }
-        red[idx] = v;
-    }
-    if (B == 32 && Cacc) {
-        // T_32 from T_A, T_B and C: X = C T_B, T_AB = -T_A X  (thread <-> entry (i, j); NTHR == 256)
-        float* Xs = red + B * 128;          // 16 x 16 scratch behind S' (the dynamic buffer has room: see launch)
-        float* Cs = Xs + 256;
-        const int i2 = tid >> 4, j2 = tid & 15;
-        Cs[tid] = __ldcg(&Cacc[tid]);
-        for (int idx = tid; idx < B * (B + 4); idx += NTHR) Ts[idx] = 0.f;
-        __syncthreads();
-        Ts[i2 * (B + 4) + j2] = __ldcg(&Tj[tid]);                    // T_A
-        Ts[(16 + i2) * (B + 4) + 16 + j2] = __ldcg(&Tj[256 + tid]);  // T_B
-        __syncthreads();
-        float xv = 0.f;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) xv = fmaf(Cs[i2 * 16 + k], Ts[(16 + k) * (B + 4) + 16 + j2], xv);
-        Xs[tid] = xv;
-        __syncthreads();
-        float tv = 0.f;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) tv = fmaf(Ts[i2 * (B + 4) + k], Xs[k * 16 + j2], tv);
-        Ts[i2 * (B + 4) + 16 + j2] = -tv;
-    } else {
-        for (int idx = tid; idx < B * B; idx += NTHR) Ts[(idx / B) * (B + 4) + (idx % B)] = __ldcg(&Tj[idx]);
-    }
-    __syncthreads();
-    {
-        constexpr int NG = NTHR / 128, TQ = B / NG;  // thread: column cc, TQ consecutive rows t of S
-        const int cc = tid & 127, tg = tid >> 7;
-        float v[TQ];
-#pragma unroll
-        for (int q = 0; q < TQ; ++q) v[q] = 0.f;
-#pragma unroll 4
-        for (int u2 = 0; u2 < B; ++u2) {  // T is zero below its diagonal
-            const float sp = red[u2 * 128 + cc];
-#pragma unroll
-            for (int q = 0; q < TQ; q += 4) {
-                const float4 t4 = *reinterpret_cast<const float4*>(&Ts[u2 * (B + 4) + tg * TQ + q]);
-                v[q] = fmaf(t4.x, sp, v[q]);
-                v[q + 1] = fmaf(t4.y, sp, v[q + 1]);
-                v[q + 2] = fmaf(t4.z, sp, v[q + 2]);
-                v[q + 3] = fmaf(t4.w, sp, v[q + 3]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < TQ; ++q) Sfin[(size_t)(tg * TQ + q) * SLD + cc] = v[q];
+        for (int q = 0; q < TQ; ++q) atomicAdd(&S[(size_t)(tg * TQ + q) * SLD], v[q]);
     }
 }
 
@@ -1661,42 +1579,6 @@ int launch_block_t(const BlockArgs& a, int CS, cudaStream_t stream) {
     return MPQR_OK;
 }
 
-template <int RPT>
-int launch_dblock_t(const BlockArgs& a, int CS, cudaStream_t stream) {
-    static bool attr = false;
-    const size_t smem = (size_t)NT * RPT * 16 * sizeof(float);
-    if (!attr) {
-        MPQR_CUDA(cudaFuncSetAttribute(panel_dblock_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cudaFuncSetAttribute(panel_dblock_kernel<RPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        attr = true;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(CS);
-    cfg.blockDim = dim3(NT);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[2];
-    int na = 0;
-    if (CS > 1) {
-        at[na].id = cudaLaunchAttributeClusterDimension;
-        at[na].val.clusterDim.x = CS;
-        at[na].val.clusterDim.y = 1;
-        at[na].val.clusterDim.z = 1;
-        ++na;
-    }
-    at[na++] = pdl_attr();
-    cfg.attrs = at;
-    cfg.numAttrs = na;
-    MPQR_CUDA(cudaLaunchKernelEx(&cfg, panel_dblock_kernel<RPT>, a, CS));
-    return MPQR_OK;
-}
-int launch_dblock(const BlockArgs& a, int RPT, int CS, cudaStream_t st) {
-    if (RPT == 1) return launch_dblock_t<1>(a, CS, st);
-    if (RPT == 2) return launch_dblock_t<2>(a, CS, st);
-    if (RPT == 4) return launch_dblock_t<4>(a, CS, st);
-    return launch_dblock_t<8>(a, CS, st);
-}
-
 int g_max_cs = 0;
 int max_cluster() {
     if (!g_max_cs) {
@@ -1807,7 +1689,7 @@ int su_attrs() {
 
 template <int B>
 int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, float* Sfin,
-              int num_sms, cudaStream_t st, long* launches, const ProfHook* prof, bool pair = false, bool pdl_first = true) {
+              int num_sms, cudaStream_t st, long* launches, const ProfHook* prof, bool pdl_first = true) {
     // one wave of CTAs over the SMs this stream may use (up to 512 rows = 32 KB of staged Y per CTA);
     // taller blocks take k balanced waves
     const int max_rows = 512;
@@ -1831,16 +1713,15 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
         if (s4_floats < tree_floats) s4_floats = tree_floats;
         cfg.dynamicSmemBytes = s4_floats * sizeof(float);
         unsigned* counter = reinterpret_cast<unsigned*>(Srep + (size_t)NREP * RMAX * SLD);
-        float* Cacc = pair ? Srep + (size_t)NREP * RMAX * SLD + 4 : nullptr;
         // pdl_first = false: the S kernel must not become resident (and hold its SMs idle) while the register-block
         // kernel before it is still running: those SMs belong to the side stream's updates during that time
         if (!pdl_first) cfg.numAttrs = 0;
         MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_s4_kernel<B>, Yj, ldy, (const float*)Arest, lda, D, ncols, Srep, counter, Tj, Sfin, rows,
-                                     ysm_floats, Cacc));
+                                     ysm_floats));
         cfg.numAttrs = 1;
         if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st, 2.0 * D * ncols * B, 4.0 * D * (2 * ncols + B)); }
         cfg.dynamicSmemBytes = (size_t)rows * B * sizeof(float);
-        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_u4_kernel<B>, Yj, ldy, Arest, lda, D, ncols, pair ? (const float*)Sfin : (const float*)Srep, pair ? 1 : 2, rows));
+        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_u4_kernel<B>, Yj, ldy, Arest, lda, D, ncols, (const float*)Srep, 2, rows));
     } else {
         cfg.blockDim = dim3(512);
         cfg.dynamicSmemBytes = (size_t)((rows * B > 3 * B * 128) ? rows * B : 3 * B * 128) * sizeof(float);
@@ -1872,14 +1753,14 @@ const MemopApi* memop_api() {
             cudaDriverEntryPointQueryResult q;
             return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
         };
-        api.ok = !getenv("MPQR_GATE_KERNEL") && get("cuStreamWaitValue32", (void**)&api.Wait32) && get("cuStreamWriteValue32", (void**)&api.Write32);
+        api.ok = get("cuStreamWaitValue32", (void**)&api.Wait32) && get("cuStreamWriteValue32", (void**)&api.Write32);
         if (!api.ok) cudaGetLastError();
     }
     return &api;
 }
 int stream_wait_geq(cudaStream_t st, unsigned* flag, unsigned want) {
     const MemopApi* m = memop_api();
-    if (m->ok) {
+    if (m->ok && !getenv("MPQR_GATE_KERNEL")) {
         if (m->Wait32((CUstream)st, (CUdeviceptr)(uintptr_t)flag, want, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS) return MPQR_OK;
         set_error("cuStreamWaitValue32 failed");
         return MPQR_ECUDA;
@@ -1890,7 +1771,7 @@ int stream_wait_geq(cudaStream_t st, unsigned* flag, unsigned want) {
 }
 int stream_post(cudaStream_t st, unsigned* flag, unsigned v) {
     const MemopApi* m = memop_api();
-    if (m->ok) {
+    if (m->ok && !getenv("MPQR_GATE_KERNEL")) {
         if (m->Write32((CUstream)st, (CUdeviceptr)(uintptr_t)flag, v, CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS) return MPQR_OK;
         set_error("cuStreamWriteValue32 failed");
         return MPQR_ECUDA;
@@ -1975,30 +1856,6 @@ size_t panel_ws_bytes(long max_rows) {
            (size_t)RMAX * RMAX * 2 + 256;
 }
 
-bool panel_lookahead_ok(const PanelArgs& a) {
-    if (!a.side || !a.side2 || !a.la_ev || !a.ws) return false;
-    const int D = a.m - a.lam, pw = a.pw;
-    if (pw <= 32 || (pw & 31) || a.next_cols < 0 || a.next_cols > 128 || (a.next_cols & 31)) return false;
-    // Measured on B200 (32768^2 and 16384^2, r = 128): with 32-column register blocks (D <= 16384, 4 blocks per panel)
-    // the look-ahead shortens the chain by ~9 %; with 16-column blocks (taller panels, 8 blocks per panel) the FP32
-    // block-by-block update of the next panel is 3x the in-panel update work and the side streams cannot keep up
-    // (162 ms against 146 ms), so tall panels keep the classic flow.  MPQR_RBLA_TALL=1 overrides (experiments).
-    static const bool tall = getenv("MPQR_RBLA_TALL") != nullptr;
-    // MPQR_FUSED=1 (experimental): tall panels take the look-ahead flow with the near update fused into the register-block
-    // kernel (fused_prev_update) and WITHOUT the FP32 update of the next panel (next_cols == 0)
-    static const bool fused_env = getenv("MPQR_FUSED") != nullptr;
-    const bool fused_tall = fused_env && a.next_cols == 0 && (long)D > block_capacity(32);
-    if ((long)D > ((tall || fused_tall) ? block_capacity(16) : block_capacity(32)) || D < 2 * pw || a.ws_rows < 256) return false;
-    if ((a.lda & 3) || (reinterpret_cast<uintptr_t>(a.A + (size_t)a.lam * a.lda + a.acol) & 15)) return false;  // vectorised S/U only
-    if (a.force_b || a.force_cs || a.force_rpt || a.prof) return false;
-    // the side streams share the panel partition with the chain: on a small partition they slow the chain down more than
-    // they take off it (B200, D = 16384: 4.3 ms per outer block on 80 SMs against 3.8 ms classic; faster from ~100 SMs)
-    static const int min_sms = getenv("MPQR_RBLA_MIN_SMS") ? atoi(getenv("MPQR_RBLA_MIN_SMS")) : 100;
-    if (g_sm_budget > 0 && g_sm_budget < min_sms && !fused_tall) return false;
-    const char* dbl_env = getenv("MPQR_DBLOCK");
-    return !(dbl_env && dbl_env[0] == '1');
-}
-
 // PanelArgs output pointers address (row blk_row0, first panel column); zr = lam - blk_row0 rows
 // above the panel are structurally zero.
 int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
@@ -2054,18 +1911,8 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     // FP32 Y of the whole panel: caller's array if given, else the workspace
     float* Yp = Y32l ? Y32l : w.Y32p;
     const long ldyp = Y32l ? a.ld32 : RMAX;
-    // MPQR_DBLOCK=1 (experimental, off by default): 16-column register blocks of tall panels are taken two at
-    // a time by panel_dblock_kernel, 32 columns per launch, and the in-panel update runs once per 32 columns.
-    // Round 1 measurement (B200, 32768^2): 88 us per double block against 2 x 41 us + one update pair (25 us);
-    // the in-kernel update between the halves still costs ~30 us, so the whole factorisation is 159 ms
-    // against 150 ms with single blocks.
-    const char* dbl_env = getenv("MPQR_DBLOCK");
-    // (its in-panel update needs the vectorised kernels: 16-byte aligned rows and widths that are multiples of 4)
-    const bool use_dblock = (B == 16) && dbl_env && dbl_env[0] == '1' && ((a.lda & 3) == 0) && ((pw & 3) == 0) &&
-                            ((reinterpret_cast<uintptr_t>(Ablk) & 15) == 0);
     // deferred outputs (panel_finalize_kernel): full register blocks only, vector-aligned A and 16-bit Y
-    static const bool no_defer = getenv("MPQR_NO_DEFER_OUT") != nullptr;
-    const bool defer = !no_defer && !use_dblock && !a.dbg && (pw % B) == 0 && D >= pw + 32 && ((a.lda & 3) == 0) &&
+    const bool defer = !a.dbg && (pw % B) == 0 && D >= pw + 32 && ((a.lda & 3) == 0) &&
                        ((reinterpret_cast<uintptr_t>(Ablk) & 15) == 0) && ((ldyp & 3) == 0) && ((reinterpret_cast<uintptr_t>(Yp) & 15) == 0) &&
                        (!Y16l || (((a.ldy16 & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y16) & 7) == 0)));
     auto finalize = [&](cudaStream_t fs) -> int {
@@ -2103,7 +1950,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
             const int j0 = jb * 16, Dj = D - j0, nfar = pw - (j0 + 32);
             MPQR_TRY(stream_wait_geq(a.chain_side, a.chain_flags, ca.base + (unsigned)(jb + 1)));
             MPQR_TRY(launch_su<16>(w.Wj + (size_t)jb * 32 * 32, Yp + (size_t)j0 * ldyp + j0, ldyp, Ablk + (size_t)j0 * a.lda + j0 + 32, a.lda, Dj,
-                                   nfar, ca.srep[jb & 1], w.Sfin, side_sms, a.chain_side, launches, a.prof, false, false));
+                                   nfar, ca.srep[jb & 1], w.Sfin, side_sms, a.chain_side, launches, a.prof, false));
             MPQR_TRY(stream_post(a.chain_side, a.chain_flags + 1, ca.base + (unsigned)(jb + 1)));
         }
         // every side update was consumed by the kernel before it finished: stream order is enough from here on
@@ -2111,125 +1958,31 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         MPQR_TRY(finalize(stream));
         if (a.prof) a.prof->end(a.prof->ctx, stream);
     }
-    const bool la = !chain && panel_lookahead_ok(a);
-    static const bool la_pdl = getenv("MPQR_RBLA_PDL") != nullptr;  // experiment: keep PDL on the near S kernel
-    cudaStream_t gtw_st = (la && a.gtw_stream) ? a.gtw_stream : stream;
-    int la_last = -1;  // index of the last register block (its "factored" event orders Gram/T/W)
-    if (la) {
-        // Register-block look-ahead.  Block jb: K (register-block kernel) on `stream`, then on `stream` only the update of
-        // the next B columns ("near": the next block; after the last block the next panel's first block).  Block jb's
-        // update of the other columns runs next to the following K's: rest of this panel on `side` (far A), the next
-        // panel's columns on `side2` (far B).  near(jb) needs far A(jb-1) (event [2(jb-1)+1]); the near update after the
-        // last block and everything of the next panel that touches its columns need far B: event [16] (side2 is one
-        // stream, so its last record covers all earlier far B's).  T of block jb lives in its own slot: the side streams
-        // still read T_jb while K(jb+1) writes T_jb+1.  S replicas: near 0-1 (cleared by K), far A 2-3, far B 4-5.
-        float* SrepA = w.Srep + (size_t)2 * RMAX * SLD;
-        float* SrepB = w.Srep + (size_t)4 * RMAX * SLD;
-        const size_t srep_bytes = (size_t)2 * RMAX * SLD * sizeof(float);
-        const int nblocks = pw / B;
-        bool prev_farA = false, b_started = false;
-        static const bool fused_env2 = getenv("MPQR_FUSED") != nullptr;
-        const bool fused = fused_env2 && B == 16 && a.next_cols == 0;  // near update inside the next register-block kernel
-        bool farA_issued[16] = {false};
-        auto su = [&](int Bw, const float* Tj, const float* Yj, float* Ar, int Dj, int nc, float* Srep, cudaStream_t s2, bool pdl_first) -> int {
-            if (Bw == 32) return launch_su<32>(Tj, Yj, ldyp, Ar, a.lda, Dj, nc, Srep, w.Sfin, sm_count(di), s2, launches, nullptr, false, pdl_first);
-            return launch_su<16>(Tj, Yj, ldyp, Ar, a.lda, Dj, nc, Srep, w.Sfin, sm_count(di), s2, launches, nullptr, false, pdl_first);
-        };
-        for (int jb = 0; jb < nblocks; ++jb) {
-            const int j0 = jb * B, Dj = D - j0, bw = B;
-            if (!pick_shape(B, Dj, 0, 0, &rpt, &cs)) { set_error("panel: sizing error D=%d", Dj); return MPQR_EINVAL; }
-            const bool last = jb == nblocks - 1;
-            const int nrest = pw - (j0 + bw);                 // columns of this panel right of the block
-            const int nnear = last ? (a.next_cols > 0 ? B : 0) : B;
-            const int nfarA = last ? 0 : nrest - B;           // rest of the panel beyond the next block
-            const int nfarB = last ? a.next_cols - nnear : a.next_cols;
-            float* Tslot = w.Wj + (size_t)jb * 32 * 32;
-            BlockArgs b{};
-            b.A = Ablk + (size_t)j0 * a.lda + j0; b.lda = a.lda; b.D = Dj; b.bw = bw;
-            b.Y32 = {Yp + (size_t)j0 * ldyp + j0, ldyp, j0 + (Y32l ? zr : 0)};
-            if (nnear + nfarA + nfarB > 0) { b.T = Tslot; b.ldt = B; b.zero_buf = w.Srep; b.zero_n = 2 * RMAX * SLD; }
-            if (fused) {
-                b.zero_buf = nullptr; b.zero_n = 0;  // no near S kernel follows
-                if (jb > 0) {
-                    b.prevY = Yp + (size_t)(j0 - B) * ldyp + (j0 - B);
-                    b.prev_ldy = ldyp;
-                    b.prevT = w.Wj + (size_t)(jb - 1) * 32 * 32;
-                    // this block's columns got blocks <= jb-2 through the side stream's far updates
-                    if (jb >= 2 && farA_issued[jb - 2]) MPQR_CUDA(cudaStreamWaitEvent(stream, a.la_ev[2 * (jb - 2) + 1], 0));
-                }
-            }
-            if (Y16l) b.Y16 = {Y16l + ((size_t)j0 * a.ldy16 + j0) * 2, a.ldy16, j0 + zr};
-            b.bf16 = a.bf16; b.dbg = a.dbg; b.defer_out = defer ? 1 : 0;
-            if (jb == 0) MPQR_CUDA(cudaStreamWaitEvent(stream, a.la_ev[18], 0));  // the previous panel's finalize still reads the FP32 Y
-            MPQR_TRY(launch_block(B, b, rpt, cs, stream));
-            if (launches) *launches += 1;
-            MPQR_CUDA(cudaEventRecord(a.la_ev[2 * jb], stream));
-            la_last = jb;
-            float* Arest = b.A + bw;  // first column right of the block
-            if (nnear > 0 && !fused) {
-                if (prev_farA) MPQR_CUDA(cudaStreamWaitEvent(stream, a.la_ev[2 * (jb - 1) + 1], 0));
-                // the previous panel's far B's wrote this panel's columns; the last block's near columns belong to far B
-                if (jb == 0 || last) MPQR_CUDA(cudaStreamWaitEvent(stream, a.la_ev[16], 0));
-                MPQR_TRY(su(B, Tslot, b.Y32.p, Arest, Dj, nnear, w.Srep, stream, la_pdl));
-            }
-            if (nfarA > 0) {
-                MPQR_CUDA(cudaStreamWaitEvent(a.side, a.la_ev[2 * jb], 0));
-                if (jb == 0) MPQR_CUDA(cudaStreamWaitEvent(a.side, a.la_ev[16], 0));
-                MPQR_CUDA(cudaMemsetAsync(SrepA, 0, srep_bytes, a.side));
-                MPQR_TRY(su(B, Tslot, b.Y32.p, Arest + B, Dj, nfarA, SrepA, a.side, true));
-                MPQR_CUDA(cudaEventRecord(a.la_ev[2 * jb + 1], a.side));
-                farA_issued[jb] = true;
-            }
-            prev_farA = nfarA > 0;
-            if (nfarB > 0) {
-                MPQR_CUDA(cudaStreamWaitEvent(a.side2, a.la_ev[2 * jb], 0));
-                if (!b_started && a.ev_next_ready) MPQR_CUDA(cudaStreamWaitEvent(a.side2, a.ev_next_ready, 0));
-                b_started = true;
-                MPQR_CUDA(cudaMemsetAsync(SrepB, 0, srep_bytes, a.side2));
-                MPQR_TRY(su(B, Tslot, b.Y32.p, Arest + nrest + (last ? nnear : 0), Dj, nfarB, SrepB, a.side2, true));
-                MPQR_CUDA(cudaEventRecord(a.la_ev[16], a.side2));
-            }
-        }
-        if (defer) {
-            // on the first side stream (idle by now: the last two blocks have no far A update)
-            MPQR_CUDA(cudaStreamWaitEvent(a.side, a.la_ev[2 * la_last], 0));
-            MPQR_TRY(finalize(a.side));
-            MPQR_CUDA(cudaEventRecord(a.la_ev[18], a.side));
-            if (gtw_st != a.side) MPQR_CUDA(cudaStreamWaitEvent(gtw_st, a.la_ev[18], 0));
-        }
-        if (gtw_st != stream && la_last >= 0) MPQR_CUDA(cudaStreamWaitEvent(gtw_st, a.la_ev[2 * la_last], 0));
-    }
-    for (int j0 = 0; !la && !chain && j0 < pw;) {
+    for (int j0 = 0; !chain && j0 < pw;) {
         const int Dj = D - j0;
         if (Dj <= 0) break;
-        const bool dbl = use_dblock && (pw - j0 > B) && (Dj > 2 * B);
-        const int BW = dbl ? 2 * B : B;  // columns of this launch
-        const int bw = (j0 + BW < pw) ? BW : pw - j0;
+        const int bw = (j0 + B < pw) ? B : pw - j0;
         if (!pick_shape(B, Dj, a.force_cs, a.force_rpt, &rpt, &cs)) { set_error("panel: sizing error D=%d", Dj); return MPQR_EINVAL; }
         const int nrest = pw - (j0 + bw);
         BlockArgs b{};
         b.A = Ablk + (size_t)j0 * a.lda + j0; b.lda = a.lda; b.D = Dj; b.bw = bw;
         b.Y32 = {Yp + (size_t)j0 * ldyp + j0, ldyp, j0 + (Y32l ? zr : 0)};
-        if (nrest > 0) { b.T = w.Wj; b.ldt = B; }  // block T for the in-panel update ([T_A | T_B] after a double block)
+        if (nrest > 0) { b.T = w.Wj; b.ldt = B; }  // block T for the in-panel update
         if (Y16l) b.Y16 = {Y16l + ((size_t)j0 * a.ldy16 + j0) * 2, a.ldy16, j0 + zr};
-        b.bf16 = a.bf16; b.dbg = a.dbg; b.defer_out = (defer && !dbl) ? 1 : 0;
-        // the following S kernel accumulates into two replicas; only the double-block (pair) flow uses all NREP
-        // replicas, the ticket counter and the cross-Gram accumulator behind them
-        if (nrest > 0) { b.zero_buf = w.Srep; b.zero_n = dbl ? NREP * RMAX * SLD + 4 + 256 : 2 * RMAX * SLD; }
+        b.bf16 = a.bf16; b.dbg = a.dbg; b.defer_out = defer ? 1 : 0;
+        if (nrest > 0) { b.zero_buf = w.Srep; b.zero_n = 2 * RMAX * SLD; }  // the following S kernel accumulates into two replicas
         if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 4.0 * Dj * bw * bw, 14.0 * Dj * bw);
-        if (dbl) MPQR_TRY(launch_dblock(b, rpt, cs, stream));
-        else MPQR_TRY(launch_block(B, b, rpt, cs, stream));
+        MPQR_TRY(launch_block(B, b, rpt, cs, stream));
         if (a.prof) a.prof->end(a.prof->ctx, stream);
         if (launches) *launches += 1;
         if (nrest > 0) {
             float* Arest = b.A + bw;
-            if (dbl) MPQR_TRY(launch_su<32>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, w.Sfin, sm_count(di), stream, launches, a.prof, true));
-            else if (B == 32) MPQR_TRY(launch_su<32>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, w.Sfin, sm_count(di), stream, launches, a.prof));
+            if (B == 32) MPQR_TRY(launch_su<32>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, w.Sfin, sm_count(di), stream, launches, a.prof));
             else MPQR_TRY(launch_su<16>(w.Wj, b.Y32.p, ldyp, Arest, a.lda, Dj, nrest, w.Srep, w.Sfin, sm_count(di), stream, launches, a.prof));
         }
         j0 += bw;
     }
-    if (defer && !la && !chain) {
+    if (defer && !chain) {
         if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 0.0, 10.0 * D * pw);  // reads the FP32 Y, writes A and the 16-bit Y
         MPQR_TRY(finalize(stream));
         if (a.prof) a.prof->end(a.prof->ctx, stream);
@@ -2245,10 +1998,10 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     if (a.prof) a.prof->begin(a.prof->ctx, 6, stream, 4.0 * D * pw * pw, 10.0 * D * pw);
     if (mixed) {
         // Gram and W on tensor cores, from the 16-bit Y the trailing update uses
-        MPQR_TRY(tc_gemm_tn(Y16l, a.ldy16, Y16l, a.ldy16, w.G, RMAX, pw, pw, D, a.bf16, 1, gtw_st, launches));
-        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, w.T16, RMAX, a.bf16, tsmem, gtw_st));
+        MPQR_TRY(tc_gemm_tn(Y16l, a.ldy16, Y16l, a.ldy16, w.G, RMAX, pw, pw, D, a.bf16, 1, stream, launches));
+        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, w.T16, RMAX, a.bf16, tsmem, stream));
         if (launches) *launches += 1;
-        MPQR_TRY(tc_gemm_nn_store(a.Y16, a.ldy16, w.T16, RMAX, a.W32, a.ld32, a.W16, a.ldw16, Dz, pw, pw, a.bf16, gtw_st, launches));
+        MPQR_TRY(tc_gemm_nn_store(a.Y16, a.ldy16, w.T16, RMAX, a.W32, a.ld32, a.W16, a.ldw16, Dz, pw, pw, a.bf16, stream, launches));
     } else {
         MPQR_TRY(sgemm_tn(Yp, ldyp, Yp, ldyp, w.G, RMAX, pw, pw, D, stream, launches));
         MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, nullptr, 0, 0, tsmem, stream));

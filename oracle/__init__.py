@@ -224,4 +224,17 @@ def ref_dev_block_qr(A, r, mixed=True):
     Q = np.eye(m, dtype=np.float32)
     fn = ref().ref_dev_mixed_precision_block_qr if mixed else ref().ref_dev_block_qr_wy
     fn(_f(P), _f(Q), m, n, r)
+    # The reference does not check its kernel launches: a failed launch leaves its error code pending in the SHARED CUDA
+    # runtime (libref_qr.so links libcudart.so like torch does), where the next torch call would trip over it.
+    global last_ref_cuda_error
+    last_ref_cuda_error = 0
+    try:
+        rt = ctypes.CDLL("libcudart.so.12")
+        rt.cudaDeviceSynchronize()
+        last_ref_cuda_error = int(rt.cudaGetLastError())
+    except OSError:
+        pass
     return P, Q
+
+
+last_ref_cuda_error = 0

@@ -13,7 +13,8 @@ def _ints(rng, shape, lo=-3, hi=4):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 256), (32, 100, 200), (16, 16, 16), (200, 300, 1000),
-                                   (256, 512, 4096), (128, 64, 20000), (1024, 1024, 2048)])
+                                   (256, 512, 4096), (128, 64, 20000), (1024, 1024, 2048),
+                                   (384, 640, 512), (130, 300, 8192), (1024, 4000, 16384)])   # CTA pairs with a half / mostly empty second CTA, split-K
 @pytest.mark.parametrize("bf16", [False, True])
 def test_gemm_tn_exact(M, N, K, bf16):
     from gpu_util import gemm_tn
@@ -44,7 +45,7 @@ def test_gemm_tn_unaligned_block(xoff, zoff):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (100, 70, 24), (300, 513, 32), (1000, 384, 128),
-                                   (2048, 2048, 1024)])
+                                   (2048, 2048, 1024), (384, 300, 64), (129, 257, 1024), (4096, 1000, 512)])
 @pytest.mark.parametrize("bf16", [False, True])
 def test_gemm_nn_exact(M, N, K, bf16):
     from gpu_util import gemm_nn
@@ -68,3 +69,18 @@ def test_gemm_nn_unaligned_c():
     assert np.array_equal(out[:, 4:94].astype(np.float64), ref)
     assert np.all(out[:, :4] == 3.0) and np.all(out[:, 94:] == 3.0)
     assert np.array_equal(sh[:, 4:94].astype(np.float64), ref)
+
+
+def test_gemm_one_cta_kernels_still_exact(monkeypatch):
+    # M > 128 and N > 128 normally take the CTA-pair kernel (tcgen05.mma.cta_group::2); the one-CTA kernel stays in use
+    # for narrower shapes and is kept covered at large ones here
+    from gpu_util import gemm_nn, gemm_tn
+    monkeypatch.setenv("MPQR_GEMM_1CTA", "1")
+    rng = np.random.default_rng(77)
+    X, Z = _ints(rng, (2048, 1024)), _ints(rng, (2048, 1024))
+    S, _ = gemm_tn(X, Z)
+    assert np.array_equal(S.astype(np.float64), X.astype(np.float64).T @ Z.astype(np.float64))
+    X, S2, C = _ints(rng, (2048, 256), -2, 3), _ints(rng, (256, 1024), -2, 3), _ints(rng, (2048, 1024), -8, 9)
+    out, sh = gemm_nn(X, S2, C)
+    ref = C.astype(np.float64) - X.astype(np.float64) @ S2.astype(np.float64)
+    assert np.array_equal(out[:, :1024].astype(np.float64), ref) and np.array_equal(sh[:, :1024].astype(np.float64), ref)

@@ -74,8 +74,11 @@ def test_panel_zero_column_and_signs():
     assert np.allclose(P[:, 0], [-2, 1 / np.sqrt(2), 0, 1 / np.sqrt(2)], atol=1e-6)
 
 
-def test_panel_double_block_kernel(monkeypatch):
-    # experimental 32-column launch for tall panels (two 16-column halves, second half staged in shared memory)
-    monkeypatch.setenv("MPQR_DBLOCK", "1")
-    _check_panel(20000, 128, 0, 128, seed=77, tol=5e-5)
-    _check_panel(18000, 80, 16, 52, seed=78, tol=5e-5)   # ragged second half (32 + 16 + 4)
+@pytest.mark.parametrize("m,n,lam,pw", [(2048, 128, 0, 128), (20000, 128, 0, 128), (5000, 256, 128, 128), (700, 64, 0, 64)])
+@pytest.mark.parametrize("mode", ["classic", "gate"])
+def test_panel_flows_agree(m, n, lam, pw, mode, monkeypatch):
+    # the persistent chain (default) is covered by the tests above; here the per-block launch flow it replaces
+    # (MPQR_NO_CHAIN=1: odd widths and unaligned shapes still take it) and the gate-kernel fallback of the side-stream
+    # ordering (MPQR_GATE_KERNEL=1: drivers without stream memory operations)
+    monkeypatch.setenv("MPQR_NO_CHAIN" if mode == "classic" else "MPQR_GATE_KERNEL", "1")
+    _check_panel(m, n, lam, pw, seed=m + 7 * pw, tol=5e-5)

@@ -30,7 +30,8 @@ def test_tall_panel_regime_vs_oracle(chain, monkeypatch):
     m, n, r = 32768, 512, 128
     A = oracle.uniform_matrix(m, n, 32768512)
     Pref, _ = oracle.block_qr(A, r, want_q=False)
-    for prec, tol_r, tol_y, tol_be in (("fp32", 2e-5, 2e-5, 3e-6), ("fp16", 6 * EPS16, 6 * EPS16, 5.5 * EPS16)):
+    # observed on B200 (profiles/r2_observed_tolerances.txt): fp32 dr 7.7e-6 dy 6.7e-6 be 3.6e-7; fp16 dr 3.1e-4 dy 7.7e-6 be 2.6e-4
+    for prec, tol_r, tol_y, tol_be in (("fp32", 2.3e-5, 2e-5, 1.1e-6), ("fp16", 9e-4, 2.3e-5, 7.8e-4)):
         A0, P, rr, _ = factor_device(A, r, prec)
         assert rr == r
         Pn = P.cpu().numpy()
@@ -58,7 +59,8 @@ def test_lookahead_tall_vs_lapack(m, n, r, nb, prec, monkeypatch):
         dr = r_rel_diff(P, Rref)
         be = sampled_backward_error(A0, P, rr)
         observe(f"lookahead_tall_{m}x{n}_r{r}_{prec}", dr=dr, be=be)
-        assert be <= 5.5 * eps and dr <= 10 * eps, (dr, be)
+        # observed: fp16 be <= 3.4e-4, dr <= 4.0e-4; bf16 be 2.9e-3, dr 4.1e-3
+        assert be <= 2.1 * eps and dr <= 2.5 * eps, (dr, be)
 
 
 def test_c3_full_size_vs_lapack():
@@ -70,7 +72,8 @@ def test_c3_full_size_vs_lapack():
     dr = r_rel_diff(P, Rref)
     be = sampled_backward_error(A0, P, rr)
     observe("c3_full_fp16", dr=dr, be=be)
-    assert be <= 5.5 * EPS16 and dr <= 10 * EPS16, (dr, be)
+    # observed: be 7.0e-4, dr 2.2e-3 (the columns right of the last reflector accumulate 64 FP16-operand updates)
+    assert be <= 4.3 * EPS16 and dr <= 13.5 * EPS16, (dr, be)
 
 
 def test_c5_full_size_vs_lapack():
@@ -90,7 +93,8 @@ def test_c5_full_size_vs_lapack():
     be = float(torch.linalg.norm(Ad - Qd @ Rd) / torch.linalg.norm(Ad))
     orth = float(torch.linalg.norm(Qd.T @ Qd - torch.eye(n, device="cuda", dtype=torch.float64)))
     observe("c5_full_tsqr", dr=dr, be=be, orth=orth)
-    assert dr <= 2e-5 and be <= 3e-6 and orth <= 5e-5, (dr, be, orth)
+    # observed: dr 2.9e-7, be 4.7e-7, orth 3.8e-6
+    assert dr <= 9e-7 and be <= 1.4e-6 and orth <= 1.2e-5, (dr, be, orth)
 
 
 def _conditioned(m, n, cond, seed):
@@ -124,10 +128,11 @@ def test_secondary_accuracy_sets(kind, prec):
     dr = r_rel_diff(P, Rref)
     observe(f"secondary_{kind}_{prec}", dr=dr, be=be)
     eps = {"fp32": None, "fp16": EPS16, "bf16": EPSB}[prec]
+    # observed: fp32 be <= 4.0e-7, dr <= 1.6e-7; fp16 be <= 5.5e-4, dr <= 4.0e-4; bf16 be <= 4.5e-3, dr <= 3.1e-3
     if prec == "fp32":
-        assert be <= 3e-6 and dr <= 3e-5, (dr, be)
+        assert be <= 1.2e-6 and dr <= 5e-7, (dr, be)
     else:
-        assert be <= 5.5 * eps and dr <= 10 * eps, (dr, be)
+        assert be <= 3.4 * eps and dr <= 2.5 * eps, (dr, be)
 
 
 def test_fp16_range_limit():
@@ -144,7 +149,7 @@ def test_fp16_range_limit():
         if ok:
             be = sampled_backward_error(A0, P, rr)
             observe(f"range_{prec}_{scale:g}", be=be)
-            assert be <= 5.5 * (EPSB if prec == "bf16" else EPS16)
+            assert be <= 3.2 * (EPSB if prec == "bf16" else EPS16)   # observed 3.9e-4 (fp16), 4.1e-3 (bf16)
 
 
 def test_run_to_run_spread_is_bounded():
@@ -152,7 +157,7 @@ def test_run_to_run_spread_is_bounded():
     # two runs on the same input agree to rounding, not bit for bit.  Bound the spread (observed on B200: see the log).
     m, n, r = 6000, 4096, 128
     A = oracle.uniform_matrix(m, n, 6000)
-    for prec, tol in (("fp32", 2e-5), ("fp16", 6 * EPS16)):
+    for prec, tol in (("fp32", 8e-7), ("fp16", 3.8e-4)):   # observed 2.6e-7 / 1.25e-4
         _, P1, _, _ = factor_device(A, r, prec)
         P1 = P1.clone()
         _, P2, _, _ = factor_device(A, r, prec)
@@ -181,10 +186,16 @@ def test_reference_gpu_drivers_on_this_box(m, n, r):
         dp = float(np.abs(np.abs(np.triu(P[:m])) - np.abs(np.triu(Pref[:m]))).max() / scale)
         be_ref = oracle.backward_error(A, oracle.strip_R(Pref), Qref)
         be = oracle.backward_error(A, oracle.strip_R(P), Q)
-        observe(f"refgpu_{m}x{n}_r{r}_mixed{int(mixed)}", dp=dp, be=be, be_ref=be_ref)
-        assert dp <= (6 * EPS16 if mixed else 2e-5), dp
-        assert be <= (5.5 * EPS16 if mixed else 3e-6)
-        assert be_ref <= m * 2.0 ** (-11 if mixed else -23)      # the reference passes its own criterion on this box
+        observe(f"refgpu_{m}x{n}_r{r}_mixed{int(mixed)}", dp=dp, be=be, be_ref=be_ref, ref_cuda_error=oracle.last_ref_cuda_error)
+        assert dp <= (3 * EPS16 if mixed else 3e-6), dp
+        assert be <= (5.5 * EPS16 if mixed else 1.5e-6)
+        if mixed and (m % 16 or n % 16):
+            # Observed on B200: the reference's own mixed driver returns NaN in Q when m - lambda is not a multiple of 16
+            # (its padded Q-panel product reads past the buffers, Cuda/qr.cu:1126 vs :1154, SURVEY 8c "GPU oracle caveats");
+            # its R (FP32 path) is still the one compared above.
+            assert not np.isfinite(be_ref) or be_ref <= m * 2.0 ** -11
+        else:
+            assert be_ref <= m * 2.0 ** (-11 if mixed else -23)      # the reference passes its own criterion on this box
 
 
 def test_c1_substitute_through_the_euroc_loader(tmp_path):
@@ -210,7 +221,7 @@ def test_c1_substitute_through_the_euroc_loader(tmp_path):
     P0 = pkg.read_euroc_jacobian(str(p))
     assert P0.shape == (m + 1, n) and np.array_equal(P0[:m], A)
     Rref = _lapack_r(A)
-    for name, fn, tol_r, tol_be in (("fp32", pkg.dev_block_qr_wy, 3e-5, 3e-6), ("fp16", pkg.dev_mixed_precision_block_qr, 10 * EPS16, 5.5 * EPS16)):
+    for name, fn, tol_r, tol_be in (("fp32", pkg.dev_block_qr_wy, 3e-6, 1.5e-6), ("fp16", pkg.dev_mixed_precision_block_qr, 3 * EPS16, 3.4 * EPS16)):
         P = P0.copy()
         fn(P, None, m, n, 16)
         dr = r_rel_diff(P, Rref)

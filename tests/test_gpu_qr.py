@@ -7,6 +7,7 @@ import pytest
 import mixedprecisionblockqr_b200 as pkg
 import oracle
 from conftest import REF_SHAPES
+from gpu_util import observe
 
 pytestmark = pytest.mark.gpu
 
@@ -31,6 +32,7 @@ def test_fp32_driver_vs_oracle(m, n, r):
     assert oracle.q_error_max(Q) <= m * 2.0 ** -23
     assert oracle.orthogonality_fro(Q) <= 2e-5
     scale = np.abs(Pref).max()
+    observe("qr_fp32_ref_shapes", be=be, orth=oracle.orthogonality_fro(Q), dP=np.abs(P - Pref).max() / scale, dQ=np.abs(Q - Qref).max())
     assert np.abs(P - Pref).max() <= 5e-5 * scale    # packed factor incl. Householder vectors
     assert np.abs(Q - Qref).max() <= 5e-5
 
@@ -44,6 +46,8 @@ def test_mixed_driver_vs_oracle(m, n, r, bf16):
     R, Rref = oracle.strip_R(P), oracle.strip_R(Pref)
     eps = 2.0 ** -8 if bf16 else 2.0 ** -11
     be = oracle.backward_error(A, R, Q)
+    observe("qr_mixed_ref_shapes_bf16" if bf16 else "qr_mixed_ref_shapes_fp16", be=be / eps, orth=oracle.orthogonality_fro(Q) / (eps * np.sqrt(m)),
+            dR=np.abs(np.abs(R) - np.abs(Rref)).max() / (eps * np.abs(Rref).max()))
     assert be <= m * eps                             # reference criterion m*2^-bits (bits=11 for FP16, Cuda/qr.cu:1889)
     assert be <= 12 * eps                            # what FP16 operands should actually give
     assert oracle.orthogonality_fro(Q) <= 40 * eps * np.sqrt(m)
@@ -66,6 +70,7 @@ def test_larger_shapes_backward_error(m, n, r, prec):
     Pref, _ = oracle.block_qr(A, r, want_q=False)
     Rref = oracle.strip_R(Pref)
     dr = np.abs(np.abs(oracle.strip_R(P)) - np.abs(Rref)).max() / np.abs(Rref).max()
+    observe(f"qr_larger_{prec}", be=be, dr=dr)
     assert dr <= (2e-5 if prec == "fp32" else 60 * lim / 12), dr
 
 
@@ -116,14 +121,14 @@ def test_reference_symbol_shim_matches_oracle():
 
 @pytest.mark.parametrize("m,n,r,nb", [(1536, 1536, 64, 256), (2048, 2048, 128, 512), (2200, 1600, 64, 256), (1024, 3072, 128, 256),
                                       (1800, 1536, 96, 384)])
-@pytest.mark.parametrize("rbla", [True, False])
-def test_lookahead_driver_vs_oracle(m, n, r, nb, rbla, monkeypatch):
-    """The look-ahead driver (green-context partitions, in-block and register-block look-ahead; normally only on from
-    12 outer blocks) forced on for small shapes: same criteria as the serial driver, against the oracle."""
+@pytest.mark.parametrize("chain", [True, False])
+def test_lookahead_driver_vs_oracle(m, n, r, nb, chain, monkeypatch):
+    """The look-ahead driver (green-context partitions, in-block look-ahead, persistent panel chain; normally only on
+    from 4 outer blocks) forced on for small shapes: same criteria as the serial driver, against the oracle."""
     import torch
     monkeypatch.setenv("MPQR_OVERLAP", "1")
-    if not rbla:
-        monkeypatch.setenv("MPQR_NO_RBLA", "1")
+    if not chain:
+        monkeypatch.setenv("MPQR_NO_CHAIN", "1")
     A = oracle.uniform_matrix(m, n, 31 * m + n)
     lda = (n + 7) // 8 * 8
     dA = torch.zeros(m + 1, lda, device="cuda")
@@ -142,6 +147,7 @@ def test_lookahead_driver_vs_oracle(m, n, r, nb, rbla, monkeypatch):
         Pref, _ = oracle.block_qr(A, r, want_q=False)
         Rref = oracle.strip_R(Pref)
         dr = np.abs(np.abs(oracle.strip_R(P)) - np.abs(Rref)).max() / np.abs(Rref).max()
+        observe("qr_lookahead_small", be=be, dr=dr)
         assert dr <= 60 * 2.0 ** -11, dr
     plan.close()
 
