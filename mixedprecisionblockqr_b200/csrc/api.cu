@@ -301,23 +301,27 @@ void overlap_destroy(mpqr_handle* h) {
     o = mpqr_handle::Overlap();
 }
 
-// Cost model of the look-ahead driver (B200 measurements of round 2 with the persistent panel chain).
-// Times in ms.  One r = 128 panel of the chain (cluster kernel + finalize + Gram/T/W + the next panel's in-block update):
-//   D > 16384 (8 rows per thread):  0.30 + 0.0078 * D/1024        D <= 16384:  0.19 + 0.0088 * D/1024
-// measured on 64-80 SM partitions; the cluster itself needs 16 SMs, the side updates and the in-block GEMMs share the rest:
-//   x (1 + 12 / SMs).   Far update: 4 D N' kb flops at ~6.6 TFLOP/s per SM (measured: 4.1e12 flop in 6.2 ms on 100 SMs).
-double model_bp_ms(const mpqr_handle* h, int c0, int c1) {
-    double t = 0;
+// Cost model of the look-ahead driver (B200 measurements of round 2: profiles/r2_partition_sweep.txt).  Times in ms.
+// Block phase of one outer block on a P-SM partition = latency of its panel chain + SM-time of everything else in it
+// (side updates, finalize, Gram / T / W, in-block tensor-core updates) on the P - 16 SMs the cluster leaves free:
+//   chain kernel of one r = 128 panel:  0.290 (D > 16384: 8 rows per thread)  /  0.140 + 0.0046 * D/1024  (D <= 16384)
+//   rest: 3.81e-3 * D SM-ms per 8 panels   (fitted: D ~ 31744 -> 9.8 / 6.4 / 4.75 / 3.35 ms on 32 / 48 / 64 / 148 SMs)
+// Far update: 4 D N' kb flops at ~8.4 TFLOP/s per SM (CTA-pair GEMMs: 4.26e12 flop in 6.0 ms on 84 SMs).
+double model_bp_ms(const mpqr_handle* h, int c0, int c1, int sms) {
+    double lat = 0, work = 0;
     for (int lam = c0; lam < c1; lam += h->r) {
         const double D = h->m - lam;
-        t += (D <= 16384) ? 0.19 + 0.0088 * D / 1024.0 : 0.30 + 0.0078 * D / 1024.0;
+        lat += (D <= 16384) ? 0.140 + 0.0046 * D / 1024.0 : 0.290;
+        work += 3.81e-3 * D / 8.0;
     }
     static const double scale = getenv("MPQR_BP_SCALE") ? atof(getenv("MPQR_BP_SCALE")) : 1.0;  // tuning knob of the cost model
-    return scale * t * (h->r / 128.0 < 0.25 ? 0.25 : h->r / 128.0);
+    const double f = h->r / 128.0 < 0.25 ? 0.25 : h->r / 128.0;
+    const int free_sms = sms > 24 ? sms - 16 : 8;
+    return scale * f * (lat + work / free_sms);
 }
 double model_far_ms(const mpqr_handle* h, int c0, int c1, int ncols, int sms) {
     const double flops = 4.0 * (double)(h->m - c0) * (double)ncols * (double)(c1 - c0);
-    return flops / (6.6e12 * sms) * 1e3;
+    return flops / (8.4e12 * sms) * 1e3;
 }
 
 int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
@@ -343,6 +347,7 @@ int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
         a.chain_side = h->chain_side; a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
+        a.chain_last_far = &h->chain_last_far; a.chain_buf = p & 1;
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         if (nt > 0) {
             float* A22 = A + (size_t)lam * lda + tau;
@@ -450,11 +455,10 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         const bool has_next = c1 < h->kmax;
         int best = -1;  // -1: whole device, serial
         if (has_next && nfar - nnext > 0) {
-            const double bp_full = model_bp_ms(h, c1, c2);
-            double best_t = bp_full + model_far_ms(h, c0, c1, nfar - nnext, o.nsm_full);
+            double best_t = model_bp_ms(h, c1, c2, o.nsm_full) + model_far_ms(h, c0, c1, nfar - nnext, o.nsm_full);
             for (size_t k = 0; k < o.pairs.size(); ++k) {
                 if (fixed_sms > 0 && o.pairs[k].nsmP != fixed_sms) continue;
-                const double tb = bp_full * (1.0 + 12.0 / o.pairs[k].nsmP);
+                const double tb = 1.05 * model_bp_ms(h, c1, c2, o.pairs[k].nsmP);
                 const double tf = model_far_ms(h, c0, c1, nfar - nnext, o.pairs[k].nsmU);
                 const double t = tb > tf ? tb : tf;
                 if (t < best_t || (fixed_sms > 0 && best < 0)) { best_t = t; best = (int)k; }
@@ -522,6 +526,8 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
     float* S32 = c.S32 ? c.S32 : h->S32;
     void* S16 = c.S16 ? c.S16 : h->S16;
     int last_rest = -1;
+    bool prev_cover = false;
+    std::vector<char> rest_rec((size_t)ceil_div(c1 - c0, r) + 1, 0);
     for (int lam = c0; lam < c1; lam += r) {
         const int p = lam / r;
         const int pw = (lam + r < c1) ? r : c1 - lam;
@@ -536,7 +542,21 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
         a.chain_side = c.chain_side ? c.chain_side : h->chain_side; a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
+        a.chain_last_far = &h->chain_last_far;
+        a.chain_buf = (int)(h->chain_panels++ & 1u);
         const int nin = c1 - tau;  // in-block trailing columns
+        const int pidx = jc / r;
+        const bool chain = panel_chain_ok(a);
+        // Next-panel coverage: the panel's register blocks update the whole next panel themselves (FP32, side stream), so the
+        // chain goes kernel -> kernel; finalize, Gram / T / W, the tensor-core update of the columns beyond the next panel
+        // and the WY accumulation follow on `rest_stream` with a panel's time of slack.
+        const bool cover = chain && c.rest_stream && c.rest_ev && c.acc_stream && nin >= r && (r % 8) == 0 && getenv("MPQR_COVER");   // EXPERIMENTAL, off: see DESIGN 7 (needs the second side stream)
+        if (cover) { a.next_cols = r; a.tail_stream = c.rest_stream; a.ev_chain = c.rest_ev[2 * pidx]; a.ev_side = h->chain_ev_side; }
+        // earlier panels' updates of THIS panel's columns: panels <= p-2 through their rest updates (rest stream, in order);
+        // panel p-1 through its in-block update on this stream, or through its side updates (flag inside a chain kernel,
+        // the side event for any other kernel)
+        if (pidx >= 2 && rest_rec[pidx - 2]) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (pidx - 2) + 1], 0));
+        if (prev_cover && !chain) MPQR_CUDA(cudaStreamWaitEvent(st, h->chain_ev_side, 0));
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         const int acol_tau = c.acol0 + jc + pw;
         // in-block update of the columns [tau + ofs, tau + ofs + nc):  S = W_p^T A ; A -= Y_p S (+ shadow)
@@ -555,12 +575,15 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
                             at16(c.Ah, c.ldh, lam, acol_tau + ofs), c.ldh, D, nc, pw, bf, pad_ok, st, &h->launches));
             return MPQR_OK;
         };
-        const int pidx = jc / r;
         // the next panel's columns on the panel stream, the rest of the block on `rest_stream` (same SM partition) next
         // to the next panel's chain kernel
-        const bool split = c.rest_stream && nin > r && (r % 8) == 0;
-        if (c.rest_stream && nin > 0) last_rest = 2 * pidx + 1;
-        if (nin > 0 && !split) {
+        const bool split = !cover && c.rest_stream && nin > r && (r % 8) == 0;
+        if (c.rest_stream && nin > 0) { last_rest = 2 * pidx + 1; rest_rec[pidx] = true; }
+        if (cover) {
+            // (launch_panel queued finalize and Gram / T / W on the rest stream behind the chain kernel)
+            if (nin - r > 0) MPQR_TRY(inblock(r, nin - r, c.rest_S32, c.rest_S16, end_is_matrix_end, c.rest_stream));
+            MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], c.rest_stream));
+        } else if (nin > 0 && !split) {
             if (c.rest_stream && pidx > 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (pidx - 1) + 1], 0));
             MPQR_TRY(inblock(0, nin, S32, S16, end_is_matrix_end, st));
             if (c.rest_stream) MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], st));
@@ -574,6 +597,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             MPQR_TRY(inblock(r, nin - r, c.rest_S32, c.rest_S16, end_is_matrix_end, c.rest_stream));
             MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], c.rest_stream));
         }
+        prev_cover = cover;
         if (jc > 0) {
             // WY accumulation: X = Y_prev^T W_p ; W_p -= W_prev X   (rows c0..m)
             const void* Wp = (char*)c.W16 + (size_t)jc * 2;
@@ -686,6 +710,7 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
         if ((rc = dev_alloc(h, (void**)&h->chain_flags, 64))) break;
         if (cudaMemset(h->chain_flags, 0, 64) != cudaSuccess) { set_error("memset failed"); rc = MPQR_ECUDA; break; }
         if (cudaStreamCreateWithFlags(&h->chain_side, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
+        if (cudaEventCreateWithFlags(&h->chain_ev_side, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); rc = MPQR_ECUDA; break; }
         h->panel_ws_rows = m;
         if ((rc = dev_alloc(h, (void**)&h->panel_ws, panel_ws_bytes(m)))) break;
         const int wide = m > n ? m : n;
@@ -744,6 +769,7 @@ int mpqr_destroy(mpqr_handle* h) {
     mg_destroy(h->mg);
     overlap_destroy(h);
     if (h->chain_side) cudaStreamDestroy(h->chain_side);
+    if (h->chain_ev_side) cudaEventDestroy(h->chain_ev_side);
     for (auto e : h->sink_ev) cudaEventDestroy(e);
     if (h->sink_stream) cudaStreamDestroy(h->sink_stream);
     for (void* p : h->allocs) cudaFree(p);
@@ -1033,6 +1059,8 @@ int mpqr_panel_factor_device(float* dA, long lda, int m, int n, int lam, int pw,
     } else {
         cudaGetLastError();
     }
+    unsigned clast = 0;
+    a.chain_last_far = &clast;
     int rc = launch_panel(a, (cudaStream_t)stream, nullptr);
     cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
     if (cside) { cudaStreamSynchronize(cside); cudaStreamDestroy(cside); }

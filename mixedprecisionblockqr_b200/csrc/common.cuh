@@ -128,6 +128,16 @@ struct PanelArgs {
     unsigned* chain_flags;    // device: [0] block done (kernel -> side stream), [1] far update done (side stream -> kernel)
     unsigned* chain_ctr;      // host mirror: the flags only grow
     long long* chain_dbg;     // optional device buffer, 8 x int64 per register block: globaltimer stamps of the cluster
+    int chain_buf;            // which of the two Y / T workspace buffers this panel uses (consecutive panels alternate)
+    unsigned* chain_last_far; // host: last value posted to chain_flags[1] so far (0 = none); updated by launch_panel
+    // Next-panel coverage (chain flow only): every block's side update also takes the `next_cols` columns right of the
+    // panel, so the next panel's kernel needs nothing from this panel's T / W and may start as soon as this kernel ends
+    // (it waits for the last side update through the flag).  finalize and Gram / T / W then run on `tail_stream`
+    // behind `ev_chain`; the 16-bit Y, W and T of the panel are ready in tail_stream order.
+    int next_cols;            // 0, or a multiple of 4 (<= 128)
+    cudaStream_t tail_stream;
+    cudaEvent_t ev_chain;     // recorded on `stream` behind the chain kernel
+    cudaEvent_t ev_side;      // optional: recorded on chain_side behind the panel's last side update
 };
 // true if launch_panel will take the persistent chain flow for this panel
 bool panel_chain_ok(const PanelArgs& a);

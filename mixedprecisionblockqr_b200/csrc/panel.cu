@@ -44,7 +44,7 @@ namespace {
 constexpr int NT = 256;
 constexpr int NW = NT / 32;
 constexpr int CSMAX = 16;
-constexpr int SLD = 128;   // leading dimension of the S replicas
+constexpr int SLD = 256;   // leading dimension of the S replicas (in-panel rest + the next panel's columns)
 constexpr int NREP = 8;    // S replicas (spreads the atomics over L2 slices)
 constexpr int RMAX = kPanelMaxWidth;
 
@@ -757,8 +757,11 @@ struct ChainArgs {
     unsigned* flag_done;
     const unsigned* flag_far;
     unsigned base;
-    float* srep[2];  // S replicas of the far updates (blocks alternate); the cluster clears srep[jb & 1] before it posts block jb
-    int srep_n;      // floats per buffer
+    float* srep[2];  // S replica pairs of the far updates (blocks alternate); the cluster clears rows 0..15 of both replicas of
+                     // srep[jb & 1] (replica stride RMAX * SLD, row stride SLD) before it posts block jb
+    int next_cols;   // > 0: every block's far update also covers the next panel's columns (so every block has one)
+    unsigned wait0;  // block 0 waits for flag_far >= wait0 when have_wait0 (the previous panel's updates of THIS panel's columns)
+    int have_wait0;
     long long* dbg;  // optional: 8 globaltimer stamps per block (CTA 0, thread 0), tools/chain_probe.py
 };
 
@@ -908,9 +911,9 @@ __global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS)
         const int roff = jb * B;
         float* Ab = a.A + roff;  // the block's first column
         CHAIN_STAMP(0);
-        if (jb >= 2 && a.flag_far) {
+        if (a.flag_far && (jb >= 2 || (jb == 0 && a.have_wait0))) {
             if (tid == 0) {
-                const unsigned want = a.base + (unsigned)(jb - 1);  // far(jb-2) posted base + jb - 1
+                const unsigned want = jb >= 2 ? a.base + (unsigned)(jb - 1) : a.wait0;  // far(jb-2) posted base + jb - 1
                 while ((int)(ld_acquire_u32(a.flag_far) - want) < 0) __nanosleep(64);
             }
             __syncthreads();
@@ -995,10 +998,12 @@ __global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS)
             const int t = tid >> 4, c = tid & 15;
             Tj[tid] = (t <= c) ? gt[t][c] : 0.f;
         }
-        if (jb + 2 < nblk) {  // far(jb) accumulates into srep[jb & 1]; its previous user far(jb-2) was awaited above
-            float4* z = reinterpret_cast<float4*>(a.srep[jb & 1]);
-            const int n4 = a.srep_n >> 2;
-            for (int idx = (int)crank * NT + tid; idx < n4; idx += CS * NT) z[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (jb + 2 < nblk || a.next_cols > 0) {  // far(jb) accumulates into srep[jb & 1]; its previous user far(jb-2) was awaited above
+            constexpr int Q = SLD / 4;  // float4 per row
+            for (int idx = (int)crank * NT + tid; idx < 2 * B * Q; idx += CS * NT) {
+                const int rep = idx / (B * Q), rem = idx - rep * (B * Q);
+                reinterpret_cast<float4*>(a.srep[jb & 1] + (size_t)rep * RMAX * SLD + (size_t)(rem / Q) * SLD)[rem % Q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
         CHAIN_STAMP(6);
         __threadfence();
@@ -1646,10 +1651,12 @@ int launch_block(int B, const BlockArgs& a, int RPT, int CS, cudaStream_t st) {
     return launch_block_t<16, 8>(a, CS, st);
 }
 
-// workspace layout (floats): Y32p [rows x RMAX] | Wj [rows x 32] | Srep [NREP x RMAX x SLD] | G [RMAX x RMAX] |
+// workspace layout (floats): Y32p [2 x rows x RMAX] | Tsl [2 x 8 x 256] | Wj [rows x 32] | Srep [NREP x RMAX x SLD] | G [RMAX x RMAX] |
 // T32 [RMAX x RMAX] | T16 [RMAX x RMAX 16-bit]
 struct Ws {
-    float* Y32p;
+    float* Y32p;     // FP32 Y of the panel; two buffers: the chain kernel of panel p+1 writes one while panel p's finalize /
+    float* Y32p2;    // side updates still read the other
+    float* Tsl;      // block T slots of the chain flow: 2 buffers x 8 blocks x 256 floats
     float* Wj;
     float* Srep;     // NREP replicas | 4 floats (ticket counter) : cleared together by the block kernel
     float* Sfin;     // RMAX x SLD: S = T^T (Y^T A_rest)
@@ -1660,7 +1667,9 @@ struct Ws {
 Ws carve(float* ws, long rows) {
     Ws w;
     w.Y32p = ws;
-    w.Wj = w.Y32p + (size_t)rows * RMAX;
+    w.Y32p2 = w.Y32p + (size_t)rows * RMAX;
+    w.Tsl = w.Y32p2 + (size_t)rows * RMAX;
+    w.Wj = w.Tsl + 2 * 8 * 256;
     w.Srep = w.Wj + (size_t)rows * 32;
     w.Sfin = w.Srep + (size_t)NREP * RMAX * SLD + 4 + 256;  // (+ ticket counter + 16 x 16 cross-Gram accumulator)
     w.G = w.Sfin + (size_t)RMAX * SLD;
@@ -1702,7 +1711,7 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
     cudaLaunchAttribute pat[1] = {pdl_attr()};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.stream = st; cfg.attrs = pat; cfg.numAttrs = 1;
-    const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(Arest) & 15) == 0) && ((ncols & 3) == 0) && ncols <= 128;
+    const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(Arest) & 15) == 0) && ((ncols & 3) == 0) && ncols <= SLD;
     if (prof) prof->begin(prof->ctx, 5, st, 2.0 * D * ncols * B, 4.0 * D * (ncols + B));
     if (vec) {
         int ysm_floats = rows * B;
@@ -1852,7 +1861,7 @@ bool panel_chain_ok(const PanelArgs& a) {
 }
 
 size_t panel_ws_bytes(long max_rows) {
-    return ((size_t)max_rows * (RMAX + 32) + (size_t)(NREP + 1) * RMAX * SLD + 4 + 256 + 2 * (size_t)RMAX * RMAX) * sizeof(float) +
+    return ((size_t)max_rows * (2 * RMAX + 32) + 2 * 8 * 256 + (size_t)(NREP + 1) * RMAX * SLD + 4 + 256 + 2 * (size_t)RMAX * RMAX) * sizeof(float) +
            (size_t)RMAX * RMAX * 2 + 256;
 }
 
@@ -1908,8 +1917,9 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     if (need_t && !mixed && a.W32 && !a.Y32) { set_error("panel: W32 needs Y32 on the FP32 path"); return MPQR_EINVAL; }
     if (mixed && !a.W32) { set_error("panel: the mixed path needs the FP32 W master"); return MPQR_EINVAL; }
     Ws w = carve(a.ws, a.ws_rows);
-    // FP32 Y of the whole panel: caller's array if given, else the workspace
-    float* Yp = Y32l ? Y32l : w.Y32p;
+    // FP32 Y of the whole panel: caller's array if given, else one of the two workspace buffers (consecutive chain panels
+    // alternate: panel p's finalize / side updates may still read its Y while panel p+1's kernel writes the other one)
+    float* Yp = Y32l ? Y32l : ((chain && (a.chain_buf & 1)) ? w.Y32p2 : w.Y32p);
     const long ldyp = Y32l ? a.ld32 : RMAX;
     // deferred outputs (panel_finalize_kernel): full register blocks only, vector-aligned A and 16-bit Y
     const bool defer = !a.dbg && (pw % B) == 0 && D >= pw + 32 && ((a.lda & 3) == 0) &&
@@ -1924,20 +1934,30 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         if (launches) *launches += 1;
         return MPQR_OK;
     };
+    // Stream of everything after the register blocks (finalize, Gram / T / W): with next-panel coverage the chain does not
+    // need it, so it moves to `tail_stream` behind an event and the next panel's kernel can follow at once.
+    const int next_cols = (chain && a.tail_stream && a.ev_chain && a.next_cols > 0 && (a.next_cols & 3) == 0 && a.next_cols <= 128) ? a.next_cols : 0;
+    cudaStream_t ts = next_cols > 0 ? a.tail_stream : stream;
     if (chain) {
         if (!pick_shape(16, D, a.force_cs, a.force_rpt, &rpt, &cs)) { set_error("panel: sizing error D=%d", D); return MPQR_EINVAL; }
         const int nblocks = pw / 16;
+        const int nfarb = next_cols > 0 ? nblocks : nblocks - 2;  // blocks with a side update
+        float* Tsl = w.Tsl + (size_t)(a.chain_buf & 1) * 8 * 256;
         ChainArgs ca{};
         ca.A = Ablk; ca.lda = a.lda; ca.D = D; ca.pw = pw;
         ca.Yp = Yp; ca.ldyp = ldyp;
-        ca.Tslots = w.Wj; ca.tstride = 32 * 32;
+        ca.Tslots = Tsl; ca.tstride = 256;
         ca.base = *a.chain_ctr;
         *a.chain_ctr += (unsigned)nblocks;
         ca.flag_done = a.chain_flags;
-        ca.flag_far = nblocks >= 3 ? a.chain_flags + 1 : nullptr;
+        ca.flag_far = a.chain_flags + 1;
+        ca.next_cols = next_cols;
+        // this panel's columns were last written by the previous panel's side updates (if it covered them): block 0 waits
+        // for the last value posted so far
+        ca.have_wait0 = (a.chain_last_far && *a.chain_last_far != 0) ? 1 : 0;
+        ca.wait0 = ca.have_wait0 ? *a.chain_last_far : 0u;
         float* SrepA = w.Srep + (size_t)2 * RMAX * SLD;
         ca.srep[0] = SrepA; ca.srep[1] = SrepA + (size_t)2 * RMAX * SLD;
-        ca.srep_n = 2 * RMAX * SLD;
         ca.dbg = a.chain_dbg;
         MPQR_TRY(chain_preload());
         if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 4.0 * D * pw * 16 + 4.0 * D * 16 * 16 * (nblocks - 1), 8.0 * D * pw);
@@ -1946,17 +1966,28 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         if (launches) *launches += 1;
         int side_sms = sm_count(di) - cs;  // the cluster keeps its SMs for the whole panel
         if (side_sms < 8) side_sms = 8;
-        for (int jb = 0; jb + 2 < nblocks; ++jb) {
-            const int j0 = jb * 16, Dj = D - j0, nfar = pw - (j0 + 32);
+        for (int jb = 0; jb < nfarb; ++jb) {
+            // block jb's reflectors -> the rest of the panel beyond block jb+1 and (next_cols) the whole next panel:
+            // one contiguous column range
+            const int j0 = jb * 16, Dj = D - j0;
+            const int cfirst = (j0 + 32 < pw) ? j0 + 32 : pw;   // first column (panel-relative)
+            const int nfar = pw - cfirst + next_cols;
             MPQR_TRY(stream_wait_geq(a.chain_side, a.chain_flags, ca.base + (unsigned)(jb + 1)));
-            MPQR_TRY(launch_su<16>(w.Wj + (size_t)jb * 32 * 32, Yp + (size_t)j0 * ldyp + j0, ldyp, Ablk + (size_t)j0 * a.lda + j0 + 32, a.lda, Dj,
+            MPQR_TRY(launch_su<16>(Tsl + (size_t)jb * 256, Yp + (size_t)j0 * ldyp + j0, ldyp, Ablk + (size_t)j0 * a.lda + cfirst, a.lda, Dj,
                                    nfar, ca.srep[jb & 1], w.Sfin, side_sms, a.chain_side, launches, a.prof, false));
             MPQR_TRY(stream_post(a.chain_side, a.chain_flags + 1, ca.base + (unsigned)(jb + 1)));
+            if (a.chain_last_far) *a.chain_last_far = ca.base + (unsigned)(jb + 1);
         }
-        // every side update was consumed by the kernel before it finished: stream order is enough from here on
-        if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 0.0, 10.0 * D * pw);
-        MPQR_TRY(finalize(stream));
-        if (a.prof) a.prof->end(a.prof->ctx, stream);
+        if (next_cols > 0) {
+            // the kernel itself only consumed the side updates up to block nblocks-3: whoever touches the next panel's columns
+            // next is ordered behind the last post (a chain kernel: through wait0; anything else: through this event)
+            if (a.ev_side) MPQR_CUDA(cudaEventRecord(a.ev_side, a.chain_side));
+            MPQR_CUDA(cudaEventRecord(a.ev_chain, stream));
+            MPQR_CUDA(cudaStreamWaitEvent(ts, a.ev_chain, 0));
+        }
+        if (a.prof) a.prof->begin(a.prof->ctx, 4, ts, 0.0, 0.0);
+        MPQR_TRY(finalize(ts));
+        if (a.prof) a.prof->end(a.prof->ctx, ts);
     }
     for (int j0 = 0; !chain && j0 < pw;) {
         const int Dj = D - j0;
@@ -1995,23 +2026,23 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     const int Dz = D + zr;  // W is produced from the enclosing block's first row on (zero rows of Y give zero rows of W)
     float* Tdst = a.T ? a.T : w.T32;
     const int ldt = a.T ? a.ldt : RMAX;
-    if (a.prof) a.prof->begin(a.prof->ctx, 6, stream, 4.0 * D * pw * pw, 10.0 * D * pw);
+    if (a.prof) a.prof->begin(a.prof->ctx, 6, ts, 4.0 * D * pw * pw, 10.0 * D * pw);
     if (mixed) {
         // Gram and W on tensor cores, from the 16-bit Y the trailing update uses
-        MPQR_TRY(tc_gemm_tn(Y16l, a.ldy16, Y16l, a.ldy16, w.G, RMAX, pw, pw, D, a.bf16, 1, stream, launches));
-        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, w.T16, RMAX, a.bf16, tsmem, stream));
+        MPQR_TRY(tc_gemm_tn(Y16l, a.ldy16, Y16l, a.ldy16, w.G, RMAX, pw, pw, D, a.bf16, 1, ts, launches));
+        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, w.T16, RMAX, a.bf16, tsmem, ts));
         if (launches) *launches += 1;
-        MPQR_TRY(tc_gemm_nn_store(a.Y16, a.ldy16, w.T16, RMAX, a.W32, a.ld32, a.W16, a.ldw16, Dz, pw, pw, a.bf16, stream, launches));
+        MPQR_TRY(tc_gemm_nn_store(a.Y16, a.ldy16, w.T16, RMAX, a.W32, a.ld32, a.W16, a.ldw16, Dz, pw, pw, a.bf16, ts, launches));
     } else {
-        MPQR_TRY(sgemm_tn(Yp, ldyp, Yp, ldyp, w.G, RMAX, pw, pw, D, stream, launches));
-        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, nullptr, 0, 0, tsmem, stream));
+        MPQR_TRY(sgemm_tn(Yp, ldyp, Yp, ldyp, w.G, RMAX, pw, pw, D, ts, launches));
+        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, nullptr, 0, 0, tsmem, ts));
         if (launches) *launches += 1;
         if (a.W32) {
-            MPQR_TRY(sgemm_nn_store(a.Y32, a.ld32, Tdst, ldt, a.W32, a.ld32, Dz, pw, pw, stream));
+            MPQR_TRY(sgemm_nn_store(a.Y32, a.ld32, Tdst, ldt, a.W32, a.ld32, Dz, pw, pw, ts));
             if (launches) *launches += 1;
         }
     }
-    if (a.prof) a.prof->end(a.prof->ctx, stream);
+    if (a.prof) a.prof->end(a.prof->ctx, ts);
     return MPQR_OK;
 }
 
