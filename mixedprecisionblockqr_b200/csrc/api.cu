@@ -365,10 +365,18 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         set_error("factor: the tensor-core path needs lda %% 4 == 0 and a 16-byte aligned dA (lda=%ld)", lda);
         return MPQR_EINVAL;
     }
-    // operand shadow of the whole matrix
-    PROF(3, 0, 6.0 * m * n, convert_f32_to_16(A, lda, h->Ah, h->ldh, m, n, bf, st));
-    h->launches += 1;
     const int nblk = ceil_div(h->kmax, nb);
+    // streamed input (host drop-in): needs the look-ahead driver and every block's W (catch-up of late chunks)
+    const bool arriving = h->arr.on && h->ov.on && nblk >= 3 && !h->prof && h->keep_wy;
+    if (!arriving) {
+        if (h->arr.on) {  // the plan fell back to the plain schedule: everything must be there first
+            for (cudaEvent_t e : h->arr.ev) MPQR_CUDA(cudaStreamWaitEvent(st, e, 0));
+        } else {
+            // operand shadow of the whole matrix
+            PROF(3, 0, 6.0 * m * n, convert_f32_to_16(A, lda, h->Ah, h->ldh, m, n, bf, st));
+            h->launches += 1;
+        }
+    }
     auto ctx_of = [&](int b, int c0) {
         BlockCtx c{};
         c.A = A; c.lda = lda; c.acol0 = c0; c.Ah = h->Ah; c.ldh = h->ldh;
@@ -418,6 +426,38 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     int nsm_bp = o.nsm_full, nsm_uprev = 0;
     const bool inblock_la = (h->r % 8) == 0;
     MPQR_CUDA(cudaStreamWaitEvent(s_bp, o.ev_start, 0));
+    // Arrival-aware far updates: `jend` = end of the admitted column range.  A chunk is admitted when it is expected to
+    // have arrived (clock of the cost model) or when the chain is about to need it (the block after next lies in it); on
+    // admission the update stream waits for the chunk's event and applies the blocks factored so far to it.
+    auto& ar = h->arr;
+    size_t ninc = arriving ? 1 : 0;
+    int jend = arriving ? ar.c1[0] : n;
+    double t_model = arriving ? ar.t_ms[0] + model_bp_ms(h, 0, nb < h->kmax ? nb : h->kmax, o.nsm_full) : 0.0;
+    if (arriving) MPQR_CUDA(cudaStreamWaitEvent(s_bp, ar.ev[0], 0));
+    // chunks up to column `upto` (exclusive start) or expected by the model clock; dry = only report the resulting end column
+    auto admit = [&](int b, int upto, bool by_clock, bool all, bool dry, cudaStream_t s_u, int nsm_u, double* extra_flops, int* jend_out) -> int {
+        size_t q = ninc;
+        int je = jend;
+        while (q < ar.c0.size() && (all || ar.c0[q] < upto || (by_clock && ar.t_ms[q] <= t_model))) {
+            if (!dry) {
+                const int a0 = ar.c0[q], wdt = ar.c1[q] - ar.c0[q];
+                MPQR_CUDA(cudaStreamWaitEvent(s_u, ar.ev[q], 0));
+                SmBudget budget(nsm_u == o.nsm_full ? 0 : nsm_u);
+                for (int k = 0; k < b; ++k) {   // blocks 0 .. b-1 (block b itself reaches the chunk with the regular far update)
+                    const int k0 = k * nb, k1 = (k0 + nb < h->kmax) ? k0 + nb : h->kmax;
+                    BlockCtx ck = ctx_of(k, k0);
+                    ck.S32 = h->S32u; ck.S16 = h->S16u;
+                    MPQR_TRY(far_update(h, ck, k0, k1, a0, wdt, s_u));
+                    if (extra_flops) *extra_flops += 4.0 * (double)(m - k0) * wdt * (k1 - k0);
+                }
+            }
+            je = ar.c1[q];
+            ++q;
+        }
+        if (!dry) { ninc = q; jend = je; }
+        if (jend_out) *jend_out = je;
+        return MPQR_OK;
+    };
     for (int c0 = 0, b = 0; c0 < h->kmax; c0 += nb, ++b) {
         const int c1 = (c0 + nb < h->kmax) ? c0 + nb : h->kmax;
         BlockCtx c = ctx_of(b, c0);
@@ -448,7 +488,12 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         MPQR_CUDA(cudaEventRecord(o.ev_bp[b], s_bp));
         if (defer_acc) MPQR_CUDA(cudaEventRecord(o.ev_accdone, s_acc));
         MPQR_TRY(emit(b, c0, c1, s_bp));
-        const int nfar = n - c1;
+        // arrival mode: the range this interval's far update will cover (dry run of the admission rule: the block after
+        // next must be in, plus whatever the model clock says has arrived; everything at the last reflector block)
+        const bool last_blk = c1 >= h->kmax;
+        int jplan = jend;
+        if (arriving) MPQR_TRY(admit(b, c1 + 2 * nb, true, last_blk, true, nullptr, 0, nullptr, &jplan));
+        const int nfar = jplan - c1;
         // ---- choose the partition of interval b
         const int nnext = nfar < nb ? nfar : nb;
         const int c2 = (c1 + nb < h->kmax) ? c1 + nb : h->kmax;
@@ -475,12 +520,30 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
             if (defer_acc) MPQR_CUDA(cudaStreamWaitEvent(s_u, o.ev_accdone, 0));
             if (b > 0) MPQR_CUDA(cudaStreamWaitEvent(s_u, o.ev_fr[b - 1], 0));
             if (o.trace) cudaEventRecord(o.tr[b].f0, s_u);
+            double catch_flops = 0;
+            if (arriving) {
+                // what the next block phase needs first (already admitted by the "block after next" rule, except at b = 0),
+                // then the newcomers with their catch-up, then the rest of the admitted range
+                MPQR_TRY(admit(b, c1 + nnext, false, false, false, s_u, nsm_u, &catch_flops, nullptr));
+                MPQR_TRY(far_update(h, cu, c0, c1, c1, nnext, s_u));
+                if (o.trace) cudaEventRecord(o.tr[b].f1, s_u);
+                MPQR_CUDA(cudaEventRecord(o.ev_fn[b], s_u));
+                MPQR_TRY(admit(b, c1 + 2 * nb, true, last_blk, false, s_u, nsm_u, &catch_flops, nullptr));
+                MPQR_TRY(far_update(h, cu, c0, c1, c1 + nnext, jend - c1 - nnext, s_u));
+                if (o.trace) cudaEventRecord(o.tr[b].f2, s_u);
+                MPQR_CUDA(cudaEventRecord(o.ev_fr[b], s_u));
+                // model clock: this interval lasts as long as the slower of the next block phase and the far work
+                const double tf = model_far_ms(h, c0, c1, jend - c1, nsm_u) + catch_flops / (8.4e12 * nsm_u) * 1e3;
+                const double tb = has_next ? model_bp_ms(h, c1, c2, best >= 0 ? o.pairs[best].nsmP : o.nsm_full) : 0.0;
+                t_model += (best >= 0) ? (tb > tf ? tb : tf) : tb + tf;
+            } else {
             MPQR_TRY(far_update(h, cu, c0, c1, c1, nnext, s_u));
             if (o.trace) cudaEventRecord(o.tr[b].f1, s_u);
             MPQR_CUDA(cudaEventRecord(o.ev_fn[b], s_u));
             MPQR_TRY(far_update(h, cu, c0, c1, c1 + nnext, nfar - nnext, s_u));
             if (o.trace) cudaEventRecord(o.tr[b].f2, s_u);
             MPQR_CUDA(cudaEventRecord(o.ev_fr[b], s_u));
+            }
         } else {
             if (defer_acc) MPQR_CUDA(cudaStreamWaitEvent(s_bp, o.ev_accdone, 0));
             MPQR_CUDA(cudaEventRecord(o.ev_fn[b], s_bp));
@@ -770,6 +833,8 @@ int mpqr_destroy(mpqr_handle* h) {
     overlap_destroy(h);
     if (h->chain_side) cudaStreamDestroy(h->chain_side);
     if (h->chain_ev_side) cudaEventDestroy(h->chain_ev_side);
+    for (auto e : h->arr.ev) cudaEventDestroy(e);
+    if (h->arr.stream) cudaStreamDestroy(h->arr.stream);
     for (auto e : h->sink_ev) cudaEventDestroy(e);
     if (h->sink_stream) cudaStreamDestroy(h->sink_stream);
     for (void* p : h->allocs) cudaFree(p);
@@ -928,7 +993,10 @@ int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned 
         set_error("mpqr_block_qr_host: bad arguments m=%d n=%d r=%d", m, n, r);
         return MPQR_EINVAL;
     }
-    const unsigned f = (flags & MPQR_PRECISION_MASK) | (Q ? MPQR_KEEP_WY : 0u);
+    // (the streamed-input schedule of the 16-bit path needs every block's W for the catch-up of late chunks: MPQR_KEEP_WY
+    //  storage; MPQR_NO_STREAM_IN=1 restores copy-then-factor)
+    const bool want_stream_in = (flags & MPQR_PRECISION_MASK) != 0 && !getenv("MPQR_NO_STREAM_IN") && (long)m * n >= (1L << 24);
+    const unsigned f = (flags & MPQR_PRECISION_MASK) | ((Q || want_stream_in) ? MPQR_KEEP_WY : 0u);
     const bool htrace = getenv("MPQR_HOST_TRACE") != nullptr;  // phase times of this call on stderr
     const bool no_cache = getenv("MPQR_NO_HOST_CACHE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -964,16 +1032,57 @@ int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned 
     float *dA = P.dA, *dQ = P.dQ;
     t_created = now();
     do {
-        cudaError_t e = cudaMemcpy2D(dA, lda * sizeof(float), A_packed, (size_t)n * sizeof(float), (size_t)n * sizeof(float),
-                                     m + 1, cudaMemcpyHostToDevice);
-        t_h2d = now();
-        if (e != cudaSuccess) { set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; break; }
+        cudaError_t e = cudaSuccess;
         // mixed path: finished column blocks go back to the host while later blocks are still being factored
         // (only for page-locked host buffers: an "async" copy to pageable memory blocks the issuing thread)
         cudaPointerAttributes pa{};
         const bool pinned = cudaPointerGetAttributes(&pa, A_packed) == cudaSuccess && pa.type == cudaMemoryTypeHost;
         if (!pinned) cudaGetLastError();
         const bool pipelined = pinned && (f & MPQR_PRECISION_MASK) != 0;
+        // Streamed input: column chunks of whole outer blocks (1, 1, 2, then 4 blocks each) are copied on their own
+        // stream, each followed by its 16-bit shadow conversion and an event; the look-ahead driver starts on block 0 as
+        // soon as it has landed and admits the later chunks as they arrive (factor_16).  PCIe is the limit either way
+        // (4.3 GB at ~55 GB/s = 79 ms at 32768^2), but it now runs next to the factorisation instead of in front of it.
+        h->arr.on = false;
+        const int nblk_outer = ceil_div(h->kmax, h->nb);
+        if (pipelined && want_stream_in && h->ov.on && nblk_outer >= 4 && h->keep_wy) {
+            auto& ar = h->arr;
+            if (!ar.stream && cudaStreamCreateWithFlags(&ar.stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
+            ar.c0.clear(); ar.c1.clear(); ar.t_ms.clear();
+            static const double gbs = getenv("MPQR_H2D_GBS") ? atof(getenv("MPQR_H2D_GBS")) : 52.0;  // expected host-to-device rate
+            double t = 0.05;
+            for (int blk = 0, k = 0; blk * h->nb < n; ++k) {
+                const int nblocks = k < 2 ? 1 : (k == 2 ? 2 : 4);
+                const int a0 = blk * h->nb;
+                int a1 = (blk + nblocks) * h->nb;
+                if (a1 > n || n - a1 < h->nb) a1 = n;   // a short tail joins the last chunk
+                ar.c0.push_back(a0); ar.c1.push_back(a1);
+                t += (double)(m + 1) * (a1 - a0) * 4.0 / (gbs * 1e6);
+                ar.t_ms.push_back(t);
+                blk = (a1 + h->nb - 1) / h->nb;
+                if (a1 >= n) break;
+            }
+            while (ar.ev.size() < ar.c0.size()) {
+                cudaEvent_t ev;
+                if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { rc = MPQR_ECUDA; break; }
+                ar.ev.push_back(ev);
+            }
+            if (rc != MPQR_OK) { set_error("event creation failed"); break; }
+            for (size_t k = 0; k < ar.c0.size() && e == cudaSuccess; ++k) {
+                const int a0 = ar.c0[k], wdt = ar.c1[k] - ar.c0[k];
+                e = cudaMemcpy2DAsync(dA + a0, lda * sizeof(float), A_packed + a0, (size_t)n * sizeof(float), (size_t)wdt * sizeof(float),
+                                      m + 1, cudaMemcpyHostToDevice, ar.stream);
+                if (e == cudaSuccess && convert_f32_to_16(dA + a0, lda, at16(h->Ah, h->ldh, 0, a0), h->ldh, m, wdt, h->prec == 2, ar.stream) != MPQR_OK) e = cudaErrorUnknown;
+                if (e == cudaSuccess) e = cudaEventRecord(ar.ev[k], ar.stream);
+            }
+            if (e != cudaSuccess) { set_error("streamed H2D failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; break; }
+            ar.on = true;
+        } else {
+            e = cudaMemcpy2D(dA, lda * sizeof(float), A_packed, (size_t)n * sizeof(float), (size_t)n * sizeof(float),
+                             m + 1, cudaMemcpyHostToDevice);
+        }
+        t_h2d = now();
+        if (e != cudaSuccess) { set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; break; }
         h->sink_host = nullptr;
         if (pipelined) {
             if (!h->sink_stream && cudaStreamCreateWithFlags(&h->sink_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
@@ -996,6 +1105,7 @@ int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned 
         if (e != cudaSuccess) { set_error("D2H copy / kernel execution failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; break; }
     } while (0);
     h->sink_host = nullptr;
+    h->arr.on = false;
     const double t_done = now();
     {
         std::lock_guard<std::mutex> lk(g_host_mu);

@@ -462,8 +462,8 @@ struct Cfg2 {
     static constexpr int BN = 256;               // pair tile: 256 x 256
     static constexpr int BNH = 128;              // columns of B staged per CTA
     static constexpr int B_STAGE_BYTES = BNH * BK * 2;  // 16 KB
-    static constexpr int STAGES = 3;             // operands are L2 hits (Y / S blocks are shared by all tiles): 3 x 0.45 us of cover
-    static constexpr int NCS2 = 7;               // C-chunk ring slots: the FP32 master comes from HBM, 5 chunks (80 KB) ahead per SM
+    static constexpr int STAGES = 4;             // (3 stages + 7 C slots measured slower on B200: TN 1382 -> 1243, NN 800 -> 708 TFLOP/s)
+    static constexpr int NCS2 = 5;               // C-chunk ring slots
     static constexpr int CBUF_BYTES = BM * CCH * 4;
     static constexpr int HBUF_BYTES = BM * CCH * 2;
     static constexpr int OFF_A = 0;

@@ -84,6 +84,16 @@ struct mpqr_handle {
     cudaStream_t sink_stream = nullptr;
     std::vector<cudaEvent_t> sink_ev;
 
+    // host source (mpqr_block_qr_host): the input arrives in column chunks while the first blocks are already being
+    // factored; far updates only cover the chunks that have been admitted, a late chunk catches up on admission
+    struct Arrival {
+        bool on = false;
+        std::vector<int> c0, c1;          // column range of each chunk (whole outer blocks, in order)
+        std::vector<cudaEvent_t> ev;      // chunk is in HBM and its 16-bit shadow is written
+        std::vector<double> t_ms;         // expected arrival time after the start of the call
+        cudaStream_t stream = nullptr;    // copy + shadow conversion
+    } arr;
+
     // multi-GPU (mg.cu)
     void* mg = nullptr;
 

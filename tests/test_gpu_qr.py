@@ -179,3 +179,32 @@ def test_host_driver_plan_cache(monkeypatch):
     monkeypatch.setenv("MPQR_NO_HOST_CACHE", "1")
     check(run())
     check(run())
+
+
+@pytest.mark.parametrize("m,n,r", [(4096, 4096, 128), (4096, 8192, 64), (6000, 5000, 128)])
+def test_host_driver_streamed_input(m, n, r, monkeypatch):
+    """Page-locked host input of >= 4 outer blocks: mpqr_block_qr_host copies column chunks in while the first blocks are
+    already being factored (arrival-aware far updates with catch-up of late chunks) and streams finished blocks back.
+    Same factor as the copy-then-factor path (MPQR_NO_STREAM_IN=1) up to FP16-level run-to-run noise, same criteria."""
+    import torch
+    from gpu_util import r_rel_diff, sampled_backward_error
+    A = oracle.uniform_matrix(m, n, 9 * m + n)
+    Rref = np.linalg.qr(A.astype(np.float64), mode="r")
+    host = torch.zeros((m + 1, n), dtype=torch.float32).pin_memory()
+    out = {}
+    for mode in ("streamed", "plain"):
+        if mode == "plain":
+            monkeypatch.setenv("MPQR_NO_STREAM_IN", "1")
+        for rep in range(2):                     # second call: cached plan, events reused
+            host[:m].copy_(torch.from_numpy(A))
+            host[m].zero_()
+            P = host.numpy()
+            pkg.dev_mixed_precision_block_qr(P, None, m, n, r)
+            dr = r_rel_diff(P, Rref)
+            be = sampled_backward_error(torch.from_numpy(A).cuda(), host.cuda(), 64)
+            observe(f"host_{mode}_{m}x{n}", dr=dr, be=be)
+            assert be <= 3.4 * 2.0 ** -11 and dr <= (13.5 if m < n else 3) * 2.0 ** -11, (mode, dr, be)
+        out[mode] = np.triu(P[:m]).copy()
+    spread = np.abs(np.abs(out["streamed"]) - np.abs(out["plain"])).max() / np.abs(out["plain"]).max()
+    assert spread <= 3 * 2.0 ** -11, spread
+    assert pkg.lib().mpqr_release_cache() == 0
