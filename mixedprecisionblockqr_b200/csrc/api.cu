@@ -234,19 +234,21 @@ void overlap_init(mpqr_handle* h, const int* sizes, int nsizes) {
         CUgreenCtx gP = nullptr, gU = nullptr;
         if (g->GreenCtxCreate(&gP, dP, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) continue;
         if (g->GreenCtxCreate(&gU, dU, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { g->GreenCtxDestroy(gP); continue; }
-        CUstream sP = nullptr, sP2 = nullptr, sP3 = nullptr, sU = nullptr;
+        CUstream sP = nullptr, sP2 = nullptr, sP3 = nullptr, sU = nullptr, sU2 = nullptr;
         if (g->GreenCtxStreamCreate(&sP, gP, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS ||
             g->GreenCtxStreamCreate(&sP2, gP, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
             g->GreenCtxStreamCreate(&sP3, gP, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS ||
-            g->GreenCtxStreamCreate(&sU, gU, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+            g->GreenCtxStreamCreate(&sU, gU, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
+            g->GreenCtxStreamCreate(&sU2, gU, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
             if (sP) cudaStreamDestroy((cudaStream_t)sP);
             if (sP2) cudaStreamDestroy((cudaStream_t)sP2);
             if (sP3) cudaStreamDestroy((cudaStream_t)sP3);
+            if (sU) cudaStreamDestroy((cudaStream_t)sU);
             g->GreenCtxDestroy(gP); g->GreenCtxDestroy(gU);
             continue;
         }
         mpqr_handle::Overlap::Pair pr;
-        pr.gP = gP; pr.gU = gU; pr.sP = (cudaStream_t)sP; pr.sP2 = (cudaStream_t)sP2; pr.sP3 = (cudaStream_t)sP3; pr.sU = (cudaStream_t)sU;
+        pr.gP = gP; pr.gU = gU; pr.sP = (cudaStream_t)sP; pr.sP2 = (cudaStream_t)sP2; pr.sP3 = (cudaStream_t)sP3; pr.sU = (cudaStream_t)sU; pr.sU2 = (cudaStream_t)sU2;
         pr.nsmP = (int)grp[0].sm.smCount; pr.nsmU = (int)rem.sm.smCount;
         o.pairs.push_back(pr);
     }
@@ -254,6 +256,8 @@ void overlap_init(mpqr_handle* h, const int* sizes, int nsizes) {
     if (cudaStreamCreateWithFlags(&o.sF, cudaStreamNonBlocking) != cudaSuccess) { o.sF = nullptr; }
     if (cudaStreamCreateWithFlags(&o.sF2, cudaStreamNonBlocking) != cudaSuccess) { o.sF2 = nullptr; }
     if (cudaStreamCreateWithFlags(&o.sF3, cudaStreamNonBlocking) != cudaSuccess) { o.sF3 = nullptr; }
+    if (cudaStreamCreateWithFlags(&o.sFd, cudaStreamNonBlocking) != cudaSuccess) { o.sFd = nullptr; }
+    cudaEventCreateWithFlags(&o.ev_dist, cudaEventDisableTiming);
     o.ev_rest.resize(2 * (ceil_div(h->nb, h->r) + 1));
     for (auto& e : o.ev_rest) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     const int nblk = ceil_div(h->kmax, h->nb);
@@ -289,6 +293,8 @@ void overlap_destroy(mpqr_handle* h) {
     if (o.sF) cudaStreamDestroy(o.sF);
     if (o.sF2) cudaStreamDestroy(o.sF2);
     if (o.sF3) cudaStreamDestroy(o.sF3);
+    if (o.sFd) cudaStreamDestroy(o.sFd);
+    if (o.ev_dist) cudaEventDestroy(o.ev_dist);
     for (auto e : o.ev_rest) cudaEventDestroy(e);
     const GreenApi* g = green_api();
     for (auto& pr : o.pairs) {
@@ -296,6 +302,7 @@ void overlap_destroy(mpqr_handle* h) {
         if (pr.sP2) cudaStreamDestroy(pr.sP2);
         if (pr.sP3) cudaStreamDestroy(pr.sP3);
         if (pr.sU) cudaStreamDestroy(pr.sU);
+        if (pr.sU2) cudaStreamDestroy(pr.sU2);
         if (g->ok) { g->GreenCtxDestroy((CUgreenCtx)pr.gP); g->GreenCtxDestroy((CUgreenCtx)pr.gU); }
     }
     o = mpqr_handle::Overlap();
@@ -367,7 +374,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     }
     const int nblk = ceil_div(h->kmax, nb);
     // streamed input (host drop-in): needs the look-ahead driver and every block's W (catch-up of late chunks)
-    const bool arriving = h->arr.on && h->ov.on && nblk >= 3 && !h->prof && h->keep_wy;
+    const bool arriving = h->arr.on && h->ov.on && nblk >= 3 && !h->prof && h->keep_wy && h->S32d && h->S16d && h->ov.sFd;
     if (!arriving) {
         if (h->arr.on) {  // the plan fell back to the plain schedule: everything must be there first
             for (cudaEvent_t e : h->arr.ev) MPQR_CUDA(cudaStreamWaitEvent(st, e, 0));
@@ -426,36 +433,45 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     int nsm_bp = o.nsm_full, nsm_uprev = 0;
     const bool inblock_la = (h->r % 8) == 0;
     MPQR_CUDA(cudaStreamWaitEvent(s_bp, o.ev_start, 0));
-    // Arrival-aware far updates: `jend` = end of the admitted column range.  A chunk is admitted when it is expected to
-    // have arrived (clock of the cost model) or when the chain is about to need it (the block after next lies in it); on
-    // admission the update stream waits for the chunk's event and applies the blocks factored so far to it.
+    // Arrival-aware far updates (streamed host input).  The chunks that have arrived form two column ranges:
+    //   NEAR    [.., jnear): updated by the regular far update of every interval on the update stream (far_next first);
+    //   DISTANT [jnear, jdist): updated on a second stream of the update partition, one block per interval, so that the
+    //           catch-up burst of a chunk that has just arrived (all blocks factored so far) never queues in front of
+    //           the columns the panel chain needs next.
+    // A distant chunk moves to the near range two blocks before the chain reaches it (its stream's event orders the
+    // hand-over); a chunk the chain needs before the model clock expects it is waited for on the update stream.
     auto& ar = h->arr;
-    size_t ninc = arriving ? 1 : 0;
-    int jend = arriving ? ar.c1[0] : n;
+    size_t nnear = arriving ? 1 : 0, ndist = 0;
+    int jnear = arriving ? ar.c1[0] : n, jdist = jnear;
     double t_model = arriving ? ar.t_ms[0] + model_bp_ms(h, 0, nb < h->kmax ? nb : h->kmax, o.nsm_full) : 0.0;
+    bool dist_started = false;
     if (arriving) MPQR_CUDA(cudaStreamWaitEvent(s_bp, ar.ev[0], 0));
-    // chunks up to column `upto` (exclusive start) or expected by the model clock; dry = only report the resulting end column
-    auto admit = [&](int b, int upto, bool by_clock, bool all, bool dry, cudaStream_t s_u, int nsm_u, double* extra_flops, int* jend_out) -> int {
-        size_t q = ninc;
-        int je = jend;
-        while (q < ar.c0.size() && (all || ar.c0[q] < upto || (by_clock && ar.t_ms[q] <= t_model))) {
-            if (!dry) {
-                const int a0 = ar.c0[q], wdt = ar.c1[q] - ar.c0[q];
-                MPQR_CUDA(cudaStreamWaitEvent(s_u, ar.ev[q], 0));
-                SmBudget budget(nsm_u == o.nsm_full ? 0 : nsm_u);
-                for (int k = 0; k < b; ++k) {   // blocks 0 .. b-1 (block b itself reaches the chunk with the regular far update)
-                    const int k0 = k * nb, k1 = (k0 + nb < h->kmax) ? k0 + nb : h->kmax;
-                    BlockCtx ck = ctx_of(k, k0);
-                    ck.S32 = h->S32u; ck.S16 = h->S16u;
-                    MPQR_TRY(far_update(h, ck, k0, k1, a0, wdt, s_u));
-                    if (extra_flops) *extra_flops += 4.0 * (double)(m - k0) * wdt * (k1 - k0);
-                }
-            }
-            je = ar.c1[q];
-            ++q;
+    // blocks k_lo .. k_hi (inclusive) applied to columns [a0, a0 + wdt) on `sx`
+    auto apply_blocks = [&](int k_lo, int k_hi, int a0, int wdt, float* xS32, void* xS16, cudaStream_t sx, int nsm, double* flops) -> int {
+        SmBudget budget(nsm == o.nsm_full ? 0 : nsm);
+        for (int k = k_lo; k <= k_hi; ++k) {
+            const int k0 = k * nb, k1 = (k0 + nb < h->kmax) ? k0 + nb : h->kmax;
+            BlockCtx ck = ctx_of(k, k0);
+            ck.S32 = xS32; ck.S16 = xS16;
+            MPQR_TRY(far_update(h, ck, k0, k1, a0, wdt, sx));
+            if (flops) *flops += 4.0 * (double)(m - k0) * wdt * (k1 - k0);
         }
-        if (!dry) { ninc = q; jend = je; }
-        if (jend_out) *jend_out = je;
+        return MPQR_OK;
+    };
+    // chunks whose first column lies left of `upto` join the near range (before the update stream touches them)
+    auto promote = [&](int b, int upto, bool all, cudaStream_t s_u, int nsm_u, double* flops) -> int {
+        while (nnear < ar.c0.size() && (all || ar.c0[nnear] < upto)) {
+            if (ndist > 0) {           // distant chunk: blocks 0 .. b-1 were applied on the distant stream
+                MPQR_CUDA(cudaStreamWaitEvent(s_u, o.ev_dist, 0));
+                --ndist;
+            } else {                   // needed before it was admitted: wait for it here and catch up at once
+                MPQR_CUDA(cudaStreamWaitEvent(s_u, ar.ev[nnear], 0));
+                MPQR_TRY(apply_blocks(0, b - 1, ar.c0[nnear], ar.c1[nnear] - ar.c0[nnear], h->S32u, h->S16u, s_u, nsm_u, flops));
+            }
+            jnear = ar.c1[nnear];
+            if (jdist < jnear) jdist = jnear;
+            ++nnear;
+        }
         return MPQR_OK;
     };
     for (int c0 = 0, b = 0; c0 < h->kmax; c0 += nb, ++b) {
@@ -488,23 +504,27 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         MPQR_CUDA(cudaEventRecord(o.ev_bp[b], s_bp));
         if (defer_acc) MPQR_CUDA(cudaEventRecord(o.ev_accdone, s_acc));
         MPQR_TRY(emit(b, c0, c1, s_bp));
-        // arrival mode: the range this interval's far update will cover (dry run of the admission rule: the block after
-        // next must be in, plus whatever the model clock says has arrived; everything at the last reflector block)
+        // arrival mode: near range after this interval's promotions (the next two blocks must be in it; everything at the
+        // last reflector block) -- only its width is needed here, for the cost model
         const bool last_blk = c1 >= h->kmax;
-        int jplan = jend;
-        if (arriving) MPQR_TRY(admit(b, c1 + 2 * nb, true, last_blk, true, nullptr, 0, nullptr, &jplan));
+        int jplan = jnear;
+        if (arriving)
+            for (size_t q = nnear; q < ar.c0.size() && (last_blk || ar.c0[q] < c1 + 2 * nb); ++q) jplan = ar.c1[q];
         const int nfar = jplan - c1;
         // ---- choose the partition of interval b
         const int nnext = nfar < nb ? nfar : nb;
         const int c2 = (c1 + nb < h->kmax) ? c1 + nb : h->kmax;
         const bool has_next = c1 < h->kmax;
         int best = -1;  // -1: whole device, serial
-        if (has_next && nfar - nnext > 0) {
-            double best_t = model_bp_ms(h, c1, c2, o.nsm_full) + model_far_ms(h, c0, c1, nfar - nnext, o.nsm_full);
+        // (arrival mode: the distant range is updated next to the near one, and a partition is always used so that late
+        //  far work never runs in front of the panel chain)
+        const int nmodel = nfar - nnext + (arriving ? (jdist > jplan ? jdist - jplan : 0) : 0);
+        if (has_next && (nfar - nnext > 0 || arriving)) {
+            double best_t = arriving ? 1e30 : model_bp_ms(h, c1, c2, o.nsm_full) + model_far_ms(h, c0, c1, nfar - nnext, o.nsm_full);
             for (size_t k = 0; k < o.pairs.size(); ++k) {
                 if (fixed_sms > 0 && o.pairs[k].nsmP != fixed_sms) continue;
                 const double tb = 1.05 * model_bp_ms(h, c1, c2, o.pairs[k].nsmP);
-                const double tf = model_far_ms(h, c0, c1, nfar - nnext, o.pairs[k].nsmU);
+                const double tf = model_far_ms(h, c0, c1, nmodel, o.pairs[k].nsmU);
                 const double t = tb > tf ? tb : tf;
                 if (t < best_t || (fixed_sms > 0 && best < 0)) { best_t = t; best = (int)k; }
             }
@@ -522,18 +542,35 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
             if (o.trace) cudaEventRecord(o.tr[b].f0, s_u);
             double catch_flops = 0;
             if (arriving) {
-                // what the next block phase needs first (already admitted by the "block after next" rule, except at b = 0),
-                // then the newcomers with their catch-up, then the rest of the admitted range
-                MPQR_TRY(admit(b, c1 + nnext, false, false, false, s_u, nsm_u, &catch_flops, nullptr));
+                cudaStream_t s_d = best >= 0 ? o.pairs[best].sU2 : o.sFd;
+                // near range: what the next block phase needs first, then the chunks two blocks ahead, then the rest
+                MPQR_TRY(promote(b, c1 + nnext, false, s_u, nsm_u, &catch_flops));
                 MPQR_TRY(far_update(h, cu, c0, c1, c1, nnext, s_u));
                 if (o.trace) cudaEventRecord(o.tr[b].f1, s_u);
                 MPQR_CUDA(cudaEventRecord(o.ev_fn[b], s_u));
-                MPQR_TRY(admit(b, c1 + 2 * nb, true, last_blk, false, s_u, nsm_u, &catch_flops, nullptr));
-                MPQR_TRY(far_update(h, cu, c0, c1, c1 + nnext, jend - c1 - nnext, s_u));
+                MPQR_TRY(promote(b, c1 + 2 * nb, last_blk, s_u, nsm_u, &catch_flops));
+                MPQR_TRY(far_update(h, cu, c0, c1, c1 + nnext, jnear - c1 - nnext, s_u));
                 if (o.trace) cudaEventRecord(o.tr[b].f2, s_u);
                 MPQR_CUDA(cudaEventRecord(o.ev_fr[b], s_u));
+                // distant range: block b for the chunks already there, blocks 0 .. b for those the clock says have arrived
+                const bool newcomers = nnear + ndist < ar.c0.size() && ar.t_ms[nnear + ndist] <= t_model;
+                if (ndist > 0 || newcomers) {
+                    if (dist_started) MPQR_CUDA(cudaStreamWaitEvent(s_d, o.ev_dist, 0));
+                    MPQR_CUDA(cudaStreamWaitEvent(s_d, o.ev_bp[b], 0));
+                    if (defer_acc) MPQR_CUDA(cudaStreamWaitEvent(s_d, o.ev_accdone, 0));
+                    if (ndist > 0) MPQR_TRY(apply_blocks(b, b, jnear, jdist - jnear, h->S32d, h->S16d, s_d, nsm_u, &catch_flops));
+                    while (nnear + ndist < ar.c0.size() && ar.t_ms[nnear + ndist] <= t_model) {
+                        const size_t q = nnear + ndist;
+                        MPQR_CUDA(cudaStreamWaitEvent(s_d, ar.ev[q], 0));
+                        MPQR_TRY(apply_blocks(0, b, ar.c0[q], ar.c1[q] - ar.c0[q], h->S32d, h->S16d, s_d, nsm_u, &catch_flops));
+                        jdist = ar.c1[q];
+                        ++ndist;
+                    }
+                    MPQR_CUDA(cudaEventRecord(o.ev_dist, s_d));
+                    dist_started = true;
+                }
                 // model clock: this interval lasts as long as the slower of the next block phase and the far work
-                const double tf = model_far_ms(h, c0, c1, jend - c1, nsm_u) + catch_flops / (8.4e12 * nsm_u) * 1e3;
+                const double tf = model_far_ms(h, c0, c1, jnear - c1, nsm_u) + catch_flops / (8.4e12 * nsm_u) * 1e3;
                 const double tb = has_next ? model_bp_ms(h, c1, c2, best >= 0 ? o.pairs[best].nsmP : o.nsm_full) : 0.0;
                 t_model += (best >= 0) ? (tb > tf ? tb : tf) : tb + tf;
             } else {
@@ -561,6 +598,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_fr[nblk - 1], 0));
     MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_bp[nblk - 1], 0));
     for (int b = 0; b + 1 < nblk; ++b) MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_fr[b], 0));
+    if (dist_started) MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_dist, 0));
     if (h->kmax < n) MPQR_TRY(emit(nblk, h->kmax, n, st));
     return MPQR_OK;
 }
@@ -980,6 +1018,8 @@ void host_plan_free(HostPlan& p) {
 }
 }  // namespace
 
+int mpqr_debug_dump_trace(mpqr_handle* h);
+
 int mpqr_release_cache(void) {
     {
         std::lock_guard<std::mutex> lk(g_host_mu);
@@ -1047,6 +1087,8 @@ int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned 
         const int nblk_outer = ceil_div(h->kmax, h->nb);
         if (pipelined && want_stream_in && h->ov.on && nblk_outer >= 4 && h->keep_wy) {
             auto& ar = h->arr;
+            if (!h->S32d && (rc = dev_alloc(h, (void**)&h->S32d, (size_t)h->sk * h->lds32 * sizeof(float)))) break;
+            if (!h->S16d && (rc = dev_alloc(h, &h->S16d, (size_t)h->sk * h->lds16 * 2))) break;
             if (!ar.stream && cudaStreamCreateWithFlags(&ar.stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
             ar.c0.clear(); ar.c1.clear(); ar.t_ms.clear();
             static const double gbs = getenv("MPQR_H2D_GBS") ? atof(getenv("MPQR_H2D_GBS")) : 52.0;  // expected host-to-device rate
@@ -1068,12 +1110,20 @@ int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned 
                 ar.ev.push_back(ev);
             }
             if (rc != MPQR_OK) { set_error("event creation failed"); break; }
+            std::vector<cudaEvent_t> tev;   // MPQR_HOST_TRACE: measured arrival times
+            if (htrace) {
+                tev.resize(ar.c0.size() + 1);
+                for (auto& t2 : tev) cudaEventCreate(&t2);
+                cudaEventRecord(tev[0], ar.stream);
+            }
+            h->arr_trace = tev;
             for (size_t k = 0; k < ar.c0.size() && e == cudaSuccess; ++k) {
                 const int a0 = ar.c0[k], wdt = ar.c1[k] - ar.c0[k];
                 e = cudaMemcpy2DAsync(dA + a0, lda * sizeof(float), A_packed + a0, (size_t)n * sizeof(float), (size_t)wdt * sizeof(float),
                                       m + 1, cudaMemcpyHostToDevice, ar.stream);
                 if (e == cudaSuccess && convert_f32_to_16(dA + a0, lda, at16(h->Ah, h->ldh, 0, a0), h->ldh, m, wdt, h->prec == 2, ar.stream) != MPQR_OK) e = cudaErrorUnknown;
                 if (e == cudaSuccess) e = cudaEventRecord(ar.ev[k], ar.stream);
+                if (htrace) cudaEventRecord(h->arr_trace[k + 1], ar.stream);
             }
             if (e != cudaSuccess) { set_error("streamed H2D failed: %s", cudaGetErrorString(e)); rc = MPQR_ECUDA; break; }
             ar.on = true;
@@ -1119,6 +1169,18 @@ int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned 
         } else {
             mpqr_destroy(P.h);
         }
+    }
+    if (htrace && !h->arr_trace.empty()) {
+        fprintf(stderr, "  chunk arrivals (ms after the first copy was issued; expected):");
+        for (size_t k = 1; k < h->arr_trace.size(); ++k) {
+            float t = 0;
+            cudaEventElapsedTime(&t, h->arr_trace[0], h->arr_trace[k]);
+            fprintf(stderr, " [%d,%d) %.1f (%.1f)", h->arr.c0[k - 1], h->arr.c1[k - 1], t, h->arr.t_ms[k - 1]);
+        }
+        fprintf(stderr, "\n");
+        for (auto t2 : h->arr_trace) cudaEventDestroy(t2);
+        h->arr_trace.clear();
+        if (h->ov.trace) mpqr_debug_dump_trace(h);
     }
     if (htrace)
         fprintf(stderr, "mpqr_block_qr_host %dx%d: plan %.1f ms (%s), H2D %.1f, issue %.1f, wait+D2H %.1f, release %.1f, total %.1f\n",

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -k 10 400 python -m pytest tests/test_gpu_qr.py -x -q --timeout 200 -k "streamed or plan_cache" > gpurun_out/r2h_host_tests.log 2>&1
+echo "rc=$?" >> gpurun_out/r2h_host_tests.log
+tail -8 gpurun_out/r2h_host_tests.log
+MPQR_TRACE=1 MPQR_HOST_TRACE=1 timeout -k 10 300 python tools/e2e_time.py > gpurun_out/r2h_e2e.log 2>&1
+grep -v "^ *[0-9]" gpurun_out/r2h_e2e.log | tail -12
+tail -36 gpurun_out/r2h_e2e.log | head -34
