@@ -365,6 +365,33 @@ int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     return MPQR_OK;
 }
 
+// per-chunk streams (in the update partition of pair `k`), events and GEMM scratch of the streamed-input schedule
+int arrival_streams(mpqr_handle* h, int k) {
+    auto& ar = h->arr;
+    const GreenApi* g = green_api();
+    const size_t nch = ar.c0.size();
+    if (ar.cs.size() < nch) { ar.cs.resize(nch, nullptr); ar.cev.resize(nch, nullptr); ar.cS32.resize(nch, nullptr); ar.cS16.resize(nch, nullptr); }
+    ar.cev_set.assign(nch, 0);
+    for (size_t q = 1; q < nch; ++q) {
+        if (!ar.cs[q]) {
+            CUstream sq = nullptr;
+            if (!g->ok || g->GreenCtxStreamCreate(&sq, (CUgreenCtx)h->ov.pairs[k].gU, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+                set_error("streamed input: stream creation failed");
+                return MPQR_ECUDA;
+            }
+            ar.cs[q] = (cudaStream_t)sq;
+            MPQR_CUDA(cudaEventCreateWithFlags(&ar.cev[q], cudaEventDisableTiming));
+        }
+        const size_t wdt = (size_t)round_up(ar.c1[q] - ar.c0[q], 8);
+        if (!ar.cS32[q]) {
+            MPQR_TRY(dev_alloc(h, (void**)&ar.cS32[q], (size_t)h->sk * h->lds32 * sizeof(float)));
+            MPQR_TRY(dev_alloc(h, &ar.cS16[q], (size_t)h->sk * h->lds16 * 2));
+        }
+        (void)wdt;
+    }
+    return MPQR_OK;
+}
+
 int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     const int m = h->m, n = h->n, nb = h->nb;
     const int bf = h->prec == 2;
@@ -374,7 +401,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     }
     const int nblk = ceil_div(h->kmax, nb);
     // streamed input (host drop-in): needs the look-ahead driver and every block's W (catch-up of late chunks)
-    const bool arriving = h->arr.on && h->ov.on && nblk >= 3 && !h->prof && h->keep_wy && h->S32d && h->S16d && h->ov.sFd;
+    const bool arriving = h->arr.on && h->ov.on && !h->ov.pairs.empty() && nblk >= 3 && !h->prof && h->keep_wy;
     if (!arriving) {
         if (h->arr.on) {  // the plan fell back to the plain schedule: everything must be there first
             for (cudaEvent_t e : h->arr.ev) MPQR_CUDA(cudaStreamWaitEvent(st, e, 0));
@@ -433,43 +460,29 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     int nsm_bp = o.nsm_full, nsm_uprev = 0;
     const bool inblock_la = (h->r % 8) == 0;
     MPQR_CUDA(cudaStreamWaitEvent(s_bp, o.ev_start, 0));
-    // Arrival-aware far updates (streamed host input).  The chunks that have arrived form two column ranges:
-    //   NEAR    [.., jnear): updated by the regular far update of every interval on the update stream (far_next first);
-    //   DISTANT [jnear, jdist): updated on a second stream of the update partition, one block per interval, so that the
-    //           catch-up burst of a chunk that has just arrived (all blocks factored so far) never queues in front of
-    //           the columns the panel chain needs next.
-    // A distant chunk moves to the near range two blocks before the chain reaches it (its stream's event orders the
-    // hand-over); a chunk the chain needs before the model clock expects it is waited for on the update stream.
+    // Arrival-aware far updates (streamed host input).  The columns form a NEAR range [.., jnear), updated by the regular
+    // far update of every interval on the update stream, and DISTANT chunks, each with its own stream in the update
+    // partition: a distant chunk waits for its arrival once and then takes block b at every interval b until it joins the
+    // near range, two blocks before the chain reaches it (its event orders the hand-over).  The backlog a late chunk has
+    // to catch up with therefore runs on its own stream when the data lands -- never in front of the columns the panel
+    // chain needs next -- and the host needs no clock.  One (panel, update) partition pair is used throughout.
     auto& ar = h->arr;
-    size_t nnear = arriving ? 1 : 0, ndist = 0;
-    int jnear = arriving ? ar.c1[0] : n, jdist = jnear;
-    double t_model = arriving ? ar.t_ms[0] + model_bp_ms(h, 0, nb < h->kmax ? nb : h->kmax, o.nsm_full) : 0.0;
-    bool dist_started = false;
-    if (arriving) MPQR_CUDA(cudaStreamWaitEvent(s_bp, ar.ev[0], 0));
-    // blocks k_lo .. k_hi (inclusive) applied to columns [a0, a0 + wdt) on `sx`
-    auto apply_blocks = [&](int k_lo, int k_hi, int a0, int wdt, float* xS32, void* xS16, cudaStream_t sx, int nsm, double* flops) -> int {
-        SmBudget budget(nsm == o.nsm_full ? 0 : nsm);
-        for (int k = k_lo; k <= k_hi; ++k) {
-            const int k0 = k * nb, k1 = (k0 + nb < h->kmax) ? k0 + nb : h->kmax;
-            BlockCtx ck = ctx_of(k, k0);
-            ck.S32 = xS32; ck.S16 = xS16;
-            MPQR_TRY(far_update(h, ck, k0, k1, a0, wdt, sx));
-            if (flops) *flops += 4.0 * (double)(m - k0) * wdt * (k1 - k0);
-        }
-        return MPQR_OK;
-    };
+    size_t nnear = arriving ? 1 : 0;
+    int jnear = arriving ? ar.c1[0] : n;
+    int arr_pair = -1;
+    if (arriving) {
+        for (size_t k = 0; k < o.pairs.size(); ++k)
+            if (arr_pair < 0 || abs(o.pairs[k].nsmP - 64) < abs(o.pairs[arr_pair].nsmP - 64)) arr_pair = (int)k;
+        MPQR_TRY(arrival_streams(h, arr_pair));
+        MPQR_CUDA(cudaStreamWaitEvent(s_bp, ar.ev[0], 0));
+        for (size_t q = 1; q < ar.c0.size(); ++q) MPQR_CUDA(cudaStreamWaitEvent(ar.cs[q], ar.ev[q], 0));
+    }
     // chunks whose first column lies left of `upto` join the near range (before the update stream touches them)
-    auto promote = [&](int b, int upto, bool all, cudaStream_t s_u, int nsm_u, double* flops) -> int {
+    auto promote = [&](int upto, bool all, cudaStream_t s_u) -> int {
         while (nnear < ar.c0.size() && (all || ar.c0[nnear] < upto)) {
-            if (ndist > 0) {           // distant chunk: blocks 0 .. b-1 were applied on the distant stream
-                MPQR_CUDA(cudaStreamWaitEvent(s_u, o.ev_dist, 0));
-                --ndist;
-            } else {                   // needed before it was admitted: wait for it here and catch up at once
-                MPQR_CUDA(cudaStreamWaitEvent(s_u, ar.ev[nnear], 0));
-                MPQR_TRY(apply_blocks(0, b - 1, ar.c0[nnear], ar.c1[nnear] - ar.c0[nnear], h->S32u, h->S16u, s_u, nsm_u, flops));
-            }
+            MPQR_CUDA(cudaStreamWaitEvent(s_u, ar.ev[nnear], 0));
+            if (ar.cev_set[nnear]) MPQR_CUDA(cudaStreamWaitEvent(s_u, ar.cev[nnear], 0));  // blocks 0 .. b-1 applied on its own stream
             jnear = ar.c1[nnear];
-            if (jdist < jnear) jdist = jnear;
             ++nnear;
         }
         return MPQR_OK;
@@ -518,11 +531,12 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         int best = -1;  // -1: whole device, serial
         // (arrival mode: the distant range is updated next to the near one, and a partition is always used so that late
         //  far work never runs in front of the panel chain)
-        const int nmodel = nfar - nnext + (arriving ? (jdist > jplan ? jdist - jplan : 0) : 0);
+        const int nmodel = nfar - nnext;
         if (has_next && (nfar - nnext > 0 || arriving)) {
             double best_t = arriving ? 1e30 : model_bp_ms(h, c1, c2, o.nsm_full) + model_far_ms(h, c0, c1, nfar - nnext, o.nsm_full);
             for (size_t k = 0; k < o.pairs.size(); ++k) {
-                if (fixed_sms > 0 && o.pairs[k].nsmP != fixed_sms) continue;
+                if (arriving && (int)k != arr_pair) continue;   // the distant chunks' streams live in this pair's update partition
+                if (fixed_sms > 0 && !arriving && o.pairs[k].nsmP != fixed_sms) continue;
                 const double tb = 1.05 * model_bp_ms(h, c1, c2, o.pairs[k].nsmP);
                 const double tf = model_far_ms(h, c0, c1, nmodel, o.pairs[k].nsmU);
                 const double t = tb > tf ? tb : tf;
@@ -542,37 +556,27 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
             if (o.trace) cudaEventRecord(o.tr[b].f0, s_u);
             double catch_flops = 0;
             if (arriving) {
-                cudaStream_t s_d = best >= 0 ? o.pairs[best].sU2 : o.sFd;
                 // near range: what the next block phase needs first, then the chunks two blocks ahead, then the rest
-                MPQR_TRY(promote(b, c1 + nnext, false, s_u, nsm_u, &catch_flops));
+                MPQR_TRY(promote(c1 + nnext, false, s_u));
                 MPQR_TRY(far_update(h, cu, c0, c1, c1, nnext, s_u));
                 if (o.trace) cudaEventRecord(o.tr[b].f1, s_u);
                 MPQR_CUDA(cudaEventRecord(o.ev_fn[b], s_u));
-                MPQR_TRY(promote(b, c1 + 2 * nb, last_blk, s_u, nsm_u, &catch_flops));
+                MPQR_TRY(promote(c1 + 2 * nb, last_blk, s_u));
                 MPQR_TRY(far_update(h, cu, c0, c1, c1 + nnext, jnear - c1 - nnext, s_u));
                 if (o.trace) cudaEventRecord(o.tr[b].f2, s_u);
                 MPQR_CUDA(cudaEventRecord(o.ev_fr[b], s_u));
-                // distant range: block b for the chunks already there, blocks 0 .. b for those the clock says have arrived
-                const bool newcomers = nnear + ndist < ar.c0.size() && ar.t_ms[nnear + ndist] <= t_model;
-                if (ndist > 0 || newcomers) {
-                    if (dist_started) MPQR_CUDA(cudaStreamWaitEvent(s_d, o.ev_dist, 0));
-                    MPQR_CUDA(cudaStreamWaitEvent(s_d, o.ev_bp[b], 0));
-                    if (defer_acc) MPQR_CUDA(cudaStreamWaitEvent(s_d, o.ev_accdone, 0));
-                    if (ndist > 0) MPQR_TRY(apply_blocks(b, b, jnear, jdist - jnear, h->S32d, h->S16d, s_d, nsm_u, &catch_flops));
-                    while (nnear + ndist < ar.c0.size() && ar.t_ms[nnear + ndist] <= t_model) {
-                        const size_t q = nnear + ndist;
-                        MPQR_CUDA(cudaStreamWaitEvent(s_d, ar.ev[q], 0));
-                        MPQR_TRY(apply_blocks(0, b, ar.c0[q], ar.c1[q] - ar.c0[q], h->S32d, h->S16d, s_d, nsm_u, &catch_flops));
-                        jdist = ar.c1[q];
-                        ++ndist;
-                    }
-                    MPQR_CUDA(cudaEventRecord(o.ev_dist, s_d));
-                    dist_started = true;
+                // distant chunks: block b each, on their own streams
+                for (size_t q = nnear; q < ar.c0.size(); ++q) {
+                    BlockCtx cd = c;
+                    cd.S32 = ar.cS32[q]; cd.S16 = ar.cS16[q];
+                    cd.acc_stream = nullptr;
+                    SmBudget budget(o.pairs[arr_pair].nsmU);
+                    MPQR_CUDA(cudaStreamWaitEvent(ar.cs[q], o.ev_bp[b], 0));
+                    if (defer_acc) MPQR_CUDA(cudaStreamWaitEvent(ar.cs[q], o.ev_accdone, 0));
+                    MPQR_TRY(far_update(h, cd, c0, c1, ar.c0[q], ar.c1[q] - ar.c0[q], ar.cs[q]));
+                    MPQR_CUDA(cudaEventRecord(ar.cev[q], ar.cs[q]));
+                    ar.cev_set[q] = 1;
                 }
-                // model clock: this interval lasts as long as the slower of the next block phase and the far work
-                const double tf = model_far_ms(h, c0, c1, jnear - c1, nsm_u) + catch_flops / (8.4e12 * nsm_u) * 1e3;
-                const double tb = has_next ? model_bp_ms(h, c1, c2, best >= 0 ? o.pairs[best].nsmP : o.nsm_full) : 0.0;
-                t_model += (best >= 0) ? (tb > tf ? tb : tf) : tb + tf;
             } else {
             MPQR_TRY(far_update(h, cu, c0, c1, c1, nnext, s_u));
             if (o.trace) cudaEventRecord(o.tr[b].f1, s_u);
@@ -598,7 +602,9 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_fr[nblk - 1], 0));
     MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_bp[nblk - 1], 0));
     for (int b = 0; b + 1 < nblk; ++b) MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_fr[b], 0));
-    if (dist_started) MPQR_CUDA(cudaStreamWaitEvent(st, o.ev_dist, 0));
+    if (arriving)
+        for (size_t q = 1; q < ar.c0.size(); ++q)
+            if (ar.cev_set[q]) MPQR_CUDA(cudaStreamWaitEvent(st, ar.cev[q], 0));
     if (h->kmax < n) MPQR_TRY(emit(nblk, h->kmax, n, st));
     return MPQR_OK;
 }
@@ -873,6 +879,8 @@ int mpqr_destroy(mpqr_handle* h) {
     if (h->chain_ev_side) cudaEventDestroy(h->chain_ev_side);
     for (auto e : h->arr.ev) cudaEventDestroy(e);
     if (h->arr.stream) cudaStreamDestroy(h->arr.stream);
+    for (auto sq : h->arr.cs) if (sq) cudaStreamDestroy(sq);
+    for (auto e : h->arr.cev) if (e) cudaEventDestroy(e);
     for (auto e : h->sink_ev) cudaEventDestroy(e);
     if (h->sink_stream) cudaStreamDestroy(h->sink_stream);
     for (void* p : h->allocs) cudaFree(p);
@@ -1087,14 +1095,12 @@ int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned 
         const int nblk_outer = ceil_div(h->kmax, h->nb);
         if (pipelined && want_stream_in && h->ov.on && nblk_outer >= 4 && h->keep_wy) {
             auto& ar = h->arr;
-            if (!h->S32d && (rc = dev_alloc(h, (void**)&h->S32d, (size_t)h->sk * h->lds32 * sizeof(float)))) break;
-            if (!h->S16d && (rc = dev_alloc(h, &h->S16d, (size_t)h->sk * h->lds16 * 2))) break;
             if (!ar.stream && cudaStreamCreateWithFlags(&ar.stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
             ar.c0.clear(); ar.c1.clear(); ar.t_ms.clear();
             static const double gbs = getenv("MPQR_H2D_GBS") ? atof(getenv("MPQR_H2D_GBS")) : 52.0;  // expected host-to-device rate
             double t = 0.05;
             for (int blk = 0, k = 0; blk * h->nb < n; ++k) {
-                const int nblocks = k < 2 ? 1 : (k == 2 ? 2 : 4);
+                const int nblocks = k == 0 ? 1 : (k == 1 ? 3 : (k == 2 ? 4 : 8));   // few, growing chunks: every distant chunk has its own stream
                 const int a0 = blk * h->nb;
                 int a1 = (blk + nblocks) * h->nb;
                 if (a1 > n || n - a1 < h->nb) a1 = n;   // a short tail joins the last chunk

@@ -95,6 +95,12 @@ struct mpqr_handle {
         std::vector<cudaEvent_t> ev;      // chunk is in HBM and its 16-bit shadow is written
         std::vector<double> t_ms;         // expected arrival time after the start of the call
         cudaStream_t stream = nullptr;    // copy + shadow conversion
+        // per chunk (from chunk 1 on): own stream in the update partition, "blocks applied so far" event, GEMM scratch
+        std::vector<cudaStream_t> cs;
+        std::vector<cudaEvent_t> cev;
+        std::vector<char> cev_set;
+        std::vector<float*> cS32;
+        std::vector<void*> cS16;
     } arr;
     std::vector<cudaEvent_t> arr_trace;   // MPQR_HOST_TRACE=1: timed events behind every chunk
 
