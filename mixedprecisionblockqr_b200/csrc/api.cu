@@ -40,8 +40,8 @@ void set_error(const char* fmt, ...) {
 }
 
 int get_device_info(DeviceInfo* out) {
-    static DeviceInfo cached;
-    static int cached_dev = -1;
+    static thread_local DeviceInfo cached;
+    static thread_local int cached_dev = -1;
     int dev;
     MPQR_CUDA(cudaGetDevice(&dev));
     if (dev != cached_dev) {
@@ -60,12 +60,26 @@ int get_device_info(DeviceInfo* out) {
     return MPQR_OK;
 }
 
+thread_local double g_host_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+bool g_host_prof_on = getenv("MPQR_HOST_TRACE") != nullptr;
+static inline double host_now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+HostProfScope::HostProfScope(int c) : cat(c), t0(g_host_prof_on ? host_now_ms() : 0.0) {}
+HostProfScope::~HostProfScope() {
+    if (g_host_prof_on) g_host_prof[cat] += host_now_ms() - t0;
+}
+
 int func_attr_once(const void* func, cudaFuncAttribute attr, int value) {
     struct Key { const void* f; int a, dev; };
     static std::mutex mu;
     static std::vector<Key> done;
     int dev = 0;
     MPQR_CUDA(cudaGetDevice(&dev));
+    static thread_local std::vector<Key> seen;   // lock-free fast path of the issuing thread
+    for (const Key& k : seen)
+        if (k.f == func && k.a == (int)attr && k.dev == dev) return MPQR_OK;
+    seen.push_back({func, (int)attr, dev});
     std::lock_guard<std::mutex> lk(mu);
     for (const Key& k : done)
         if (k.f == func && k.a == (int)attr && k.dev == dev) return MPQR_OK;
@@ -234,21 +248,19 @@ void overlap_init(mpqr_handle* h, const int* sizes, int nsizes) {
         CUgreenCtx gP = nullptr, gU = nullptr;
         if (g->GreenCtxCreate(&gP, dP, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) continue;
         if (g->GreenCtxCreate(&gU, dU, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { g->GreenCtxDestroy(gP); continue; }
-        CUstream sP = nullptr, sP2 = nullptr, sP3 = nullptr, sU = nullptr, sU2 = nullptr;
+        CUstream sP = nullptr, sP2 = nullptr, sP3 = nullptr, sU = nullptr;
         if (g->GreenCtxStreamCreate(&sP, gP, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS ||
             g->GreenCtxStreamCreate(&sP2, gP, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
             g->GreenCtxStreamCreate(&sP3, gP, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS ||
-            g->GreenCtxStreamCreate(&sU, gU, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS ||
-            g->GreenCtxStreamCreate(&sU2, gU, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+            g->GreenCtxStreamCreate(&sU, gU, CU_STREAM_NON_BLOCKING, -1) != CUDA_SUCCESS) {
             if (sP) cudaStreamDestroy((cudaStream_t)sP);
             if (sP2) cudaStreamDestroy((cudaStream_t)sP2);
             if (sP3) cudaStreamDestroy((cudaStream_t)sP3);
-            if (sU) cudaStreamDestroy((cudaStream_t)sU);
             g->GreenCtxDestroy(gP); g->GreenCtxDestroy(gU);
             continue;
         }
         mpqr_handle::Overlap::Pair pr;
-        pr.gP = gP; pr.gU = gU; pr.sP = (cudaStream_t)sP; pr.sP2 = (cudaStream_t)sP2; pr.sP3 = (cudaStream_t)sP3; pr.sU = (cudaStream_t)sU; pr.sU2 = (cudaStream_t)sU2;
+        pr.gP = gP; pr.gU = gU; pr.sP = (cudaStream_t)sP; pr.sP2 = (cudaStream_t)sP2; pr.sP3 = (cudaStream_t)sP3; pr.sU = (cudaStream_t)sU;
         pr.nsmP = (int)grp[0].sm.smCount; pr.nsmU = (int)rem.sm.smCount;
         o.pairs.push_back(pr);
     }
@@ -256,8 +268,6 @@ void overlap_init(mpqr_handle* h, const int* sizes, int nsizes) {
     if (cudaStreamCreateWithFlags(&o.sF, cudaStreamNonBlocking) != cudaSuccess) { o.sF = nullptr; }
     if (cudaStreamCreateWithFlags(&o.sF2, cudaStreamNonBlocking) != cudaSuccess) { o.sF2 = nullptr; }
     if (cudaStreamCreateWithFlags(&o.sF3, cudaStreamNonBlocking) != cudaSuccess) { o.sF3 = nullptr; }
-    if (cudaStreamCreateWithFlags(&o.sFd, cudaStreamNonBlocking) != cudaSuccess) { o.sFd = nullptr; }
-    cudaEventCreateWithFlags(&o.ev_dist, cudaEventDisableTiming);
     o.ev_rest.resize(2 * (ceil_div(h->nb, h->r) + 1));
     for (auto& e : o.ev_rest) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     const int nblk = ceil_div(h->kmax, h->nb);
@@ -293,8 +303,6 @@ void overlap_destroy(mpqr_handle* h) {
     if (o.sF) cudaStreamDestroy(o.sF);
     if (o.sF2) cudaStreamDestroy(o.sF2);
     if (o.sF3) cudaStreamDestroy(o.sF3);
-    if (o.sFd) cudaStreamDestroy(o.sFd);
-    if (o.ev_dist) cudaEventDestroy(o.ev_dist);
     for (auto e : o.ev_rest) cudaEventDestroy(e);
     const GreenApi* g = green_api();
     for (auto& pr : o.pairs) {
@@ -302,7 +310,6 @@ void overlap_destroy(mpqr_handle* h) {
         if (pr.sP2) cudaStreamDestroy(pr.sP2);
         if (pr.sP3) cudaStreamDestroy(pr.sP3);
         if (pr.sU) cudaStreamDestroy(pr.sU);
-        if (pr.sU2) cudaStreamDestroy(pr.sU2);
         if (g->ok) { g->GreenCtxDestroy((CUgreenCtx)pr.gP); g->GreenCtxDestroy((CUgreenCtx)pr.gU); }
     }
     o = mpqr_handle::Overlap();
@@ -423,6 +430,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     // columns [c0, c1) are final once block_phase(b) is done on `producer`: ship them to the host sink
     auto emit = [&](int b, int c0, int c1, cudaStream_t producer) -> int {
         if (!h->sink_host) return MPQR_OK;
+        HostProfScope hp(6);
         if ((int)h->sink_ev.size() <= b) {
             const size_t old = h->sink_ev.size();
             h->sink_ev.resize(b + 1);
@@ -554,7 +562,6 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
             if (defer_acc) MPQR_CUDA(cudaStreamWaitEvent(s_u, o.ev_accdone, 0));
             if (b > 0) MPQR_CUDA(cudaStreamWaitEvent(s_u, o.ev_fr[b - 1], 0));
             if (o.trace) cudaEventRecord(o.tr[b].f0, s_u);
-            double catch_flops = 0;
             if (arriving) {
                 // near range: what the next block phase needs first, then the chunks two blocks ahead, then the rest
                 MPQR_TRY(promote(c1 + nnext, false, s_u));
@@ -570,7 +577,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
                     BlockCtx cd = c;
                     cd.S32 = ar.cS32[q]; cd.S16 = ar.cS16[q];
                     cd.acc_stream = nullptr;
-                    SmBudget budget(o.pairs[arr_pair].nsmU);
+                    SmBudget budget(o.pairs[arr_pair].nsmU / 2);   // far_next must always find free SMs in the update partition
                     MPQR_CUDA(cudaStreamWaitEvent(ar.cs[q], o.ev_bp[b], 0));
                     if (defer_acc) MPQR_CUDA(cudaStreamWaitEvent(ar.cs[q], o.ev_accdone, 0));
                     MPQR_TRY(far_update(h, cd, c0, c1, ar.c0[q], ar.c1[q] - ar.c0[q], ar.cs[q]));
@@ -670,6 +677,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         const void* Wpp = (char*)c.W16 + ((size_t)jc * c.ldw + jc) * 2;   // the panel's own W / Y, rows lam..
         const void* Ypp = (char*)c.Y16 + ((size_t)jc * c.ldy + jc) * 2;
         auto inblock = [&](int ofs, int nc, float* xS32, void* xS16, int pad_ok, cudaStream_t st) -> int {
+            HostProfScope hp(2);
             int w16 = 0;
             PROF(1, 2.0 * pw * nc * D, tn_bytes(pw, nc, D),
                  tc_gemm_tn16(Wpp, c.ldw, at16(c.Ah, c.ldh, lam, acol_tau + ofs), c.ldh, xS32, h->lds32, xS16, h->lds16, &w16, pw, nc, D, bf, 1, st, &h->launches));
@@ -720,6 +728,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
                 aS32 = c.acc_S32; aS16 = c.acc_S16;
             }
             {
+                HostProfScope hp(3);
                 cudaStream_t st = c.acc_stream ? c.acc_stream : st_panel;  // (PROF records on `st`)
                 SmBudget budget(c.acc_stream ? c.acc_sms : g_sm_budget);
                 int w16 = 0;
@@ -744,6 +753,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
 
 int far_update(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int afar, int nfar, cudaStream_t st) {
     if (nfar <= 0) return MPQR_OK;
+    HostProfScope hp(4);
     const int bf = h->prec == 2;
     const int Dblk = h->m - c0, kb = c1 - c0;
     float* S32 = c.S32 ? c.S32 : h->S32;
@@ -874,13 +884,14 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
 int mpqr_destroy(mpqr_handle* h) {
     if (!h) return MPQR_OK;
     mg_destroy(h->mg);
+    for (auto sq : h->arr.cs) if (sq) cudaStreamDestroy(sq);   // (streams of a green context: before the contexts go)
+    for (auto e : h->arr.cev) if (e) cudaEventDestroy(e);
     overlap_destroy(h);
     if (h->chain_side) cudaStreamDestroy(h->chain_side);
     if (h->chain_ev_side) cudaEventDestroy(h->chain_ev_side);
     for (auto e : h->arr.ev) cudaEventDestroy(e);
     if (h->arr.stream) cudaStreamDestroy(h->arr.stream);
-    for (auto sq : h->arr.cs) if (sq) cudaStreamDestroy(sq);
-    for (auto e : h->arr.cev) if (e) cudaEventDestroy(e);
+
     for (auto e : h->sink_ev) cudaEventDestroy(e);
     if (h->sink_stream) cudaStreamDestroy(h->sink_stream);
     for (void* p : h->allocs) cudaFree(p);
@@ -1187,6 +1198,11 @@ int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned 
         for (auto t2 : h->arr_trace) cudaEventDestroy(t2);
         h->arr_trace.clear();
         if (h->ov.trace) mpqr_debug_dump_trace(h);
+    }
+    if (htrace) {
+        fprintf(stderr, "  host issue by category (ms): chain+side %.1f, finalize/G/T/W %.1f, in-block %.1f, accumulation %.1f, far (incl. distant) %.1f, sink %.1f, single-block panels %.1f\n",
+                g_host_prof[0], g_host_prof[1], g_host_prof[2], g_host_prof[3], g_host_prof[4], g_host_prof[6], g_host_prof[7]);
+        for (double& v : g_host_prof) v = 0;
     }
     if (htrace)
         fprintf(stderr, "mpqr_block_qr_host %dx%d: plan %.1f ms (%s), H2D %.1f, issue %.1f, wait+D2H %.1f, release %.1f, total %.1f\n",

@@ -52,6 +52,18 @@ struct SmBudget {
 };
 inline int sm_count(const DeviceInfo& di) { return g_sm_budget > 0 ? g_sm_budget : di.num_sms; }
 
+// Host-side issue profile (MPQR_HOST_TRACE=1): wall time the issuing thread spends per category of calls.
+//   0 chain kernel + side-stream items   1 finalize + Gram / T / W   2 in-block GEMMs   3 WY accumulation
+//   4 far updates   5 distant-chunk updates (streamed input)   6 D2H sink   7 panel (single block / classic flow)
+extern thread_local double g_host_prof[8];
+extern bool g_host_prof_on;
+struct HostProfScope {
+    int cat;
+    double t0;
+    explicit HostProfScope(int c);
+    ~HostProfScope();
+};
+
 // cudaFuncSetAttribute(func, attr, value) once per (function, attribute, device): function attributes are per device,
 // and the library is used on several devices from one process (host plan cache, TSQR lanes, multi-GPU tests).
 int func_attr_once(const void* func, cudaFuncAttribute attr, int value);

@@ -22,6 +22,8 @@
 //                             TMA reduce-add for split-K)
 // All global traffic goes through TMA; arbitrary (M,N,K) are handled by tensor-map bounds
 // (zero fill on load, clipping on store).
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace mpqr {
@@ -742,8 +744,40 @@ int get_encode(EncodeTiledFn* out) {
 
 // 2-D row-major tensor map: `cols` x `rows` elements visible (everything beyond is OOB: zero
 // on load, clipped on store), row pitch ld elements.
+// A tensor map depends only on these parameters; a factorisation repeated on the same plan and buffers (every bench step,
+// every call of the cached host plan) asks for the same ~7000 maps again, and cuTensorMapEncodeTiled is a noticeable part
+// of the host's issue time once the device chain is short (host issue 96 ms of a 140 ms factorisation in round 1).
+struct MapKey {
+    const void* base;
+    long cols, rows, ld;
+    int eb, bf, bc, br, swz;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && cols == o.cols && rows == o.rows && ld == o.ld && eb == o.eb && bf == o.bf && bc == o.bc && br == o.br && swz == o.swz;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        uint64_t h = (uint64_t)(uintptr_t)k.base * 0x9E3779B97F4A7C15ull;
+        h ^= ((uint64_t)k.cols * 0xBF58476D1CE4E5B9ull) ^ ((uint64_t)k.rows * 0x94D049BB133111EBull) ^ ((uint64_t)k.ld << 17);
+        h ^= (uint64_t)(k.eb | (k.bf << 4) | (k.bc << 8) | (k.br << 18) | (k.swz << 28));
+        return (size_t)(h ^ (h >> 29));
+    }
+};
+int make_map_uncached(CUtensorMap* map, const void* base, int elem_bytes, int is_bf16, long cols, long rows, long ld,
+                      int box_cols, int box_rows, CUtensorMapSwizzle swz);
 int make_map(CUtensorMap* map, const void* base, int elem_bytes, int is_bf16, long cols, long rows, long ld,
              int box_cols, int box_rows, CUtensorMapSwizzle swz) {
+    static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{base, cols, rows, ld, elem_bytes, is_bf16, box_cols, box_rows, (int)swz};
+    auto it = cache.find(key);
+    if (it != cache.end()) { *map = it->second; return MPQR_OK; }
+    MPQR_TRY(make_map_uncached(map, base, elem_bytes, is_bf16, cols, rows, ld, box_cols, box_rows, swz));
+    if (cache.size() > (1u << 16)) cache.clear();
+    cache.emplace(key, *map);
+    return MPQR_OK;
+}
+int make_map_uncached(CUtensorMap* map, const void* base, int elem_bytes, int is_bf16, long cols, long rows, long ld,
+                      int box_cols, int box_rows, CUtensorMapSwizzle swz) {
     EncodeTiledFn enc;
     MPQR_TRY(get_encode(&enc));
     if (((uintptr_t)base & 15) || ((ld * elem_bytes) & 15)) {

@@ -57,16 +57,15 @@ struct mpqr_handle {
         struct Pair {
             void* gP = nullptr;  // CUgreenCtx: panel partition
             void* gU = nullptr;  // CUgreenCtx: update partition
-            cudaStream_t sP = nullptr, sP2 = nullptr, sP3 = nullptr, sU = nullptr, sU2 = nullptr;  // sP2 (in-block rest), sP3 (chain side): more
-                                                                                                  // streams of the panel partition; sU2: distant columns (streamed input)
+            cudaStream_t sP = nullptr, sP2 = nullptr, sP3 = nullptr, sU = nullptr;  // sP2 (in-block rest), sP3 (chain side): more streams of the panel partition
             int nsmP = 0, nsmU = 0;
         };
         std::vector<Pair> pairs;
-        cudaStream_t sF = nullptr, sF2 = nullptr, sF3 = nullptr, sFd = nullptr;  // whole-device streams (intervals that are not worth splitting)
+        cudaStream_t sF = nullptr, sF2 = nullptr, sF3 = nullptr;  // whole-device streams (intervals that are not worth splitting)
         std::vector<cudaEvent_t> ev_rest;  // BlockCtx::rest_ev
         int nsm_full = 0;
         std::vector<cudaEvent_t> ev_bp, ev_fn, ev_fr;
-        cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_accdone = nullptr, ev_dist = nullptr;
+        cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_accdone = nullptr;
         std::vector<cudaEvent_t> ev_acc;  // per panel of an outer block: in-block update done -> WY accumulation may start
         // MPQR_TRACE=1: timed events around block_phase / far_next / far_rest of every interval
         bool trace = false;
@@ -77,8 +76,6 @@ struct mpqr_handle {
     void* S16r = nullptr;
     float* S32u = nullptr;  // scratch of the update stream (same shape as S32 / S16)
     void* S16u = nullptr;
-    float* S32d = nullptr;  // scratch of the distant-column stream (streamed host input)
-    void* S16d = nullptr;
     void* W16b = nullptr;   // second W buffer (blocks alternate) when the look-ahead driver is on
 
     // host sink (mpqr_block_qr_host): finished column blocks are copied back while later blocks compute

@@ -1939,6 +1939,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     const int next_cols = (chain && a.tail_stream && a.ev_chain && a.next_cols > 0 && (a.next_cols & 3) == 0 && a.next_cols <= 128) ? a.next_cols : 0;
     cudaStream_t ts = next_cols > 0 ? a.tail_stream : stream;
     if (chain) {
+        HostProfScope hp(0);
         if (!pick_shape(16, D, a.force_cs, a.force_rpt, &rpt, &cs)) { set_error("panel: sizing error D=%d", D); return MPQR_EINVAL; }
         const int nblocks = pw / 16;
         const int nfarb = next_cols > 0 ? nblocks : nblocks - 2;  // blocks with a side update
@@ -2021,6 +2022,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     if (a.dbg_caps) { a.dbg_caps[0] = max_cluster(); a.dbg_caps[1] = cs; a.dbg_caps[2] = rpt; }
     if (!need_t) return MPQR_OK;
 
+    HostProfScope hp1(1);
     const size_t tsmem = ((size_t)RMAX * TLD + 64 * 65) * sizeof(float);
     MPQR_TRY(func_attr_once((const void*)tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     const int Dz = D + zr;  // W is produced from the enclosing block's first row on (zero rows of Y give zero rows of W)
