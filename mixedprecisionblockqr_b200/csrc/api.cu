@@ -361,7 +361,7 @@ int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
         a.chain_side = h->chain_side; a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
-        a.chain_last_far = &h->chain_last_far; a.chain_buf = p & 1;
+        a.chain_last_far = &h->chain_last_far; a.chain_buf = p & 1; a.ev_start = h->chain_ev_start;
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         if (nt > 0) {
             float* A22 = A + (size_t)lam * lda + tau;
@@ -657,6 +657,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
         a.chain_side = c.chain_side ? c.chain_side : h->chain_side; a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
         a.chain_last_far = &h->chain_last_far;
+        a.ev_start = h->chain_ev_start;
         a.chain_buf = (int)(h->chain_panels++ & 1u);
         const int nin = c1 - tau;  // in-block trailing columns
         const int pidx = jc / r;
@@ -827,7 +828,8 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
         if ((rc = dev_alloc(h, (void**)&h->chain_flags, 64))) break;
         if (cudaMemset(h->chain_flags, 0, 64) != cudaSuccess) { set_error("memset failed"); rc = MPQR_ECUDA; break; }
         if (cudaStreamCreateWithFlags(&h->chain_side, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
-        if (cudaEventCreateWithFlags(&h->chain_ev_side, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); rc = MPQR_ECUDA; break; }
+        if (cudaEventCreateWithFlags(&h->chain_ev_side, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->chain_ev_start, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); rc = MPQR_ECUDA; break; }
         h->panel_ws_rows = m;
         if ((rc = dev_alloc(h, (void**)&h->panel_ws, panel_ws_bytes(m)))) break;
         const int wide = m > n ? m : n;
@@ -889,6 +891,7 @@ int mpqr_destroy(mpqr_handle* h) {
     overlap_destroy(h);
     if (h->chain_side) cudaStreamDestroy(h->chain_side);
     if (h->chain_ev_side) cudaEventDestroy(h->chain_ev_side);
+    if (h->chain_ev_start) cudaEventDestroy(h->chain_ev_start);
     for (auto e : h->arr.ev) cudaEventDestroy(e);
     if (h->arr.stream) cudaStreamDestroy(h->arr.stream);
 

@@ -150,6 +150,7 @@ struct PanelArgs {
     cudaStream_t tail_stream;
     cudaEvent_t ev_chain;     // recorded on `stream` behind the chain kernel
     cudaEvent_t ev_side;      // optional: recorded on chain_side behind the panel's last side update
+    cudaEvent_t ev_start;     // optional: recorded on `stream` in front of the cluster launch; holds back the first side kernel
 };
 // true if launch_panel will take the persistent chain flow for this panel
 bool panel_chain_ok(const PanelArgs& a);

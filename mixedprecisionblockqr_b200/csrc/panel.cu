@@ -91,6 +91,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void store16(void* base, long idx, float v, int bf16) {
     if (bf16) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
     else reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
@@ -773,11 +779,6 @@ __device__ __forceinline__ long long gtime_ns() {
 #define CHAIN_STAMP(k)                                                       \
     if (a.dbg && crank == 0 && tid == 0) a.dbg[jb * 8 + (k)] = gtime_ns();
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // Near update from shared memory.  ysl: this thread's Y_{jb-1} rows, float4 index (g * RPT + u) * NT + tid holds columns
 // 4g..4g+3 of row u.  gtT: T_{jb-1} (upper triangular, zeros below).  pred: NW x 256 floats, pslotP: CSMAX x 256.
@@ -1245,8 +1246,12 @@ template <int B> struct Su4 {
 template <int B>
 __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* __restrict__ Y, long ldy, const float* __restrict__ A,
                                                                   long lda, int D, int ncols, float* __restrict__ Srep,
-                                                                  unsigned* __restrict__ counter, const float* __restrict__ Tj,
+                                                                  const unsigned* gate, unsigned gate_want, const float* __restrict__ Tj,
                                                                   float* __restrict__ Sfin, int rows_per_cta, int ysm_floats) {
+    // gate != null (persistent panel chain): the kernel is issued ahead of its producer and every CTA waits here until
+    // the cluster has posted the register block whose reflectors it applies (flag >= gate_want).  In-kernel gating
+    // instead of a stream wait: cuStreamWaitValue32 / WriteValue32 cost the issuing thread ~30 us each on B200
+    // (12 per panel = 90-130 ms of host time per 32768^2 factorisation: the whole path became launch-bound).
     constexpr int NTHR = Su4<B>::NTHR, NWARP = NTHR / 32, RB = Su4<B>::RB;
     extern __shared__ __align__(16) float sm[];
     float* ysm = sm;               // rows_per_cta x B  (later: T, B x (B+4))
@@ -1257,8 +1262,13 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
     if (nrows > rows_per_cta) nrows = rows_per_cta;
     const int c0 = blockIdx.y * 128, col = c0 + 4 * lane;
     const bool on = col < ncols;
-    pdl_launch_dependents();
     pdl_wait();
+    if (gate) {
+        if (tid == 0)
+            while ((int)(ld_acquire_u32(gate) - gate_want) < 0) __nanosleep(128);
+        __syncthreads();
+    }
+    pdl_launch_dependents();
     const float* Ap = A + (size_t)r0 * lda + col;
     float4 a4[RB];
 #pragma unroll
@@ -1355,8 +1365,10 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
 
 template <int B>
 __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* __restrict__ Y, long ldy, float* __restrict__ A, long lda,
-                                                                  int D, int ncols, const float* __restrict__ Sfin, int nrep, int rows_per_cta) {
+                                                                  int D, int ncols, const float* __restrict__ Sfin, int nrep, int rows_per_cta,
+                                                                  unsigned* post, unsigned post_val, unsigned* ticket) {
     // Sfin: nrep replicas (stride RMAX * SLD) of S = T^T (Y^T A_rest), summed here
+    // post != null (persistent panel chain): the last CTA to finish publishes post_val (ticket counter, reset for the next launch)
     constexpr int NTHR = Su4<B>::NTHR, NWARP = NTHR / 32, RB = Su4<B>::RB;
     extern __shared__ __align__(16) float sm[];
     float* ysm = sm;
@@ -1390,8 +1402,7 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* _
         ysm[idx] = __ldcg(&Y[(size_t)(r0 + rr) * ldy + t]);
     }
     __syncthreads();
-    if (!on) return;
-    for (int rb = warp; rb < nrows; rb += NWARP * RB) {
+    for (int rb = warp; on && rb < nrows; rb += NWARP * RB) {
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
             const int r2 = rb + u * NWARP;
@@ -1417,6 +1428,18 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* _
         for (int u = 0; u < RB; ++u) {
             const int r2 = rb + NWARP * RB + u * NWARP;
             a4[u] = (r2 < nrows) ? __ldcg(reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    if (post) {
+        __threadfence();   // this thread's stores before the CTA's ticket
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned total = gridDim.x * gridDim.y;
+            if (atomicAdd(ticket, 1u) == total - 1) {
+                *ticket = 0u;          // (no CTA of this launch touches it again; the next launch is stream-ordered behind)
+                __threadfence();
+                atomicExch(post, post_val);
+            }
         }
     }
 }
@@ -1698,10 +1721,11 @@ int su_attrs() {
 
 template <int B>
 int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, float* Sfin,
-              int num_sms, cudaStream_t st, long* launches, const ProfHook* prof, bool pdl_first = true) {
-    // one wave of CTAs over the SMs this stream may use (up to 512 rows = 32 KB of staged Y per CTA);
+              int num_sms, cudaStream_t st, long* launches, const ProfHook* prof, bool pdl_first = true,
+              const unsigned* gate = nullptr, unsigned gate_want = 0, unsigned* post = nullptr, unsigned post_val = 0, unsigned* ticket = nullptr,
+              int max_rows = 512) {
+    // one wave of CTAs over the SMs this stream may use (up to max_rows rows = 32-64 KB of staged Y per CTA);
     // taller blocks take k balanced waves
-    const int max_rows = 512;
     const int waves = ceil_div(D, max_rows * num_sms);
     int rows = ceil_div(D, waves * num_sms);
     rows = round_up(rows < 16 ? 16 : rows, 16);
@@ -1721,16 +1745,15 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
         const size_t tree_floats = (size_t)(Su4<B>::NTHR / 32) * B * 64;
         if (s4_floats < tree_floats) s4_floats = tree_floats;
         cfg.dynamicSmemBytes = s4_floats * sizeof(float);
-        unsigned* counter = reinterpret_cast<unsigned*>(Srep + (size_t)NREP * RMAX * SLD);
         // pdl_first = false: the S kernel must not become resident (and hold its SMs idle) while the register-block
         // kernel before it is still running: those SMs belong to the side stream's updates during that time
         if (!pdl_first) cfg.numAttrs = 0;
-        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_s4_kernel<B>, Yj, ldy, (const float*)Arest, lda, D, ncols, Srep, counter, Tj, Sfin, rows,
+        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_s4_kernel<B>, Yj, ldy, (const float*)Arest, lda, D, ncols, Srep, gate, gate_want, Tj, Sfin, rows,
                                      ysm_floats));
         cfg.numAttrs = 1;
         if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st, 2.0 * D * ncols * B, 4.0 * D * (2 * ncols + B)); }
         cfg.dynamicSmemBytes = (size_t)rows * B * sizeof(float);
-        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_u4_kernel<B>, Yj, ldy, Arest, lda, D, ncols, (const float*)Srep, 2, rows));
+        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_u4_kernel<B>, Yj, ldy, Arest, lda, D, ncols, (const float*)Srep, 2, rows, post, post_val, ticket));
     } else {
         cfg.blockDim = dim3(512);
         cfg.dynamicSmemBytes = (size_t)((rows * B > 3 * B * 128) ? rows * B : 3 * B * 128) * sizeof(float);
@@ -1961,22 +1984,34 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         ca.srep[0] = SrepA; ca.srep[1] = SrepA + (size_t)2 * RMAX * SLD;
         ca.dbg = a.chain_dbg;
         MPQR_TRY(chain_preload());
+        if (a.ev_start) MPQR_CUDA(cudaEventRecord(a.ev_start, stream));   // everything before the cluster launch on this stream
         if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 4.0 * D * pw * 16 + 4.0 * D * 16 * 16 * (nblocks - 1), 8.0 * D * pw);
         MPQR_TRY(launch_chain(ca, rpt, cs, stream));  // issued BEFORE the side stream's waits (a wait never queues ahead of its producer)
         if (a.prof) a.prof->end(a.prof->ctx, stream);
         if (launches) *launches += 1;
         int side_sms = sm_count(di) - cs;  // the cluster keeps its SMs for the whole panel
         if (side_sms < 8) side_sms = 8;
+        // In-kernel ordering (default): the S kernel of block jb is issued ahead of time and its CTAs wait for the cluster's
+        // flag themselves, the U kernel's last CTA posts the side flag.  Waiting CTAs hold their SMs, so the side grids are
+        // capped at 32 CTAs (1024 rows each at D = 32768): the rest of the partition stays free for the tensor-core in-block
+        // updates of the rest stream.  The first S kernel of a panel is held back by an event until the stream reaches the
+        // cluster launch.  MPQR_MEMOPS=1 / MPQR_GATE_KERNEL=1: stream-level ordering (stream memory operations cost the
+        // issuing thread ~26 us each on B200: 12 per panel made the whole path launch-bound).
+        const bool inkernel = !getenv("MPQR_MEMOPS") && !getenv("MPQR_GATE_KERNEL");
+        if (inkernel && side_sms > 32) side_sms = 32;
+        if (inkernel && a.ev_start) MPQR_CUDA(cudaStreamWaitEvent(a.chain_side, a.ev_start, 0));
         for (int jb = 0; jb < nfarb; ++jb) {
             // block jb's reflectors -> the rest of the panel beyond block jb+1 and (next_cols) the whole next panel:
             // one contiguous column range
             const int j0 = jb * 16, Dj = D - j0;
             const int cfirst = (j0 + 32 < pw) ? j0 + 32 : pw;   // first column (panel-relative)
             const int nfar = pw - cfirst + next_cols;
-            MPQR_TRY(stream_wait_geq(a.chain_side, a.chain_flags, ca.base + (unsigned)(jb + 1)));
+            if (!inkernel) MPQR_TRY(stream_wait_geq(a.chain_side, a.chain_flags, ca.base + (unsigned)(jb + 1)));
             MPQR_TRY(launch_su<16>(Tsl + (size_t)jb * 256, Yp + (size_t)j0 * ldyp + j0, ldyp, Ablk + (size_t)j0 * a.lda + cfirst, a.lda, Dj,
-                                   nfar, ca.srep[jb & 1], w.Sfin, side_sms, a.chain_side, launches, a.prof, false));
-            MPQR_TRY(stream_post(a.chain_side, a.chain_flags + 1, ca.base + (unsigned)(jb + 1)));
+                                   nfar, ca.srep[jb & 1], w.Sfin, side_sms, a.chain_side, launches, a.prof, false,
+                                   inkernel ? a.chain_flags : nullptr, ca.base + (unsigned)(jb + 1),
+                                   inkernel ? a.chain_flags + 1 : nullptr, ca.base + (unsigned)(jb + 1), a.chain_flags + 2, inkernel ? 1024 : 512));
+            if (!inkernel) MPQR_TRY(stream_post(a.chain_side, a.chain_flags + 1, ca.base + (unsigned)(jb + 1)));
             if (a.chain_last_far) *a.chain_last_far = ca.base + (unsigned)(jb + 1);
         }
         if (next_cols > 0) {

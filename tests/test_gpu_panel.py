@@ -75,10 +75,11 @@ def test_panel_zero_column_and_signs():
 
 
 @pytest.mark.parametrize("m,n,lam,pw", [(2048, 128, 0, 128), (20000, 128, 0, 128), (5000, 256, 128, 128), (700, 64, 0, 64)])
-@pytest.mark.parametrize("mode", ["classic", "gate"])
+@pytest.mark.parametrize("mode", ["classic", "gate", "memops"])
 def test_panel_flows_agree(m, n, lam, pw, mode, monkeypatch):
-    # the persistent chain (default) is covered by the tests above; here the per-block launch flow it replaces
-    # (MPQR_NO_CHAIN=1: odd widths and unaligned shapes still take it) and the gate-kernel fallback of the side-stream
-    # ordering (MPQR_GATE_KERNEL=1: drivers without stream memory operations)
-    monkeypatch.setenv("MPQR_NO_CHAIN" if mode == "classic" else "MPQR_GATE_KERNEL", "1")
+    # the persistent chain with in-kernel ordering of the side updates (default) is covered by the tests above; here the
+    # per-block launch flow it replaces (MPQR_NO_CHAIN=1: odd widths and unaligned shapes still take it) and the two
+    # stream-level orderings of the side updates (MPQR_MEMOPS=1: cuStreamWaitValue32 / WriteValue32; MPQR_GATE_KERNEL=1:
+    # one-thread gate / post kernels)
+    monkeypatch.setenv({"classic": "MPQR_NO_CHAIN", "gate": "MPQR_GATE_KERNEL", "memops": "MPQR_MEMOPS"}[mode], "1")
     _check_panel(m, n, lam, pw, seed=m + 7 * pw, tol=5e-5)
