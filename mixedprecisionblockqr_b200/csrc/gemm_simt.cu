@@ -100,6 +100,154 @@ sgemm_kernel(const TI* __restrict__ X, long ldx, const TI* __restrict__ Z, long 
     }
 }
 
+
+// ---- FP32 fast path (16-byte aligned operands, M % 4 == N % 4 == 0): 128 x 128 tiles, BK = 16, 8 x 8 per thread as a
+// 2 x 2 arrangement of 4 x 4 sub-tiles (conflict-free LDS.128), global -> register prefetch of the next K slice while
+// the current one is multiplied.  The 64 x 64 kernel above stays as the general-shape / 16-bit-operand fallback.
+// [B200] TSQR and the FP32 driver were bound by the old kernel's ~12 TFLOP/s (4 x 4 micro-tile, scalar LDS).
+constexpr int FM = 128, FN = 128, FK = 16, FLD = FM + 4;
+
+template <bool TRANS_A, int MODE>
+__global__ void __launch_bounds__(256, 2)
+sgemm_fast_kernel(const float* __restrict__ X, long ldx, const float* __restrict__ Z, long ldz, float* __restrict__ C, long ldc,
+                  int M, int N, int K, int kchunk) {
+    __shared__ __align__(16) float Xs[2][FK][FLD];
+    __shared__ __align__(16) float Zs[2][FK][FLD];
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.y * FM, j0 = blockIdx.x * FN;
+    const int kbeg = blockIdx.z * kchunk;
+    const int kend = (kbeg + kchunk < K) ? kbeg + kchunk : K;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[8][8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[u][v] = 0.f;
+    float4 xr[2], zr[2];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int idx = tid + t * 256;
+            {   // Z / S tile: FK x FN, row k contiguous in j
+                const int kk = idx >> 5, j = (idx & 31) * 4;
+                const int gk = k0 + kk, gj = j0 + j;
+                zr[t] = (gk < kend && gj < N) ? *reinterpret_cast<const float4*>(Z + (size_t)gk * ldz + gj) : zero4;
+            }
+            if (TRANS_A) {
+                const int kk = idx >> 5, i = (idx & 31) * 4;
+                const int gk = k0 + kk, gi = i0 + i;
+                xr[t] = (gk < kend && gi < M) ? *reinterpret_cast<const float4*>(X + (size_t)gk * ldx + gi) : zero4;
+            } else {
+                const int i = idx >> 2, kq = (idx & 3) * 4;
+                const int gk = k0 + kq, gi = i0 + i;
+                xr[t] = (gk < kend && gi < M) ? *reinterpret_cast<const float4*>(X + (size_t)gi * ldx + gk) : zero4;
+            }
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int idx = tid + t * 256;
+            {
+                const int kk = idx >> 5, j = (idx & 31) * 4;
+                *reinterpret_cast<float4*>(&Zs[buf][kk][j]) = zr[t];
+            }
+            if (TRANS_A) {
+                const int kk = idx >> 5, i = (idx & 31) * 4;
+                *reinterpret_cast<float4*>(&Xs[buf][kk][i]) = xr[t];
+            } else {
+                const int i = idx >> 2, kq = (idx & 3) * 4;
+                Xs[buf][kq][i] = xr[t].x; Xs[buf][kq + 1][i] = xr[t].y; Xs[buf][kq + 2][i] = xr[t].z; Xs[buf][kq + 3][i] = xr[t].w;
+            }
+        }
+    };
+    fetch(kbeg);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += FK) {
+        const bool more = k0 + FK < kend;
+        if (more) fetch(k0 + FK);
+#pragma unroll
+        for (int kk = 0; kk < FK; ++kk) {
+            const float4 xa = *reinterpret_cast<const float4*>(&Xs[buf][kk][ty * 4]);
+            const float4 xb = *reinterpret_cast<const float4*>(&Xs[buf][kk][64 + ty * 4]);
+            const float4 za = *reinterpret_cast<const float4*>(&Zs[buf][kk][tx * 4]);
+            const float4 zb = *reinterpret_cast<const float4*>(&Zs[buf][kk][64 + tx * 4]);
+            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            const float zv[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) acc[u][v] = fmaf(xv[u], zv[v], acc[u][v]);
+        }
+        if (more) {
+            stash(buf ^ 1);   // (the other buffer: its readers finished before the barrier that ended the previous slice)
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int gi = i0 + (u < 4 ? ty * 4 + u : 64 + ty * 4 + (u - 4));
+        if (gi >= M) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int gj = j0 + h * 64 + tx * 4;
+            if (gj >= N) continue;
+            float* p = C + (size_t)gi * ldc + gj;
+            const float4 a4 = make_float4(acc[u][4 * h], acc[u][4 * h + 1], acc[u][4 * h + 2], acc[u][4 * h + 3]);
+            if (MODE == 0) {
+                *reinterpret_cast<float4*>(p) = a4;
+            } else if (MODE == 1) {
+                float4 c4 = *reinterpret_cast<const float4*>(p);
+                c4.x -= a4.x; c4.y -= a4.y; c4.z -= a4.z; c4.w -= a4.w;
+                *reinterpret_cast<float4*>(p) = c4;
+            } else {
+                atomicAdd(p, a4.x); atomicAdd(p + 1, a4.y); atomicAdd(p + 2, a4.z); atomicAdd(p + 3, a4.w);
+            }
+        }
+    }
+}
+
+inline bool fast_ok(const void* X, long ldx, const void* Z, long ldz, const void* C, long ldc, int M, int N) {
+    static const bool off = getenv("MPQR_SGEMM_OLD") != nullptr;
+    return !off && ((ldx | ldz | ldc) & 3) == 0 && ((M | N) & 3) == 0 && M >= 64 && N >= 64 &&
+           ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(C)) & 15) == 0;
+}
+
+int tn_fast(const float* X, long ldx, const float* Z, long ldz, float* S, long lds, int M, int N, int K, cudaStream_t stream) {
+    DeviceInfo di;
+    MPQR_TRY(get_device_info(&di));
+    const int tiles = ceil_div(M, FM) * ceil_div(N, FN);
+    int splits = 1;
+    if (K > 4 * FK) {
+        const int want = ceil_div(2 * sm_count(di), tiles);   // two CTAs per SM
+        const int maxs = ceil_div(K, 8 * FK);
+        splits = want < 1 ? 1 : (want > maxs ? maxs : want);
+    }
+    const int kchunk = round_up(ceil_div(K, splits), FK);
+    splits = ceil_div(K, kchunk);
+    dim3 grid(ceil_div(N, FN), ceil_div(M, FM), splits);
+    if (splits > 1) {
+        MPQR_CUDA(cudaMemset2DAsync(S, lds * sizeof(float), 0, (size_t)N * sizeof(float), M, stream));
+        sgemm_fast_kernel<true, 2><<<grid, 256, 0, stream>>>(X, ldx, Z, ldz, S, lds, M, N, K, kchunk);
+    } else {
+        sgemm_fast_kernel<true, 0><<<grid, 256, 0, stream>>>(X, ldx, Z, ldz, S, lds, M, N, K, kchunk);
+    }
+    MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+
+int nn_fast(const float* X, long ldx, const float* S, long lds, float* C, long ldc, int M, int N, int K, cudaStream_t stream, int store) {
+    dim3 grid(ceil_div(N, FN), ceil_div(M, FM), 1);
+    if (store) sgemm_fast_kernel<false, 0><<<grid, 256, 0, stream>>>(X, ldx, S, lds, C, ldc, M, N, K, K);
+    else sgemm_fast_kernel<false, 1><<<grid, 256, 0, stream>>>(X, ldx, S, lds, C, ldc, M, N, K, K);
+    MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+
 template <typename TI>
 int tn_any(const TI* X, long ldx, const TI* Z, long ldz, float* S, long lds, int M, int N, int K,
            cudaStream_t stream) {
@@ -140,7 +288,8 @@ int nn_any(const TI* X, long ldx, const TI* S, long lds, float* C, long ldc, TI*
 int sgemm_tn(const float* X, long ldx, const float* Z, long ldz, float* S, long lds, int M, int N,
              int K, cudaStream_t stream, long* launches) {
     if (M <= 0 || N <= 0) return MPQR_OK;
-    MPQR_TRY(tn_any<float>(X, ldx, Z, ldz, S, lds, M, N, K, stream));
+    if (fast_ok(X, ldx, Z, ldz, S, lds, M, N)) MPQR_TRY(tn_fast(X, ldx, Z, ldz, S, lds, M, N, K, stream));
+    else MPQR_TRY(tn_any<float>(X, ldx, Z, ldz, S, lds, M, N, K, stream));
     if (launches) *launches += 1;
     return MPQR_OK;
 }
@@ -148,7 +297,8 @@ int sgemm_tn(const float* X, long ldx, const float* Z, long ldz, float* S, long 
 int sgemm_nn_sub(const float* X, long ldx, const float* S, long lds, float* C, long ldc, int M,
                  int N, int K, cudaStream_t stream, long* launches) {
     if (M <= 0 || N <= 0 || K <= 0) return MPQR_OK;
-    MPQR_TRY(nn_any<float>(X, ldx, S, lds, C, ldc, nullptr, 0, M, N, K, stream));
+    if (fast_ok(X, ldx, S, lds, C, ldc, M, N) && (K & 3) == 0) MPQR_TRY(nn_fast(X, ldx, S, lds, C, ldc, M, N, K, stream, 0));
+    else MPQR_TRY(nn_any<float>(X, ldx, S, lds, C, ldc, nullptr, 0, M, N, K, stream));
     if (launches) *launches += 1;
     return MPQR_OK;
 }
@@ -157,6 +307,7 @@ int sgemm_nn_sub(const float* X, long ldx, const float* S, long lds, float* C, l
 int sgemm_nn_store(const float* X, long ldx, const float* S, long lds, float* C, long ldc, int M, int N, int K,
                    cudaStream_t stream) {
     if (M <= 0 || N <= 0) return MPQR_OK;
+    if (fast_ok(X, ldx, S, lds, C, ldc, M, N) && (K & 3) == 0) return nn_fast(X, ldx, S, lds, C, ldc, M, N, K, stream, 1);
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), 1);
     sgemm_kernel<false, 0, float><<<grid, GT, 0, stream>>>(X, ldx, S, lds, C, ldc, nullptr, 0, M, N, K, K);
     MPQR_CUDA(cudaGetLastError());
@@ -178,3 +329,13 @@ int simt16_gemm_nn(const void* X, long ldx, const void* S16, long lds16, float* 
 }
 
 }  // namespace mpqr
+
+// Tuning hook (tools/sgemm_time.py; not part of the public header): the FP32 GEMMs on their own.
+// op 0: S = X^T Z (X: K x M, Z: K x N)   1: C -= X S (X: M x K, S: K x N)   2: C = X S
+extern "C" int mpqr_debug_sgemm(int op, const float* X, long ldx, const float* Z, long ldz, float* C, long ldc, int M, int N, int K,
+                                void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (op == 0) return mpqr::sgemm_tn(X, ldx, Z, ldz, C, ldc, M, N, K, st, nullptr);
+    if (op == 1) return mpqr::sgemm_nn_sub(X, ldx, Z, ldz, C, ldc, M, N, K, st, nullptr);
+    return mpqr::sgemm_nn_store(X, ldx, Z, ldz, C, ldc, M, N, K, st);
+}

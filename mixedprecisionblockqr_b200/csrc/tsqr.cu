@@ -9,9 +9,10 @@
 //
 // The row blocks are independent: they are spread over up to 4 LANES (MPQR_TSQR_LANES) (stream + handle + buffers
 // each, SM budget = device / lanes), so several blocks' register-block clusters (16 SMs each) run
-// at the same time instead of one latency-bound panel chain.  Every block is factored ONCE: its
-// thin Q_b is formed right away into the output rows and multiplied by its n x n slice of the
-// stack's Q after the tree is known.
+// at the same time instead of one latency-bound panel chain.  Every block is factored ONCE and its
+// reflectors (Y_b, W_b: FP32, m x n each for the whole matrix) stay resident until the tree is known;
+// the thin Q rows of block b are then Q_b [Qstack_b; 0], i.e. the block's panels applied to its n x n
+// slice of the stack's Q instead of to the identity: one pass, no separate Q_b and no m x n x n product.
 #include <mutex>
 
 #include "internal.h"
@@ -48,19 +49,27 @@ int grid_of(long total) {
     return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));
 }
 
-// thin Q (rows x n) of a factored block: backward accumulation on [I_n; 0]
-int form_thin_q(mpqr_handle* h, float* Q, long ldq, cudaStream_t st) {
+// thin Q (rows x n) of a factored block: backward accumulation on [X; 0], X = I_n (seed == null) or the n x n
+// matrix `seed` (the block's slice of the stack's Q: the rows come out as Q_b [seed; 0]).  Y / W: the block's
+// reflectors (m x ld32, element (0, 0)).
+int form_thin_q(mpqr_handle* h, const float* Yall, const float* Wall, float* Q, long ldq, const float* seed, long ldseed, cudaStream_t st) {
     const int m = h->m, n = h->n;
     MPQR_CUDA(cudaMemset2DAsync(Q, ldq * sizeof(float), 0, (size_t)n * sizeof(float), m, st));
-    MPQR_TRY(set_identity(Q, ldq, n < m ? n : m, st));
+    if (seed) MPQR_CUDA(cudaMemcpy2DAsync(Q, ldq * sizeof(float), seed, ldseed * sizeof(float), (size_t)n * sizeof(float), n < m ? n : m,
+                                          cudaMemcpyDeviceToDevice, st));
+    else MPQR_TRY(set_identity(Q, ldq, n < m ? n : m, st));
     for (int p = h->npanels - 1; p >= 0; --p) {
         const int lam = p * h->r;
         const int pw = (lam + h->r < h->kmax) ? h->r : h->kmax - lam;
-        const int D = m - lam, nc = n - lam;
-        float* Y = h->Y32 + (size_t)lam * h->ld32 + lam;
-        float* W = h->W32 + (size_t)lam * h->ld32 + lam;
-        float* Qs = Q + (size_t)lam * ldq + lam;
-        MPQR_TRY(sgemm_tn(Y, h->ld32, Qs, ldq, h->S32, h->lds32, pw, nc, D, st, &h->launches));
+        const int D = m - lam;
+        // identity seed: columns left of lam are untouched by panel p; a dense seed fills all n columns
+        const int cofs = seed ? 0 : lam, nc = n - cofs;
+        // rows below n are still zero when the LAST panel is applied first: its product Y^T Q only needs rows lam .. n
+        const int Dk = (p == h->npanels - 1 && n - lam < D) ? n - lam : D;
+        const float* Y = Yall + (size_t)lam * h->ld32 + lam;
+        const float* W = Wall + (size_t)lam * h->ld32 + lam;
+        float* Qs = Q + (size_t)lam * ldq + cofs;
+        MPQR_TRY(sgemm_tn(Y, h->ld32, Qs, ldq, h->S32, h->lds32, pw, nc, Dk, st, &h->launches));
         MPQR_TRY(sgemm_nn_sub(W, h->ld32, h->S32, h->lds32, Qs, ldq, D, nc, pw, st, &h->launches));
     }
     return MPQR_OK;
@@ -70,7 +79,6 @@ struct Lane {
     cudaStream_t s = nullptr;   // own stream (always: a plan outlives the caller's stream)
     cudaEvent_t done = nullptr;
     float* work = nullptr;   // (hrows + 1) x ldp packed factor of the current block
-    float* qblk = nullptr;   // hrows x ldp thin Q of the current block (pass 2 source)
     mpqr_handle* hb = nullptr;
     mpqr_handle* hl = nullptr;  // handle of the (shorter) last block, on the lane that owns it
 };
@@ -95,19 +103,21 @@ struct Plan {
     int budget = 0;
     std::vector<Lane> lanes;
     float *rstack = nullptr, *qstack = nullptr;
+    float *Yall = nullptr, *Wall = nullptr;   // nblk x hrows x ld32 each: every block's reflectors (with-Q plans, nblk > 1)
+    long ld32 = 0;
     cudaEvent_t ev_start = nullptr, ev_tree = nullptr;
     bool busy = false;  // a recursive call never shares its caller's plan (different m), but be explicit
     ~Plan() {
         for (auto& L : lanes) {
             if (L.hb) mpqr_destroy(L.hb);
             if (L.hl) mpqr_destroy(L.hl);
-            cudaFree(L.work); cudaFree(L.qblk);
+            cudaFree(L.work);
             if (L.done) cudaEventDestroy(L.done);
             if (L.s) cudaStreamDestroy(L.s);
         }
         if (ev_start) cudaEventDestroy(ev_start);
         if (ev_tree) cudaEventDestroy(ev_tree);
-        cudaFree(rstack); cudaFree(qstack);
+        cudaFree(rstack); cudaFree(qstack); cudaFree(Yall); cudaFree(Wall);
     }
 };
 std::mutex g_plans_mu;
@@ -115,7 +125,7 @@ std::vector<Plan*> g_plans;
 constexpr size_t kMaxPlans = 8;
 
 int build_plan(Plan* P, const DeviceInfo& di) {
-    const long HMAX = 32768;
+    static const long HMAX = (getenv("MPQR_TSQR_HMAX") && atol(getenv("MPQR_TSQR_HMAX")) >= 1024 && atol(getenv("MPQR_TSQR_HMAX")) <= 32768) ? atol(getenv("MPQR_TSQR_HMAX")) : 32768;   // tuning knob: leaf height
     const long m = P->m;
     const int n = P->n;
     const int r = n < 128 ? n : 128;
@@ -135,12 +145,16 @@ int build_plan(Plan* P, const DeviceInfo& di) {
         cudaEventCreateWithFlags(&P->ev_tree, cudaEventDisableTiming) != cudaSuccess) { set_error("tsqr: event creation failed"); return MPQR_ECUDA; }
     if (nblk > 1 && cudaMalloc(&P->rstack, (size_t)nblk * n * ldp * sizeof(float)) != cudaSuccess) return fail_alloc();
     if (nblk > 1 && P->with_q && cudaMalloc(&P->qstack, (size_t)nblk * n * ldp * sizeof(float)) != cudaSuccess) return fail_alloc();
+    P->ld32 = round_up(n, 4);   // = the FP32 driver's ld32 with MPQR_KEEP_WY (kmax = n for every block)
+    if (nblk > 1 && P->with_q) {
+        if (cudaMalloc(&P->Yall, (size_t)nblk * hrows * P->ld32 * sizeof(float)) != cudaSuccess) return fail_alloc();
+        if (cudaMalloc(&P->Wall, (size_t)nblk * hrows * P->ld32 * sizeof(float)) != cudaSuccess) return fail_alloc();
+    }
     for (int l = 0; l < P->NL; ++l) {
         Lane& L = P->lanes[l];
         if (cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking) != cudaSuccess) { set_error("tsqr: stream creation failed"); return MPQR_ECUDA; }
         if (cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming) != cudaSuccess) { set_error("tsqr: event creation failed"); return MPQR_ECUDA; }
         if (cudaMalloc(&L.work, (size_t)(hrows + 1) * ldp * sizeof(float)) != cudaSuccess) return fail_alloc();
-        if (P->with_q && nblk > 1 && cudaMalloc(&L.qblk, (size_t)hrows * ldp * sizeof(float)) != cudaSuccess) return fail_alloc();
         MPQR_TRY(mpqr_create(&L.hb, (int)hrows, n, r, 0, flags));
         if (P->hlast != hrows && (int)((nblk - 1) % P->NL) == l) MPQR_TRY(mpqr_create(&L.hl, (int)P->hlast, n, r, 0, flags));
     }
@@ -190,21 +204,29 @@ int run_plan(Plan* P, const float* dA, long lda, float* dQ, long ldq, float* dR,
     int rc = MPQR_OK;
     MPQR_CUDA(cudaEventRecord(P->ev_start, st));
     for (auto& L : lanes) MPQR_CUDA(cudaStreamWaitEvent(L.s, P->ev_start, 0));
-    // Pass 1: every block is factored once; R_b goes to the stack.  A lane's buffers are reused block after
-    // block, so the block's thin Q_b (rows x n) is parked in the OUTPUT rows until the tree is known.
+    // Pass 1: every block is factored once; R_b goes to the stack, the block's reflectors into its slice of Yall / Wall
+    // (the handle's own Y32 / W32 pointers are redirected for the call: same layout, ld32).
     for (long b = 0; b < nblk && rc == MPQR_OK; ++b) {
         Lane& L = lanes[b % NL];
         SmBudget sb(budget);
         const long rows = (b == nblk - 1) ? hlast : hrows;
         mpqr_handle* h = (rows == hrows) ? L.hb : L.hl;
         copy_block_kernel<<<grid_of(rows * n), 256, 0, L.s>>>(dA + (size_t)b * hrows * lda, lda, L.work, ldp, rows, n);
-        if ((rc = mpqr_factor_device(h, L.work, ldp, L.s))) break;
+        float *y0 = h->Y32, *w0 = h->W32;
+        if (P->Yall) {
+            if (h->ld32 != P->ld32) { set_error("tsqr: internal layout mismatch"); return MPQR_ESTATE; }
+            h->Y32 = P->Yall + (size_t)b * hrows * P->ld32;
+            h->W32 = P->Wall + (size_t)b * hrows * P->ld32;
+        }
+        rc = mpqr_factor_device(h, L.work, ldp, L.s);
+        const float *yb = h->Y32, *wb = h->W32;
+        h->Y32 = y0; h->W32 = w0;
+        if (rc) break;
         if (nblk == 1) {
             extract_r_kernel<<<grid_of((long)n * n), 256, 0, L.s>>>(L.work, ldp, dR, ldr, n);
-            if (dQ) rc = form_thin_q(h, dQ, ldq, L.s);
+            if (dQ) rc = form_thin_q(h, yb, wb, dQ, ldq, nullptr, 0, L.s);
         } else {
             extract_r_kernel<<<grid_of((long)n * n), 256, 0, L.s>>>(L.work, ldp, P->rstack + (size_t)b * n * ldp, ldp, n);
-            if (dQ) rc = form_thin_q(h, dQ + (size_t)b * hrows * ldq, ldq, L.s);
         }
     }
     // join the lanes on the caller's stream
@@ -213,16 +235,16 @@ int run_plan(Plan* P, const float* dA, long lda, float* dQ, long ldq, float* dR,
     // factor the stacked R's ((nblk*n) x n) — recursion handles a tall stack
     MPQR_TRY(mpqr_tsqr_device(P->rstack, ldp, nblk * (long)n, n, dQ ? P->qstack : nullptr, ldp, dR, ldr, st));
     if (!dQ) return MPQR_OK;
-    // Pass 2: thin Q rows of block b = Q_b[:, :n] * Qstack[b*n:(b+1)*n, :]   (Q_b parked in the output rows)
+    // Pass 2: thin Q rows of block b = Q_b [Qstack[b*n:(b+1)*n, :]; 0]
     MPQR_CUDA(cudaEventRecord(P->ev_tree, st));
     for (auto& L : lanes) MPQR_CUDA(cudaStreamWaitEvent(L.s, P->ev_tree, 0));
     for (long b = 0; b < nblk && rc == MPQR_OK; ++b) {
         Lane& L = lanes[b % NL];
         SmBudget sb(budget);
         const long rows = (b == nblk - 1) ? hlast : hrows;
-        float* Qb = dQ + (size_t)b * hrows * ldq;
-        copy_block_kernel<<<grid_of(rows * n), 256, 0, L.s>>>(Qb, ldq, L.qblk, ldp, rows, n);
-        rc = sgemm_nn_store(L.qblk, ldp, P->qstack + (size_t)b * n * ldp, ldp, Qb, ldq, (int)rows, n, n, L.s);
+        mpqr_handle* h = (rows == hrows) ? L.hb : L.hl;
+        rc = form_thin_q(h, P->Yall + (size_t)b * hrows * P->ld32, P->Wall + (size_t)b * hrows * P->ld32, dQ + (size_t)b * hrows * ldq, ldq,
+                         P->qstack + (size_t)b * n * ldp, ldp, L.s);
     }
     for (auto& L : lanes) { cudaEventRecord(L.done, L.s); cudaStreamWaitEvent(st, L.done, 0); }
     return rc;
