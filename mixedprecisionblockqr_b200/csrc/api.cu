@@ -145,6 +145,16 @@ int grid_for(long total) {
 
 }  // namespace
 
+int preload_util_kernels() {
+    const void* fns[] = {(const void*)fill_uniform_kernel, (const void*)convert_kernel<__half>, (const void*)convert_kernel<__nv_bfloat16>,
+                         (const void*)identity_kernel, (const void*)zero16_kernel};
+    for (const void* f : fns) {
+        cudaFuncAttributes fa;
+        MPQR_CUDA(cudaFuncGetAttributes(&fa, f));
+    }
+    return MPQR_OK;
+}
+
 int fill_uniform(float* A, long lda, long n_total, long row0, long rows, long col0, long cols, uint64_t seed,
                  cudaStream_t stream) {
     if (rows <= 0 || cols <= 0) return MPQR_OK;
@@ -503,6 +513,9 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         c.chain_side = s_bp3;
         if (inblock_la) {
             c.rest_stream = s_bp2; c.rest_S32 = h->S32r; c.rest_S16 = h->S16r; c.rest_ev = o.ev_rest.data();
+            // leave the cluster (16 SMs) and a share for its side updates free
+            static const int rest_keep = getenv("MPQR_REST_KEEP") ? atoi(getenv("MPQR_REST_KEEP")) : 32;   // SMs kept free of rest-stream GEMMs
+            c.rest_sms = nsm_bp - rest_keep >= 24 ? nsm_bp - rest_keep : (nsm_bp >= 40 ? nsm_bp - 16 : 0);
             // (the previous block's last rest event completed before fn(b-1), which this block waits for)
         }
         // WY accumulation of this block (only the far update needs it): on the update partition of the previous
@@ -511,7 +524,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         cudaStream_t s_acc = defer_u ? s_uprev : (inblock_la ? s_bp2 : nullptr);
         if (s_acc) {
             c.acc_stream = s_acc;
-            c.acc_sms = defer_u ? (nsm_uprev == o.nsm_full ? 0 : nsm_uprev) : (nsm_bp == o.nsm_full ? 0 : nsm_bp);
+            c.acc_sms = defer_u ? (nsm_uprev == o.nsm_full ? 0 : nsm_uprev) : (c.rest_sms > 0 ? c.rest_sms : (nsm_bp == o.nsm_full ? 0 : nsm_bp));
             c.acc_S32 = defer_u ? h->S32u : h->S32r; c.acc_S16 = defer_u ? h->S16u : h->S16r; c.acc_ev = o.ev_acc.data();
         }
         const bool defer_acc = s_acc != nullptr;
@@ -667,6 +680,17 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         // and the WY accumulation follow on `rest_stream` with a panel's time of slack.
         const bool cover = chain && c.rest_stream && c.rest_ev && c.acc_stream && nin >= r && (r % 8) == 0 && getenv("MPQR_COVER");   // EXPERIMENTAL, off: see DESIGN 7 (needs the second side stream)
         if (cover) { a.next_cols = r; a.tail_stream = c.rest_stream; a.ev_chain = c.rest_ev[2 * pidx]; a.ev_side = h->chain_ev_side; }
+        // the next panel's columns on the panel stream, the rest of the block on `rest_stream` (same SM partition) next
+        // to the next panel's chain kernel
+        const bool split = !cover && c.rest_stream && nin > r && (r % 8) == 0;
+        // Merged Gram / next-panel product (PanelArgs::gs_ncols): the panel's T kernel leaves S = T^T Y^T A_next in S16, the
+        // in-block update of the next panel's columns is one NN GEMM, and W = Y T (only the rest of the block, the WY
+        // accumulation and the far update need it) moves to the rest stream.  Needs Y in the shadow's dead columns.
+        static const bool no_merge = getenv("MPQR_NO_GS_MERGE") != nullptr;
+        const bool y_in_shadow = c.Y16 == (void*)at16(c.Ah, c.ldh, c0, c.acol0) && c.ldy == c.ldh;
+        const bool merged = !no_merge && !cover && !h->prof && y_in_shadow && nin > 0 && (split || nin <= r) && (r % 8) == 0 && (pw % 8) == 0 &&
+                            (h->lds16 % 8) == 0;
+        if (merged) { a.gs_ncols = nin < r ? nin : r; a.gs_S16 = S16; a.gs_lds16 = h->lds16; a.defer_w = 1; }
         // earlier panels' updates of THIS panel's columns: panels <= p-2 through their rest updates (rest stream, in order);
         // panel p-1 through its in-block update on this stream, or through its side updates (flag inside a chain kernel,
         // the side event for any other kernel)
@@ -691,17 +715,28 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
                             at16(c.Ah, c.ldh, lam, acol_tau + ofs), c.ldh, D, nc, pw, bf, pad_ok, st, &h->launches));
             return MPQR_OK;
         };
-        // the next panel's columns on the panel stream, the rest of the block on `rest_stream` (same SM partition) next
-        // to the next panel's chain kernel
-        const bool split = !cover && c.rest_stream && nin > r && (r % 8) == 0;
+        // the merged flow's in-block update of the next panel's columns: S is already in S16
+        auto inblock_nn_only = [&](int nc, int pad_ok, cudaStream_t st) -> int {
+            HostProfScope hp(2);
+            return tc_gemm_nn(Ypp, c.ldy, S16, h->lds16, c.A + (size_t)lam * c.lda + acol_tau, c.lda, at16(c.Ah, c.ldh, lam, acol_tau), c.ldh,
+                              D, nc, pw, bf, pad_ok, st, &h->launches);
+        };
         if (c.rest_stream && nin > 0) { last_rest = 2 * pidx + 1; rest_rec[pidx] = true; }
         if (cover) {
             // (launch_panel queued finalize and Gram / T / W on the rest stream behind the chain kernel)
-            if (nin - r > 0) MPQR_TRY(inblock(r, nin - r, c.rest_S32, c.rest_S16, end_is_matrix_end, c.rest_stream));
+            if (nin - r > 0) {
+                SmBudget rb(c.rest_sms > 0 ? c.rest_sms : g_sm_budget);
+                MPQR_TRY(inblock(r, nin - r, c.rest_S32, c.rest_S16, end_is_matrix_end, c.rest_stream));
+            }
             MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], c.rest_stream));
         } else if (nin > 0 && !split) {
             if (c.rest_stream && pidx > 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (pidx - 1) + 1], 0));
-            MPQR_TRY(inblock(0, nin, S32, S16, end_is_matrix_end, st));
+            if (merged) {
+                MPQR_TRY(inblock_nn_only(nin, end_is_matrix_end, st));
+                MPQR_TRY(panel_form_w(a, st, &h->launches));
+            } else {
+                MPQR_TRY(inblock(0, nin, S32, S16, end_is_matrix_end, st));
+            }
             if (c.rest_stream) MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], st));
         } else if (nin > 0) {
             // the rest of the block on the second stream (it only needs this panel's Y, W and the previous rest)
@@ -709,8 +744,26 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             MPQR_CUDA(cudaStreamWaitEvent(c.rest_stream, c.rest_ev[2 * pidx], 0));
             // the next panel's columns were last written by the previous panel's rest update
             if (pidx > 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (pidx - 1) + 1], 0));
-            MPQR_TRY(inblock(0, r, S32, S16, 0, st));
-            MPQR_TRY(inblock(r, nin - r, c.rest_S32, c.rest_S16, end_is_matrix_end, c.rest_stream));
+            if (merged) MPQR_TRY(inblock_nn_only(r, 0, st));
+            else MPQR_TRY(inblock(0, r, S32, S16, 0, st));
+            {
+                // the rest-of-block GEMMs start once the NEXT panel's cluster is resident (they would keep it from being placed)
+                // [B200, r2p] EXPERIMENTAL, off: the cluster then starts at once (gap between two chain kernels 184 -> 111 us at
+                // 32768 rows), but the rest GEMMs now run next to its side updates and slow them down by as much; the whole
+                // factorisation is far-update-bound in those intervals anyway (114.1-114.8 ms either way).  MPQR_REST_GATE=1.
+                static const bool rest_gate = getenv("MPQR_REST_GATE") != nullptr;
+                if (rest_gate && chain) {
+                    PanelArgs nx = a;
+                    nx.lam = tau; nx.acol = c.acol0 + jc + pw; nx.pw = (tau + r < c1) ? r : c1 - tau;
+                    nx.gs_ncols = 0; nx.defer_w = 0;
+                    if (panel_chain_ok(nx)) MPQR_TRY(chain_wait_started(c.rest_stream, h->chain_flags, h->chain_ctr));
+                }
+            }
+            {
+                SmBudget rb(c.rest_sms > 0 ? c.rest_sms : g_sm_budget);
+                if (merged) MPQR_TRY(panel_form_w(a, c.rest_stream, &h->launches));
+                MPQR_TRY(inblock(r, nin - r, c.rest_S32, c.rest_S16, end_is_matrix_end, c.rest_stream));
+            }
             MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], c.rest_stream));
         }
         prev_cover = cover;
@@ -791,6 +844,7 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
     }
     DeviceInfo di;
     MPQR_TRY(get_device_info(&di));
+    MPQR_TRY(chain_preload_all());   // (once per device)
     mpqr_handle* h = new mpqr_handle();
     h->m = m; h->n = n; h->flags = flags; h->prec = (int)prec;
     h->keep_wy = (flags & MPQR_KEEP_WY) != 0;
@@ -799,8 +853,9 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
     {
         // The packed result does not depend on the panel grouping beyond rounding, so a narrow caller r (the reference's
         // r = 16 / 32 / 64) is widened to a multiple of it near 128: fewer, better filled panels.
+        // On by default (MPQR_MIN_R=0 keeps the caller's r): [B200] 2048^2 r = 32: 5.6 -> 3.7 ms, 4096 x 16384 r = 64: 8.2 -> 7.4 ms.
         const char* e = getenv("MPQR_MIN_R");
-        const int min_r = e ? atoi(e) : 0;
+        const int min_r = e ? atoi(e) : kPanelMaxWidth;
         if (min_r > h->r && min_r <= kPanelMaxWidth) h->r = (min_r / h->r) * h->r;
     }
     if (h->r > h->kmax) h->r = h->kmax;

@@ -151,7 +151,25 @@ struct PanelArgs {
     cudaEvent_t ev_chain;     // recorded on `stream` behind the chain kernel
     cudaEvent_t ev_side;      // optional: recorded on chain_side behind the panel's last side update
     cudaEvent_t ev_start;     // optional: recorded on `stream` in front of the cluster launch; holds back the first side kernel
+    // Merged Gram / next-panel product (mixed path; the 16-bit Y lives in the dead columns of the operand shadow, so the
+    // gs_ncols columns right of the panel in the SAME array are the shadow of the next panel's columns): ONE TN GEMM gives
+    // [G | Sy] = Y^T [Y | A_next], the T kernel also writes S = T^T Sy (16-bit, gs_S16: gs_ncols columns, ld gs_lds16),
+    // which is what the in-block update A_next -= Y S needs -- W = Y T is not on the way to the next panel any more.
+    int gs_ncols;             // 0: plain Gram
+    void* gs_S16;
+    long gs_lds16;
+    int defer_w;              // 1: launch_panel does not form W; the caller issues panel_form_w (any stream behind `stream`)
 };
+// W = Y T of a panel factored with defer_w (same arguments; mixed path)
+int panel_form_w(const PanelArgs& a, cudaStream_t stream, long* launches);
+int chain_wait_started(cudaStream_t st, unsigned* chain_flags, unsigned next_base);
+// CUDA loads kernels lazily and a first-time load may need the device to drain: while a gate kernel / the cluster spins on
+// a flag that a later launch has to satisfy, that load would never return.  Every kernel a factorisation can launch is
+// therefore loaded (and given its attributes) before the first one is issued on a device (chain_preload, panel.cu).
+int preload_tc_gemm();
+int preload_simt_gemm();
+int preload_util_kernels();
+int chain_preload_all();
 // true if launch_panel will take the persistent chain flow for this panel
 bool panel_chain_ok(const PanelArgs& a);
 size_t panel_ws_bytes(long max_rows);

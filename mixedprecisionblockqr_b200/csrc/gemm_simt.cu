@@ -285,6 +285,23 @@ int nn_any(const TI* X, long ldx, const TI* S, long lds, float* C, long ldc, TI*
 
 }  // namespace
 
+int preload_simt_gemm() {
+    const void* fns[] = {
+        (const void*)sgemm_fast_kernel<true, 0>, (const void*)sgemm_fast_kernel<true, 2>, (const void*)sgemm_fast_kernel<false, 0>,
+        (const void*)sgemm_fast_kernel<false, 1>,
+        (const void*)sgemm_kernel<true, 0, float>, (const void*)sgemm_kernel<true, 2, float>, (const void*)sgemm_kernel<false, 0, float>,
+        (const void*)sgemm_kernel<false, 1, float>,
+        (const void*)sgemm_kernel<true, 0, __half>, (const void*)sgemm_kernel<true, 2, __half>, (const void*)sgemm_kernel<false, 0, __half>,
+        (const void*)sgemm_kernel<false, 1, __half>,
+        (const void*)sgemm_kernel<true, 0, __nv_bfloat16>, (const void*)sgemm_kernel<true, 2, __nv_bfloat16>,
+        (const void*)sgemm_kernel<false, 0, __nv_bfloat16>, (const void*)sgemm_kernel<false, 1, __nv_bfloat16>};
+    for (const void* f : fns) {
+        cudaFuncAttributes fa;
+        MPQR_CUDA(cudaFuncGetAttributes(&fa, f));
+    }
+    return MPQR_OK;
+}
+
 int sgemm_tn(const float* X, long ldx, const float* Z, long ldz, float* S, long lds, int M, int N,
              int K, cudaStream_t stream, long* launches) {
     if (M <= 0 || N <= 0) return MPQR_OK;

@@ -827,6 +827,22 @@ int launch2(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
     MPQR_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm2_kernel<kAMN, kEpi>, tA, tB, tC, tH, p, fmt16));
     return MPQR_OK;
 }
+}  // namespace
+int preload_tc_gemm() {
+    EncodeTiledFn enc;
+    MPQR_TRY(get_encode(&enc));
+    MPQR_TRY(func_attr_once((const void*)tc_gemm_kernel<256, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+    MPQR_TRY(func_attr_once((const void*)tc_gemm_kernel<128, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
+    MPQR_TRY(func_attr_once((const void*)tc_gemm_kernel<256, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+    MPQR_TRY(func_attr_once((const void*)tc_gemm_kernel<128, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
+    MPQR_TRY(func_attr_once((const void*)tc_gemm_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+    MPQR_TRY(func_attr_once((const void*)tc_gemm_kernel<128, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
+    MPQR_TRY(func_attr_once((const void*)tc_gemm2_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
+    MPQR_TRY(func_attr_once((const void*)tc_gemm2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
+    MPQR_TRY(func_attr_once((const void*)tc_gemm2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
+    return MPQR_OK;
+}
+namespace {
 // 2-CTA kernel: worth it from two 128-row tiles on (MPQR_GEMM_1CTA=1 keeps the one-CTA kernel: A/B comparisons)
 inline bool use_2cta(int M, int N) { return M > BM && N > 128 && !getenv("MPQR_GEMM_1CTA"); }
 

@@ -209,6 +209,9 @@ struct BlockCtx {
     float* rest_S32;           // its GEMM scratch (r x lds32)
     void* rest_S16;
     cudaEvent_t* rest_ev;      // 2 events per panel: [2p] panel factored, [2p+1] rest of panel p's in-block update done
+    int rest_sms;              // SM budget of the GEMMs issued on rest_stream (0: the caller's budget).  They run NEXT TO the
+                               // next panel's cluster and its side updates: a persistent GEMM grid over the whole partition
+                               // kept the 16-CTA cluster waiting for ~47 us per panel at 32768 rows (profiles/r2_timeline_c4.txt)
     cudaStream_t chain_side;   // side stream of the persistent panel chain (null: the handle's own)
 };
 // panels + in-block updates + WY accumulation of block [c0, c1); `ncols_in` = columns of A

@@ -761,6 +761,7 @@ struct ChainArgs {
     float* Tslots;   // block jb's T at Tslots + jb * tstride (16 x 16, ld 16)
     int tstride;
     unsigned* flag_done;
+    unsigned* flag_started;  // optional: base + 1 as soon as the cluster is resident (gates work that would keep it from being placed)
     const unsigned* flag_far;
     unsigned base;
     float* srep[2];  // S replica pairs of the far updates (blocks alternate); the cluster clears rows 0..15 of both replicas of
@@ -904,6 +905,7 @@ __global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS)
         cluster_sync_all();
     }
     pdl_wait();
+    if (a.flag_started && crank == 0 && tid == 0) atomicExch(a.flag_started, a.base + 1u);
 
     long long dummy_acc[1];
     long long dummy_prev = 0;
@@ -1009,10 +1011,7 @@ __global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS)
         CHAIN_STAMP(6);
         __threadfence();
         if (CS > 1) cluster_sync_all(); else __syncthreads();
-        if (crank == 0 && tid == 0) {
-            atomicExch(a.flag_done, a.base + (unsigned)(jb + 1));
-            __threadfence_system();
-        }
+        if (crank == 0 && tid == 0) atomicExch(a.flag_done, a.base + (unsigned)(jb + 1));   // (ordered behind every CTA's fenced stores by the barrier)
         CHAIN_STAMP(7);
     }
     // shared memory must stay alive until no peer can signal into it any more (the last cluster barrier above covers it)
@@ -1450,13 +1449,22 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* _
 // (ldg); T goes to T32 (pw x pw, zero below the diagonal) and optionally to a 16-bit copy.
 constexpr int TLD = RMAX + 1;
 __global__ void __launch_bounds__(1024) tinv_kernel(const float* __restrict__ G, long ldg, int pw, float* __restrict__ T32, int ldt,
-                                                     void* __restrict__ T16, long ldt16, int bf16) {
+                                                    void* __restrict__ T16, long ldt16, int bf16, const float* Sy, long ldsy, int ns,
+                                                    void* __restrict__ S16, long lds16) {
+    // Sy != null: also S = T^T Sy (pw x ns, ns <= RMAX; Sy FP32 with ld ldsy) -> S16 (16-bit, ld lds16)
     extern __shared__ __align__(16) float sm[];
     float* Ts = sm;               // RMAX x TLD
     float* Xs = sm + RMAX * TLD;  // 64 x 65 temp
+    float* Ss = Xs + 64 * 65;     // pw x RMAX: Sy (only when Sy != null)
     const int tid = threadIdx.x;
     pdl_launch_dependents();
     pdl_wait();
+    if (Sy) {
+        for (int idx = tid; idx < pw * RMAX; idx += 1024) {
+            const int t = idx / RMAX, c = idx - t * RMAX;
+            Ss[idx] = (c < ns) ? __ldcg(&Sy[(size_t)t * ldsy + c]) : 0.f;
+        }
+    }
     int R = 16;
     while (R < pw) R *= 2;
     for (int idx = tid; idx < R * R; idx += 1024) {
@@ -1547,6 +1555,34 @@ __global__ void __launch_bounds__(1024) tinv_kernel(const float* __restrict__ G,
         const float v = (t <= c) ? Ts[t * TLD + c] : 0.f;
         if (T32) T32[(size_t)t * ldt + c] = v;
         if (T16) store16(T16, (long)t * ldt16 + c, v, bf16);
+    }
+    if (Sy) {
+        // S[a][c] = sum_{b <= a} T[b][a] Sy[b][c]: thread = 4 rows a x 4 columns c (one LDS.128 of Sy and four broadcast
+        // reads of T per 16 FMAs; the first version, 16 rows x 1 column per thread, was bound by 2048 LDS per thread: +17 us)
+        const int c4 = 4 * (tid & 31), a4 = 4 * (tid >> 5);
+        if (a4 < pw) {
+            float v[4][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.f;
+            const int bmax = (a4 + 4 < pw) ? a4 + 4 : pw;   // T is zero below its diagonal
+#pragma unroll 4
+            for (int b = 0; b < bmax; ++b) {
+                const float4 sy = *reinterpret_cast<const float4*>(&Ss[b * RMAX + c4]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float t = Ts[b * TLD + a4 + q];
+                    v[q][0] = fmaf(t, sy.x, v[q][0]); v[q][1] = fmaf(t, sy.y, v[q][1]);
+                    v[q][2] = fmaf(t, sy.z, v[q][2]); v[q][3] = fmaf(t, sy.w, v[q][3]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (a4 + q < pw) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (c4 + k < ns) store16(S16, (long)(a4 + q) * lds16 + c4 + k, v[q][k], bf16);
+                }
+        }
     }
 }
 
@@ -1695,18 +1731,19 @@ Ws carve(float* ws, long rows) {
     w.Wj = w.Tsl + 2 * 8 * 256;
     w.Srep = w.Wj + (size_t)rows * 32;
     w.Sfin = w.Srep + (size_t)NREP * RMAX * SLD + 4 + 256;  // (+ ticket counter + 16 x 16 cross-Gram accumulator)
-    w.G = w.Sfin + (size_t)RMAX * SLD;
-    w.T32 = w.G + (size_t)RMAX * RMAX;
-    w.T16 = (void*)(w.T32 + (size_t)RMAX * RMAX);
-    return w;
+    w.G = w.Sfin + (size_t)RMAX * SLD;              // RMAX x 2 RMAX: [G | Sy] of the merged Gram / next-panel product
+    w.T32 = w.G + (size_t)2 * RMAX * RMAX;
+    w.T16 = (void*)(w.T32 + (size_t)RMAX * RMAX);   // two buffers (consecutive panels alternate: a deferred W = Y T reads one
+    return w;                                       // while the next panel's T kernel writes the other)
 }
 
-int launch_tinv(const float* G, long ldg, int pw, float* T32, int ldt, void* T16, long ldt16, int bf16, size_t smem, cudaStream_t st) {
+int launch_tinv(const float* G, long ldg, int pw, float* T32, int ldt, void* T16, long ldt16, int bf16, size_t smem, cudaStream_t st,
+                const float* Sy = nullptr, long ldsy = 0, int ns = 0, void* S16 = nullptr, long lds16 = 0) {
     cudaLaunchAttribute pat[1] = {pdl_attr()};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(1); cfg.blockDim = dim3(1024); cfg.stream = st; cfg.attrs = pat; cfg.numAttrs = 1;
     cfg.dynamicSmemBytes = smem;
-    MPQR_CUDA(cudaLaunchKernelEx(&cfg, tinv_kernel, G, ldg, pw, T32, ldt, T16, ldt16, bf16));
+    MPQR_CUDA(cudaLaunchKernelEx(&cfg, tinv_kernel, G, ldg, pw, T32, ldt, T16, ldt16, bf16, Sy, ldsy, ns, S16, lds16));
     return MPQR_OK;
 }
 
@@ -1826,9 +1863,33 @@ int chain_preload() {
     for (int d : done)
         if (d == dev) return MPQR_OK;
     MPQR_TRY(su_attrs<16>());
+    MPQR_TRY(su_attrs<32>());
+    (void)max_cluster();
     const void* fns[] = {(const void*)inpanel_s_kernel<16>, (const void*)inpanel_u_kernel<16>, (const void*)inpanel_s4_kernel<16>,
                          (const void*)inpanel_u4_kernel<16>, (const void*)chain_gate_kernel, (const void*)chain_post_kernel,
-                         (const void*)panel_finalize_kernel};
+                         (const void*)panel_finalize_kernel,
+                         // everything else a factorisation may launch for the first time while a gate kernel spins
+                         (const void*)inpanel_s_kernel<32>, (const void*)inpanel_u_kernel<32>, (const void*)inpanel_s4_kernel<32>,
+                         (const void*)inpanel_u4_kernel<32>, (const void*)tinv_kernel,
+                         (const void*)panel_chain_kernel<1>, (const void*)panel_chain_kernel<2>, (const void*)panel_chain_kernel<4>,
+                         (const void*)panel_chain_kernel<8>,
+                         (const void*)panel_block_kernel<16, 1>, (const void*)panel_block_kernel<16, 2>, (const void*)panel_block_kernel<16, 4>,
+                         (const void*)panel_block_kernel<16, 8>, (const void*)panel_block_kernel<32, 1>, (const void*)panel_block_kernel<32, 2>,
+                         (const void*)panel_block_kernel<32, 4>};
+    MPQR_TRY(func_attr_once((const void*)tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(((size_t)RMAX * TLD + 64 * 65 + (size_t)RMAX * RMAX) * sizeof(float))));
+    {
+        const void* ch[4] = {(const void*)panel_chain_kernel<1>, (const void*)panel_chain_kernel<2>, (const void*)panel_chain_kernel<4>,
+                             (const void*)panel_chain_kernel<8>};
+        const int rp[4] = {1, 2, 4, 8};
+        for (int i = 0; i < 4; ++i) {
+            MPQR_TRY(func_attr_once(ch[i], cudaFuncAttributeMaxDynamicSharedMemorySize, rp[i] * NT * 64));
+            if (max_cluster() > 8) MPQR_TRY(func_attr_once(ch[i], cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
+    }
+    MPQR_TRY(preload_tc_gemm());
+    MPQR_TRY(preload_simt_gemm());
+    MPQR_TRY(preload_util_kernels());
     for (const void* f : fns) {
         cudaFuncAttributes fa;
         MPQR_CUDA(cudaFuncGetAttributes(&fa, f));
@@ -1884,8 +1945,8 @@ bool panel_chain_ok(const PanelArgs& a) {
 }
 
 size_t panel_ws_bytes(long max_rows) {
-    return ((size_t)max_rows * (2 * RMAX + 32) + 2 * 8 * 256 + (size_t)(NREP + 1) * RMAX * SLD + 4 + 256 + 2 * (size_t)RMAX * RMAX) * sizeof(float) +
-           (size_t)RMAX * RMAX * 2 + 256;
+    return ((size_t)max_rows * (2 * RMAX + 32) + 2 * 8 * 256 + (size_t)(NREP + 1) * RMAX * SLD + 4 + 256 + 3 * (size_t)RMAX * RMAX) * sizeof(float) +
+           2 * (size_t)RMAX * RMAX * 2 + 256;
 }
 
 // PanelArgs output pointers address (row blk_row0, first panel column); zr = lam - blk_row0 rows
@@ -1975,6 +2036,7 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         *a.chain_ctr += (unsigned)nblocks;
         ca.flag_done = a.chain_flags;
         ca.flag_far = a.chain_flags + 1;
+        ca.flag_started = a.chain_flags + 3;
         ca.next_cols = next_cols;
         // this panel's columns were last written by the previous panel's side updates (if it covered them): block 0 waits
         // for the last value posted so far
@@ -1997,8 +2059,15 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         // updates of the rest stream.  The first S kernel of a panel is held back by an event until the stream reaches the
         // cluster launch.  MPQR_MEMOPS=1 / MPQR_GATE_KERNEL=1: stream-level ordering (stream memory operations cost the
         // issuing thread ~26 us each on B200: 12 per panel made the whole path launch-bound).
-        const bool inkernel = !getenv("MPQR_MEMOPS") && !getenv("MPQR_GATE_KERNEL");
-        if (inkernel && side_sms > 32) side_sms = 32;
+        // [B200, r2i] in-kernel gating of the FIRST S kernel of a panel deadlocked: its CTAs (32-64 x 512 threads) could start
+        // spinning before the cluster was placed and leave no GPC with 16 free SMs for it.  The first S kernel is therefore
+        // always ordered at stream level (a one-thread gate kernel cannot keep a cluster out), and in-kernel gating of the
+        // later ones is opt-in (MPQR_INKERNEL=1) until it has run the whole suite.
+        static const bool inkernel_env = getenv("MPQR_INKERNEL") != nullptr;
+        const bool inkernel = inkernel_env && !getenv("MPQR_MEMOPS") && !getenv("MPQR_GATE_KERNEL");
+        static const int inkernel_cap = getenv("MPQR_INKERNEL") ? atoi(getenv("MPQR_INKERNEL")) : 0;   // 1: capped at 32 CTAs, >= 2: that many
+        if (inkernel && side_sms > (inkernel_cap >= 2 ? inkernel_cap : 32)) side_sms = inkernel_cap >= 2 ? inkernel_cap : 32;
+        static const int su_rows = getenv("MPQR_SU_MAXROWS") ? atoi(getenv("MPQR_SU_MAXROWS")) : 0;   // tuning knob: rows per S/U CTA
         if (inkernel && a.ev_start) MPQR_CUDA(cudaStreamWaitEvent(a.chain_side, a.ev_start, 0));
         for (int jb = 0; jb < nfarb; ++jb) {
             // block jb's reflectors -> the rest of the panel beyond block jb+1 and (next_cols) the whole next panel:
@@ -2007,10 +2076,15 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
             const int cfirst = (j0 + 32 < pw) ? j0 + 32 : pw;   // first column (panel-relative)
             const int nfar = pw - cfirst + next_cols;
             if (!inkernel) MPQR_TRY(stream_wait_geq(a.chain_side, a.chain_flags, ca.base + (unsigned)(jb + 1)));
+            else if (jb == 0) {
+                chain_gate_kernel<<<1, 1, 0, a.chain_side>>>(a.chain_flags, ca.base + 1u);
+                MPQR_CUDA(cudaGetLastError());
+            }
             MPQR_TRY(launch_su<16>(Tsl + (size_t)jb * 256, Yp + (size_t)j0 * ldyp + j0, ldyp, Ablk + (size_t)j0 * a.lda + cfirst, a.lda, Dj,
                                    nfar, ca.srep[jb & 1], w.Sfin, side_sms, a.chain_side, launches, a.prof, false,
                                    inkernel ? a.chain_flags : nullptr, ca.base + (unsigned)(jb + 1),
-                                   inkernel ? a.chain_flags + 1 : nullptr, ca.base + (unsigned)(jb + 1), a.chain_flags + 2, inkernel ? 1024 : 512));
+                                   inkernel ? a.chain_flags + 1 : nullptr, ca.base + (unsigned)(jb + 1), a.chain_flags + 2,
+                                   su_rows >= 64 ? su_rows : (inkernel ? 1024 : 512)));
             if (!inkernel) MPQR_TRY(stream_post(a.chain_side, a.chain_flags + 1, ca.base + (unsigned)(jb + 1)));
             if (a.chain_last_far) *a.chain_last_far = ca.base + (unsigned)(jb + 1);
         }
@@ -2058,21 +2132,26 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     if (!need_t) return MPQR_OK;
 
     HostProfScope hp1(1);
-    const size_t tsmem = ((size_t)RMAX * TLD + 64 * 65) * sizeof(float);
-    MPQR_TRY(func_attr_once((const void*)tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    const size_t tsmem_max = ((size_t)RMAX * TLD + 64 * 65 + (size_t)RMAX * RMAX) * sizeof(float);
+    MPQR_TRY(func_attr_once((const void*)tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem_max));
+    // merged Gram / next-panel product: the columns right of the panel in the Y16 array must be the operand shadow
+    const int gsn = (mixed && a.gs_ncols > 0 && a.gs_ncols <= RMAX && a.gs_S16 && a.T) ? a.gs_ncols : 0;
+    const size_t tsmem = ((size_t)RMAX * TLD + 64 * 65 + (gsn ? (size_t)RMAX * RMAX : 0)) * sizeof(float);
+    void* T16p = (char*)w.T16 + (size_t)(a.chain_buf & 1) * RMAX * RMAX * 2;
     const int Dz = D + zr;  // W is produced from the enclosing block's first row on (zero rows of Y give zero rows of W)
     float* Tdst = a.T ? a.T : w.T32;
     const int ldt = a.T ? a.ldt : RMAX;
     if (a.prof) a.prof->begin(a.prof->ctx, 6, ts, 4.0 * D * pw * pw, 10.0 * D * pw);
     if (mixed) {
         // Gram and W on tensor cores, from the 16-bit Y the trailing update uses
-        MPQR_TRY(tc_gemm_tn(Y16l, a.ldy16, Y16l, a.ldy16, w.G, RMAX, pw, pw, D, a.bf16, 1, ts, launches));
-        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, w.T16, RMAX, a.bf16, tsmem, ts));
+        const long ldg = gsn ? 2 * RMAX : RMAX;
+        MPQR_TRY(tc_gemm_tn(Y16l, a.ldy16, Y16l, a.ldy16, w.G, ldg, pw, pw + gsn, D, a.bf16, 1, ts, launches));
+        MPQR_TRY(launch_tinv(w.G, ldg, pw, Tdst, ldt, T16p, RMAX, a.bf16, tsmem, ts, gsn ? w.G + pw : nullptr, ldg, gsn, a.gs_S16, a.gs_lds16));
         if (launches) *launches += 1;
-        MPQR_TRY(tc_gemm_nn_store(a.Y16, a.ldy16, w.T16, RMAX, a.W32, a.ld32, a.W16, a.ldw16, Dz, pw, pw, a.bf16, ts, launches));
+        if (!a.defer_w) MPQR_TRY(tc_gemm_nn_store(a.Y16, a.ldy16, T16p, RMAX, a.W32, a.ld32, a.W16, a.ldw16, Dz, pw, pw, a.bf16, ts, launches));
     } else {
         MPQR_TRY(sgemm_tn(Yp, ldyp, Yp, ldyp, w.G, RMAX, pw, pw, D, ts, launches));
-        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, nullptr, 0, 0, tsmem, ts));
+        MPQR_TRY(launch_tinv(w.G, RMAX, pw, Tdst, ldt, nullptr, 0, 0, tsmem, ts));   // (FP32 path: plain Gram, W formed here)
         if (launches) *launches += 1;
         if (a.W32) {
             MPQR_TRY(sgemm_nn_store(a.Y32, a.ld32, Tdst, ldt, a.W32, a.ld32, Dz, pw, pw, ts));
@@ -2081,6 +2160,28 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
     }
     if (a.prof) a.prof->end(a.prof->ctx, ts);
     return MPQR_OK;
+}
+
+
+int chain_preload_all() { return chain_preload(); }
+
+// Holds `st` back until the chain kernel whose base is `next_base` is resident (one spinning thread).  A 16-CTA cluster needs
+// 16 free SMs of ONE GPC: a GEMM that is already spread over the partition keeps it out until its CTAs retire
+// ([B200] 47-83 us per panel at 32768 rows, profiles/r2_timeline_c4.txt), so the rest-of-block GEMMs queue behind this.
+int chain_wait_started(cudaStream_t st, unsigned* chain_flags, unsigned next_base) {
+    MPQR_TRY(chain_preload());
+    chain_gate_kernel<<<1, 1, 0, st>>>(chain_flags + 3, next_base + 1u);
+    MPQR_CUDA(cudaGetLastError());
+    return MPQR_OK;
+}
+
+int panel_form_w(const PanelArgs& a, cudaStream_t stream, long* launches) {
+    if (!a.Y16 || !a.W16 || !a.W32 || !a.ws) { set_error("panel_form_w: mixed-path arguments missing"); return MPQR_EINVAL; }
+    HostProfScope hp1(1);
+    Ws w = carve(a.ws, a.ws_rows);
+    void* T16p = (char*)w.T16 + (size_t)(a.chain_buf & 1) * RMAX * RMAX * 2;
+    const int Dz = a.m - a.blk_row0;
+    return tc_gemm_nn_store(a.Y16, a.ldy16, T16p, RMAX, a.W32, a.ld32, a.W16, a.ldw16, Dz, a.pw, a.pw, a.bf16, stream, launches);
 }
 
 }  // namespace mpqr

@@ -135,7 +135,7 @@ def test_lookahead_driver_vs_oracle(m, n, r, nb, chain, monkeypatch):
     dA[:m, :n] = torch.from_numpy(A).cuda()
     st = torch.cuda.current_stream().cuda_stream
     plan = pkg.BlockQR(m, n, r, nb=nb, precision="fp16")
-    assert plan.nb == nb and plan.r == r
+    assert plan.nb == nb and plan.r % r == 0 and plan.r <= max(r, 128)   # (narrow caller widths are widened to a multiple near 128)
     for _ in range(2):          # twice: event / stream reuse across calls
         dA[:m, :n] = torch.from_numpy(A).cuda()
         dA[m].zero_()
