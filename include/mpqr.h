@@ -47,6 +47,12 @@ extern "C" {
 #define MPQR_PRECISION_MASK 0x3u
 #define MPQR_KEEP_WY 0x10u   /* retain W (=Y T) for every outer block so that Q can be formed /
                                 WY factors read back after the factorisation */
+#define MPQR_STREAM_ORDERED 0x20u /* panels as plain stream-ordered kernels: no persistent panel kernel that waits on device
+                                flags for work issued behind it.  Use it when several handles factor concurrently on one device
+                                next to other host-side CUDA activity: [B200] the TSQR driver, 4 lanes with persistent kernels
+                                plus a plan being built meanwhile, stopped for good in about one run of three (csrc/tsqr.cu);
+                                a single handle was never seen to (tools/alloc_hazard.py allocates while it runs).  Costs
+                                ~15 % of the panel time of tall panels. */
 
 typedef struct mpqr_handle mpqr_handle;
 

@@ -20,6 +20,7 @@ MPQR_FP32 = 0x0
 MPQR_FP16 = 0x1
 MPQR_BF16 = 0x2
 MPQR_KEEP_WY = 0x10
+MPQR_STREAM_ORDERED = 0x20   # no persistent (flag-waiting) panel kernel: see include/mpqr.h
 NCCL_UID_BYTES = 128
 
 # every symbol include/mpqr.h declares (tests/test_abi.py checks they are all exported)
@@ -141,10 +142,12 @@ class BlockQR:
     """Device-resident plan (mpqr_create / mpqr_factor_device / mpqr_form_q_device).  Pointers
     are raw device addresses (e.g. torch.Tensor.data_ptr()); stream is a cudaStream_t int."""
 
-    def __init__(self, m, n, r, nb=0, precision="fp16", keep_wy=False):
+    def __init__(self, m, n, r, nb=0, precision="fp16", keep_wy=False, stream_ordered=False):
         flags = {"fp32": MPQR_FP32, "fp16": MPQR_FP16, "bf16": MPQR_BF16}[precision]
         if keep_wy:
             flags |= MPQR_KEEP_WY
+        if stream_ordered:
+            flags |= MPQR_STREAM_ORDERED
         self._h = ctypes.c_void_p()
         check(lib().mpqr_create(ctypes.byref(self._h), m, n, r, nb, flags), "mpqr_create")
         self.m, self.n = m, n

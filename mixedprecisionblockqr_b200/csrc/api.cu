@@ -370,7 +370,7 @@ int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         a.T = h->T + (size_t)p * r * r; a.ldt = r;
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
-        a.chain_side = h->chain_side; a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
+        a.chain_side = h->no_chain ? nullptr : h->chain_side; a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
         a.chain_last_far = &h->chain_last_far; a.chain_buf = p & 1; a.ev_start = h->chain_ev_start;
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         if (nt > 0) {
@@ -668,7 +668,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         a.T = h->T + (size_t)p * r * r; a.ldt = r;
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
-        a.chain_side = c.chain_side ? c.chain_side : h->chain_side; a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
+        a.chain_side = h->no_chain ? nullptr : (c.chain_side ? c.chain_side : h->chain_side); a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
         a.chain_last_far = &h->chain_last_far;
         a.ev_start = h->chain_ev_start;
         a.chain_buf = (int)(h->chain_panels++ & 1u);
@@ -848,6 +848,7 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
     mpqr_handle* h = new mpqr_handle();
     h->m = m; h->n = n; h->flags = flags; h->prec = (int)prec;
     h->keep_wy = (flags & MPQR_KEEP_WY) != 0;
+    h->no_chain = (flags & MPQR_STREAM_ORDERED) != 0;
     h->kmax = m < n ? m : n;
     h->r = r > kPanelMaxWidth ? kPanelMaxWidth : r;
     {

@@ -27,6 +27,7 @@ struct mpqr_handle {
     unsigned chain_last_far = 0;   // last value posted to chain_flags[1]
     unsigned chain_panels = 0;     // chain panels issued so far (picks the Y / T workspace buffer)
     cudaStream_t chain_side = nullptr;
+    bool no_chain = false;         // MPQR_STREAM_ORDERED: never launch the persistent (flag-waiting) panel kernel
     cudaEvent_t chain_ev_start = nullptr; // in front of a panel's cluster launch (holds back its first side kernel)
     cudaEvent_t chain_ev_side = nullptr;  // behind the last side update of a panel that covered the next panel's columns
     float* T = nullptr;    // npanels * r * r

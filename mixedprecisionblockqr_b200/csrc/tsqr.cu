@@ -85,7 +85,7 @@ struct Lane {
 
 int tsqr_lanes(long nblk) {
     const char* e = getenv("MPQR_TSQR_LANES");
-    long want = e ? atol(e) : 4;  // B200, 1048576 x 256: 68 ms with 1 lane, 59 ms with 4, 75 ms with 8 (clusters queue for SMs)
+    long want = e ? atol(e) : 8;  // [B200, r2t] 1048576 x 256, stream-ordered lanes (see build_plan): 23.6 ms with 4 lanes, 21.7 ms with 8
     if (want < 1) want = 1;
     if (want > 16) want = 16;
     return (int)(want < nblk ? want : nblk);
@@ -138,7 +138,14 @@ int build_plan(Plan* P, const DeviceInfo& di) {
     P->NL = tsqr_lanes(nblk);
     P->budget = P->NL > 1 ? (di.num_sms / P->NL < 16 ? 16 : di.num_sms / P->NL) : 0;
     P->lanes.resize(P->NL);
-    const unsigned flags = MPQR_FP32 | (P->with_q ? MPQR_KEEP_WY : 0u);
+    // TSQR handles never use the persistent panel kernel (MPQR_STREAM_ORDERED): a persistent cluster waits on device flags for
+    // side-stream work issued behind it, and with several lanes' clusters resident while this driver went on to build the plan of
+    // the R stack (mpqr_create: allocations, default-stream memsets, stream creation) pass 1 stopped for good, in about one run of
+    // three.  [B200, r2t] tests/test_gpu_parity_large.py::test_c5_full_size_vs_lapack: two panel_chain_kernel clusters resident,
+    // nothing else dispatched, host in build_plan's cudaDeviceSynchronize (cuda-gdb listing: profiles/r2_tsqr_hang_cuda_gdb.txt).
+    // The trigger was not isolated (a single handle takes cuMemAlloc in flight without harm, tools/alloc_hazard.py), so nothing
+    // that waits runs here at all; stream-ordered lanes are not slower (23.7 ms at 8 lanes against 24.4 ms with the chain).
+    const unsigned flags = MPQR_FP32 | (P->with_q ? MPQR_KEEP_WY : 0u) | MPQR_STREAM_ORDERED;
     const long ldp = P->ldp;
     auto fail_alloc = [&]() { set_error("tsqr: device allocation failed"); cudaGetLastError(); return MPQR_ENOMEM; };
     if (cudaEventCreateWithFlags(&P->ev_start, cudaEventDisableTiming) != cudaSuccess ||

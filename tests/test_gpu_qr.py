@@ -152,6 +152,37 @@ def test_lookahead_driver_vs_oracle(m, n, r, nb, chain, monkeypatch):
     plan.close()
 
 
+def test_stream_ordered_flag_allows_allocation_in_flight():
+    """MPQR_STREAM_ORDERED (include/mpqr.h): the same factor from plain stream-ordered kernels, and a device allocation
+    while the factorisation is in flight neither stalls nor changes it (the TSQR lanes rely on this)."""
+    import ctypes
+    import torch
+    m, n, r = 6144, 2048, 128
+    A = oracle.uniform_matrix(m, n, 6144)
+    st = torch.cuda.current_stream().cuda_stream
+    drv = ctypes.CDLL("libcuda.so.1")
+    out = {}
+    for ordered in (False, True):
+        plan = pkg.BlockQR(m, n, r, precision="fp16", stream_ordered=ordered)
+        dA = torch.zeros(m + 1, n, device="cuda")
+        dA[:m] = torch.from_numpy(A).cuda()
+        torch.cuda.synchronize()
+        plan.factor(dA.data_ptr(), n, st)
+        if ordered:
+            ptr = ctypes.c_uint64()
+            assert drv.cuMemAlloc_v2(ctypes.byref(ptr), ctypes.c_size_t(192 << 20)) == 0
+            torch.cuda.synchronize()
+            assert drv.cuMemFree_v2(ptr) == 0
+        torch.cuda.synchronize()
+        out[ordered] = dA.cpu().numpy()
+        plan.close()
+    be = oracle.backward_error_packed(A, out[True])
+    R0, R1 = oracle.strip_R(out[False]), oracle.strip_R(out[True])
+    dr = np.abs(np.abs(R0) - np.abs(R1)).max() / np.abs(R0).max()
+    observe("qr_stream_ordered", be=be, dr=dr)
+    assert be <= 3.4 * 2.0 ** -11 and dr <= 3 * 2.0 ** -11, (be, dr)
+
+
 def test_host_driver_plan_cache(monkeypatch):
     """mpqr_block_qr_host keeps its plan between calls of the same shape: repeated calls, a shape change in between,
     the explicit release and MPQR_NO_HOST_CACHE=1 must all give the same factor (to FP16-level run-to-run noise)."""
