@@ -489,8 +489,9 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     int jnear = arriving ? ar.c1[0] : n;
     int arr_pair = -1;
     if (arriving) {
+        static const int arr_sms = getenv("MPQR_ARR_SMS") ? atoi(getenv("MPQR_ARR_SMS")) : 64;   // tuning knob: panel partition of the streamed schedule
         for (size_t k = 0; k < o.pairs.size(); ++k)
-            if (arr_pair < 0 || abs(o.pairs[k].nsmP - 64) < abs(o.pairs[arr_pair].nsmP - 64)) arr_pair = (int)k;
+            if (arr_pair < 0 || abs(o.pairs[k].nsmP - arr_sms) < abs(o.pairs[arr_pair].nsmP - arr_sms)) arr_pair = (int)k;
         MPQR_TRY(arrival_streams(h, arr_pair));
         MPQR_CUDA(cudaStreamWaitEvent(s_bp, ar.ev[0], 0));
         for (size_t q = 1; q < ar.c0.size(); ++q) MPQR_CUDA(cudaStreamWaitEvent(ar.cs[q], ar.ev[q], 0));
@@ -1167,10 +1168,24 @@ int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned 
             auto& ar = h->arr;
             if (!ar.stream && cudaStreamCreateWithFlags(&ar.stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
             ar.c0.clear(); ar.c1.clear(); ar.t_ms.clear();
+            // outer blocks per chunk (the last entry repeats); MPQR_H2D_CHUNKS="1,3,4,8" is a tuning knob
+            static const std::vector<int> chunk_sched = [] {
+                std::vector<int> v;
+                if (const char* e = getenv("MPQR_H2D_CHUNKS"))
+                    for (const char* p = e; *p;) {
+                        const int x = atoi(p);
+                        if (x >= 1) v.push_back(x);
+                        while (*p && *p != ',') ++p;
+                        if (*p == ',') ++p;
+                    }
+                if (v.empty()) v = {1, 3, 4, 8};
+                return v;
+            }();
+            auto chunk_blocks = [&](int k) { return chunk_sched[(size_t)k < chunk_sched.size() ? (size_t)k : chunk_sched.size() - 1]; };
             static const double gbs = getenv("MPQR_H2D_GBS") ? atof(getenv("MPQR_H2D_GBS")) : 52.0;  // expected host-to-device rate
             double t = 0.05;
             for (int blk = 0, k = 0; blk * h->nb < n; ++k) {
-                const int nblocks = k == 0 ? 1 : (k == 1 ? 3 : (k == 2 ? 4 : 8));   // few, growing chunks: every distant chunk has its own stream
+                const int nblocks = chunk_blocks(k);   // few, growing chunks: every distant chunk has its own stream
                 const int a0 = blk * h->nb;
                 int a1 = (blk + nblocks) * h->nb;
                 if (a1 > n || n - a1 < h->nb) a1 = n;   // a short tail joins the last chunk

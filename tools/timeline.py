@@ -9,13 +9,26 @@ from torch.profiler import profile, ProfilerActivity
 import mixedprecisionblockqr_b200 as pkg
 
 spec = sys.argv[1].split(",")
+tsqr = spec[0] == "tsqr"   # tsqr,m,n : mpqr_tsqr_device (R + thin Q)
+if tsqr:
+    spec = [spec[1], spec[2], "128", "fp32"]
 m, n, r, prec = int(spec[0]), int(spec[1]), int(spec[2]), spec[3]
 w0 = float(sys.argv[2]) if len(sys.argv) > 2 else 20.0
 w1 = float(sys.argv[3]) if len(sys.argv) > 3 else 21.5
 lda = (n + 7) // 8 * 8
 A = torch.zeros(m + 1, lda, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-plan = pkg.BlockQR(m, n, r, precision=prec)
+if tsqr:
+    class _T:   # same interface as a plan
+        def __init__(self):
+            self.Q = torch.zeros(m, n, device="cuda"); self.R = torch.zeros(n, n, device="cuda")
+        def factor(self, a, ld, s):
+            pkg.tsqr(a, ld, m, n, self.Q.data_ptr(), n, self.R.data_ptr(), n, s)
+        def close(self):
+            pass
+    plan = _T()
+else:
+    plan = pkg.BlockQR(m, n, r, precision=prec)
 for it in range(2):
     pkg.fill_uniform(A.data_ptr(), lda, n, 0, m, 0, n, 1234, st)
     plan.factor(A.data_ptr(), lda, st)
@@ -47,6 +60,19 @@ for e in ev:
 print("totals by kernel (count, total ms, avg us):")
 for k, (c, d) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print(f"  {c:6d} {d / 1e3:9.2f} {d / c:8.1f}  {k}")
+# activity per millisecond: kernels started, summed kernel time, streams in use
+nbin = int((end - t0) / 1e3) + 1
+if nbin <= 64:
+    print("per ms: kernels started / summed kernel ms / streams / top kernel")
+    for b in range(nbin):
+        sel = [e for e in ev if b <= (e["ts"] - t0) / 1e3 < b + 1]
+        if not sel:
+            print(f"  {b:3d}: -")
+            continue
+        byname = collections.Counter()
+        for e in sel:
+            byname[short(e["name"])] += e["dur"]
+        print(f"  {b:3d}: {len(sel):5d} {sum(e['dur'] for e in sel) / 1e3:7.2f} {len({e.get('args', {}).get('stream') for e in sel}):3d}  {byname.most_common(1)[0][0]}")
 os.makedirs("gpurun_out", exist_ok=True)
 with open(f"gpurun_out/timeline_{m}x{n}.csv", "w") as f:
     f.write("start_us,dur_us,stream,grid,name\n")
