@@ -338,10 +338,9 @@ double model_bp_ms(const mpqr_handle* h, int c0, int c1, int sms) {
         lat += (D <= 16384) ? 0.140 + 0.0046 * D / 1024.0 : 0.290;
         work += 3.81e-3 * D / 8.0;
     }
-    static const double scale = getenv("MPQR_BP_SCALE") ? atof(getenv("MPQR_BP_SCALE")) : 1.0;  // tuning knob of the cost model
     const double f = h->r / 128.0 < 0.25 ? 0.25 : h->r / 128.0;
     const int free_sms = sms > 24 ? sms - 16 : 8;
-    return scale * f * (lat + work / free_sms);
+    return f * (lat + work / free_sms);
 }
 double model_far_ms(const mpqr_handle* h, int c0, int c1, int ncols, int sms) {
     const double flops = 4.0 * (double)(h->m - c0) * (double)ncols * (double)(c1 - c0);
@@ -371,7 +370,7 @@ int factor_fp32(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         a.sync_ws = h->sync_ws; a.host_ctr = &h->sync_ctr; a.scratch = h->scratch; a.scratch_rows = h->scratch_rows;
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
         a.chain_side = h->no_chain ? nullptr : h->chain_side; a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
-        a.chain_last_far = &h->chain_last_far; a.chain_buf = p & 1; a.ev_start = h->chain_ev_start;
+        a.chain_last_far = &h->chain_last_far; a.chain_buf = p & 1;
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         if (nt > 0) {
             float* A22 = A + (size_t)lam * lda + tau;
@@ -489,7 +488,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
     int jnear = arriving ? ar.c1[0] : n;
     int arr_pair = -1;
     if (arriving) {
-        static const int arr_sms = getenv("MPQR_ARR_SMS") ? atoi(getenv("MPQR_ARR_SMS")) : 64;   // tuning knob: panel partition of the streamed schedule
+        constexpr int arr_sms = 64;   // panel partition of the streamed schedule ([B200, r2v] 80 SMs: 191 ms against 167 ms)
         for (size_t k = 0; k < o.pairs.size(); ++k)
             if (arr_pair < 0 || abs(o.pairs[k].nsmP - arr_sms) < abs(o.pairs[arr_pair].nsmP - arr_sms)) arr_pair = (int)k;
         MPQR_TRY(arrival_streams(h, arr_pair));
@@ -515,7 +514,7 @@ int factor_16(mpqr_handle* h, float* A, long lda, cudaStream_t st) {
         if (inblock_la) {
             c.rest_stream = s_bp2; c.rest_S32 = h->S32r; c.rest_S16 = h->S16r; c.rest_ev = o.ev_rest.data();
             // leave the cluster (16 SMs) and a share for its side updates free
-            static const int rest_keep = getenv("MPQR_REST_KEEP") ? atoi(getenv("MPQR_REST_KEEP")) : 32;   // SMs kept free of rest-stream GEMMs
+            constexpr int rest_keep = 32;   // SMs kept free of rest-stream GEMMs ([B200, r2p] 0 / 32 / 48: 114.1 / 114.2 / 114.4 ms)
             c.rest_sms = nsm_bp - rest_keep >= 24 ? nsm_bp - rest_keep : (nsm_bp >= 40 ? nsm_bp - 16 : 0);
             // (the previous block's last rest event completed before fn(b-1), which this block waits for)
         }
@@ -654,7 +653,6 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
     float* S32 = c.S32 ? c.S32 : h->S32;
     void* S16 = c.S16 ? c.S16 : h->S16;
     int last_rest = -1;
-    bool prev_cover = false;
     std::vector<char> rest_rec((size_t)ceil_div(c1 - c0, r) + 1, 0);
     for (int lam = c0; lam < c1; lam += r) {
         const int p = lam / r;
@@ -671,32 +669,24 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
         a.ws = h->panel_ws; a.ws_rows = h->panel_ws_rows; a.prof = h->prof ? &h->hook : nullptr;
         a.chain_side = h->no_chain ? nullptr : (c.chain_side ? c.chain_side : h->chain_side); a.chain_flags = h->chain_flags; a.chain_ctr = &h->chain_ctr;
         a.chain_last_far = &h->chain_last_far;
-        a.ev_start = h->chain_ev_start;
         a.chain_buf = (int)(h->chain_panels++ & 1u);
         const int nin = c1 - tau;  // in-block trailing columns
         const int pidx = jc / r;
         const bool chain = panel_chain_ok(a);
-        // Next-panel coverage: the panel's register blocks update the whole next panel themselves (FP32, side stream), so the
-        // chain goes kernel -> kernel; finalize, Gram / T / W, the tensor-core update of the columns beyond the next panel
-        // and the WY accumulation follow on `rest_stream` with a panel's time of slack.
-        const bool cover = chain && c.rest_stream && c.rest_ev && c.acc_stream && nin >= r && (r % 8) == 0 && getenv("MPQR_COVER");   // EXPERIMENTAL, off: see DESIGN 7 (needs the second side stream)
-        if (cover) { a.next_cols = r; a.tail_stream = c.rest_stream; a.ev_chain = c.rest_ev[2 * pidx]; a.ev_side = h->chain_ev_side; }
         // the next panel's columns on the panel stream, the rest of the block on `rest_stream` (same SM partition) next
         // to the next panel's chain kernel
-        const bool split = !cover && c.rest_stream && nin > r && (r % 8) == 0;
+        const bool split = c.rest_stream && nin > r && (r % 8) == 0;
         // Merged Gram / next-panel product (PanelArgs::gs_ncols): the panel's T kernel leaves S = T^T Y^T A_next in S16, the
         // in-block update of the next panel's columns is one NN GEMM, and W = Y T (only the rest of the block, the WY
         // accumulation and the far update need it) moves to the rest stream.  Needs Y in the shadow's dead columns.
-        static const bool no_merge = getenv("MPQR_NO_GS_MERGE") != nullptr;
         const bool y_in_shadow = c.Y16 == (void*)at16(c.Ah, c.ldh, c0, c.acol0) && c.ldy == c.ldh;
-        const bool merged = !no_merge && !cover && !h->prof && y_in_shadow && nin > 0 && (split || nin <= r) && (r % 8) == 0 && (pw % 8) == 0 &&
+        const bool merged = !h->prof && y_in_shadow && nin > 0 && (split || nin <= r) && (r % 8) == 0 && (pw % 8) == 0 &&
                             (h->lds16 % 8) == 0;
         if (merged) { a.gs_ncols = nin < r ? nin : r; a.gs_S16 = S16; a.gs_lds16 = h->lds16; a.defer_w = 1; }
         // earlier panels' updates of THIS panel's columns: panels <= p-2 through their rest updates (rest stream, in order);
         // panel p-1 through its in-block update on this stream, or through its side updates (flag inside a chain kernel,
         // the side event for any other kernel)
         if (pidx >= 2 && rest_rec[pidx - 2]) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (pidx - 2) + 1], 0));
-        if (prev_cover && !chain) MPQR_CUDA(cudaStreamWaitEvent(st, h->chain_ev_side, 0));
         PROF(0, 4.0 * D * pw * pw, 8.0 * D * pw, launch_panel(a, st, &h->launches));
         const int acol_tau = c.acol0 + jc + pw;
         // in-block update of the columns [tau + ofs, tau + ofs + nc):  S = W_p^T A ; A -= Y_p S (+ shadow)
@@ -723,14 +713,7 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
                               D, nc, pw, bf, pad_ok, st, &h->launches);
         };
         if (c.rest_stream && nin > 0) { last_rest = 2 * pidx + 1; rest_rec[pidx] = true; }
-        if (cover) {
-            // (launch_panel queued finalize and Gram / T / W on the rest stream behind the chain kernel)
-            if (nin - r > 0) {
-                SmBudget rb(c.rest_sms > 0 ? c.rest_sms : g_sm_budget);
-                MPQR_TRY(inblock(r, nin - r, c.rest_S32, c.rest_S16, end_is_matrix_end, c.rest_stream));
-            }
-            MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], c.rest_stream));
-        } else if (nin > 0 && !split) {
+        if (nin > 0 && !split) {
             if (c.rest_stream && pidx > 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (pidx - 1) + 1], 0));
             if (merged) {
                 MPQR_TRY(inblock_nn_only(nin, end_is_matrix_end, st));
@@ -747,19 +730,9 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             if (pidx > 0) MPQR_CUDA(cudaStreamWaitEvent(st, c.rest_ev[2 * (pidx - 1) + 1], 0));
             if (merged) MPQR_TRY(inblock_nn_only(r, 0, st));
             else MPQR_TRY(inblock(0, r, S32, S16, 0, st));
-            {
-                // the rest-of-block GEMMs start once the NEXT panel's cluster is resident (they would keep it from being placed)
-                // [B200, r2p] EXPERIMENTAL, off: the cluster then starts at once (gap between two chain kernels 184 -> 111 us at
-                // 32768 rows), but the rest GEMMs now run next to its side updates and slow them down by as much; the whole
-                // factorisation is far-update-bound in those intervals anyway (114.1-114.8 ms either way).  MPQR_REST_GATE=1.
-                static const bool rest_gate = getenv("MPQR_REST_GATE") != nullptr;
-                if (rest_gate && chain) {
-                    PanelArgs nx = a;
-                    nx.lam = tau; nx.acol = c.acol0 + jc + pw; nx.pw = (tau + r < c1) ? r : c1 - tau;
-                    nx.gs_ncols = 0; nx.defer_w = 0;
-                    if (panel_chain_ok(nx)) MPQR_TRY(chain_wait_started(c.rest_stream, h->chain_flags, h->chain_ctr));
-                }
-            }
+            // (holding the rest-of-block GEMMs back until the NEXT panel's cluster is resident -- they keep it from being placed for
+            //  47-83 us -- was measured and dropped: the cluster starts sooner, but the GEMMs then run next to its side updates
+            //  and slow them down by as much; [B200, r2p] 114.1-114.8 ms either way)
             {
                 SmBudget rb(c.rest_sms > 0 ? c.rest_sms : g_sm_budget);
                 if (merged) MPQR_TRY(panel_form_w(a, c.rest_stream, &h->launches));
@@ -767,7 +740,6 @@ int block_phase(mpqr_handle* h, const BlockCtx& c, int c0, int c1, int end_is_ma
             }
             MPQR_CUDA(cudaEventRecord(c.rest_ev[2 * pidx + 1], c.rest_stream));
         }
-        prev_cover = cover;
         if (jc > 0) {
             // WY accumulation: X = Y_prev^T W_p ; W_p -= W_prev X   (rows c0..m)
             const void* Wp = (char*)c.W16 + (size_t)jc * 2;
@@ -885,8 +857,6 @@ int mpqr_create(mpqr_handle** out, int m, int n, int r, int nb, unsigned flags) 
         if ((rc = dev_alloc(h, (void**)&h->chain_flags, 64))) break;
         if (cudaMemset(h->chain_flags, 0, 64) != cudaSuccess) { set_error("memset failed"); rc = MPQR_ECUDA; break; }
         if (cudaStreamCreateWithFlags(&h->chain_side, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
-        if (cudaEventCreateWithFlags(&h->chain_ev_side, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->chain_ev_start, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); rc = MPQR_ECUDA; break; }
         h->panel_ws_rows = m;
         if ((rc = dev_alloc(h, (void**)&h->panel_ws, panel_ws_bytes(m)))) break;
         const int wide = m > n ? m : n;
@@ -947,8 +917,6 @@ int mpqr_destroy(mpqr_handle* h) {
     for (auto e : h->arr.cev) if (e) cudaEventDestroy(e);
     overlap_destroy(h);
     if (h->chain_side) cudaStreamDestroy(h->chain_side);
-    if (h->chain_ev_side) cudaEventDestroy(h->chain_ev_side);
-    if (h->chain_ev_start) cudaEventDestroy(h->chain_ev_start);
     for (auto e : h->arr.ev) cudaEventDestroy(e);
     if (h->arr.stream) cudaStreamDestroy(h->arr.stream);
 
@@ -1168,24 +1136,12 @@ int mpqr_block_qr_host(float* A_packed, float* Q, int m, int n, int r, unsigned 
             auto& ar = h->arr;
             if (!ar.stream && cudaStreamCreateWithFlags(&ar.stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); rc = MPQR_ECUDA; break; }
             ar.c0.clear(); ar.c1.clear(); ar.t_ms.clear();
-            // outer blocks per chunk (the last entry repeats); MPQR_H2D_CHUNKS="1,3,4,8" is a tuning knob
-            static const std::vector<int> chunk_sched = [] {
-                std::vector<int> v;
-                if (const char* e = getenv("MPQR_H2D_CHUNKS"))
-                    for (const char* p = e; *p;) {
-                        const int x = atoi(p);
-                        if (x >= 1) v.push_back(x);
-                        while (*p && *p != ',') ++p;
-                        if (*p == ',') ++p;
-                    }
-                if (v.empty()) v = {1, 3, 4, 8};
-                return v;
-            }();
-            auto chunk_blocks = [&](int k) { return chunk_sched[(size_t)k < chunk_sched.size() ? (size_t)k : chunk_sched.size() - 1]; };
-            static const double gbs = getenv("MPQR_H2D_GBS") ? atof(getenv("MPQR_H2D_GBS")) : 52.0;  // expected host-to-device rate
+            constexpr double gbs = 52.0;  // expected host-to-device rate ([B200] 51-52 GB/s measured for pinned memory)
             double t = 0.05;
             for (int blk = 0, k = 0; blk * h->nb < n; ++k) {
-                const int nblocks = chunk_blocks(k);   // few, growing chunks: every distant chunk has its own stream
+                const int nblocks = k == 0 ? 1 : (k == 1 ? 3 : (k == 2 ? 4 : 8));   // few, growing chunks: every distant chunk has its own stream
+                // ([B200, r2v] finer schedules lose: 1,3,4,4,4,8,4,2,2 blocks 227 ms, 1,3,4,8,8,4,2,2 234 ms, against 167 ms: every
+                //  distant chunk adds a far update per outer block to the update partition)
                 const int a0 = blk * h->nb;
                 int a1 = (blk + nblocks) * h->nb;
                 if (a1 > n || n - a1 < h->nb) a1 = n;   // a short tail joins the last chunk

@@ -142,15 +142,6 @@ struct PanelArgs {
     long long* chain_dbg;     // optional device buffer, 8 x int64 per register block: globaltimer stamps of the cluster
     int chain_buf;            // which of the two Y / T workspace buffers this panel uses (consecutive panels alternate)
     unsigned* chain_last_far; // host: last value posted to chain_flags[1] so far (0 = none); updated by launch_panel
-    // Next-panel coverage (chain flow only): every block's side update also takes the `next_cols` columns right of the
-    // panel, so the next panel's kernel needs nothing from this panel's T / W and may start as soon as this kernel ends
-    // (it waits for the last side update through the flag).  finalize and Gram / T / W then run on `tail_stream`
-    // behind `ev_chain`; the 16-bit Y, W and T of the panel are ready in tail_stream order.
-    int next_cols;            // 0, or a multiple of 4 (<= 128)
-    cudaStream_t tail_stream;
-    cudaEvent_t ev_chain;     // recorded on `stream` behind the chain kernel
-    cudaEvent_t ev_side;      // optional: recorded on chain_side behind the panel's last side update
-    cudaEvent_t ev_start;     // optional: recorded on `stream` in front of the cluster launch; holds back the first side kernel
     // Merged Gram / next-panel product (mixed path; the 16-bit Y lives in the dead columns of the operand shadow, so the
     // gs_ncols columns right of the panel in the SAME array are the shadow of the next panel's columns): ONE TN GEMM gives
     // [G | Sy] = Y^T [Y | A_next], the T kernel also writes S = T^T Sy (16-bit, gs_S16: gs_ncols columns, ld gs_lds16),
@@ -162,7 +153,6 @@ struct PanelArgs {
 };
 // W = Y T of a panel factored with defer_w (same arguments; mixed path)
 int panel_form_w(const PanelArgs& a, cudaStream_t stream, long* launches);
-int chain_wait_started(cudaStream_t st, unsigned* chain_flags, unsigned next_base);
 // CUDA loads kernels lazily and a first-time load may need the device to drain: while a gate kernel / the cluster spins on
 // a flag that a later launch has to satisfy, that load would never return.  Every kernel a factorisation can launch is
 // therefore loaded (and given its attributes) before the first one is issued on a device (chain_preload, panel.cu).

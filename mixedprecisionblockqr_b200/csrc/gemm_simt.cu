@@ -212,8 +212,7 @@ sgemm_fast_kernel(const float* __restrict__ X, long ldx, const float* __restrict
 }
 
 inline bool fast_ok(const void* X, long ldx, const void* Z, long ldz, const void* C, long ldc, int M, int N) {
-    static const bool off = getenv("MPQR_SGEMM_OLD") != nullptr;
-    return !off && ((ldx | ldz | ldc) & 3) == 0 && ((M | N) & 3) == 0 && M >= 64 && N >= 64 &&
+    return ((ldx | ldz | ldc) & 3) == 0 && ((M | N) & 3) == 0 && M >= 64 && N >= 64 &&
            ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(C)) & 15) == 0;
 }
 

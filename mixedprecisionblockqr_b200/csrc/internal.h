@@ -28,8 +28,6 @@ struct mpqr_handle {
     unsigned chain_panels = 0;     // chain panels issued so far (picks the Y / T workspace buffer)
     cudaStream_t chain_side = nullptr;
     bool no_chain = false;         // MPQR_STREAM_ORDERED: never launch the persistent (flag-waiting) panel kernel
-    cudaEvent_t chain_ev_start = nullptr; // in front of a panel's cluster launch (holds back its first side kernel)
-    cudaEvent_t chain_ev_side = nullptr;  // behind the last side update of a panel that covered the next panel's columns
     float* T = nullptr;    // npanels * r * r
     float* S32 = nullptr;  // sk x lds32
     long lds32 = 0;

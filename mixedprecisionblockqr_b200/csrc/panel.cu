@@ -64,11 +64,7 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, unsigned ran
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
     return r;
 }
-// remote 4-byte store that signals 4 bytes on the destination CTA's mbarrier
-__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
-                 ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_mbar) : "memory");
-}
+// remote 16-byte store that signals 16 bytes on the destination CTA's mbarrier
 __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_mbar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                  ::"r"(remote_addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
@@ -766,7 +762,6 @@ struct ChainArgs {
     unsigned base;
     float* srep[2];  // S replica pairs of the far updates (blocks alternate); the cluster clears rows 0..15 of both replicas of
                      // srep[jb & 1] (replica stride RMAX * SLD, row stride SLD) before it posts block jb
-    int next_cols;   // > 0: every block's far update also covers the next panel's columns (so every block has one)
     unsigned wait0;  // block 0 waits for flag_far >= wait0 when have_wait0 (the previous panel's updates of THIS panel's columns)
     int have_wait0;
     long long* dbg;  // optional: 8 globaltimer stamps per block (CTA 0, thread 0), tools/chain_probe.py
@@ -1001,7 +996,7 @@ __global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS)
             const int t = tid >> 4, c = tid & 15;
             Tj[tid] = (t <= c) ? gt[t][c] : 0.f;
         }
-        if (jb + 2 < nblk || a.next_cols > 0) {  // far(jb) accumulates into srep[jb & 1]; its previous user far(jb-2) was awaited above
+        if (jb + 2 < nblk) {  // far(jb) accumulates into srep[jb & 1]; its previous user far(jb-2) was awaited above
             constexpr int Q = SLD / 4;  // float4 per row
             for (int idx = (int)crank * NT + tid; idx < 2 * B * Q; idx += CS * NT) {
                 const int rep = idx / (B * Q), rem = idx - rep * (B * Q);
@@ -1019,10 +1014,6 @@ __global__ void __launch_bounds__(NT, 1) panel_chain_kernel(ChainArgs a, int CS)
 
 __global__ void chain_gate_kernel(const unsigned* flag, unsigned want) {
     while ((int)(ld_acquire_u32(flag) - want) < 0) __nanosleep(200);
-}
-__global__ void chain_post_kernel(unsigned* flag, unsigned v) {
-    atomicExch(flag, v);
-    __threadfence_system();
 }
 
 // ------------------------------------------------------------------ deferred outputs of a multi-block panel
@@ -1258,12 +1249,8 @@ template <int B> struct Su4 {
 template <int B>
 __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* __restrict__ Y, long ldy, const float* __restrict__ A,
                                                                   long lda, int D, int ncols, float* __restrict__ Srep,
-                                                                  const unsigned* gate, unsigned gate_want, const float* __restrict__ Tj,
+                                                                  const float* __restrict__ Tj,
                                                                   float* __restrict__ Sfin, int rows_per_cta, int ysm_floats) {
-    // gate != null (persistent panel chain): the kernel is issued ahead of its producer and every CTA waits here until
-    // the cluster has posted the register block whose reflectors it applies (flag >= gate_want).  In-kernel gating
-    // instead of a stream wait: cuStreamWaitValue32 / WriteValue32 cost the issuing thread ~30 us each on B200
-    // (12 per panel = 90-130 ms of host time per 32768^2 factorisation: the whole path became launch-bound).
     constexpr int NTHR = Su4<B>::NTHR, NWARP = NTHR / 32, RB = Su4<B>::RB;
     extern __shared__ __align__(16) float sm[];
     float* ysm = sm;               // rows_per_cta x B  (later: T, B x (B+4))
@@ -1275,12 +1262,7 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_s4_kernel(const float* _
     const int c0 = blockIdx.y * 128, col = c0 + 4 * lane;
     const bool on = col < ncols;
     pdl_wait();
-    if (gate) {
-        if (tid == 0)
-            while ((int)(ld_acquire_u32(gate) - gate_want) < 0) __nanosleep(128);
-        __syncthreads();
-    }
-    pdl_launch_dependents();
+    pdl_launch_dependents();   // (after the wait: the U kernel behind this one fetches A_rest and Y before ITS wait)
     const float* Ap = A + (size_t)r0 * lda + col;
     float4 a4[RB];
 #pragma unroll
@@ -1391,7 +1373,9 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* _
     const int c0 = blockIdx.y * 128, col = c0 + 4 * lane;
     const bool on = col < ncols;
     pdl_launch_dependents();
-    pdl_wait();
+    // This launch always follows the S kernel of the same update directly (launch_su).  That kernel only READS A_rest and Y,
+    // and whatever wrote them had finished before its CTAs passed their own griddepcontrol.wait -- which all of them had done
+    // when this grid was let in.  The first batch of rows and the Y slab are therefore fetched BEFORE the wait; only S needs it.
     float* Ap = A + (size_t)r0 * lda + col;
     float4 a4[RB];
 #pragma unroll
@@ -1399,6 +1383,11 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* _
         const int r2 = warp + u * NWARP;
         a4[u] = (on && r2 < nrows) ? __ldcg(reinterpret_cast<const float4*>(Ap + (size_t)r2 * lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    for (int idx = tid; idx < nrows * B; idx += NTHR) {
+        const int rr = idx / B, t = idx - rr * B;
+        ysm[idx] = __ldcg(&Y[(size_t)(r0 + rr) * ldy + t]);
+    }
+    pdl_wait();
     float sv[B][4];
 #pragma unroll
     for (int t = 0; t < B; ++t) {
@@ -1408,10 +1397,6 @@ __global__ void __launch_bounds__(Su4<B>::NTHR) inpanel_u4_kernel(const float* _
             s4.x += s5.x; s4.y += s5.y; s4.z += s5.z; s4.w += s5.w;
         }
         sv[t][0] = s4.x; sv[t][1] = s4.y; sv[t][2] = s4.z; sv[t][3] = s4.w;
-    }
-    for (int idx = tid; idx < nrows * B; idx += NTHR) {
-        const int rr = idx / B, t = idx - rr * B;
-        ysm[idx] = __ldcg(&Y[(size_t)(r0 + rr) * ldy + t]);
     }
     __syncthreads();
     for (int rb = warp; on && rb < nrows; rb += NWARP * RB) {
@@ -1772,8 +1757,7 @@ int su_attrs() {
 template <int B>
 int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda, int D, int ncols, float* Srep, float* Sfin,
               int num_sms, cudaStream_t st, long* launches, const ProfHook* prof, bool pdl_first = true,
-              const unsigned* gate = nullptr, unsigned gate_want = 0, unsigned* post = nullptr, unsigned post_val = 0, unsigned* ticket = nullptr,
-              int max_rows = 512) {
+              unsigned* post = nullptr, unsigned post_val = 0, unsigned* ticket = nullptr, int max_rows = 512) {
     // one wave of CTAs over the SMs this stream may use (up to max_rows rows = 32-64 KB of staged Y per CTA);
     // taller blocks take k balanced waves
     const int waves = ceil_div(D, max_rows * num_sms);
@@ -1786,6 +1770,10 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.stream = st; cfg.attrs = pat; cfg.numAttrs = 1;
     const bool vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(Arest) & 15) == 0) && ((ncols & 3) == 0) && ncols <= SLD;
+    if (!vec && post) {   // only the vectorised pair knows the chain's flags (panel_chain_ok guarantees its alignment)
+        set_error("in-panel update: flag-ordered launch needs the vectorised kernels (lda=%ld ncols=%d)", lda, ncols);
+        return MPQR_EINVAL;
+    }
     if (prof) prof->begin(prof->ctx, 5, st, 2.0 * D * ncols * B, 4.0 * D * (ncols + B));
     if (vec) {
         int ysm_floats = rows * B;
@@ -1798,7 +1786,7 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
         // pdl_first = false: the S kernel must not become resident (and hold its SMs idle) while the register-block
         // kernel before it is still running: those SMs belong to the side stream's updates during that time
         if (!pdl_first) cfg.numAttrs = 0;
-        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_s4_kernel<B>, Yj, ldy, (const float*)Arest, lda, D, ncols, Srep, gate, gate_want, Tj, Sfin, rows,
+        MPQR_CUDA(cudaLaunchKernelEx(&cfg, inpanel_s4_kernel<B>, Yj, ldy, (const float*)Arest, lda, D, ncols, Srep, Tj, Sfin, rows,
                                      ysm_floats));
         cfg.numAttrs = 1;
         if (prof) { prof->end(prof->ctx, st); prof->begin(prof->ctx, 7, st, 2.0 * D * ncols * B, 4.0 * D * (2 * ncols + B)); }
@@ -1818,12 +1806,11 @@ int launch_su(const float* Tj, const float* Yj, long ldy, float* Arest, long lda
 }
 
 // ---- persistent panel chain: host side
-// Stream memory operations (driver API, resolved at run time like the green-context calls in api.cu): the side stream
-// waits on the kernel's progress flag and posts its own without any kernel of ours occupying an SM.  MPQR_GATE_KERNEL=1
-// (or a driver without the entry points) uses a one-thread gate / post kernel instead.
+// Stream memory operation (driver API, resolved at run time like the green-context calls in api.cu): the side stream waits
+// on the kernel's progress flag without any kernel of ours occupying an SM.  MPQR_GATE_KERNEL=1 (or a driver without the
+// entry point) uses a one-thread gate kernel instead.
 struct MemopApi {
     CUresult (*Wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-    CUresult (*Write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
     bool ok;
 };
 const MemopApi* memop_api() {
@@ -1835,14 +1822,15 @@ const MemopApi* memop_api() {
             cudaDriverEntryPointQueryResult q;
             return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
         };
-        api.ok = get("cuStreamWaitValue32", (void**)&api.Wait32) && get("cuStreamWriteValue32", (void**)&api.Write32);
+        api.ok = get("cuStreamWaitValue32", (void**)&api.Wait32);
         if (!api.ok) cudaGetLastError();
     }
     return &api;
 }
 int stream_wait_geq(cudaStream_t st, unsigned* flag, unsigned want) {
     const MemopApi* m = memop_api();
-    if (m->ok && !getenv("MPQR_GATE_KERNEL")) {
+    static const bool gate_kernel = getenv("MPQR_GATE_KERNEL") != nullptr;
+    if (m->ok && !gate_kernel) {
         if (m->Wait32((CUstream)st, (CUdeviceptr)(uintptr_t)flag, want, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS) return MPQR_OK;
         set_error("cuStreamWaitValue32 failed");
         return MPQR_ECUDA;
@@ -1851,18 +1839,6 @@ int stream_wait_geq(cudaStream_t st, unsigned* flag, unsigned want) {
     MPQR_CUDA(cudaGetLastError());
     return MPQR_OK;
 }
-int stream_post(cudaStream_t st, unsigned* flag, unsigned v) {
-    const MemopApi* m = memop_api();
-    if (m->ok && !getenv("MPQR_GATE_KERNEL")) {
-        if (m->Write32((CUstream)st, (CUdeviceptr)(uintptr_t)flag, v, CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS) return MPQR_OK;
-        set_error("cuStreamWriteValue32 failed");
-        return MPQR_ECUDA;
-    }
-    chain_post_kernel<<<1, 1, 0, st>>>(flag, v);
-    MPQR_CUDA(cudaGetLastError());
-    return MPQR_OK;
-}
-
 // CUDA loads kernels lazily, and loading one may need a context synchronisation: a first-time load of a side-stream
 // kernel WHILE the cluster spins on that side stream's flag would never return (CUDA programming guide, lazy loading,
 // "concurrent execution").  Everything that is issued between a chain launch and the end of its side-stream items is
@@ -1879,7 +1855,7 @@ int chain_preload() {
     MPQR_TRY(su_attrs<32>());
     (void)max_cluster();
     const void* fns[] = {(const void*)inpanel_s_kernel<16>, (const void*)inpanel_u_kernel<16>, (const void*)inpanel_s4_kernel<16>,
-                         (const void*)inpanel_u4_kernel<16>, (const void*)chain_gate_kernel, (const void*)chain_post_kernel,
+                         (const void*)inpanel_u4_kernel<16>, (const void*)chain_gate_kernel,
                          (const void*)panel_finalize_kernel,
                          // everything else a factorisation may launch for the first time while a gate kernel spins
                          (const void*)inpanel_s_kernel<32>, (const void*)inpanel_u_kernel<32>, (const void*)inpanel_s4_kernel<32>,
@@ -2031,15 +2007,12 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         if (launches) *launches += 1;
         return MPQR_OK;
     };
-    // Stream of everything after the register blocks (finalize, Gram / T / W): with next-panel coverage the chain does not
-    // need it, so it moves to `tail_stream` behind an event and the next panel's kernel can follow at once.
-    const int next_cols = (chain && a.tail_stream && a.ev_chain && a.next_cols > 0 && (a.next_cols & 3) == 0 && a.next_cols <= 128) ? a.next_cols : 0;
-    cudaStream_t ts = next_cols > 0 ? a.tail_stream : stream;
+    cudaStream_t ts = stream;   // everything after the register blocks (finalize, Gram / T / W)
     if (chain) {
         HostProfScope hp(0);
         if (!pick_shape(16, D, a.force_cs, a.force_rpt, &rpt, &cs)) { set_error("panel: sizing error D=%d", D); return MPQR_EINVAL; }
         const int nblocks = pw / 16;
-        const int nfarb = next_cols > 0 ? nblocks : nblocks - 2;  // blocks with a side update
+        const int nfarb = nblocks - 2;  // blocks with a side update (the cluster applies block jb to block jb+1 itself)
         float* Tsl = w.Tsl + (size_t)(a.chain_buf & 1) * 8 * 256;
         ChainArgs ca{};
         ca.A = Ablk; ca.lda = a.lda; ca.D = D; ca.pw = pw;
@@ -2050,7 +2023,6 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         ca.flag_done = a.chain_flags;
         ca.flag_far = a.chain_flags + 1;
         ca.flag_started = a.chain_flags + 3;
-        ca.next_cols = next_cols;
         // this panel's columns were last written by the previous panel's side updates (if it covered them): block 0 waits
         // for the last value posted so far
         ca.have_wait0 = (a.chain_last_far && *a.chain_last_far != 0) ? 1 : 0;
@@ -2059,54 +2031,30 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
         ca.srep[0] = SrepA; ca.srep[1] = SrepA + (size_t)2 * RMAX * SLD;
         ca.dbg = a.chain_dbg;
         MPQR_TRY(chain_preload());
-        if (a.ev_start) MPQR_CUDA(cudaEventRecord(a.ev_start, stream));   // everything before the cluster launch on this stream
         if (a.prof) a.prof->begin(a.prof->ctx, 4, stream, 4.0 * D * pw * 16 + 4.0 * D * 16 * 16 * (nblocks - 1), 8.0 * D * pw);
         MPQR_TRY(launch_chain(ca, rpt, cs, stream));  // issued BEFORE the side stream's waits (a wait never queues ahead of its producer)
         if (a.prof) a.prof->end(a.prof->ctx, stream);
         if (launches) *launches += 1;
         int side_sms = sm_count(di) - cs;  // the cluster keeps its SMs for the whole panel
         if (side_sms < 8) side_sms = 8;
-        // In-kernel ordering (default): the S kernel of block jb is issued ahead of time and its CTAs wait for the cluster's
-        // flag themselves, the U kernel's last CTA posts the side flag.  Waiting CTAs hold their SMs, so the side grids are
-        // capped at 32 CTAs (1024 rows each at D = 32768): the rest of the partition stays free for the tensor-core in-block
-        // updates of the rest stream.  The first S kernel of a panel is held back by an event until the stream reaches the
-        // cluster launch.  MPQR_MEMOPS=1 / MPQR_GATE_KERNEL=1: stream-level ordering (stream memory operations cost the
-        // issuing thread ~26 us each on B200: 12 per panel made the whole path launch-bound).
-        // [B200, r2i] in-kernel gating of the FIRST S kernel of a panel deadlocked: its CTAs (32-64 x 512 threads) could start
-        // spinning before the cluster was placed and leave no GPC with 16 free SMs for it.  The first S kernel is therefore
-        // always ordered at stream level (a one-thread gate kernel cannot keep a cluster out), and in-kernel gating of the
-        // later ones is opt-in (MPQR_INKERNEL=1) until it has run the whole suite.
-        static const bool inkernel_env = getenv("MPQR_INKERNEL") != nullptr;
-        const bool inkernel = inkernel_env && !getenv("MPQR_MEMOPS") && !getenv("MPQR_GATE_KERNEL");
-        static const int inkernel_cap = getenv("MPQR_INKERNEL") ? atoi(getenv("MPQR_INKERNEL")) : 0;   // 1: capped at 32 CTAs, >= 2: that many
-        if (inkernel && side_sms > (inkernel_cap >= 2 ? inkernel_cap : 32)) side_sms = inkernel_cap >= 2 ? inkernel_cap : 32;
-        static const int su_rows = getenv("MPQR_SU_MAXROWS") ? atoi(getenv("MPQR_SU_MAXROWS")) : 0;   // tuning knob: rows per S/U CTA
-        if (inkernel && a.ev_start) MPQR_CUDA(cudaStreamWaitEvent(a.chain_side, a.ev_start, 0));
+        // Ordering of the side updates.  S(jb) is held back at STREAM level until the cluster has posted block jb
+        // (cuStreamWaitValue32; a one-thread gate kernel where the driver lacks it); the side flag is posted by the U kernel's last
+        // CTA (ticket counter): a stream write behind the kernel would add the kernel's completion and the memory operation's
+        // own latency to every block of the chain, and nothing spins for a kernel-side post.  Stream memory operations cost
+        // the issuing thread ~26 us each on B200, so the six writes per panel that this saves are 40 ms of host time at 32768^2.
+        // Dropped after measurement: S kernels that wait for the cluster's flag themselves (issued ahead, CTAs spinning).  It
+        // was slower (117.4 against 113.1 ms: waiting CTAs hold SMs the rest-stream GEMMs need) and [B200, r2i] deadlocked when
+        // the first S kernel of a panel filled the partition before the 16-CTA cluster had been placed (16 free SMs in ONE GPC).
         for (int jb = 0; jb < nfarb; ++jb) {
-            // block jb's reflectors -> the rest of the panel beyond block jb+1 and (next_cols) the whole next panel:
-            // one contiguous column range
+            // block jb's reflectors -> the rest of the panel beyond block jb+1
             const int j0 = jb * 16, Dj = D - j0;
             const int cfirst = (j0 + 32 < pw) ? j0 + 32 : pw;   // first column (panel-relative)
-            const int nfar = pw - cfirst + next_cols;
-            if (!inkernel) MPQR_TRY(stream_wait_geq(a.chain_side, a.chain_flags, ca.base + (unsigned)(jb + 1)));
-            else if (jb == 0) {
-                chain_gate_kernel<<<1, 1, 0, a.chain_side>>>(a.chain_flags, ca.base + 1u);
-                MPQR_CUDA(cudaGetLastError());
-            }
+            const int nfar = pw - cfirst;
+            MPQR_TRY(stream_wait_geq(a.chain_side, a.chain_flags, ca.base + (unsigned)(jb + 1)));
             MPQR_TRY(launch_su<16>(Tsl + (size_t)jb * 256, Yp + (size_t)j0 * ldyp + j0, ldyp, Ablk + (size_t)j0 * a.lda + cfirst, a.lda, Dj,
                                    nfar, ca.srep[jb & 1], w.Sfin, side_sms, a.chain_side, launches, a.prof, false,
-                                   inkernel ? a.chain_flags : nullptr, ca.base + (unsigned)(jb + 1),
-                                   inkernel ? a.chain_flags + 1 : nullptr, ca.base + (unsigned)(jb + 1), a.chain_flags + 2,
-                                   su_rows >= 64 ? su_rows : (inkernel ? 1024 : 512)));
-            if (!inkernel) MPQR_TRY(stream_post(a.chain_side, a.chain_flags + 1, ca.base + (unsigned)(jb + 1)));
+                                   a.chain_flags + 1, ca.base + (unsigned)(jb + 1), a.chain_flags + 2));
             if (a.chain_last_far) *a.chain_last_far = ca.base + (unsigned)(jb + 1);
-        }
-        if (next_cols > 0) {
-            // the kernel itself only consumed the side updates up to block nblocks-3: whoever touches the next panel's columns
-            // next is ordered behind the last post (a chain kernel: through wait0; anything else: through this event)
-            if (a.ev_side) MPQR_CUDA(cudaEventRecord(a.ev_side, a.chain_side));
-            MPQR_CUDA(cudaEventRecord(a.ev_chain, stream));
-            MPQR_CUDA(cudaStreamWaitEvent(ts, a.ev_chain, 0));
         }
         if (a.prof) a.prof->begin(a.prof->ctx, 4, ts, 0.0, 0.0);
         MPQR_TRY(finalize(ts));
@@ -2177,16 +2125,6 @@ int launch_panel(const PanelArgs& a, cudaStream_t stream, long* launches) {
 
 
 int chain_preload_all() { return chain_preload(); }
-
-// Holds `st` back until the chain kernel whose base is `next_base` is resident (one spinning thread).  A 16-CTA cluster needs
-// 16 free SMs of ONE GPC: a GEMM that is already spread over the partition keeps it out until its CTAs retire
-// ([B200] 47-83 us per panel at 32768 rows, profiles/r2_timeline_c4.txt), so the rest-of-block GEMMs queue behind this.
-int chain_wait_started(cudaStream_t st, unsigned* chain_flags, unsigned next_base) {
-    MPQR_TRY(chain_preload());
-    chain_gate_kernel<<<1, 1, 0, st>>>(chain_flags + 3, next_base + 1u);
-    MPQR_CUDA(cudaGetLastError());
-    return MPQR_OK;
-}
 
 int panel_form_w(const PanelArgs& a, cudaStream_t stream, long* launches) {
     if (!a.Y16 || !a.W16 || !a.W32 || !a.ws) { set_error("panel_form_w: mixed-path arguments missing"); return MPQR_EINVAL; }

@@ -125,7 +125,7 @@ std::vector<Plan*> g_plans;
 constexpr size_t kMaxPlans = 8;
 
 int build_plan(Plan* P, const DeviceInfo& di) {
-    static const long HMAX = (getenv("MPQR_TSQR_HMAX") && atol(getenv("MPQR_TSQR_HMAX")) >= 1024 && atol(getenv("MPQR_TSQR_HMAX")) <= 32768) ? atol(getenv("MPQR_TSQR_HMAX")) : 32768;   // tuning knob: leaf height
+    constexpr long HMAX = 32768;   // leaf height: what one register-resident cluster holds
     const long m = P->m;
     const int n = P->n;
     const int r = n < 128 ? n : 128;
