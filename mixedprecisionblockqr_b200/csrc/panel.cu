@@ -1829,8 +1829,7 @@ const MemopApi* memop_api() {
 }
 int stream_wait_geq(cudaStream_t st, unsigned* flag, unsigned want) {
     const MemopApi* m = memop_api();
-    static const bool gate_kernel = getenv("MPQR_GATE_KERNEL") != nullptr;
-    if (m->ok && !gate_kernel) {
+    if (m->ok && !getenv("MPQR_GATE_KERNEL")) {   // (read per call: the panel tests switch it inside one process)
         if (m->Wait32((CUstream)st, (CUdeviceptr)(uintptr_t)flag, want, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS) return MPQR_OK;
         set_error("cuStreamWaitValue32 failed");
         return MPQR_ECUDA;

@@ -75,11 +75,11 @@ def test_panel_zero_column_and_signs():
 
 
 @pytest.mark.parametrize("m,n,lam,pw", [(2048, 128, 0, 128), (20000, 128, 0, 128), (5000, 256, 128, 128), (700, 64, 0, 64)])
-@pytest.mark.parametrize("mode", ["classic", "gate", "memops"])
+@pytest.mark.parametrize("mode", ["classic", "gate"])
 def test_panel_flows_agree(m, n, lam, pw, mode, monkeypatch):
-    # the persistent chain with in-kernel ordering of the side updates (default) is covered by the tests above; here the
-    # per-block launch flow it replaces (MPQR_NO_CHAIN=1: odd widths and unaligned shapes still take it) and the two
-    # stream-level orderings of the side updates (MPQR_MEMOPS=1: cuStreamWaitValue32 / WriteValue32; MPQR_GATE_KERNEL=1:
-    # one-thread gate / post kernels)
-    monkeypatch.setenv({"classic": "MPQR_NO_CHAIN", "gate": "MPQR_GATE_KERNEL", "memops": "MPQR_MEMOPS"}[mode], "1")
+    # the persistent chain in its default ordering (side updates behind cuStreamWaitValue32, side flag posted by the U kernel)
+    # is covered by the tests above; here the per-block launch flow it replaces (MPQR_NO_CHAIN=1 -- what MPQR_STREAM_ORDERED
+    # handles, odd widths and unaligned shapes take) and the chain with one-thread gate kernels instead of stream memory
+    # operations (MPQR_GATE_KERNEL=1: the fallback for drivers without the entry point)
+    monkeypatch.setenv({"classic": "MPQR_NO_CHAIN", "gate": "MPQR_GATE_KERNEL"}[mode], "1")
     _check_panel(m, n, lam, pw, seed=m + 7 * pw, tol=5e-5)

@@ -238,6 +238,6 @@ def test_host_driver_streamed_input(m, n, r, monkeypatch):
         out[mode] = np.triu(P[:m]).copy()
     spread = np.abs(np.abs(out["streamed"]) - np.abs(out["plain"])).max() / np.abs(out["plain"]).max()
     # (two runs of the SAME path differ at this level too: FP32 atomics in the in-panel products, split-K reduce-add; the wide
-    #  shape accumulates it over 4096 more trailing columns: observed 1.6e-3 with MPQR_INKERNEL=48, 1.3e-3 by default)
+    #  shape accumulates it over 4096 more trailing columns: observed 1.3e-3 - 1.6e-3)
     assert spread <= (7 if m < n else 3) * 2.0 ** -11, spread
     assert pkg.lib().mpqr_release_cache() == 0

@@ -25,7 +25,7 @@ for (m, n, lam, pw) in [(300, 64, 0, 64), (2048, 128, 0, 128), (5000, 256, 128, 
 
 tmo = int(sys.argv[1]) if len(sys.argv) > 1 else 90
 for name, env in [("classic (MPQR_NO_CHAIN=1)", {"MPQR_NO_CHAIN": "1"}), ("chain + gate kernels", {"MPQR_GATE_KERNEL": "1"}),
-                  ("chain + stream memops", {})]:
+                  ("chain, default ordering (stream wait + kernel-side post)", {})]:
     e = dict(os.environ); e.update(env)
     print(name, flush=True)
     try:

@@ -1,5 +1,5 @@
 """FP32 CUDA-core GEMMs of the FP32 driver / TSQR on their own: correctness against torch (FP64) and TFLOP/s.
-python tools/sgemm_time.py   (MPQR_SGEMM_OLD=1: the 64 x 64 fallback kernel)"""
+python tools/sgemm_time.py"""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
