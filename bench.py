@@ -391,9 +391,9 @@ def main_native(args):
     # classes panel_* are the parts of "panel"; shares are taken over the leaf classes only
     leaves = [k for k in prof if k != "panel"] if any(prof[k]["launches"] for k in prof if k.startswith("panel_")) else list(prof)
     by_kernel, total_kernel_ms = {}, sum(prof[k]["ms"] for k in leaves) or 1.0
-    # `traffic`: DRAM bytes per launch from an ncu --set full capture of THIS workload (profiles/ncu_traffic.json:
+    # `traffic`: DRAM bytes of one launch from an ncu --set full capture of THIS workload (profiles/ncu_traffic.json:
     # {workload: {class: {"dram_bytes_per_launch": ..., "algorithmic_bytes_that_launch": ..., "shape": ...}}}); null when
-    # no capture of the benchmarked workload exists (never a figure taken at another shape)
+    # no capture of the benchmarked workload exists (never a figure taken at another workload)
     traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     traffic = {}
     if os.path.exists(traffic_file):
@@ -401,20 +401,33 @@ def main_native(args):
             traffic = json.load(open(traffic_file)).get(args.workload, {})
         except Exception:   # noqa: BLE001
             traffic = {}
+    def traffic_of(name):
+        """(DRAM bytes of the captured launch, its description): the capture is ONE launch of the benchmarked workload (its
+        shape and its own algorithmic bytes are in `traffic_capture`), not the average launch `achieved` is computed from."""
+        t = traffic.get(name)
+        if not isinstance(t, dict):
+            return None, None
+        cap = {k: t[k] for k in ("shape", "algorithmic_bytes_that_launch", "tensor_pipe_active_pct", "tflops_that_launch", "dram_gbs_that_launch") if k in t}
+        if t.get("algorithmic_bytes_that_launch"):
+            cap["dram_over_algorithmic"] = t["dram_bytes_per_launch"] / t["algorithmic_bytes_that_launch"]
+        return t.get("dram_bytes_per_launch"), cap
+
     for name in leaves:
         v = prof[name]
         if v["launches"] == 0:
             continue
         avg_ms = v["ms"] / v["launches"]
+        tr, cap = traffic_of(name)
         if name in ("gemm_tn", "gemm_nn"):
             ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
             by_kernel[name] = {"bound": "tensor", "achieved": ach, "peak": peaks["tc_sustained"], "unit": "TFLOP/s",
-                               "frac": ach / peaks["tc_sustained"], "traffic": traffic.get(name),
-                               "hbm_gbs_algorithmic": v["bytes"] / (v["ms"] * 1e-3) / 1e9}
+                               "frac": ach / peaks["tc_sustained"], "traffic": tr, "traffic_capture": cap,
+                               "hbm_gbs_algorithmic": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
+                               "hbm_frac_algorithmic": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
         else:
             ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9
             by_kernel[name] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                               "frac": ach / peaks["hbm_gbs"], "traffic": traffic.get(name)}
+                               "frac": ach / peaks["hbm_gbs"], "traffic": tr, "traffic_capture": cap}
         by_kernel[name].update({"share_of_kernel_time": v["ms"] / total_kernel_ms, "avg_launch_ms": avg_ms,
                                 "launches_per_step": v["launches"], "algorithmic_bytes_per_launch": v["bytes"] / v["launches"]})
     dominant = max(by_kernel, key=lambda k: by_kernel[k]["share_of_kernel_time"])

@@ -28,13 +28,13 @@ def test_fp32_driver_vs_oracle(m, n, r):
     R = oracle.strip_R(P)
     be = oracle.backward_error(A, R, Q)
     assert be <= m * 2.0 ** -23                      # reference criterion
-    assert be <= 3e-6                                # FP32-vs-FP32: tighter
+    assert be <= 1.8e-6                              # FP32-vs-FP32: tighter (observed <= 5.9e-7)
     assert oracle.q_error_max(Q) <= m * 2.0 ** -23
-    assert oracle.orthogonality_fro(Q) <= 2e-5
+    assert oracle.orthogonality_fro(Q) <= 3e-5       # (observed <= 1.43e-5)
     scale = np.abs(Pref).max()
     observe("qr_fp32_ref_shapes", be=be, orth=oracle.orthogonality_fro(Q), dP=np.abs(P - Pref).max() / scale, dQ=np.abs(Q - Qref).max())
-    assert np.abs(P - Pref).max() <= 5e-5 * scale    # packed factor incl. Householder vectors
-    assert np.abs(Q - Qref).max() <= 5e-5
+    assert np.abs(P - Pref).max() <= 3e-6 * scale    # packed factor incl. Householder vectors (observed <= 9.3e-7)
+    assert np.abs(Q - Qref).max() <= 4e-6            # (observed <= 1.2e-6)
 
 
 @pytest.mark.parametrize("m,n,r", REF_SHAPES)
@@ -49,10 +49,11 @@ def test_mixed_driver_vs_oracle(m, n, r, bf16):
     observe("qr_mixed_ref_shapes_bf16" if bf16 else "qr_mixed_ref_shapes_fp16", be=be / eps, orth=oracle.orthogonality_fro(Q) / (eps * np.sqrt(m)),
             dR=np.abs(np.abs(R) - np.abs(Rref)).max() / (eps * np.abs(Rref).max()))
     assert be <= m * eps                             # reference criterion m*2^-bits (bits=11 for FP16, Cuda/qr.cu:1889)
-    assert be <= 12 * eps                            # what FP16 operands should actually give
-    assert oracle.orthogonality_fro(Q) <= 40 * eps * np.sqrt(m)
+    # tolerances = 3 x the largest value observed over the shape list (profiles/r2_observed_test_gpu_qr.jsonl: 1.74, 2.7, 1.15)
+    assert be <= 5.5 * eps                           # what 16-bit operands should actually give
+    assert oracle.orthogonality_fro(Q) <= 8.5 * eps * np.sqrt(m)
     # elementwise |R| agreement at FP16-GEMM error level
-    assert np.abs(np.abs(R) - np.abs(Rref)).max() <= 40 * eps * np.abs(Rref).max()
+    assert np.abs(np.abs(R) - np.abs(Rref)).max() <= 4 * eps * np.abs(Rref).max()
 
 
 @pytest.mark.parametrize("m,n,r,prec", [(1024, 1024, 32, "fp32"), (1024, 1024, 32, "fp16"), (2048, 2048, 32, "fp16"),
@@ -65,13 +66,13 @@ def test_larger_shapes_backward_error(m, n, r, prec):
     kw = {"bf16": True} if prec == "bf16" else {}
     fn(P, None, m, n, r, **kw)
     be = oracle.backward_error_packed(A, P)
-    lim = {"fp32": 5e-6, "fp16": 12 * 2.0 ** -11, "bf16": 12 * 2.0 ** -8}[prec]
+    lim = {"fp32": 2.1e-6, "fp16": 5.5 * 2.0 ** -11, "bf16": 5.5 * 2.0 ** -8}[prec]   # observed 7.0e-7, 1.7 eps, 1.24 eps
     assert be <= lim, be
     Pref, _ = oracle.block_qr(A, r, want_q=False)
     Rref = oracle.strip_R(Pref)
     dr = np.abs(np.abs(oracle.strip_R(P)) - np.abs(Rref)).max() / np.abs(Rref).max()
     observe(f"qr_larger_{prec}", be=be, dr=dr)
-    assert dr <= (2e-5 if prec == "fp32" else 60 * lim / 12), dr
+    assert dr <= (8e-6 if prec == "fp32" else 17 * lim / 5.5), dr   # observed 2.6e-6 / 5.7 eps (the wide 512 x 2048 case) / 0.96 eps
 
 
 def test_python_fixtures_match_lapack():
@@ -143,12 +144,12 @@ def test_lookahead_driver_vs_oracle(m, n, r, nb, chain, monkeypatch):
         torch.cuda.synchronize()
         P = np.ascontiguousarray(dA.cpu().numpy()[:, :n])
         be = oracle.backward_error_packed(A, P)
-        assert be <= 12 * 2.0 ** -11, be
+        assert be <= 4.5 * 2.0 ** -11, be           # observed <= 1.4 eps
         Pref, _ = oracle.block_qr(A, r, want_q=False)
         Rref = oracle.strip_R(Pref)
         dr = np.abs(np.abs(oracle.strip_R(P)) - np.abs(Rref)).max() / np.abs(Rref).max()
         observe("qr_lookahead_small", be=be, dr=dr)
-        assert dr <= 60 * 2.0 ** -11, dr
+        assert dr <= 13 * 2.0 ** -11, dr            # observed <= 4.3 eps (the wide 1024 x 3072 case)
     plan.close()
 
 
