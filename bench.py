@@ -434,6 +434,10 @@ def main_native(args):
     roofline = dict(by_kernel[dominant])
     roofline["kernel"] = dominant
     roofline["peak_source"] = peaks["source"] + (", sustained bf16 cuBLAS" if roofline["bound"] == "tensor" else ", copy bandwidth")
+    if dominant == "panel_block":
+        roofline["note"] = ("latency-bound, not a bandwidth kernel: one cluster per panel runs 16 sequential reflector steps per register "
+                            "block (~1.2 us each at 32768 rows); ncu: 12.5 % warps active, DRAM reads 1.02 x the block data "
+                            "(profiles/r2_ncu_chain_kernel.txt); algorithmic bytes = 8*D*r per panel (SURVEY 8d)")
     # whole-QR roofline: every class at its own bound (SURVEY 8d T_roof)
     t_roof = sum(max(prof[k]["flops"] / (peaks["tc_sustained"] * 1e12) if k in ("gemm_tn", "gemm_nn") else 0.0,
                      prof[k]["bytes"] / (peaks["hbm_gbs"] * 1e9)) for k in leaves)

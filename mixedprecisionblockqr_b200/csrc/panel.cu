@@ -746,8 +746,8 @@ __global__ void __launch_bounds__(NT, 1) panel_block_kernel(BlockArgs a, int CS)
 //   outputs          FP32 Y (compact, coalesced), the block's first 32 packed rows of A, T_jb; Y_jb -> shared memory
 //   signal           flag_done = base + jb + 1 once every CTA's stores are fenced
 // The update of the rest of the panel (blocks jb+2 ..) stays on the device-wide S/U kernels, issued by the host on a
-// side stream BEHIND a stream wait on flag_done (cuStreamWaitValue32, or a one-thread gate kernel) and followed by a
-// stream write of flag_far, which the cluster polls before it loads block jb+2.  Flags only grow (host mirror `base`).
+// side stream BEHIND a stream wait on flag_done (cuStreamWaitValue32, or a one-thread gate kernel); the U kernel's last
+// CTA posts flag_far, which the cluster polls before it loads block jb+2.  Flags only grow (host mirror `base`).
 struct ChainArgs {
     float* A;        // element (panel row 0, panel column 0) of the packed FP32 master
     long lda;
@@ -757,7 +757,7 @@ struct ChainArgs {
     float* Tslots;   // block jb's T at Tslots + jb * tstride (16 x 16, ld 16)
     int tstride;
     unsigned* flag_done;
-    unsigned* flag_started;  // optional: base + 1 as soon as the cluster is resident (gates work that would keep it from being placed)
+    unsigned* flag_started;  // optional: base + 1 as soon as the cluster is resident (diagnostic: nothing waits on it)
     const unsigned* flag_far;
     unsigned base;
     float* srep[2];  // S replica pairs of the far updates (blocks alternate); the cluster clears rows 0..15 of both replicas of
