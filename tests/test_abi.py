@@ -21,6 +21,18 @@ def test_header_symbols_all_exported():
     assert b"sm_100a" in L.mpqr_version()
 
 
+def test_header_flags_match_the_python_mirror():
+    # flag and error constants of include/mpqr.h against the ctypes mirror (a drifted bit would silently change a plan)
+    hdr = open(os.path.join(ROOT, "include", "mpqr.h")).read()
+    defs = {k: int(v.rstrip("u"), 0) for k, v in re.findall(r"#define\s+(MPQR_[A-Z0-9_]+)\s+\(?(-?(?:0x[0-9a-fA-F]+|\d+)u?)\)?", hdr)}
+    for name in ("MPQR_FP32", "MPQR_FP16", "MPQR_BF16", "MPQR_KEEP_WY", "MPQR_STREAM_ORDERED"):
+        assert defs[name] == getattr(pkg, name), name
+    assert defs["MPQR_NCCL_UID_BYTES"] == pkg.NCCL_UID_BYTES
+    flags = [defs[n] for n in ("MPQR_FP16", "MPQR_BF16", "MPQR_KEEP_WY", "MPQR_STREAM_ORDERED")]
+    assert len({f for f in flags}) == len(flags) and all(f & (f - 1) == 0 for f in flags)   # distinct single bits
+    assert defs["MPQR_PRECISION_MASK"] == defs["MPQR_FP16"] | defs["MPQR_BF16"]
+
+
 def test_no_cpu_fallback():
     try:
         import torch
