@@ -7,8 +7,10 @@
 // against libmpqr_refshim.so instead of its own qr.cu drivers, unchanged.
 //
 // Contract kept: caller owns A ((m+1)*n floats, rows 0..m-1 = input, row m = 0) and
-// Q (m*m floats); both are overwritten in place; nothing stays resident on the device; errors
-// print a message and exit(EXIT_FAILURE) like checkCudaErrors (Cuda/helper_cuda.h:583-595).
+// Q (m*m floats); both are overwritten in place; errors print a message and exit(EXIT_FAILURE) like
+// checkCudaErrors (Cuda/helper_cuda.h:583-595).  One deviation: the reference frees everything per call
+// (Cuda/qr.cu:1221-1226), mpqr_block_qr_host keeps the plan of the last shape (handle + device copies,
+// ~12 GB at 32768^2) for the next call; mpqr_release_cache() or MPQR_NO_HOST_CACHE=1 give the memory back.
 #include <cstdio>
 #include <cstdlib>
 
