@@ -72,7 +72,9 @@ def test_larger_shapes_backward_error(m, n, r, prec):
     Rref = oracle.strip_R(Pref)
     dr = np.abs(np.abs(oracle.strip_R(P)) - np.abs(Rref)).max() / np.abs(Rref).max()
     observe(f"qr_larger_{prec}", be=be, dr=dr)
-    assert dr <= (8e-6 if prec == "fp32" else 17 * lim / 5.5), dr   # observed 2.6e-6 / 5.7 eps (the wide 512 x 2048 case) / 0.96 eps
+    # observed 2.6e-6 (fp32); 5.7 and 9.7 eps in two runs for the wide 512 x 2048 fp16 case (the atomics' summation order moves
+    # single entries of its long R rows by that much), 0.96 eps for bf16: 3 x the largest
+    assert dr <= (8e-6 if prec == "fp32" else 29 * lim / 5.5), dr
 
 
 def test_python_fixtures_match_lapack():
