@@ -4,7 +4,7 @@ BASELINE configs C3 and C5 at full size, the secondary accuracy sets of SURVEY 8
 U diag(s) V^T as python/utils.py:13-24), the FP16 range limit, run-to-run spread, and the reference's own GPU drivers
 (Cuda/qr.cu:958, :1049) on the same box.  References: the oracle where it finishes in seconds, else LAPACK in FP64
 (|R| is unique up to row signs for full-rank input).  Tolerances are <= 3x the figures observed on B200
-(gpurun_out/observed.jsonl -> profiles/r2_observed_tolerances.txt)."""
+(gpurun_out/observed.jsonl -> profiles/r2_observed_test_gpu_parity_large.jsonl)."""
 import numpy as np
 import pytest
 import torch
@@ -30,7 +30,7 @@ def test_tall_panel_regime_vs_oracle(chain, monkeypatch):
     m, n, r = 32768, 512, 128
     A = oracle.uniform_matrix(m, n, 32768512)
     Pref, _ = oracle.block_qr(A, r, want_q=False)
-    # observed on B200 (profiles/r2_observed_tolerances.txt): fp32 dr 7.7e-6 dy 6.7e-6 be 3.6e-7; fp16 dr 3.1e-4 dy 7.7e-6 be 2.6e-4
+    # observed on B200 (profiles/r2_observed_test_gpu_parity_large.jsonl): fp32 dr 7.7e-6 dy 6.7e-6 be 3.6e-7; fp16 dr 3.1e-4 dy 7.7e-6 be 2.6e-4
     for prec, tol_r, tol_y, tol_be in (("fp32", 2.3e-5, 2e-5, 1.1e-6), ("fp16", 9e-4, 2.3e-5, 7.8e-4)):
         A0, P, rr, _ = factor_device(A, r, prec)
         assert rr == r
@@ -93,8 +93,8 @@ def test_c5_full_size_vs_lapack():
     be = float(torch.linalg.norm(Ad - Qd @ Rd) / torch.linalg.norm(Ad))
     orth = float(torch.linalg.norm(Qd.T @ Qd - torch.eye(n, device="cuda", dtype=torch.float64)))
     observe("c5_full_tsqr", dr=dr, be=be, orth=orth)
-    # observed: dr 2.9e-7, be 4.7e-7, orth 3.8e-6
-    assert dr <= 9e-7 and be <= 1.4e-6 and orth <= 1.2e-5, (dr, be, orth)
+    # observed: dr 2.9e-7 - 3.7e-7, be 4.7e-7 - 4.9e-7, orth 3.8e-6 - 3.9e-6
+    assert dr <= 1.1e-6 and be <= 1.4e-6 and orth <= 1.2e-5, (dr, be, orth)
 
 
 def _conditioned(m, n, cond, seed):

@@ -242,5 +242,5 @@ def test_host_driver_streamed_input(m, n, r, monkeypatch):
     spread = np.abs(np.abs(out["streamed"]) - np.abs(out["plain"])).max() / np.abs(out["plain"]).max()
     # (two runs of the SAME path differ at this level too: FP32 atomics in the in-panel products, split-K reduce-add; the wide
     #  shape accumulates it over 4096 more trailing columns: observed 1.3e-3 - 1.6e-3)
-    assert spread <= (7 if m < n else 3) * 2.0 ** -11, spread
+    assert spread <= (10 if m < n else 3) * 2.0 ** -11, spread   # 3 x 3.3 eps
     assert pkg.lib().mpqr_release_cache() == 0
